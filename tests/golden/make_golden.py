@@ -1,0 +1,64 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/diffuerase.py through oracle/reference_harness.py) on small seeded
+clips.  Run in the build container only:  python tests/golden/make_golden.py
+
+Every file stores the inputs' generator arguments (so tests regenerate the same
+inputs from videovanish_b200.synth) plus the reference's outputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import reference_harness as rh          # noqa: E402
+from videovanish_b200 import synth                  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# (name, T, H0, W0, h, w, dilation N, feather F, keep_unmasked)
+CASES = [
+    ("c1_small", 2, 360, 640, 176, 320, 8, 3, True),            # BASELINE config 1 shape, first 2 frames
+    ("odd_sizes", 3, 97, 131, 40, 56, 3, 3, True),              # ragged: W not a multiple of 16/4
+    ("dil1_f5", 2, 120, 160, 56, 80, 1, 5, True),
+    ("dil25_f2", 2, 144, 256, 72, 128, 25, 2, True),            # GUI maximum dilation
+    ("dil0_fill", 2, 64, 96, 32, 48, 0, 3, True),               # iterations=0 -> until convergence (KAT T2)
+    ("hard_alpha", 2, 90, 160, 40, 80, 4, 0, True),             # feather_px <= 0 -> hard composite
+    ("no_keep", 2, 90, 160, 40, 80, 4, 3, False),               # keep_unmasked_original=False: resize only
+    ("same_size", 2, 72, 128, 72, 128, 2, 3, True),             # no resize-back branch
+    ("frac_feather", 2, 80, 112, 40, 56, 2, 2.5, True),         # float feather_px
+    ("hd_crop", 1, 270, 480, 136, 240, 8, 3, True),
+]
+
+
+def inputs(t, h0, w0, h, w, seed):
+    fr = synth.frames(t, h0, w0, seed=seed)
+    mk = synth.masks(t, h0, w0, seed=seed + 1, salt=0.002)
+    inp = synth.noise_frames(t, h, w, seed=seed + 2)
+    return fr, mk, inp
+
+
+def main():
+    assert rh.available(), "needs /root/reference"
+    for ci, (name, t, h0, w0, h, w, n, f, keep) in enumerate(CASES):
+        seed = 100 + 10 * ci
+        fr, mk, inp = inputs(t, h0, w0, h, w, seed)
+        if name == "dil0_fill":
+            mk[1] = 0                                             # an empty frame must stay empty
+        outs, dil = rh.ref_post_all_frames(list(fr), list(mk), list(inp), mask_dilation_iter=n,
+                                           keep_unmasked_original=keep, feather_px=f)
+        lit, _, kw = rh.ref_run_literal(list(fr), list(mk), list(inp), mask_dilation_iter=n,
+                                        keep_unmasked_original=keep, feather_px=f)
+        np.savez_compressed(
+            os.path.join(OUT, name + ".npz"),
+            args=np.array([t, h0, w0, h, w, n, seed], np.int64), feather=np.float64(f), keep=np.bool_(keep),
+            empty_frame1=np.bool_(name == "dil0_fill"),
+            dilated=np.stack(dil), out=np.stack(outs), literal_frame0=lit[0],
+            literal_rest_raw=np.bool_(all(np.array_equal(a, b) for a, b in zip(lit[1:], inp[1:]))))
+        print(name, "dilated px", int(np.stack(dil).astype(bool).sum()), "out", np.stack(outs).shape)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+"""Pin the oracle: closed-form models == the reference's library calls == the
+UNMODIFIED reference run (golden vectors; live when /root/reference exists).
+CPU only.  Encodes SURVEY.md KATs T1-T9."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import prepost as op
+from oracle import reference_harness as rh
+from videovanish_b200 import synth
+from tests.golden.make_golden import inputs as golden_inputs
+
+cv2 = pytest.importorskip("cv2")
+scipy_ndimage = pytest.importorskip("scipy.ndimage")
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def load_case(path):
+    z = np.load(path)
+    t, h0, w0, h, w, n, seed = [int(v) for v in z["args"]]
+    fr, mk, inp = golden_inputs(t, h0, w0, h, w, seed)
+    if bool(z["empty_frame1"]):
+        mk[1] = 0
+    return z, fr, mk, inp, n, float(z["feather"]), bool(z["keep"])
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 10
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_matches_golden(path):
+    """ref_* (library restatement) and model_* (closed form) both reproduce the
+    reference's own outputs bit for bit."""
+    z, fr, mk, inp, n, f, keep = load_case(path)
+    dil_ref = op.ref_binarize_dilate(list(mk), n)
+    dil_model = op.model_binarize_dilate(list(mk), n)
+    assert np.array_equal(np.stack(dil_ref), z["dilated"])
+    assert np.array_equal(np.stack(dil_model), z["dilated"])
+    for i in range(len(fr)):
+        o_ref = op.ref_post_frame(inp[i], fr[i], dil_ref[i], keep, f)
+        o_model = op.model_post_frame(inp[i], fr[i], dil_model[i], keep, f)
+        assert np.array_equal(o_ref, z["out"][i])
+        d = np.abs(o_model.astype(int) - z["out"][i].astype(int))
+        if f <= 3:
+            assert d.max() == 0, "closed-form model must be bit-exact at feather_px <= 3"
+        else:
+            assert d.max() <= 1
+    assert bool(z["literal_rest_raw"])          # reference bug :114 - frames 1.. returned raw
+    assert np.array_equal(z["literal_frame0"], z["out"][0])
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not rh.available(), reason="/root/reference not present")
+def test_oracle_matches_live_reference():
+    fr = synth.frames(3, 90, 150, seed=7)
+    mk = synth.masks(3, 90, 150, seed=8, salt=0.003)
+    inp = synth.noise_frames(3, 40, 72, seed=9)
+    outs, dil = rh.ref_post_all_frames(list(fr), list(mk), list(inp), mask_dilation_iter=5, feather_px=3)
+    assert np.array_equal(np.stack(dil), np.stack(op.ref_binarize_dilate(list(mk), 5)))
+    got = op.ref_run_infill_on_frames(list(fr), list(mk), lambda *a, **k: [x.copy() for x in inp],
+                                      mask_dilation_iter=5, propainer_frames=list(fr))
+    assert np.array_equal(np.stack(got), np.stack(outs))
+    lit, _, kw = rh.ref_run_literal(list(fr), list(mk), list(inp), mask_dilation_iter=5)
+    bug = op.ref_run_infill_on_frames(list(fr), list(mk), lambda *a, **k: [x.copy() for x in inp],
+                                      mask_dilation_iter=5, propainer_frames=list(fr), bug_compat=True)
+    assert all(np.array_equal(a, b) for a, b in zip(lit, bug))
+    assert kw == {"max_img_size": 960, "mask_dilation_iter": 0, "guidance_scale": None, "progress": None}
+
+
+# ---------------------------------------------------------------- KATs T1-T3: dilation
+@pytest.mark.parametrize("n", [1, 3, 8, 25])
+def test_T1_dilation_is_l1_ball(n):
+    rng = np.random.default_rng(n)
+    m = rng.random((97, 131)) < 0.003
+    ref = scipy_ndimage.binary_dilation(m, iterations=n)
+    ys, xs = np.nonzero(m)
+    yy, xx = np.mgrid[0:97, 0:131]
+    dist = np.min(np.abs(yy[..., None] - ys) + np.abs(xx[..., None] - xs), axis=2)
+    assert np.array_equal(ref, dist <= n)
+    assert np.array_equal(op.model_dilate_l1(m, n), ref.astype(np.uint8) * 255)
+
+
+def test_T2_iterations_zero_fills_frame():
+    m = np.zeros((20, 30), bool)
+    assert not scipy_ndimage.binary_dilation(m, iterations=0).any()
+    assert op.model_dilate_l1(m, 0).max() == 0
+    m[7, 11] = True
+    assert scipy_ndimage.binary_dilation(m, iterations=0).all()
+    assert op.model_dilate_l1(m, 0).min() == 255
+    assert op.model_dilate_l1(m, -3).min() == 255
+
+
+def test_T3_binarize_any_channel():
+    rng = np.random.default_rng(3)
+    m = (rng.integers(0, 256, (40, 50, 3)) * (rng.random((40, 50, 3)) < 0.05)).astype(np.uint8)
+    assert np.array_equal(np.any(m > 0, axis=2).astype(np.uint8), op.model_binarize(m))
+
+
+# ---------------------------------------------------------------- KATs T4/T5/T9: resize
+RESIZE_CASES = [(540, 960, 1080, 1920), (536, 960, 1080, 1920), (176, 320, 360, 640), (1080, 1920, 540, 960),
+                (1080, 1920, 536, 960), (97, 131, 200, 333), (200, 333, 97, 131), (7, 5, 31, 47), (1, 1, 8, 8),
+                (2, 3, 9, 9), (100, 100, 25, 25), (2160, 3840, 536, 952), (64, 64, 64, 200), (300, 400, 150, 100)]
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", RESIZE_CASES)
+def test_T5_linear_model_bit_exact(sh, sw, dh, dw):
+    rng = np.random.default_rng(sh * 7 + dw)
+    for c in (1, 3):
+        src = rng.integers(0, 256, (sh, sw, c), dtype=np.uint8)
+        ref = cv2.resize(src, (dw, dh)).reshape(dh, dw, c)
+        assert np.array_equal(op.model_resize_linear(src, dh, dw), ref)
+
+
+def test_T4_half_scale_is_box():
+    rng = np.random.default_rng(4)
+    src = rng.integers(0, 256, (180, 320, 3), dtype=np.uint8).astype(np.int32)
+    box = ((src[0::2, 0::2] + src[0::2, 1::2] + src[1::2, 0::2] + src[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    assert np.array_equal(box, cv2.resize(src.astype(np.uint8), (160, 90)))
+    assert np.array_equal(box, op.model_resize_linear(src.astype(np.uint8), 90, 160))
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", RESIZE_CASES)
+def test_T9_nearest_model_bit_exact(sh, sw, dh, dw):
+    rng = np.random.default_rng(sh + dw)
+    src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+    ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_NEAREST)
+    assert np.array_equal(op.model_resize_nearest(src, dh, dw), ref)
+
+
+def test_inference_size():
+    assert op.inference_size(1080, 1920, 960) == (536, 960)
+    assert op.inference_size(360, 640, 960) == (360, 640)
+    assert op.inference_size(360, 640, 320) == (176, 320)
+    assert op.inference_size(2160, 3840, 960) == (536, 960)
+    assert op.inference_size(1920, 1080, 960) == (960, 536)
+
+
+# ---------------------------------------------------------------- KATs T6-T8: feather + composite
+@pytest.mark.parametrize("f", [1, 2, 3, 2.5, 4, 5, 8])
+def test_T6_feather_alpha_model(f):
+    rng = np.random.default_rng(int(f * 10))
+    for dens in (0.01, 0.3, 0.7, 0.99):
+        m = (rng.random((83, 117)) < dens).astype(np.uint8) * 255
+        m[:9, :13] = 255
+        m[-6:, -20:] = 0
+        m[30:50, 40:80] = 255
+        a_ref = op.ref_feather_alpha(m, f)
+        a_mod = op.model_feather_alpha(m, f)
+        if f <= 3:
+            assert np.array_equal(a_ref, a_mod)
+        else:
+            assert np.allclose(a_ref, a_mod, rtol=1e-6, atol=1e-7)
+    for m in (np.zeros((9, 9), np.uint8), np.full((9, 9), 255, np.uint8)):
+        assert np.array_equal(op.ref_feather_alpha(m, f), op.model_feather_alpha(m, f))
+
+
+def test_T7_alpha_levels_at_F3():
+    rng = np.random.default_rng(5)
+    m = (rng.random((200, 200)) < 0.4).astype(np.uint8) * 255
+    m[50:120, 60:150] = 255
+    m[130:190, 10:100] = 0
+    lv = np.unique(op.ref_feather_alpha(m, 3))
+    expect = np.array([0, .0333, .1339, .1667, .2667, .3333, .6667, .7333, .8333, .8662, .9667, 1], np.float32)
+    assert len(lv) <= 12 and all(np.min(np.abs(expect - v)) < 1e-3 for v in lv)
+    assert not np.any(lv == np.float32(0.5))
+
+
+def test_T8_composite_model_bit_exact():
+    rng = np.random.default_rng(6)
+    a = rng.choice(np.unique(op.model_feather_alpha(
+        (rng.random((64, 64)) < 0.4).astype(np.uint8) * 255, 3)), (120, 160)).astype(np.float32)
+    out = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    orig = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    assert np.array_equal(op.ref_composite(a, out, orig), op.model_composite(a, out, orig))
+    a2 = rng.random((120, 160)).astype(np.float32)
+    assert np.array_equal(op.ref_composite(a2, out, orig), op.model_composite(a2, out, orig))
+
+
+def test_empty_and_full_masks_post():
+    fr = synth.frames(1, 48, 64, seed=1)[0]
+    inp = synth.noise_frames(1, 24, 32, seed=2)[0]
+    up = cv2.resize(inp, (64, 48))
+    assert np.array_equal(op.ref_post_frame(inp, fr, np.zeros((48, 64), np.uint8)), fr)
+    assert np.array_equal(op.ref_post_frame(inp, fr, np.full((48, 64), 255, np.uint8)), up)
+    assert np.array_equal(op.model_post_frame(inp, fr, np.zeros((48, 64), np.uint8)), fr)
+    assert np.array_equal(op.model_post_frame(inp, fr, np.full((48, 64), 255, np.uint8)), up)
