@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark: 1080p frames/s of the pre/post + propagation pixel path.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; N>1 under torchrun)
+    python bench.py --impl reference --gpus N ...            (reference CPU path on host cores)
+
+Workload (BASELINE.json configs[1]): synthetic 1080p 300-frame clip, inference resolution
+960x540.  One step = one pass of the hot path over the whole clip:
+    K1 mask binarise + dilate(8) (+ fused NEAREST low-res mask)      diffuerase.py:28-31
+    K2 bilinear down-size of the frames to 960x540                    row A9
+    K4 flow-guided propagation prior at 960x540, 50+10-frame windows  row A10
+    K3 resize-back + feather(3) + composite                           diffuerase.py:70-112
+    (N > 1 only) K5 halo blend of the `overlap` frames shared with the neighbour ranks
+`value` times that with inputs resident in HBM; `e2e` times the reference-facing
+`run_infill_on_frames(list of host frames)` call (pre + post through the host pipeline, stub
+models, H2D/D2H inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "c2_1080p: 300x1080x1920 clip, infer 960x540, dilate 8, feather 3, K1+K2+K4+K3"
+T_FRAMES, H0, W0, HS, WS = 300, 1080, 1920, 540, 960
+DILATE, FEATHER, OVERLAP = 8, 3, 16
+
+
+def algorithmic_bytes(t):
+    """SURVEY section 8d per-frame figures x frames."""
+    px, spx = H0 * W0, HS * WS
+    return {
+        "K1_binarize_dilate": t * (4 * px + spx),                # 3-ch mask in, 1-ch out (+ low-res mask out)
+        "K2_resize_down": t * (3 * px + 3 * spx),
+        "K4_propagate": t * 56 * spx,
+        "K3_upscale_feather_composite": t * (7 * px + 3 * spx),
+    }
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    out["sm_max_mhz"] = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# reference / CPU-baseline arm: the oracle port of the same path on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_inputs(n):
+    from videovanish_b200 import synth
+    fr = synth.frames(n, H0, W0, seed=2)
+    mk = synth.masks(n, H0, W0, seed=3)
+    inp = synth.noise_frames(n, HS, WS, seed=4)
+    ff, fb = synth.flows(n, HS, WS, seed=5)
+    return fr, mk, inp, ff, fb
+
+
+def cpu_reference_step(fr, mk, inp, ff, fb, threads):
+    """The reference's CPU implementation of the path on a sample of frames: its own cv2 / scipy /
+    numpy calls per frame (oracle.prepost.ref_*, restating diffuerase.py:28-31, :70-112) spread over
+    `threads` host threads (frames are independent and the library calls release the GIL), plus the
+    torch-CPU restatement of the propagation prior (oracle.propagation)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import prepost as op
+    from oracle import propagation as opp
+    n = len(fr)
+
+    def pre(i):
+        d = op.ref_binarize_dilate([mk[i]], DILATE)[0]
+        return d, op.ref_resize_nearest(d, HS, WS), op.ref_resize_linear(fr[i], HS, WS)
+
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(pre, range(n)))
+        dil = [r[0] for r in res]
+        low = np.stack([r[1] for r in res])
+        small = np.stack([r[2] for r in res])
+        opp.img_propagation_torch(small, low, ff, fb)
+        out = list(ex.map(lambda i: op.ref_post_frame(inp[i], fr[i], dil[i], True, FEATHER), range(n)))
+    return out
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n = args.cpu_sample
+    data = cpu_sample_inputs(n)
+    for _ in range(args.warmup):
+        cpu_reference_step(*data, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(*data, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    fps = n / dt
+    sample = "%d of the %d frames per step (oracle port: cv2/scipy/numpy per frame over %d threads + torch-CPU propagation)" % (
+        n, T_FRAMES, threads)
+    line = {
+        "impl": "reference", "metric": "1080p frames/sec (pre/post+propagation)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": n},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def make_workload(t, device, seed):
+    """Host (pinned) and device copies of the synthetic clip.  Frames / inpainted frames repeat a
+    32-frame seeded set (generation cost), masks move every frame, flows are drawn on the device."""
+    import torch
+    from videovanish_b200 import synth
+    base = min(t, 32)
+    reps = (t + base - 1) // base
+    fr = np.tile(synth.frames(base, H0, W0, seed=seed), (reps, 1, 1, 1))[:t]
+    inp = np.tile(synth.noise_frames(base, HS, WS, seed=seed + 2), (reps, 1, 1, 1))[:t]
+    mk = synth.masks(t, H0, W0, seed=seed + 1)
+    host = {}
+    for k, a in (("frames", fr), ("masks", mk), ("inpainted", inp)):
+        p = torch.empty(a.shape, dtype=torch.uint8, pin_memory=True)
+        p.numpy()[...] = a
+        host[k] = p
+    dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 3)
+    n = max(t - 1, 1)
+    basef = torch.tensor([3.0, -1.5], device=device)
+    ff = basef + 0.05 * torch.randn((n, HS, WS, 2), device=device, generator=g)
+    fb = -ff + 0.05 * torch.randn((n, HS, WS, 2), device=device, generator=g)
+    bad = torch.rand((n, HS, WS), device=device, generator=g) < 0.02
+    ff[bad] += (torch.rand((int(bad.sum()), 2), device=device, generator=g) - 0.5) * 40.0
+    dev["flows_f"], dev["flows_b"] = ff.contiguous(), fb.contiguous()
+    torch.cuda.synchronize()
+    return host, dev
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from videovanish_b200 import _lib, chunking, ops
+    from videovanish_b200 import diffuerase as vvd
+
+    t = args.frames
+    host, dev = make_workload(t, device, seed=10 + rank)
+    stages = ["K1_binarize_dilate", "K2_resize_down", "K4_propagate", "K3_upscale_feather_composite"]
+    if world > 1:
+        stages.append("K5_halo_blend")
+    out_buf = torch.empty((t, H0, W0, 3), dtype=torch.uint8, device=device)
+
+    def step(ev=None):
+        def mark(i):
+            if ev is not None:
+                ev[i].record()
+        mark(0)
+        dil, low = ops.binarize_dilate(dev["masks"], DILATE, lowres_size=(HS, WS))
+        mark(1)
+        small = ops.resize(dev["frames"], HS, WS)
+        mark(2)
+        packed = ops.propagate(small, low, dev["flows_f"], dev["flows_b"])
+        mark(3)
+        out = ops.upscale_feather_composite(dev["inpainted"], dev["frames"], dil, FEATHER, out=out_buf)
+        mark(4)
+        if world > 1:
+            chunking.blend_rank_boundaries(out, OVERLAP, mode="nccl")
+            mark(5)
+        return out, packed
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n_marks = len(stages) + 1
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
+    _lib.reset_launch_count()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(evs[k])
+    e1.record()
+    sync_all()
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    tm = torch.tensor([ms_total], device=device)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_step = float(tm.item()) / args.steps
+    stage_ms = {s: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
+                for i, s in enumerate(stages)}
+
+    # ---- end to end through the reference-facing call, host buffers in, host buffers out
+    class _StubModel:                       # stands in for DiffuEraser / ProPainter (out of scope)
+        def forward(self, frames, masks, priors, **kw):
+            return list(inpainted_host)
+
+    frames_host = list(host["frames"].numpy())
+    masks_host = list(host["masks"].numpy())
+    inpainted_host = list(host["inpainted"].numpy())
+    vvd.set_models(diffueraser=_StubModel())
+    e2e_steps = max(1, min(args.steps, 3))
+    vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host, max_img_size=960 if HS == 536 else 961)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host,
+                                       max_img_size=960 if HS == 536 else 961)
+    torch.cuda.synchronize()
+    e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_fps = world * t / float(e2e_dt.item())
+    fh, fw = res[0].shape[:2]
+    px, spx = H0 * W0, inpainted_host[0].shape[0] * inpainted_host[0].shape[1]
+    h2d = t * (3 * px + 3 * spx + 3 * px)           # masks (pre) + inpainted + originals (post)
+    d2h = t * (px + 3 * px)                         # dilated masks (model hand-off) + composited frames
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg = algorithmic_bytes(t)
+        dom = max((s for s in stages if s in alg), key=lambda s: stage_ms[s])
+        achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        line = {
+            "metric": "1080p frames/sec (pre/post+propagation)", "value": world * t / (ms_step * 1e-3),
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": t, "l2": "inputs (>4 GB/step) larger than L2",
+                       "halo_overlap": OVERLAP if world > 1 else 0},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg[dom]},
+            "stages": {s: {"ms": stage_ms[s], "GBps": (alg[s] / (stage_ms[s] * 1e-3) / 1e9) if s in alg else None,
+                           "frac": (alg[s] / (stage_ms[s] * 1e-3) / 1e9 / peak) if s in alg else None} for s in stages},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "diffuerase.run_infill_on_frames(list of pinned host frames), stub models, K1 + K3 via "
+                            "the host pipeline; result %dx%d" % (fh, fw)},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n = args.cpu_sample
+            data = cpu_sample_inputs(n)
+            cpu_reference_step(*data, threads)
+            c0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                cpu_reference_step(*data, threads)
+            cdt = (time.perf_counter() - c0) / reps
+            line["cpu_baseline"] = {
+                "value": n / cdt, "unit": "frames/s", "cores": threads, "kind": "port",
+                "sample": "%d frames of the workload x %d passes: reference cv2/scipy/numpy stages per frame over %d "
+                          "host threads + torch-CPU propagation restatement" % (n, reps, threads)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=T_FRAMES, help="frames per GPU per step (default: the named config)")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="frames in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

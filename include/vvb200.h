@@ -1,0 +1,171 @@
+/*
+ * vvb200.h - C ABI of libvvb200.so: the B200 (sm_100a) pixel pipeline that sits behind
+ * VideoVanish's `diffuerase.run_infill_on_frames` (reference: diffuerase.py:20-114).
+ *
+ * Every entry point takes plain pointers and sizes; there are no torch / C++ types in
+ * the signatures.  `*_dev` style arguments are DEVICE pointers into contiguous NHWC
+ * ("[T,H,W,C]", C fastest) uint8 arrays unless stated otherwise; `stream` is a
+ * `cudaStream_t` passed as `void*` (NULL = the legacy default stream).  All functions
+ * are asynchronous with respect to the host (they only enqueue work on `stream`) except
+ * the `*_host` family, which owns its staging buffers and returns when the result is in
+ * the caller's host memory.
+ *
+ * Return value: 0 on success, a negative VV_ERR_* code on failure; `vv_last_error()`
+ * returns a thread-local, human-readable message for the last failure on this thread.
+ * There is no CPU fallback anywhere: without a CUDA device every call fails with
+ * VV_ERR_CUDA.
+ *
+ * The reference is pure Python; the binding a maintainer adds on the reference side is a
+ * `ctypes.CDLL` stub.  Each declaration cites the reference lines
+ * it replaces (paths relative to /root/reference).
+ */
+#ifndef VVB200_H_
+#define VVB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VV_API __attribute__((visibility("default")))
+#else
+#define VV_API
+#endif
+
+#define VV_OK 0
+#define VV_ERR_INVALID (-1)     /* bad argument (NULL pointer, non-positive size, ...) */
+#define VV_ERR_CUDA (-2)        /* CUDA runtime error / no device */
+#define VV_ERR_UNSUPPORTED (-3) /* valid request outside what the kernels implement */
+
+#define VV_INTER_NEAREST 0 /* cv2.INTER_NEAREST semantics (diffuerase.py:86, tools.py:42) */
+#define VV_INTER_LINEAR 1  /* cv2.INTER_LINEAR u8 fixed-point semantics (diffuerase.py:73) */
+
+/* Library / device introspection. */
+VV_API int vv_version(void);
+VV_API const char *vv_last_error(void);
+VV_API int vv_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+/* Number of kernels this library has launched since load (or since the last reset);
+ * bench.py reports it as `gpu_launches`. */
+VV_API unsigned long long vv_launch_count(void);
+VV_API void vv_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------
+ * K1  mask binarise + L1 dilation.                       Replaces diffuerase.py:28-31
+ *   out[t,y,x] = 255 if some pixel q with any(mask[t,q,:] > 0) has |p-q|_1 <= iterations
+ *   (scipy.ndimage.binary_dilation, cross structure, border 0); iterations < 1 means
+ *   "until convergence": the whole frame is set if any pixel is set.
+ *   mask: u8 [T,H,W,C], C in {1,3,4}.  out: u8 [T,H,W] in {0,255}.
+ *   workspace: vv_binarize_dilate_workspace_bytes(T,H,W) bytes of device scratch (bit planes).
+ *   lowres_out (optional, may be NULL): u8 [T,lh,lw] = INTER_NEAREST down-size of `out`
+ *   written by the same pass (the model-side mask of SURVEY row A9).
+ * --------------------------------------------------------------------------------- */
+VV_API size_t vv_binarize_dilate_workspace_bytes(int T, int H, int W);
+VV_API int vv_binarize_dilate(const uint8_t *mask, int T, int H, int W, int C, int iterations,
+                       uint8_t *out, uint8_t *lowres_out, int lh, int lw,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * K2  resize.            Replaces cv2.resize at diffuerase.py:73 / :86, tools.py:42 and the
+ *   un-vendored down-size to inference resolution triggered by diffuerase.py:62-64.
+ *   src: u8 [T,H,W,C] -> dst: u8 [T,h,w,C]; C in {1,3,4}; interp = VV_INTER_*.
+ *   LINEAR is bit-exact with OpenCV's u8 path (11-bit coefficients; exact x2 down-scale
+ *   == 2x2 box).  workspace: vv_resize_workspace_bytes(h,w) bytes (tap tables).
+ * --------------------------------------------------------------------------------- */
+VV_API size_t vv_resize_workspace_bytes(int h, int w);
+VV_API int vv_resize(const uint8_t *src, int T, int H, int W, int C, uint8_t *dst, int h, int w,
+              int interp, void *workspace, size_t workspace_bytes, void *stream);
+/* (h, w) the model wrapper picks for `max_img_size`. */
+VV_API int vv_inference_size(int H0, int W0, int max_img_size, int *h, int *w);
+
+/* ---------------------------------------------------------------------------------
+ * K3  resize-back + feather alpha + composite, fused.   Replaces diffuerase.py:70-112
+ *   inp:  u8 [T,h,w,3]    inpainted frames at inference resolution
+ *   orig: u8 [T,H0,W0,3]  original frames        (ignored when keep_unmasked == 0)
+ *   mask: u8 [T,H0,W0]    dilated mask, > 0 = masked (ignored when keep_unmasked == 0)
+ *   out:  u8 [T,H0,W0,3]
+ *   alpha = clip(0.5 + (d_in - d_out) / (2*feather_px), 0, 1) with the 5x5 chamfer
+ *   distance transforms of cv2.distanceTransform(DIST_L2, 5); feather_px <= 0 gives the
+ *   hard composite; out = u8(rint(f32(alpha*up) + f32((1-alpha)*orig))), round-half-even.
+ *   feather_px up to VV_MAX_FEATHER is supported.
+ * --------------------------------------------------------------------------------- */
+#define VV_MAX_FEATHER 8.0f
+VV_API size_t vv_composite_workspace_bytes(int H0, int W0);
+VV_API int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, int w,
+                                 const uint8_t *orig, const uint8_t *mask, int H0, int W0,
+                                 float feather_px, int keep_unmasked, uint8_t *out,
+                                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * K4  ProPainter-style flow-guided propagation prior (image propagation, 'nearest').
+ *   Replaces the un-vendored propainter.forward call at diffuerase.py:49-57
+ *   [BidirectionalPropagation(learnable=False) + fbConsistencyCheck + flow_warp].
+ *   The clip is given once; `n_sub` sub-video windows [sub_start[s], sub_start[s]+sub_len[s])
+ *   (HOST int arrays; propainter/inference.py uses 50 frames + 10 pad frames each side) are
+ *   independent scans and are advanced in lock step.
+ *   frames:   u8  [N,h,w,3]        masks: u8 [N,h,w] (>0 = hole)
+ *   flows_f:  f32 [N-1,h,w,2]      flow t -> t+1 (x,y in pixels);  flows_b: t+1 -> t
+ *   out:      u32 [sum(sub_len),h,w], windows concatenated in the given order; each word is
+ *             R | G<<8 | B<<16 | state<<24 of the forward pass; state bit0 = still a hole,
+ *             bit1 = value is the float 0.0 of the masked frame (hole or zero-padded warp)
+ *             rather than a u8 level.
+ *   workspace: vv_propagate_workspace_bytes(sum(sub_len), h, w) bytes.
+ * --------------------------------------------------------------------------------- */
+VV_API size_t vv_propagate_workspace_bytes(int n_out_frames, int h, int w);
+VV_API int vv_propagate(const uint8_t *frames, const uint8_t *masks, const float *flows_f,
+                 const float *flows_b, int n_frames, int h, int w, const int *sub_start,
+                 const int *sub_len, int n_sub, uint32_t *out, void *workspace,
+                 size_t workspace_bytes, void *stream);
+/* Unpack K4's output: rgb u8 [N,3] (zero-valued pixels get `zero_level`), hole mask u8 [N]
+ * in {0,255}.  Either output may be NULL. */
+VV_API int vv_propagate_unpack(const uint32_t *packed, size_t n_pixels, uint8_t zero_level,
+                        uint8_t *rgb, uint8_t *hole_mask, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * K5  chunk-overlap feather blend (builder-defined spec; the reference
+ *   only lists it as a TODO, README.md:76).  For overlap frame k in [k0, k0+O):
+ *   w = f32(k+1)/f32(O_total+1); out = u8(rint(f32((1-w)*A) + f32(w*B))).
+ *   A = earlier chunk's tail, B = later chunk's head, both u8 [O,H,W,C]; B may be a
+ *   peer-GPU pointer (P2P / IPC mapped) - the kernel reads it in place over NVLink.
+ * --------------------------------------------------------------------------------- */
+VV_API int vv_chunk_blend(const uint8_t *A, const uint8_t *B, int O, size_t frame_bytes, int k0,
+                   int O_total, uint8_t *out, void *stream);
+
+/* ---------------------------------------------------------------------------------
+ * Host-buffer pipeline (the path the Python drop-in takes for lists of numpy frames, i.e. the
+ * whole of diffuerase.py:26-31 and :69-114 with per-frame HOST pointers in and out).
+ * A context owns device buffers, streams and (lazily) pinned staging rings for one original
+ * geometry H0 x W0; batches of `frames_per_batch` frames rotate over `n_slots` streams so that
+ * H2D, kernels and D2H of neighbouring batches overlap.  Page-locked host buffers are copied
+ * directly, pageable ones through the staging ring.  Calls block until the results are in the
+ * caller's host buffers.  One job at a time per context (internally locked).
+ * --------------------------------------------------------------------------------- */
+typedef struct vv_pipeline vv_pipeline;
+VV_API int vv_pipeline_create(vv_pipeline **p, int device, int H0, int W0, int frames_per_batch,
+                              int n_slots);
+VV_API void vv_pipeline_destroy(vv_pipeline *p);
+/* pre (diffuerase.py:28-31): T host pointers to u8 [H0,W0,C] masks -> host u8 [H0,W0] dilated
+ * masks, and optionally (lowres_out != NULL) the NEAREST [lh,lw] masks.  Device copies of the
+ * dilated masks stay resident in the context for the matching vv_pipeline_post call. */
+VV_API int vv_pipeline_pre(vv_pipeline *p, const uint8_t *const *masks, int T, int C, int iterations,
+                           uint8_t *const *dilated_out, uint8_t *const *lowres_out, int lh, int lw);
+/* down-size frames for the model (row A9): host [H0,W0,3] -> host [h,w,3]. */
+VV_API int vv_pipeline_downsize(vv_pipeline *p, const uint8_t *const *frames, int T, int h, int w,
+                                uint8_t *const *small_out);
+/* post (diffuerase.py:70-112): inpainted [h,w,3] + originals [H0,W0,3] -> out [H0,W0,3].
+ * `dilated` may be NULL to reuse the masks kept by the preceding vv_pipeline_pre. */
+VV_API int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted, int h, int w,
+                            const uint8_t *const *orig, const uint8_t *const *dilated, int T,
+                            float feather_px, int keep_unmasked, uint8_t *const *out);
+
+/* Peer-memory helpers for the multi-GPU halo blend (one process per GPU). */
+VV_API int vv_ipc_get_handle(const void *dev_ptr, void *handle_out_64B);
+VV_API int vv_ipc_open_handle(const void *handle_64B, void **mapped_ptr);
+VV_API int vv_ipc_close_handle(void *mapped_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VVB200_H_ */

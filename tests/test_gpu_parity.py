@@ -1,0 +1,315 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): every call goes through the C ABI
+(ctypes -> libvvb200.so) and is compared with the CPU oracle on the same seeded inputs and with
+the golden vectors the unmodified reference produced (tests/golden).
+
+Tolerances (BASELINE.json north_star): masks bit-exact; u8 frames within +-1 LSB - and in fact
+asserted bit-exact wherever the closed-form model is (feather_px <= 3, every resize)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import chunk_blend as ocb
+from oracle import prepost as op
+from oracle import propagation as opp
+from videovanish_b200 import synth
+from tests.golden.make_golden import inputs as golden_inputs
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from videovanish_b200 import ops as _ops
+    return _ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_pre_and_post(ops, path):
+    z = np.load(path)
+    t, h0, w0, h, w, n, seed = [int(v) for v in z["args"]]
+    f, keep = float(z["feather"]), bool(z["keep"])
+    fr, mk, inp = golden_inputs(t, h0, w0, h, w, seed)
+    if bool(z["empty_frame1"]):
+        mk[1] = 0
+    dil = ops.binarize_dilate(dev(mk), n)
+    assert np.array_equal(host(dil), z["dilated"]), "dilated masks must be bit-exact"
+    out = ops.upscale_feather_composite(dev(inp), dev(fr), dil, feather_px=f, keep_unmasked_original=keep)
+    d = np.abs(host(out).astype(int) - z["out"].astype(int))
+    assert d.max() <= 1
+    if f <= 3:
+        assert d.max() == 0, "bit-exact expected at feather_px <= 3"
+
+
+# ------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 8, 9, 16, 17, 25, 32, 33, 40, 70])
+def test_k1_dilation_radii(ops, n):
+    mk = synth.masks(2, 150, 208, seed=n, salt=0.001)
+    ref = np.stack(op.model_binarize_dilate(list(mk), n))
+    assert np.array_equal(host(ops.binarize_dilate(dev(mk), n)), ref)
+
+
+@pytest.mark.parametrize("h,w,c", [(97, 131, 3), (64, 64, 1), (33, 1000, 4), (1, 17, 3), (40, 2048 + 16, 3), (5, 3, 3)])
+def test_k1_shapes_and_channels(ops, h, w, c):
+    rng = np.random.default_rng(h * w)
+    mk = (rng.integers(0, 256, (3, h, w, c)) * (rng.random((3, h, w, c)) < 0.004)).astype(np.uint8)
+    ref = np.stack([op.model_dilate_l1(op.model_binarize(m), 6) for m in mk])
+    assert np.array_equal(host(ops.binarize_dilate(dev(mk), 6)), ref)
+
+
+def test_k1_iterations_zero_fills(ops):
+    mk = synth.masks(3, 72, 96, seed=1, salt=0.0005)
+    mk[1] = 0
+    for it in (0, -2):
+        got = host(ops.binarize_dilate(dev(mk), it))
+        assert got[0].min() == 255 and got[2].min() == 255 and got[1].max() == 0
+
+
+def test_k1_scipy_cross_check(ops):
+    mk = synth.masks(2, 120, 176, seed=3, salt=0.002)
+    ref = np.stack(op.ref_binarize_dilate(list(mk), 8))
+    assert np.array_equal(host(ops.binarize_dilate(dev(mk), 8)), ref)
+
+
+def test_k1_fused_lowres_mask(ops):
+    mk = synth.masks(2, 180, 320, seed=4, salt=0.002)
+    full, low = ops.binarize_dilate(dev(mk), 8, lowres_size=(88, 160))
+    ref_full = np.stack(op.model_binarize_dilate(list(mk), 8))
+    assert np.array_equal(host(full), ref_full)
+    assert np.array_equal(host(low), np.stack([op.ref_resize_nearest(m, 88, 160) for m in ref_full]))
+    full0, low0 = ops.binarize_dilate(dev(mk), 0, lowres_size=(88, 160))
+    assert host(low0).min() == 255
+
+
+# ------------------------------------------------------------------------------- K2
+RESIZE = [(540, 960, 1080, 1920), (176, 320, 360, 640), (1080, 1920, 540, 960), (1080, 1920, 536, 960),
+          (97, 131, 200, 333), (200, 333, 97, 131), (7, 5, 31, 47), (1, 1, 8, 8), (360, 640, 176, 320),
+          (64, 64, 64, 200), (300, 400, 150, 100), (50, 70, 50, 70)]
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", RESIZE)
+def test_k2_linear_bit_exact_vs_cv2(ops, sh, sw, dh, dw):
+    rng = np.random.default_rng(sh + 3 * dw)
+    for c in (3, 1, 4):
+        src = rng.integers(0, 256, (2, sh, sw, c), dtype=np.uint8)
+        ref = np.stack([op.ref_resize_linear(s, dh, dw).reshape(dh, dw, c) for s in src])
+        assert np.array_equal(host(ops.resize(dev(src), dh, dw, ops.INTER_LINEAR)), ref)
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", RESIZE)
+def test_k2_nearest_bit_exact_vs_cv2(ops, sh, sw, dh, dw):
+    rng = np.random.default_rng(sh + dw)
+    src = rng.integers(0, 256, (2, sh, sw, 3), dtype=np.uint8)
+    ref = np.stack([op.ref_resize_nearest(s, dh, dw) for s in src])
+    assert np.array_equal(host(ops.resize(dev(src), dh, dw, ops.INTER_NEAREST)), ref)
+
+
+# ------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("f", [3, 1, 2, 2.5, 0, -1, 0.5, 4, 5, 8])
+def test_k3_feather_values(ops, f):
+    fr = synth.frames(2, 120, 176, seed=11)
+    inp = synth.noise_frames(2, 56, 88, seed=12)
+    dil = np.stack(op.model_binarize_dilate(list(synth.masks(2, 120, 176, seed=13, salt=0.003)), 3))
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, f) for i in range(2)])
+    got = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=f))
+    d = np.abs(got.astype(int) - ref.astype(int))
+    assert d.max() <= 1
+    if f <= 3:
+        assert d.max() == 0
+
+
+@pytest.mark.parametrize("h0,w0,h,w", [(97, 131, 40, 56), (360, 640, 176, 320), (72, 128, 72, 128), (50, 1040, 24, 520),
+                                        (35, 16, 70, 32), (1, 16, 1, 8)])
+def test_k3_shapes(ops, h0, w0, h, w):
+    fr = synth.frames(2, h0, w0, seed=h0)
+    inp = synth.noise_frames(2, h, w, seed=w0)
+    rng = np.random.default_rng(h0 * w0)
+    dil = ((rng.random((2, h0, w0)) < 0.3) * 255).astype(np.uint8)
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, 3) for i in range(2)])
+    got = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=3))
+    assert np.array_equal(got, ref)
+
+
+def test_k3_empty_full_masks_and_no_keep(ops):
+    fr = synth.frames(2, 64, 96, seed=1)
+    inp = synth.noise_frames(2, 32, 48, seed=2)
+    up = np.stack([op.ref_resize_linear(i, 64, 96) for i in inp])
+    z = np.zeros((2, 64, 96), np.uint8)
+    assert np.array_equal(host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(z))), fr)
+    assert np.array_equal(host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(z + 255))), up)
+    assert np.array_equal(host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(z), keep_unmasked_original=False)), up)
+
+
+def test_k3_unsupported_feather_raises(ops):
+    fr = synth.frames(1, 32, 32, seed=1)
+    with pytest.raises(RuntimeError, match="feather_px"):
+        ops.upscale_feather_composite(dev(fr), dev(fr), dev(fr[..., 0]), feather_px=50)
+
+
+# ------------------------------------------------------------------------------- K4
+def prop_clip(t, h, w, seed, shift=0.0):
+    fr = synth.frames(t, h, w, seed=seed)
+    m = (synth.masks(t, h, w, seed=seed + 1, salt=0.002).max(axis=3) > 0).astype(np.uint8) * 255
+    ff, fb = synth.flows(t, h, w, seed=seed + 2)
+    ff[..., 0] += shift
+    fb[..., 0] -= shift
+    return fr, m, ff, fb
+
+
+@pytest.mark.parametrize("t,h,w,shift", [(6, 48, 64, 0.0), (5, 40, 56, 9.0), (12, 72, 96, 0.0), (2, 33, 47, 0.0),
+                                         (1, 16, 16, 0.0), (7, 35, 51, 0.0)])
+def test_k4_matches_model_and_torch(ops, t, h, w, shift):
+    fr, m, ff, fb = prop_clip(t, h, w, seed=t * 100 + h, shift=shift)
+    got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb))).view(np.uint32)
+    assert np.array_equal(got, opp.model_propagate(fr, m, ff, fb)), "packed state must equal the explicit model"
+    ref_frames, ref_masks = opp.img_propagation_torch(fr, m, ff, fb)
+    gf, gm = opp.decode_state(got)
+    assert (gm != ref_masks).mean() <= 1e-5 and (gf != ref_frames).mean() <= 1e-5
+
+
+def test_k4_zero_padding_fill(ops):
+    """Holes on the left border with a small outward flow are filled from the zero padding."""
+    t, h, w = 3, 24, 32
+    fr = synth.frames(t, h, w, seed=5)
+    m = np.zeros((t, h, w), np.uint8)
+    m[:, 4:20, 0:2] = 255
+    ff = np.zeros((t - 1, h, w, 2), np.float32)
+    fb = np.zeros((t - 1, h, w, 2), np.float32)
+    ff[..., 0] = -0.61
+    fb[..., 0] = 0.58
+    want = opp.model_propagate(fr, m, ff, fb)
+    assert ((want >> 24) == 2).sum() > 0
+    got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb))).view(np.uint32)
+    assert np.array_equal(got, want)
+    rf, rm = opp.img_propagation_torch(fr, m, ff, fb)
+    gf, gm = opp.decode_state(got)
+    assert np.array_equal(gf, rf) and np.array_equal(gm, rm)
+
+
+def test_k4_subvideo_windows(ops):
+    fr, m, ff, fb = prop_clip(23, 32, 48, seed=77)
+    got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb), subvideo_length=6, pad_len=2)).view(np.uint32)
+    assert np.array_equal(got, opp.model_propagate_clip(fr, m, ff, fb, subvideo_length=6, pad_len=2))
+    rgb, hole = ops.propagate_unpack(dev(got.view(np.int32)), zero_level=127)
+    assert np.array_equal(host(hole) > 0, (got >> 24) & 1 == 1)
+
+
+# ------------------------------------------------------------------------------- K5
+@pytest.mark.parametrize("o,shape", [(16, (36, 64, 3)), (3, (17, 13, 3)), (1, (8, 8, 1))])
+def test_k5_chunk_blend(ops, o, shape):
+    rng = np.random.default_rng(o)
+    a = rng.integers(0, 256, (o,) + shape, dtype=np.uint8)
+    b = rng.integers(0, 256, (o,) + shape, dtype=np.uint8)
+    assert np.array_equal(host(ops.chunk_blend(dev(a), dev(b))), ocb.blend_overlap(a, b))
+    if o > 2:       # a slice of a longer overlap (what a rank holding half the overlap computes)
+        got = host(ops.chunk_blend(dev(a[1:]), dev(b[1:]), k0=1, overlap_total=o))
+        assert np.array_equal(got, ocb.blend_overlap(a, b)[1:])
+
+
+# ------------------------------------------------------------------------------- drop-in + pipeline
+class _StubDiffuEraser:
+    def __init__(self, inpainted):
+        self.inpainted, self.seen = inpainted, None
+
+    def forward(self, frames, masks, priors, **kw):
+        self.seen = dict(masks=[m.copy() for m in masks], kw=kw, n=len(frames))
+        return [f.copy() for f in self.inpainted]
+
+
+@pytest.mark.parametrize("pinned_inputs", [False, True])
+def test_dropin_run_infill_on_frames(ops, pinned_inputs):
+    from videovanish_b200 import diffuerase as vvd, hostpipe
+    t, h0, w0 = 11, 180, 320
+    h, w = ops.inference_size(h0, w0, 160)
+    fr, mk, inp = synth.frames(t, h0, w0, seed=21), synth.masks(t, h0, w0, seed=22), synth.noise_frames(t, h, w, seed=23)
+    frames, masks = list(fr), list(mk)
+    if pinned_inputs:
+        frames = hostpipe.pinned_frames(t, (h0, w0, 3))
+        masks = hostpipe.pinned_frames(t, (h0, w0, 3))
+        for i in range(t):
+            frames[i][...] = fr[i]
+            masks[i][...] = mk[i]
+    stub = _StubDiffuEraser(list(inp))
+    vvd.set_models(diffueraser=stub)
+    calls = []
+    out = vvd.run_infill_on_frames(frames, masks, mask_dilation_iter=5, propainer_frames=frames, max_img_size=160,
+                                   prog=lambda p, s: calls.append((p, s)))
+    ref = op.ref_run_infill_on_frames(list(fr), list(mk), lambda *a, **k: [x.copy() for x in inp],
+                                      mask_dilation_iter=5, propainer_frames=list(fr), max_img_size=160)
+    assert isinstance(out, list) and len(out) == t
+    assert all(o.dtype == np.uint8 and o.flags.c_contiguous and o.shape == (h0, w0, 3) for o in out)
+    assert np.array_equal(np.stack(out), np.stack(ref))
+    assert np.array_equal(np.stack(stub.seen["masks"]), np.stack(op.ref_binarize_dilate(list(mk), 5)))
+    assert stub.seen["kw"] == {"max_img_size": 160, "mask_dilation_iter": 0, "guidance_scale": None,
+                               "progress": calls and stub.seen["kw"]["progress"]}
+    assert [c[0] for c in calls] == [5, 10, 50, 90]
+    assert np.array_equal(np.stack(frames), fr), "inputs must not be mutated"
+    vvd.BUG_COMPAT = True
+    try:
+        lit = vvd.run_infill_on_frames(list(fr), list(mk), mask_dilation_iter=5, propainer_frames=list(fr), max_img_size=160)
+    finally:
+        vvd.BUG_COMPAT = False
+    assert np.array_equal(lit[0], ref[0]) and all(np.array_equal(a, b) for a, b in zip(lit[1:], inp[1:]))
+
+
+def test_pipeline_batches_and_downsize(ops):
+    from videovanish_b200 import hostpipe
+    t, h0, w0, h, w = 21, 90, 160, 40, 80
+    fr, mk, inp = synth.frames(t, h0, w0, seed=31), synth.masks(t, h0, w0, seed=32), synth.noise_frames(t, h, w, seed=33)
+    pipe = hostpipe.HostPipeline(h0, w0, h, w, frames_per_batch=4, n_slots=2)
+    dil, low = pipe.pre(list(mk), 3, want_lowres=True)
+    ref_dil = op.ref_binarize_dilate(list(mk), 3)
+    assert np.array_equal(np.stack(dil), np.stack(ref_dil))
+    assert np.array_equal(np.stack(low), np.stack([op.ref_resize_nearest(m, h, w) for m in ref_dil]))
+    small = pipe.downsize(list(fr))
+    assert np.array_equal(np.stack(small), np.stack([op.ref_resize_linear(f, h, w) for f in fr]))
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], ref_dil[i], True, 3) for i in range(t)])
+    assert np.array_equal(np.stack(pipe.post(list(inp), list(fr))), ref)                 # resident masks
+    assert np.array_equal(np.stack(pipe.post(list(inp), list(fr), dilated=ref_dil)), ref)  # supplied masks
+    pipe.close()
+
+
+# ------------------------------------------------------------------------------- full-size properties
+def test_full_size_1080p_properties(ops):
+    """BASELINE config 2 shape (a 12-frame slice): oracle comparison on 2 frames, plus
+    size-independent properties on all of them."""
+    t, h0, w0, h, w = 12, 1080, 1920, 540, 960
+    fr, mk, inp = synth.frames(t, h0, w0, seed=2), synth.masks(t, h0, w0, seed=3), synth.noise_frames(t, h, w, seed=4)
+    dmk, dfr, dinp = dev(mk), dev(fr), dev(inp)
+    dil = ops.binarize_dilate(dmk, 8)
+    hd = host(dil)
+    for i in (0, t - 1):
+        assert np.array_equal(hd[i], op.ref_binarize_dilate([mk[i]], 8)[0])
+    # idempotence of binarisation, monotonicity and composition of L1 balls
+    assert np.array_equal(host(ops.binarize_dilate(dil, 0 + 1)), host(ops.binarize_dilate(dmk, 9)))
+    assert np.array_equal(host(ops.binarize_dilate(ops.binarize_dilate(dmk, 3), 5)), hd)
+    assert np.all(hd >= (mk.max(axis=3) > 0) * 255)
+    out = ops.upscale_feather_composite(dinp, dfr, dil, 3)
+    ho = host(out)
+    for i in (0, t - 1):
+        assert np.array_equal(ho[i], op.ref_post_frame(inp[i], fr[i], hd[i], True, 3))
+    # outside the feathered mask the original must come back untouched; deep inside, the resized frame
+    far = host(ops.binarize_dilate(dil, 3)) == 0
+    assert np.array_equal(ho[far], fr[far])
+    small = ops.resize(dfr, h, w)
+    for i in (0, t - 1):
+        assert np.array_equal(host(small[i]), op.ref_resize_linear(fr[i], h, w))
+    # linearity check of the box filter: resize(255 - x) == 255 - resize(x) up to rounding
+    inv = host(ops.resize(255 - dfr, h, w)).astype(int)
+    assert np.abs((255 - inv) - host(small).astype(int)).max() <= 1

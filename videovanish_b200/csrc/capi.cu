@@ -1,0 +1,70 @@
+// Library-level pieces of the C ABI (include/vvb200.h): error reporting, introspection,
+// launch accounting and the CUDA-IPC helpers used by the multi-GPU halo blend.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vv {
+
+static thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace vv
+
+using namespace vv;
+
+extern "C" int vv_version(void) { return 100; }
+
+extern "C" const char *vv_last_error(void) { return g_err; }
+
+extern "C" unsigned long long vv_launch_count(void) { return g_launches.load(); }
+
+extern "C" void vv_reset_launch_count(void) { g_launches.store(0); }
+
+extern "C" int vv_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceProperties");
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return VV_OK;
+}
+
+extern "C" int vv_ipc_get_handle(const void *dev_ptr, void *handle_out_64B) {
+    VV_CHECK_ARG(dev_ptr && handle_out_64B, "vv_ipc_get_handle: NULL pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaIpcGetMemHandle");
+    memcpy(handle_out_64B, &h, 64);
+    return VV_OK;
+}
+
+extern "C" int vv_ipc_open_handle(const void *handle_64B, void **mapped_ptr) {
+    VV_CHECK_ARG(handle_64B && mapped_ptr, "vv_ipc_open_handle: NULL pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64B, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(mapped_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaIpcOpenMemHandle");
+    return VV_OK;
+}
+
+extern "C" int vv_ipc_close_handle(void *mapped_ptr) {
+    VV_CHECK_ARG(mapped_ptr, "vv_ipc_close_handle: NULL pointer");
+    cudaError_t e = cudaIpcCloseMemHandle(mapped_ptr);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaIpcCloseMemHandle");
+    return VV_OK;
+}

@@ -1,0 +1,299 @@
+// K1: mask binarise + L1 dilation.   Replaces /root/reference/diffuerase.py:28-31
+//
+//   m = np.any(m > 0, axis=2)                                   (:29)
+//   m = scipy.ndimage.binary_dilation(m, iterations=N) * 255    (:30)
+//
+// Two streaming passes over HBM with a bit plane (1 bit / pixel) in between:
+//   k1a binarize_pack   u8 [T,H,W,C] -> u32 bit plane [T*H,Wp]          reads C B/px, writes 1/8 B/px
+//   k1b dilate_expand   bit plane -> u8 [T,H,W] in {0,255}               reads ~1/8 B/px, writes 1 B/px
+// so the C-byte mask is read exactly once whatever the dilation radius (no halo re-reads of
+// the wide input); halos are paid on the bit plane, which is 24x smaller and L2 resident.
+// The dilation itself is N rounds of the 4-connected cross done entirely in registers:
+// one warp owns a 32-word x ROWS tile (lane <-> word column, rows unrolled in registers),
+// horizontal carries come from the neighbour lanes by warp shuffle; no shared memory and no
+// block barriers.  Cells outside the frame behave as free space, which cannot change any
+// in-frame result because L1 shortest paths between in-frame pixels stay inside the frame.
+//
+// Bit plane layout: row r (= t*H + y) holds Wp = ceil(W/32) little-endian u32 words, pixel x
+// is bit (x & 31) of word (x >> 5); bits at x >= W are zero.
+#include "common.cuh"
+
+namespace vv {
+
+// ------------------------------------------------------------------ k1a: binarise + pack
+// One thread packs 16 pixels into one u16 of the bit plane (u16 index = 2*word + half).
+template <int C, bool VEC>
+__global__ void __launch_bounds__(256) k1a_binarize_pack(const uint8_t *__restrict__ mask, uint16_t *__restrict__ bits,
+                                                         int W, int halves_per_row, long long n_rows) {
+    const long long total = n_rows * halves_per_row;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long row = idx / halves_per_row;
+        const int hw = (int)(idx - row * halves_per_row);
+        const int x0 = hw * 16;
+        uint32_t out = 0;
+        if (x0 < W) {
+            const uint8_t *p = mask + (row * W + x0) * C;
+            if (VEC && x0 + 16 <= W) {
+                if (C == 1) {
+                    out = nonzero_bits16(ldg128(p));
+                } else if (C == 3) {
+                    const uint4 a = ldg128(p), b = ldg128(p + 16), c = ldg128(p + 32);
+                    const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {   // 4 pixels per 3 words
+                        const uint32_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
+                        out |= (uint32_t)((w0 & 0x00ffffffu) != 0) << (4 * g);
+                        out |= (uint32_t)(((w0 & 0xff000000u) | (w1 & 0x0000ffffu)) != 0) << (4 * g + 1);
+                        out |= (uint32_t)(((w1 & 0xffff0000u) | (w2 & 0x000000ffu)) != 0) << (4 * g + 2);
+                        out |= (uint32_t)((w2 & 0xffffff00u) != 0) << (4 * g + 3);
+                    }
+                } else {   // C == 4: one word per pixel
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 v = ldg128(p + 16 * q);
+                        out |= ((uint32_t)(v.x != 0) | ((uint32_t)(v.y != 0) << 1) | ((uint32_t)(v.z != 0) << 2) |
+                                ((uint32_t)(v.w != 0) << 3))
+                               << (4 * q);
+                    }
+                }
+            } else {
+                const int n = min(16, W - x0);
+                for (int i = 0; i < n; ++i) {
+                    uint32_t any = 0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) any |= p[i * C + c];
+                    out |= (uint32_t)(any != 0) << i;
+                }
+            }
+        }
+        bits[idx] = (uint16_t)out;
+    }
+}
+
+// ------------------------------------------------------------------ k1b: dilate (+ expand)
+// Warp tile: lanes 1..30 own output word columns tx*30 + (lane-1); lanes 0 and 31 carry the
+// 32-pixel horizontal halo (enough for n_iter <= 32).  Register row i <-> frame row
+// y0 - NMAX + i.  After n_iter rounds rows [NMAX, NMAX+RB) of lanes 1..30 are exact.
+template <int NMAX, int RB>
+__global__ void __launch_bounds__(128)
+    k1b_dilate_expand(const uint32_t *__restrict__ bits_in, uint32_t *__restrict__ bits_out, uint8_t *__restrict__ out,
+                      int H, int W, int Wp, int n_iter, int tiles_x, int tiles_y, long long n_tiles, int vec_ok) {
+    constexpr int ROWS = RB + 2 * NMAX;
+    const int lane = threadIdx.x & 31;
+    const long long tile = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;   // whole warp exits together
+    const int tx = (int)(tile % tiles_x);
+    const long long rest = tile / tiles_x;
+    const int ty = (int)(rest % tiles_y);
+    const long long t = rest / tiles_y;
+    const int wx = tx * 30 + lane - 1;
+    const int y0 = ty * RB;
+    const bool col_ok = wx >= 0 && wx < Wp;
+    const uint32_t *src = bits_in + t * H * (long long)Wp + wx;
+
+    uint32_t r[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+        const int y = y0 - NMAX + i;
+        const bool need = (i >= NMAX - n_iter) && (i < NMAX + RB + n_iter);
+        r[i] = (col_ok && need && y >= 0 && y < H) ? __ldg(src + (long long)y * Wp) : 0u;
+    }
+
+#pragma unroll 1
+    for (int it = 0; it < n_iter; ++it) {
+        uint32_t prev = 0;
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            const uint32_t c = r[i];
+            uint32_t l = __shfl_up_sync(0xffffffffu, c, 1);
+            uint32_t rt = __shfl_down_sync(0xffffffffu, c, 1);
+            if (lane == 0) l = 0;
+            if (lane == 31) rt = 0;
+            const uint32_t nxt = (i + 1 < ROWS) ? r[i + 1] : 0u;
+            r[i] = c | (c << 1) | (c >> 1) | (l >> 31) | (rt << 31) | prev | nxt;
+            prev = c;
+        }
+    }
+
+    if (lane == 0 || lane == 31 || !col_ok) return;
+    // bits beyond the frame edge may have been dilated into; clear them in the last word
+    const int valid_bits = W - wx * 32;
+    const uint32_t keep = valid_bits >= 32 ? 0xffffffffu : ((1u << valid_bits) - 1u);
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+        const int y = y0 + i;
+        if (y >= H) break;
+        const uint32_t v = r[NMAX + i] & keep;
+        const long long row = t * H + y;
+        if (bits_out) bits_out[row * Wp + wx] = v;
+        if (out) {
+            uint8_t *o = out + row * W + wx * 32;
+            if (vec_ok && valid_bits >= 32) {
+                uint4 a, b;
+                a.x = expand4(v), a.y = expand4(v >> 4), a.z = expand4(v >> 8), a.w = expand4(v >> 12);
+                b.x = expand4(v >> 16), b.y = expand4(v >> 20), b.z = expand4(v >> 24), b.w = expand4(v >> 28);
+                stg128_stream(o, a);
+                stg128_stream(o + 16, b);
+            } else {
+                const int n = min(32, valid_bits);
+                for (int k = 0; k < n; ++k) o[k] = ((v >> k) & 1u) ? 255 : 0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ iterations < 1: fill
+// scipy repeats the cross until nothing changes: a frame with any set pixel ends up full.
+__global__ void __launch_bounds__(256) k1c_any_per_frame(const uint32_t *__restrict__ bits, long long words_per_frame,
+                                                         uint32_t *__restrict__ flags) {
+    const long long t = blockIdx.y;
+    const uint32_t *p = bits + t * words_per_frame;
+    uint32_t acc = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < words_per_frame;
+         i += (long long)gridDim.x * blockDim.x)
+        acc |= __ldg(p + i);
+    acc = __reduce_or_sync(0xffffffffu, acc);
+    if ((threadIdx.x & 31) == 0 && acc) atomicOr(flags + t, 1u);
+}
+
+__global__ void __launch_bounds__(256) k1c_fill(const uint32_t *__restrict__ flags, uint8_t *__restrict__ out,
+                                                long long bytes_per_frame) {
+    const long long t = blockIdx.y;
+    const uint8_t v = flags[t] ? 255 : 0;
+    uint8_t *o = out + t * bytes_per_frame;
+    const long long n16 = ((uintptr_t)o % 16 == 0) ? bytes_per_frame / 16 : 0;
+    const uint32_t w = v * 0x01010101u;
+    const uint4 v4 = make_uint4(w, w, w, w);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+        stg128_stream(o + 16 * i, v4);
+    for (long long i = n16 * 16 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < bytes_per_frame;
+         i += (long long)gridDim.x * blockDim.x)
+        o[i] = v;
+}
+
+// ------------------------------------------------------------------ fused low-res mask
+// INTER_NEAREST down-size of the dilated mask (SURVEY row A9 mask path), sampled from the
+// dilated bit plane so the full-resolution u8 mask is not re-read.
+__global__ void __launch_bounds__(256)
+    k1d_lowres_from_bits(const uint32_t *__restrict__ bits, int H, int W, int Wp, uint8_t *__restrict__ low, int lh,
+                         int lw, long long T) {
+    const long long total = T * lh * (long long)lw;
+    const double sy = 1.0 / ((double)lh / (double)H), sx = 1.0 / ((double)lw / (double)W);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % lw);
+        const long long q = idx / lw;
+        const int y = (int)(q % lh);
+        const long long t = q / lh;
+        const int srcy = min((int)floor(__dmul_rn((double)y, sy)), H - 1);
+        const int srcx = min((int)floor(__dmul_rn((double)x, sx)), W - 1);
+        const uint32_t w = __ldg(bits + (t * H + srcy) * Wp + (srcx >> 5));
+        low[idx] = ((w >> (srcx & 31)) & 1u) ? 255 : 0;
+    }
+}
+
+template <int C>
+static int launch_k1a(const uint8_t *mask, uint16_t *bits, int W, int Wp, long long n_rows, bool vec, int grid,
+                      cudaStream_t st) {
+    if (vec)
+        k1a_binarize_pack<C, true><<<grid, 256, 0, st>>>(mask, bits, W, 2 * Wp, n_rows);
+    else
+        k1a_binarize_pack<C, false><<<grid, 256, 0, st>>>(mask, bits, W, 2 * Wp, n_rows);
+    VV_POST_LAUNCH("k1a_binarize_pack");
+    return VV_OK;
+}
+
+template <int NMAX, int RB>
+static int launch_k1b(const uint32_t *in, uint32_t *bits_out, uint8_t *out, int T, int H, int W, int Wp, int n_iter,
+                      bool vec, cudaStream_t st) {
+    const int tiles_x = ceil_div(Wp, 30), tiles_y = ceil_div(H, RB);
+    const long long n_tiles = (long long)T * tiles_x * tiles_y;
+    const int grid = ceil_div(n_tiles, 4);
+    k1b_dilate_expand<NMAX, RB><<<grid, 128, 0, st>>>(in, bits_out, out, H, W, Wp, n_iter, tiles_x, tiles_y, n_tiles,
+                                                      vec ? 1 : 0);
+    VV_POST_LAUNCH("k1b_dilate_expand");
+    return VV_OK;
+}
+
+static int dilate_pass(const uint32_t *in, uint32_t *bits_out, uint8_t *out, int T, int H, int W, int Wp, int n,
+                       bool vec, cudaStream_t st) {
+    if (n <= 4) return launch_k1b<4, 32>(in, bits_out, out, T, H, W, Wp, n, vec, st);
+    if (n <= 8) return launch_k1b<8, 32>(in, bits_out, out, T, H, W, Wp, n, vec, st);
+    if (n <= 16) return launch_k1b<16, 32>(in, bits_out, out, T, H, W, Wp, n, vec, st);
+    return launch_k1b<32, 16>(in, bits_out, out, T, H, W, Wp, n, vec, st);
+}
+
+}  // namespace vv
+
+using namespace vv;
+
+extern "C" size_t vv_binarize_dilate_workspace_bytes(int T, int H, int W) {
+    if (T <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t plane = align_up((size_t)T * H * ceil_div(W, 32) * 4, 256);
+    return 2 * plane + align_up((size_t)T * 4, 256);
+}
+
+extern "C" int vv_binarize_dilate(const uint8_t *mask, int T, int H, int W, int C, int iterations, uint8_t *out,
+                                  uint8_t *lowres_out, int lh, int lw, void *workspace, size_t workspace_bytes,
+                                  void *stream) {
+    VV_CHECK_ARG(mask && out && workspace, "vv_binarize_dilate: NULL pointer");
+    VV_CHECK_ARG(T > 0 && H > 0 && W > 0, "vv_binarize_dilate: bad shape T=%d H=%d W=%d", T, H, W);
+    VV_CHECK_ARG(C == 1 || C == 3 || C == 4, "vv_binarize_dilate: C must be 1, 3 or 4 (got %d)", C);
+    VV_CHECK_ARG(workspace_bytes >= vv_binarize_dilate_workspace_bytes(T, H, W),
+                 "vv_binarize_dilate: workspace too small");
+    VV_CHECK_ARG(!lowres_out || (lh > 0 && lw > 0), "vv_binarize_dilate: bad low-res size %dx%d", lh, lw);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Wp = ceil_div(W, 32);
+    const size_t plane = align_up((size_t)T * H * Wp * 4, 256);
+    uint32_t *bits0 = (uint32_t *)workspace;
+    uint32_t *bits1 = (uint32_t *)((uint8_t *)workspace + plane);
+    uint32_t *flags = (uint32_t *)((uint8_t *)workspace + 2 * plane);
+    const long long n_rows = (long long)T * H;
+    const bool vec_in = (W % 16 == 0) && ((uintptr_t)mask % 16 == 0);
+    const bool vec_out = (W % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const int grid_a = (int)min((long long)ceil_div(n_rows * 2 * Wp, 256), (long long)148 * 64);
+    int rc = C == 1   ? launch_k1a<1>(mask, (uint16_t *)bits0, W, Wp, n_rows, vec_in, grid_a, st)
+             : C == 3 ? launch_k1a<3>(mask, (uint16_t *)bits0, W, Wp, n_rows, vec_in, grid_a, st)
+                      : launch_k1a<4>(mask, (uint16_t *)bits0, W, Wp, n_rows, vec_in, grid_a, st);
+    if (rc) return rc;
+
+    if (iterations < 1) {   // until convergence == flood the frame if anything is set
+        cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)T * 4, st);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
+        const long long wpf = (long long)H * Wp;
+        dim3 g1((unsigned)min((long long)ceil_div(wpf, 256), 64LL), (unsigned)T);
+        k1c_any_per_frame<<<g1, 256, 0, st>>>(bits0, wpf, flags);
+        VV_POST_LAUNCH("k1c_any_per_frame");
+        const long long bpf = (long long)H * W;
+        dim3 g2((unsigned)min((long long)ceil_div(bpf, 256 * 16), 256LL), (unsigned)T);
+        k1c_fill<<<g2, 256, 0, st>>>(flags, out, bpf);
+        VV_POST_LAUNCH("k1c_fill");
+        if (lowres_out) {
+            dim3 g3((unsigned)min((long long)ceil_div((long long)lh * lw, 256 * 16), 256LL), (unsigned)T);
+            k1c_fill<<<g3, 256, 0, st>>>(flags, lowres_out, (long long)lh * lw);
+            VV_POST_LAUNCH("k1c_fill");
+        }
+        return VV_OK;
+    }
+
+    // chains of <= 32 rounds (diamond_a (+) diamond_b == diamond_{a+b}); the last pass expands to bytes
+    uint32_t *cur = bits0, *nxt = bits1;
+    int left = iterations;
+    while (left > 32) {
+        rc = dilate_pass(cur, nxt, nullptr, T, H, W, Wp, 32, vec_out, st);
+        if (rc) return rc;
+        uint32_t *tmp = cur;
+        cur = nxt, nxt = tmp;
+        left -= 32;
+    }
+    rc = dilate_pass(cur, lowres_out ? nxt : nullptr, out, T, H, W, Wp, left, vec_out, st);
+    if (rc) return rc;
+    if (lowres_out) {
+        const long long total = (long long)T * lh * lw;
+        k1d_lowres_from_bits<<<(int)min((long long)ceil_div(total, 256), (long long)148 * 32), 256, 0, st>>>(
+            nxt, H, W, Wp, lowres_out, lh, lw, T);
+        VV_POST_LAUNCH("k1d_lowres_from_bits");
+    }
+    return VV_OK;
+}

@@ -1,0 +1,376 @@
+// K3: resize-back + feather alpha + composite, fused.  Replaces /root/reference/diffuerase.py:70-112
+//
+//   up    = cv2.resize(inpainted, (W0, H0))                                   (:73)   11-bit fixed point
+//   d_in  = cv2.distanceTransform(m_bin,  DIST_L2, 5)                          (:95)
+//   d_out = cv2.distanceTransform(~m_bin, DIST_L2, 5)                          (:96)
+//   alpha = clip(0.5 + (d_in - d_out) / (2*feather_px), 0, 1)                  (:99-100)
+//   out   = u8(clip(rint(alpha*up + (1-alpha)*orig)))                          (:112)  fp32, no FMA
+//
+// The two full-frame distance transforms are never materialised: alpha only leaves {0,1}
+// where the chamfer distance is < feather_px, and a 5x5-chamfer distance < F is decided by
+// the mask bits within Chebyshev radius ceil(F)-1 (oracle/prepost.py model_feather_alpha,
+// bit-exact against cv2 4.13).  One CTA owns a strip of TH full-width output rows:
+//   phase 1  mask rows [y0-R, y0+TH+R) -> bit rows in shared memory (128-bit loads, 1 bit/px)
+//   phase 2  each thread takes 16-pixel groups: 5 (or 2R+1) bit-row windows -> per-pixel chamfer
+//            class by bit-parallel shifts -> alpha level; groups with alpha == 0 everywhere are a
+//            straight 48-byte copy of `orig`; only pixels with alpha > 0 fetch bilinear taps.
+// HBM traffic per frame: orig 3 + mask 1 (x (TH+2R)/TH from L2) + out 3 B/px, plus the small
+// inference-resolution frame, i.e. the algorithmic 7*H0*W0 + 3*h*w of SURVEY section 8d.
+#include <math.h>
+
+#include <algorithm>
+#include <queue>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vv {
+
+struct Tap {
+    int ofs;
+    int w;
+};
+int build_linear_taps(void *workspace, int H, int W, int h, int w, const Tap **xt, const Tap **yt, cudaStream_t st);
+
+constexpr int K3_TH = 16;          // output rows per CTA strip
+constexpr int K3_MAX_ENTRIES = 224;   // window offsets with cost < feather_px, radius <= 7
+
+struct FeatherTable {      // passed by value as a kernel parameter (constant bank, uniform reads)
+    float div;             // f32(2 * feather_px)
+    int radius;            // window radius R = ceil(F) - 1
+    int n;                 // entries below, sorted by ascending cost, all < feather_px (generic path)
+    float cost[K3_MAX_ENTRIES];
+    int8_t dx[K3_MAX_ENTRIES];
+    int8_t dy[K3_MAX_ENTRIES];
+};
+
+__device__ __forceinline__ float alpha_from(float d_in, float d_out, float div) {
+    const float a = __fadd_rn(0.5f, __fdiv_rn(__fsub_rn(d_in, d_out), div));
+    return fminf(fmaxf(a, 0.f), 1.f);
+}
+
+__device__ __forceinline__ uint32_t blend_u8(float a, float one_minus_a, uint32_t up, uint32_t orig) {
+    const float v = __fadd_rn(__fmul_rn(a, (float)up), __fmul_rn(one_minus_a, (float)orig));
+    int r = __float2int_rn(v);                     // round-half-even, like np.rint
+    return (uint32_t)min(max(r, 0), 255);
+}
+
+__device__ __forceinline__ int vlin3(int b0, int b1, int h0, int h1) {
+    return (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+}
+
+// 32-bit window of a shared-memory bit row starting at frame column `col0` (may be negative
+// down to -32; the row has one zero pad word on each side).
+__device__ __forceinline__ uint32_t bit_window(const uint32_t *row, int col0) {
+    const int c = col0 + 32;                       // shift into the padded coordinate system
+    const int k = c >> 5, off = c & 31;
+    return __funnelshift_r(row[k], row[k + 1], off);
+}
+
+template <bool VEC, bool SMALL_R>
+__global__ void __launch_bounds__(256)
+    k3_upscale_feather_composite(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig,
+                                 const uint8_t *__restrict__ mask, uint8_t *__restrict__ out,
+                                 const Tap *__restrict__ xt, const Tap *__restrict__ yt, int h, int w, int H0, int W0,
+                                 int strips_per_frame, const __grid_constant__ FeatherTable ft) {
+    extern __shared__ uint32_t smem[];
+    const int R = SMALL_R ? 2 : ft.radius;
+    const int Wp = (W0 + 31) >> 5;
+    const int row_words = Wp + 2;
+    const int rows_s = K3_TH + 2 * R;
+    uint32_t *bits = smem;                                 // [rows_s][row_words]
+    float *lut = reinterpret_cast<float *>(smem + rows_s * row_words);   // [16] alpha levels (SMALL_R)
+
+    const long long t = blockIdx.x / strips_per_frame;
+    const int y0 = (blockIdx.x % strips_per_frame) * K3_TH;
+    const uint8_t *mask_t = mask + t * H0 * (long long)W0;
+
+    // ---------------- phase 1: mask strip -> bit rows
+    {
+        uint16_t *b16 = reinterpret_cast<uint16_t *>(bits);
+        const int halves = 2 * row_words;
+        for (int id = threadIdx.x; id < rows_s * halves; id += blockDim.x) {
+            const int i = id / halves, hw = id - i * halves;
+            const int y = y0 - R + i, x0 = (hw - 2) * 16;
+            uint32_t v = 0;
+            if (y >= 0 && y < H0 && x0 >= 0 && x0 < W0) {
+                const uint8_t *p = mask_t + (long long)y * W0 + x0;
+                if (VEC) {
+                    v = nonzero_bits16(ldg128(p));
+                } else {
+                    const int n = min(16, W0 - x0);
+                    for (int k = 0; k < n; ++k) v |= (uint32_t)(p[k] != 0) << k;
+                }
+            }
+            b16[id] = (uint16_t)v;
+        }
+        if (SMALL_R && threadIdx.x < 16) {
+            // alpha levels: index = class (0 = no hit within the window, 1..5 = cost classes
+            // 1, 1.4, 2, 2.1969, 2.8) | inside << 3
+            const float cost[6] = {8192.f, 1.0f, 1.4f, 2.0f, 2.1969f, __fadd_rn(1.4f, 1.4f)};
+            const int cls = threadIdx.x & 7, inside = threadIdx.x >> 3;
+            float a = inside ? 1.f : 0.f;
+            if (cls <= 5) a = inside ? alpha_from(cost[cls], 0.f, ft.div) : alpha_from(0.f, cost[cls], ft.div);
+            lut[threadIdx.x] = a;
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: 16-pixel groups
+    const int G = (W0 + 15) >> 4;
+    const uint8_t *orig_t = orig + t * H0 * (long long)W0 * 3;
+    uint8_t *out_t = out + t * H0 * (long long)W0 * 3;
+    const uint8_t *inp_t = inp + t * h * (long long)w * 3;
+
+    for (int id = threadIdx.x; id < K3_TH * G; id += blockDim.x) {
+        const int row = id / G, g = id - row * G;
+        const int y = y0 + row;
+        if (y >= H0) break;
+        const int x0 = g * 16;
+        const int npx = VEC ? 16 : min(16, W0 - x0);
+        const long long pix_off = ((long long)y * W0 + x0) * 3;
+
+        // original pixels (issued first: independent of the mask logic)
+        uint32_t o[12];
+        if (VEC) {
+            const uint4 a = ldg128(orig_t + pix_off), b = ldg128(orig_t + pix_off + 16), c = ldg128(orig_t + pix_off + 32);
+            o[0] = a.x, o[1] = a.y, o[2] = a.z, o[3] = a.w, o[4] = b.x, o[5] = b.y, o[6] = b.z, o[7] = b.w;
+            o[8] = c.x, o[9] = c.y, o[10] = c.z, o[11] = c.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) o[k] = 0;
+            for (int k = 0; k < npx * 3; ++k) o[k >> 2] |= (uint32_t)orig_t[pix_off + k] << (8 * (k & 3));
+        }
+
+        // window of valid columns: bit j <-> column x0 - 8 + j
+        const int c0 = x0 - 8;
+        const int lo = max(0, -c0), hi = min(32, W0 - c0);
+        const uint32_t colvalid = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+        const uint32_t *brow = bits + (row + R) * row_words;   // centre row of this pixel row
+        const uint32_t M2 = bit_window(brow, c0);
+        const uint32_t px_bits = ((npx >= 16 ? 0xffffu : ((1u << npx) - 1u)) << 8);
+
+        float alpha[16];
+        uint32_t need_up = 0;      // pixels (bit i) with alpha > 0
+        if (SMALL_R) {
+            uint32_t Mw[5], Zw[5];
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                const int yy = y + d - 2;
+                Mw[d] = bit_window(brow + (d - 2) * row_words, c0);
+                Zw[d] = (yy >= 0 && yy < H0) ? (~Mw[d] & colvalid) : 0u;
+            }
+            const uint32_t anyM = Mw[0] | Mw[1] | Mw[2] | Mw[3] | Mw[4];
+            // window of pixel i covers bits i+6 .. i+10, i.e. bits 6..25 for the whole group
+            if ((anyM & 0x03ffffc0u) == 0) {
+                need_up = 0;        // no masked pixel near this group: alpha == 0 everywhere
+#pragma unroll
+                for (int i = 0; i < 16; ++i) alpha[i] = 0.f;
+            } else {
+                auto classes = [](const uint32_t *S, uint32_t *hc) {
+                    const uint32_t A1 = S[1] | S[3], A0 = S[0] | S[4];
+                    hc[0] = (S[2] << 1) | (S[2] >> 1) | A1;                                  // cost 1
+                    hc[1] = (A1 << 1) | (A1 >> 1);                                           // 1.4
+                    hc[2] = (S[2] << 2) | (S[2] >> 2) | A0;                                  // 2
+                    hc[3] = (A0 << 1) | (A0 >> 1) | (A1 << 2) | (A1 >> 2);                   // 2.1969
+                    hc[4] = (A0 << 2) | (A0 >> 2);                                           // 2.8
+                };
+                uint32_t hm[5], hz[5], hsel[5];
+                classes(Mw, hm);
+                classes(Zw, hz);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) hsel[k] = (hz[k] & M2) | (hm[k] & ~M2);   // inside pixels look for zeros
+                // priority encode: level = first class hit (1..5), 0 if none
+                const uint32_t p1 = hsel[0];
+                const uint32_t p2 = hsel[1] & ~p1;
+                const uint32_t s12 = p1 | hsel[1];
+                const uint32_t p3 = hsel[2] & ~s12;
+                const uint32_t s123 = s12 | hsel[2];
+                const uint32_t p4 = hsel[3] & ~s123;
+                const uint32_t p5 = hsel[4] & ~(s123 | hsel[3]);
+                const uint32_t L0 = p1 | p3 | p5, L1 = p2 | p3, L2 = p4 | p5;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int b = i + 8;
+                    const uint32_t idx = ((L0 >> b) & 1u) | (((L1 >> b) & 1u) << 1) | (((L2 >> b) & 1u) << 2) |
+                                         (((M2 >> b) & 1u) << 3);
+                    alpha[i] = lut[idx];
+                }
+                need_up = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) need_up |= (uint32_t)(alpha[i] > 0.f) << i;
+            }
+        } else {
+            // generic radius: first (cheapest) window offset whose opposite-class bit is set
+            const bool hard = ft.n == 0;
+#pragma unroll 1
+            for (int i = 0; i < 16; ++i) {
+                const bool inside = (M2 >> (i + 8)) & 1u;
+                float d = 8192.f;
+                if (!hard && i < npx) {
+                    for (int e = 0; e < ft.n; ++e) {
+                        const int yy = y + ft.dy[e], xx = x0 + i + ft.dx[e];
+                        if (yy < 0 || yy >= H0 || xx < 0 || xx >= W0) continue;
+                        const uint32_t wv = bits[(row + R + ft.dy[e]) * row_words + 1 + (xx >> 5)];
+                        const bool set = (wv >> (xx & 31)) & 1u;
+                        if (set != inside) {
+                            d = ft.cost[e];
+                            break;
+                        }
+                    }
+                }
+                alpha[i] = hard ? (inside ? 1.f : 0.f) : (inside ? alpha_from(d, 0.f, ft.div) : alpha_from(0.f, d, ft.div));
+            }
+            need_up = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) need_up |= (uint32_t)(alpha[i] > 0.f) << i;
+        }
+        need_up &= (px_bits >> 8);
+
+        if (need_up) {
+            const Tap ty = yt[y];
+            const int b0 = (short)(ty.w & 0xffff), b1 = ty.w >> 16;
+            const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
+            const uint8_t *r0 = inp_t + (long long)ya * w * 3;
+            const uint8_t *r1 = inp_t + (long long)yb * w * 3;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if ((need_up >> i) & 1u) {
+                    const Tap tx = xt[x0 + i];
+                    const int a0 = (short)(tx.w & 0xffff), a1 = tx.w >> 16;
+                    const int s0 = tx.ofs * 3, s1 = min(tx.ofs + 1, w - 1) * 3;
+                    const float a = alpha[i], na = __fsub_rn(1.f, a);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int h0 = __ldg(r0 + s0 + c) * a0 + __ldg(r0 + s1 + c) * a1;
+                        const int h1 = __ldg(r1 + s0 + c) * a0 + __ldg(r1 + s1 + c) * a1;
+                        const uint32_t up = (uint32_t)vlin3(b0, b1, h0, h1);
+                        const int ob = 3 * i + c;
+                        const uint32_t og = byte_of(o[ob >> 2], ob & 3);
+                        const uint32_t res = blend_u8(a, na, up, og);
+                        o[ob >> 2] = (o[ob >> 2] & ~(0xffu << (8 * (ob & 3)))) | (res << (8 * (ob & 3)));
+                    }
+                }
+            }
+        }
+
+        if (VEC) {
+            stg128_stream(out_t + pix_off, make_uint4(o[0], o[1], o[2], o[3]));
+            stg128_stream(out_t + pix_off + 16, make_uint4(o[4], o[5], o[6], o[7]));
+            stg128_stream(out_t + pix_off + 32, make_uint4(o[8], o[9], o[10], o[11]));
+        } else {
+            for (int k = 0; k < npx * 3; ++k) out_t[pix_off + k] = (uint8_t)byte_of(o[k >> 2], k & 3);
+        }
+    }
+}
+
+// Host: float32 Dijkstra over the 5x5-chamfer step set (same construction as
+// oracle/prepost.py chamfer_cost_table, verified bit-exact against cv2.distanceTransform).
+static void build_feather_table(float feather_px, FeatherTable *ft) {
+    ft->div = (float)(2.0 * (double)feather_px);
+    ft->n = 0;
+    ft->radius = 0;
+    if (!(feather_px > 0.f)) return;
+    const int R = (int)ceilf(feather_px) - 1;
+    ft->radius = R < 0 ? 0 : R;
+    if (R <= 0) return;       // every neighbour is >= 1 >= F away: alpha is the hard mask
+    const int lim = 3 * R + 6, S = 2 * lim + 1;
+    std::vector<float> dist(S * S, -1.f);
+    typedef std::tuple<float, int, int> Node;
+    std::priority_queue<Node, std::vector<Node>, std::greater<Node>> pq;
+    const float A = 1.0f, B = 1.4f, Cc = 2.1969f;
+    const int sx[16] = {1, -1, 0, 0, 1, 1, -1, -1, 2, 2, -2, -2, 1, 1, -1, -1};
+    const int sy[16] = {0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 2, -2, 2, -2};
+    const float sc[16] = {A, A, A, A, B, B, B, B, Cc, Cc, Cc, Cc, Cc, Cc, Cc, Cc};
+    pq.push(Node(0.f, 0, 0));
+    while (!pq.empty()) {
+        Node nd = pq.top();
+        pq.pop();
+        const float d = std::get<0>(nd);
+        const int x = std::get<1>(nd), y = std::get<2>(nd);
+        float &slot = dist[(y + lim) * S + (x + lim)];
+        if (slot >= 0.f) continue;
+        slot = d;
+        for (int k = 0; k < 16; ++k) {
+            const int nx = x + sx[k], ny = y + sy[k];
+            if (abs(nx) > lim || abs(ny) > lim) continue;
+            if (dist[(ny + lim) * S + (nx + lim)] >= 0.f) continue;
+            volatile float nd2 = d + sc[k];   // force a rounded fp32 sum
+            pq.push(Node(nd2, nx, ny));
+        }
+    }
+    std::vector<std::tuple<float, int, int>> ent;
+    for (int dy = -R; dy <= R; ++dy)
+        for (int dx = -R; dx <= R; ++dx) {
+            if (!dx && !dy) continue;
+            const float c = dist[(dy + lim) * S + (dx + lim)];
+            if (c < feather_px) ent.push_back(std::make_tuple(c, dy, dx));
+        }
+    std::sort(ent.begin(), ent.end());
+    for (size_t i = 0; i < ent.size() && i < (size_t)K3_MAX_ENTRIES; ++i) {
+        ft->cost[i] = std::get<0>(ent[i]);
+        ft->dy[i] = (int8_t)std::get<1>(ent[i]);
+        ft->dx[i] = (int8_t)std::get<2>(ent[i]);
+        ft->n = (int)i + 1;
+    }
+}
+
+}  // namespace vv
+
+using namespace vv;
+
+extern "C" size_t vv_composite_workspace_bytes(int H0, int W0) { return vv_resize_workspace_bytes(H0, W0); }
+
+extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, int w, const uint8_t *orig,
+                                            const uint8_t *mask, int H0, int W0, float feather_px, int keep_unmasked,
+                                            uint8_t *out, void *workspace, size_t workspace_bytes, void *stream) {
+    VV_CHECK_ARG(inp && out && workspace, "vv_upscale_feather_composite: NULL pointer");
+    VV_CHECK_ARG(T > 0 && h > 0 && w > 0 && H0 > 0 && W0 > 0, "vv_upscale_feather_composite: bad shape");
+    VV_CHECK_ARG(workspace_bytes >= vv_composite_workspace_bytes(H0, W0),
+                 "vv_upscale_feather_composite: workspace too small");
+    if (!keep_unmasked)   // diffuerase.py:75 - resize-back only
+        return vv_resize(inp, T, h, w, 3, out, H0, W0, VV_INTER_LINEAR, workspace, workspace_bytes, stream);
+    VV_CHECK_ARG(orig && mask, "vv_upscale_feather_composite: orig/mask required when keep_unmasked != 0");
+    if (feather_px > VV_MAX_FEATHER) {
+        set_error("vv_upscale_feather_composite: feather_px %.3f > supported maximum %.1f", feather_px, VV_MAX_FEATHER);
+        return VV_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const Tap *xt, *yt;
+    int rc = build_linear_taps(workspace, h, w, H0, W0, &xt, &yt, st);
+    if (rc) return rc;
+
+    FeatherTable ft;
+    build_feather_table(feather_px, &ft);
+    const bool small_r = feather_px > 0.f && ft.radius <= 2;
+    const int R = small_r ? 2 : ft.radius;
+    const int Wp = ceil_div(W0, 32);
+    const size_t smem = (size_t)(K3_TH + 2 * R) * (Wp + 2) * 4 + 64;
+    const bool vec = (W0 % 16 == 0) && ((uintptr_t)orig % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                     ((uintptr_t)mask % 16 == 0);
+    const int strips = ceil_div(H0, K3_TH);
+    const long long grid = (long long)T * strips;
+    VV_CHECK_ARG(grid < 2147483647LL, "vv_upscale_feather_composite: too many strips");
+
+#define VV_K3_LAUNCH(V, S)                                                                                      \
+    do {                                                                                                        \
+        auto kfn = k3_upscale_feather_composite<V, S>;                                                          \
+        if (smem > 48 * 1024) {                                                                                 \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(k3)");                              \
+        }                                                                                                       \
+        kfn<<<(unsigned)grid, 256, smem, st>>>(inp, orig, mask, out, xt, yt, h, w, H0, W0, strips, ft);         \
+    } while (0)
+    if (vec && small_r)
+        VV_K3_LAUNCH(true, true);
+    else if (vec)
+        VV_K3_LAUNCH(true, false);
+    else if (small_r)
+        VV_K3_LAUNCH(false, true);
+    else
+        VV_K3_LAUNCH(false, false);
+#undef VV_K3_LAUNCH
+    VV_POST_LAUNCH("k3_upscale_feather_composite");
+    return VV_OK;
+}

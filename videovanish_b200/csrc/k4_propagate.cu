@@ -1,0 +1,261 @@
+// K4: ProPainter-style flow-guided propagation prior (image propagation, 'nearest').
+// Replaces the un-vendored `propainter.forward` call at /root/reference/diffuerase.py:49-57
+// [BidirectionalPropagation(learnable=False) + fbConsistencyCheck + flow_warp; upstream files
+// cited in oracle/propagation.py].  PARITY UNPINNED by the reference; the oracle is the torch-CPU
+// restatement and its explicit float32 model (oracle/propagation.py::_step), which this kernel
+// follows operation for operation:
+//   sample position  p + flow_prop(p), normalised and un-normalised exactly as flow_warp +
+//                    grid_sample(align_corners=True) do in fp32
+//   flow check       bilinear (zeros padding, fma chain) warp of flow_check, then
+//                    |f + bw|^2 < 0.01 (|f|^2 + |bw|^2) + 0.5
+//   mask validity    bilinear warp of the previous hole mask > 0.1
+//   fill             hole & valid & !mask_valid -> copy the NEAREST previous pixel (or zero padding)
+// With 'nearest' and binary masks the pixel path is a pure select, so pixels stay u8: the state
+// is one packed word per pixel, R | G<<8 | B<<16 | state<<24 (bit0 hole, bit1 "value is the
+// masked frame's 0.0").  The four bilinear taps of the previous state give both the mask warp and
+// the nearest pixel, so one 4-word gather serves both.
+//
+// The scan is serial in time; parallelism comes from the frame (one thread = 4 pixels) and from
+// advancing up to 32 independent sub-videos (propainter/inference.py windows: 50 frames + 10 pad
+// each side) in lock step, one launch per time step and direction.  Only hole pixels touch the
+// flows; known pixels are a 16-byte pass-through.
+#include "common.cuh"
+
+namespace vv {
+
+constexpr uint32_t ST_HOLE = 1u << 24;
+constexpr uint32_t ST_ZERO = 2u << 24;
+constexpr int K4_MAX_SUB = 32;
+
+struct SubDesc {
+    int start;            // first frame of the window in the clip arrays
+    int len;              // frames in the window
+    long long out_frame;  // first frame of the window in the packed output / workspace
+};
+struct SubBatch {
+    SubDesc sub[K4_MAX_SUB];
+    int n;
+};
+
+__device__ __forceinline__ float unnormalized(float pos, int size) {
+    // flow_warp: 2*g/max(size-1,1) - 1 ; grid_sample(align_corners=True): (c+1) * ((size-1)/2)
+    const float n = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, pos), (float)max(size - 1, 1)), 1.0f);
+    return __fmul_rn(__fadd_rn(n, 1.0f), (float)(size - 1) * 0.5f);
+}
+
+// One hole pixel: returns the new packed state.
+__device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, uint32_t cur,
+                                                    const float2 *__restrict__ flow_prop,
+                                                    const float2 *__restrict__ flow_check,
+                                                    const uint32_t *__restrict__ prev) {
+    const float2 f = __ldg(flow_prop + (long long)y * w + x);
+    const float ix = unnormalized(__fadd_rn((float)x, f.x), w);
+    const float iy = unnormalized(__fadd_rn((float)y, f.y), h);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wx = __fsub_rn(ix, x0f), wy = __fsub_rn(iy, y0f);
+    const float ex = __fsub_rn(1.f, wx), sy = __fsub_rn(1.f, wy);
+    const float nw = __fmul_rn(sy, ex), ne = __fmul_rn(sy, wx), sw = __fmul_rn(wy, ex), se = __fmul_rn(wy, wx);
+    // clamp before the int conversion so absurd flows cannot overflow
+    const int x0 = (int)fminf(fmaxf(x0f, -4.f), (float)w + 4.f);
+    const int y0 = (int)fminf(fmaxf(y0f, -4.f), (float)h + 4.f);
+    const bool xa = x0 >= 0 && x0 < w, xb = x0 + 1 >= 0 && x0 + 1 < w;
+    const bool ya = y0 >= 0 && y0 < h, yb = y0 + 1 >= 0 && y0 + 1 < h;
+    const long long i00 = (long long)y0 * w + x0;
+
+    float2 c00 = make_float2(0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
+    uint32_t p00 = 0, p01 = 0, p10 = 0, p11 = 0;          // out-of-frame taps: not a hole
+    if (ya && xa) c00 = __ldg(flow_check + i00), p00 = prev[i00];
+    if (ya && xb) c01 = __ldg(flow_check + i00 + 1), p01 = prev[i00 + 1];
+    if (yb && xa) c10 = __ldg(flow_check + i00 + w), p10 = prev[i00 + w];
+    if (yb && xb) c11 = __ldg(flow_check + i00 + w + 1), p11 = prev[i00 + w + 1];
+
+    // bilinear, torch CPU order: r = a*nw; r = fma(b, ne, r); r = fma(c, sw, r); r = fma(d, se, r)
+    const float bwx = __fmaf_rn(c11.x, se, __fmaf_rn(c10.x, sw, __fmaf_rn(c01.x, ne, __fmul_rn(c00.x, nw))));
+    const float bwy = __fmaf_rn(c11.y, se, __fmaf_rn(c10.y, sw, __fmaf_rn(c01.y, ne, __fmul_rn(c00.y, nw))));
+    const float dx = __fadd_rn(f.x, bwx), dy = __fadd_rn(f.y, bwy);
+    const float diff = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    const float mag = __fadd_rn(__fadd_rn(__fmul_rn(f.x, f.x), __fmul_rn(f.y, f.y)),
+                                __fadd_rn(__fmul_rn(bwx, bwx), __fmul_rn(bwy, bwy)));
+    const float thr = __fadd_rn(__fmul_rn(0.01f, mag), 0.5f);
+    const bool valid = diff < thr;
+
+    const float h00 = (p00 & ST_HOLE) ? 1.f : 0.f, h01 = (p01 & ST_HOLE) ? 1.f : 0.f;
+    const float h10 = (p10 & ST_HOLE) ? 1.f : 0.f, h11 = (p11 & ST_HOLE) ? 1.f : 0.f;
+    const float mpv = __fmaf_rn(h11, se, __fmaf_rn(h10, sw, __fmaf_rn(h01, ne, __fmul_rn(h00, nw))));
+    if (!valid || mpv > 0.1f) return cur;
+
+    // nearest source: rint (half-to-even) of the same un-normalised position; it is one of the 4 taps
+    const float xr = rintf(ix), yr = rintf(iy);
+    const bool right = xr > x0f, down = yr > y0f;
+    const bool inb = (right ? xb : xa) && (down ? yb : ya);
+    const uint32_t src = down ? (right ? p11 : p10) : (right ? p01 : p00);
+    return inb ? (src & ~ST_HOLE) : ST_ZERO;
+}
+
+// One time step of one direction for every sub-video of the batch.  blockIdx.y = sub-video.
+//   PASS2 == false (backward pass, t = len-1 .. 0): current = input frame + mask, prev = ws[idx+1]
+//   PASS2 == true  (forward pass,  t = 0 .. len-1): current = ws[idx],          prev = out[idx-1]
+template <bool PASS2, bool VEC>
+__global__ void __launch_bounds__(256)
+    k4_step(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, const float2 *__restrict__ flows_f,
+            const float2 *__restrict__ flows_b, uint32_t *__restrict__ ws, uint32_t *__restrict__ out, int h, int w,
+            int step, const __grid_constant__ SubBatch batch) {
+    const SubDesc sd = batch.sub[blockIdx.y];
+    if (step >= sd.len) return;
+    const long long npx = (long long)h * w;
+    const int idx = PASS2 ? step : sd.len - 1 - step;
+    const long long gframe = sd.start + idx;
+    // flows: backward pass uses flow index idx (prop = forward flow), forward pass idx-1 (prop = backward flow)
+    const long long fi = PASS2 ? gframe - 1 : gframe;
+    const float2 *flow_prop = (PASS2 ? flows_b : flows_f) + fi * npx;
+    const float2 *flow_check = (PASS2 ? flows_f : flows_b) + fi * npx;
+    uint32_t *dst = (PASS2 ? out : ws) + (sd.out_frame + idx) * npx;
+    const uint32_t *prev = PASS2 ? out + (sd.out_frame + idx - 1) * npx : ws + (sd.out_frame + idx + 1) * npx;
+    const uint32_t *cur_packed = ws + (sd.out_frame + idx) * npx;
+    const uint8_t *fr = frames + gframe * npx * 3;
+    const uint8_t *mk = masks + gframe * npx;
+    const bool first = step == 0;
+
+    const long long ngroups = (npx + 3) >> 2;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < ngroups;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long p0 = g * 4;
+        uint32_t c[4];
+        int n = 4;
+        if (VEC) {
+            if (PASS2) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(cur_packed + p0);
+                c[0] = v.x, c[1] = v.y, c[2] = v.z, c[3] = v.w;
+            } else {
+                const uint32_t m4 = __ldg(reinterpret_cast<const uint32_t *>(mk + p0));
+                const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0 * 3);
+                const uint32_t a = __ldg(f3), b = __ldg(f3 + 1), d = __ldg(f3 + 2);
+                c[0] = a & 0x00ffffffu;
+                c[1] = (a >> 24) | ((b & 0x0000ffffu) << 8);
+                c[2] = (b >> 16) | ((d & 0x000000ffu) << 16);
+                c[3] = d >> 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (byte_of(m4, i)) c[i] = ST_HOLE | ST_ZERO;
+            }
+        } else {
+            n = (int)min(4LL, npx - p0);
+            for (int i = 0; i < 4; ++i) {
+                c[i] = 0;
+                if (i < n) {
+                    if (PASS2) {
+                        c[i] = cur_packed[p0 + i];
+                    } else {
+                        const uint8_t *q = fr + (p0 + i) * 3;
+                        c[i] = mk[p0 + i] ? (ST_HOLE | ST_ZERO) : (q[0] | (q[1] << 8) | ((uint32_t)q[2] << 16));
+                    }
+                }
+            }
+        }
+        if (!first) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < n && (c[i] & ST_HOLE)) {
+                    const long long p = p0 + i;
+                    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
+                    c[i] = propagate_pixel(x, y, h, w, c[i], flow_prop, flow_check, prev);
+                }
+            }
+        }
+        if (VEC) {
+            *reinterpret_cast<uint4 *>(dst + p0) = make_uint4(c[0], c[1], c[2], c[3]);
+        } else {
+            for (int i = 0; i < n; ++i) dst[p0 + i] = c[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k4_unpack(const uint32_t *__restrict__ packed, long long n, uint8_t zero_level, uint8_t *__restrict__ rgb,
+              uint8_t *__restrict__ hole) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t v = packed[i];
+        if (rgb) {
+            const bool z = v & ST_ZERO;
+            rgb[3 * i] = z ? zero_level : (uint8_t)v;
+            rgb[3 * i + 1] = z ? zero_level : (uint8_t)(v >> 8);
+            rgb[3 * i + 2] = z ? zero_level : (uint8_t)(v >> 16);
+        }
+        if (hole) hole[i] = (v & ST_HOLE) ? 255 : 0;
+    }
+}
+
+}  // namespace vv
+
+using namespace vv;
+
+extern "C" size_t vv_propagate_workspace_bytes(int n_out_frames, int h, int w) {
+    if (n_out_frames <= 0 || h <= 0 || w <= 0) return 0;
+    return align_up((size_t)n_out_frames * h * w * 4, 256);
+}
+
+extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const float *flows_f, const float *flows_b,
+                            int n_frames, int h, int w, const int *sub_start, const int *sub_len, int n_sub,
+                            uint32_t *out, void *workspace, size_t workspace_bytes, void *stream) {
+    VV_CHECK_ARG(frames && masks && out && workspace && sub_start && sub_len, "vv_propagate: NULL pointer");
+    VV_CHECK_ARG(n_frames > 0 && h > 0 && w > 0 && n_sub > 0, "vv_propagate: bad shape");
+    VV_CHECK_ARG(n_frames == 1 || (flows_f && flows_b), "vv_propagate: flows required when there is more than one frame");
+    long long total = 0;
+    int maxlen = 0;
+    for (int s = 0; s < n_sub; ++s) {
+        VV_CHECK_ARG(sub_len[s] > 0 && sub_start[s] >= 0 && sub_start[s] + sub_len[s] <= n_frames,
+                     "vv_propagate: sub-video %d [%d,+%d) outside the clip of %d frames", s, sub_start[s], sub_len[s],
+                     n_frames);
+        total += sub_len[s];
+        if (sub_len[s] > maxlen) maxlen = sub_len[s];
+    }
+    VV_CHECK_ARG(workspace_bytes >= vv_propagate_workspace_bytes((int)total, h, w), "vv_propagate: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long npx = (long long)h * w;
+    const bool vec = (npx % 4 == 0) && ((uintptr_t)frames % 4 == 0) && ((uintptr_t)masks % 4 == 0) &&
+                     ((uintptr_t)out % 16 == 0) && ((uintptr_t)workspace % 16 == 0);
+    uint32_t *ws = (uint32_t *)workspace;
+    const float2 *ff = (const float2 *)flows_f, *fb = (const float2 *)flows_b;
+
+    long long out_frame = 0;
+    for (int base = 0; base < n_sub; base += K4_MAX_SUB) {
+        SubBatch b;
+        b.n = min(K4_MAX_SUB, n_sub - base);
+        int blen = 0;
+        for (int s = 0; s < b.n; ++s) {
+            b.sub[s].start = sub_start[base + s];
+            b.sub[s].len = sub_len[base + s];
+            b.sub[s].out_frame = out_frame;
+            out_frame += sub_len[base + s];
+            blen = max(blen, sub_len[base + s]);
+        }
+        // enough CTAs to fill 148 SMs a few times, split over the sub-videos of the batch
+        const int gx = max(1, min(ceil_div((npx + 3) / 4, 256), ceil_div(148 * 8, b.n)));
+        dim3 grid(gx, b.n);
+        for (int pass = 0; pass < 2; ++pass)
+            for (int step = 0; step < blen; ++step) {
+                if (pass == 0) {
+                    if (vec)
+                        k4_step<false, true><<<grid, 256, 0, st>>>(frames, masks, ff, fb, ws, out, h, w, step, b);
+                    else
+                        k4_step<false, false><<<grid, 256, 0, st>>>(frames, masks, ff, fb, ws, out, h, w, step, b);
+                } else {
+                    if (vec)
+                        k4_step<true, true><<<grid, 256, 0, st>>>(frames, masks, ff, fb, ws, out, h, w, step, b);
+                    else
+                        k4_step<true, false><<<grid, 256, 0, st>>>(frames, masks, ff, fb, ws, out, h, w, step, b);
+                }
+                VV_POST_LAUNCH("k4_step");
+            }
+    }
+    return VV_OK;
+}
+
+extern "C" int vv_propagate_unpack(const uint32_t *packed, size_t n_pixels, uint8_t zero_level, uint8_t *rgb,
+                                   uint8_t *hole_mask, void *stream) {
+    VV_CHECK_ARG(packed && n_pixels > 0 && (rgb || hole_mask), "vv_propagate_unpack: bad argument");
+    const int grid = (int)min((long long)ceil_div((long long)n_pixels, 256), (long long)148 * 32);
+    k4_unpack<<<grid, 256, 0, (cudaStream_t)stream>>>(packed, (long long)n_pixels, zero_level, rgb, hole_mask);
+    VV_POST_LAUNCH("k4_unpack");
+    return VV_OK;
+}

@@ -1,0 +1,133 @@
+"""Drop-in for the reference's ``diffuerase`` module (/root/reference/diffuerase.py).
+
+``run_infill_on_frames`` keeps the reference's signature, progress milestones, model hand-off
+contract and return convention (the list returned by the model's ``forward``,
+post-processed in place, C-contiguous uint8 HxWx3 arrays).  The two pixel loops
+(diffuerase.py:28-31 and :70-112) run on the GPU through ``libvvb200.so``; the DiffuEraser /
+ProPainter networks are out of scope and are used exactly as the reference uses them (lazy import
+of the un-vendored packages, module-level cache), or injected with ``set_models`` for tests.
+
+Differences, all deliberate and documented in DESIGN.md:
+* diffuerase.py:114 returns inside the ``for`` loop, so the reference post-processes frame 0 only.
+  Here every frame is processed (the evident intent); ``BUG_COMPAT = True`` restores the literal
+  behaviour.
+* There is no CPU fallback: without a CUDA device the call raises.
+"""
+import numpy as np
+
+from . import hostpipe, ops
+
+BUG_COMPAT = False           # True: reproduce the early return of diffuerase.py:114
+
+device = None
+last_ckpt = None
+video_inpainting_sd = None
+propainter = None
+_pipeline = None
+
+
+def set_models(diffueraser=None, propainter_model=None):
+    """Inject model objects exposing the upstream ``forward`` signatures (tests, benchmarks)."""
+    global video_inpainting_sd, propainter, last_ckpt
+    if diffueraser is not None:
+        video_inpainting_sd = diffueraser
+        last_ckpt = "2-Step"
+    if propainter_model is not None:
+        propainter = propainter_model
+
+
+def _get_pipeline(h0, w0, h, w):
+    global _pipeline
+    if _pipeline is None or _pipeline.geometry != (h0, w0, h, w):
+        if _pipeline is not None:
+            _pipeline.close()
+        _pipeline = hostpipe.HostPipeline(h0, w0, h, w)
+    return _pipeline
+
+
+def run_infill_on_frames(frames_rgb, mask_frames, mask_dilation_iter=8, ckpt="2-Step",
+                         propainer_frames=None, max_img_size=960, keep_unmasked_original=True, feather_px=3,
+                         prog=None):
+    """Same contract as reference diffuerase.py:20-114."""
+    global device, last_ckpt, video_inpainting_sd, propainter
+
+    H0, W0 = frames_rgb[0].shape[:2]
+    h, w = ops.inference_size(H0, W0, max_img_size)
+    pipe = _get_pipeline(H0, W0, h, w)
+
+    if prog is not None: prog(5, "dilating frames")
+    dilated_mask_frames = pipe.pre(mask_frames, mask_dilation_iter)                      # :27-31 (K1)
+
+    if prog is not None: prog(10, "loading weights")
+    if last_ckpt != ckpt and video_inpainting_sd is None:                                # :35-45
+        from diffueraser.diffueraser import DiffuEraser
+        from propainter.inference import get_device
+        device = get_device()
+        ckpt = "2-Step"
+        last_ckpt = ckpt
+        video_inpainting_sd = DiffuEraser(device, "stable-diffusion-v1-5/stable-diffusion-v1-5",
+                                          "stabilityai/sd-vae-ft-mse", "lixiaowen/diffuEraser", ckpt=ckpt)
+
+    if propainer_frames is None:                                                         # :47-57
+        if propainter is None:
+            from propainter.inference import Propainter
+            propainter = Propainter("ruffy369/propainter", device=device)
+        if prog is not None: prog(20, "running propainter prior")
+        propainer_frames = propainter.forward(frames_rgb, dilated_mask_frames, ref_stride=10, neighbor_length=10,
+                                              subvideo_length=50, mask_dilation=0, progress=prog)
+
+    if prog is not None: prog(50, "running DiffuEraser")
+    guidance_scale = None
+    inpainted_frames = video_inpainting_sd.forward(frames_rgb, dilated_mask_frames, propainer_frames,   # :62-67
+                                                   max_img_size=max_img_size, mask_dilation_iter=0,
+                                                   guidance_scale=guidance_scale, progress=prog)
+
+    if prog is not None: prog(90, "resizing and merging finished frames")
+    n = 1 if BUG_COMPAT else len(inpainted_frames)                                       # :114
+    if n == 0:
+        return inpainted_frames
+    fh, fw = inpainted_frames[0].shape[:2]
+    if (fh, fw) == (H0, W0) and not keep_unmasked_original:
+        return inpainted_frames                                                          # nothing to do (:72, :75)
+    resident = True
+    if (fh, fw) != (h, w):            # the model picked another size than row A9 predicts
+        pipe = _get_pipeline(H0, W0, fh, fw)
+        resident = False
+    out = pipe.post(inpainted_frames[:n], frames_rgb[:n], None if resident else dilated_mask_frames[:n],
+                    feather_px, keep_unmasked_original)                                  # :70-112 (K3)
+    for i in range(n):
+        inpainted_frames[i] = out[i]
+    return inpainted_frames
+
+
+def main():
+    """CLI of reference diffuerase.py:121-151 (same flags).  The reference's inverted
+    ``--prior_video`` test (:142) is NOT reproduced: the prior is loaded when it is given."""
+    import argparse
+    import os
+
+    from . import tools
+    ap = argparse.ArgumentParser(description="Vanish masked objects from a video (B200 pixel pipeline).")
+    ap.add_argument("--color_video", required=True, type=str)
+    ap.add_argument("--mask_video", required=True, type=str)
+    ap.add_argument("--prior_video", required=False, type=str)
+    ap.add_argument("--start_frame", type=int, default=0)
+    ap.add_argument("--max_frames", type=int, default=-1)
+    ap.add_argument("--out", type=str, default=None)
+    args = ap.parse_args()
+    assert os.path.isfile(args.color_video), "input video missing"
+    out_video = args.out or (args.color_video + "_vanished.mkv")
+    frames, fps = tools.load_video_frames_from_path(args.color_video, args.start_frame, args.max_frames)
+    H0, W0 = frames[0].shape[:2]
+    mask_frames, _ = tools.load_video_frames_from_path(args.mask_video, args.start_frame, args.max_frames)
+    assert mask_frames[0].shape[:2] == (H0, W0), "mask and color video are diffrent sizes"
+    prior_frames = None
+    if args.prior_video is not None:
+        prior_frames, _ = tools.load_video_frames_from_path(args.prior_video, args.start_frame, args.max_frames)
+        assert prior_frames[0].shape[:2] == (H0, W0), "prior and color video are diffrent sizes"
+    result = run_infill_on_frames(frames, mask_frames, propainer_frames=prior_frames)
+    tools.write_video_frames_to_path(out_video, result, fps, H0, W0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,94 @@
+"""Host-buffer pipeline front-end (``vv_pipeline_*`` in include/vvb200.h).
+
+The reference's interface is lists of per-frame numpy arrays; this class
+turns such lists into arrays of host pointers and lets the native runtime in
+``csrc/pipeline.cu`` overlap H2D copies, kernels and D2H copies over several streams.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib
+
+
+def _ptr_array(frames, shape=None):
+    """Per-frame host pointers.  Returns (ctypes array, keep-alive list)."""
+    keep = []
+    arr = (ctypes.c_void_p * len(frames))()
+    for i, f in enumerate(frames):
+        a = f if (isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.flags.c_contiguous) else \
+            np.ascontiguousarray(f, dtype=np.uint8)
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError("frame %d has shape %s, expected %s" % (i, a.shape, tuple(shape)))
+        keep.append(a)
+        arr[i] = a.ctypes.data
+    return arr, keep
+
+
+def pinned_frames(t, shape):
+    """``t`` uint8 frames of ``shape`` as numpy views of ONE page-locked block: D2H copies land in
+    them directly and they satisfy the reference's contract (C-contiguous uint8 HxW[x3] arrays,
+    kept alive by the views themselves)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("videovanish_b200: CUDA device required (there is no CPU fallback)")
+    block = torch.empty((t,) + tuple(shape), dtype=torch.uint8, pin_memory=True)
+    whole = block.numpy()
+    return [whole[i] for i in range(t)]
+
+
+class HostPipeline:
+    def __init__(self, h0, w0, h, w, device=None, frames_per_batch=8, n_slots=3):
+        if not torch.cuda.is_available():
+            raise RuntimeError("videovanish_b200: CUDA device required (there is no CPU fallback)")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.geometry = (int(h0), int(w0), int(h), int(w))
+        handle = ctypes.c_void_p()
+        _lib.check(lib.vv_pipeline_create(ctypes.byref(handle), self.device, int(h0), int(w0), int(h), int(w),
+                                          int(frames_per_batch), int(n_slots)), "vv_pipeline_create")
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.vv_pipeline_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def pre(self, mask_frames, iterations, want_lowres=False):
+        """diffuerase.py:28-31 over a list of HxWxC masks -> list of HxW u8 {0,255} (+ low-res)."""
+        h0, w0, h, w = self.geometry
+        c = 1 if mask_frames[0].ndim == 2 else mask_frames[0].shape[2]
+        shape = (h0, w0) if mask_frames[0].ndim == 2 else (h0, w0, c)
+        src, keep = _ptr_array(mask_frames, shape)
+        t = len(mask_frames)
+        dil = pinned_frames(t, (h0, w0))
+        dptr, _ = _ptr_array(dil)
+        low = pinned_frames(t, (h, w)) if want_lowres else None
+        lptr = _ptr_array(low)[0] if want_lowres else None
+        _lib.check(lib.vv_pipeline_pre(self._h, src, t, c, int(iterations), dptr, lptr), "vv_pipeline_pre")
+        del keep
+        return (dil, low) if want_lowres else dil
+
+    def downsize(self, frames):
+        h0, w0, h, w = self.geometry
+        src, keep = _ptr_array(frames, (h0, w0, 3))
+        out = pinned_frames(len(frames), (h, w, 3))
+        _lib.check(lib.vv_pipeline_downsize(self._h, src, len(frames), _ptr_array(out)[0]), "vv_pipeline_downsize")
+        del keep
+        return out
+
+    def post(self, inpainted, orig, dilated=None, feather_px=3, keep_unmasked_original=True):
+        """diffuerase.py:70-112 over lists; ``dilated=None`` reuses the masks left on the device
+        by the preceding ``pre`` call."""
+        h0, w0, h, w = self.geometry
+        t = len(inpainted)
+        iptr, k1 = _ptr_array(inpainted, (h, w, 3))
+        optr, k2 = _ptr_array(orig, (h0, w0, 3)) if keep_unmasked_original else (None, None)
+        mptr, k3 = _ptr_array(dilated, (h0, w0)) if (dilated is not None and keep_unmasked_original) else (None, None)
+        out = pinned_frames(t, (h0, w0, 3))
+        _lib.check(lib.vv_pipeline_post(self._h, iptr, optr, mptr, t, float(feather_px),
+                                        1 if keep_unmasked_original else 0, _ptr_array(out)[0]), "vv_pipeline_post")
+        del k1, k2, k3
+        return out

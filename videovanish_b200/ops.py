@@ -1,0 +1,184 @@
+"""Device-resident operators: thin torch-tensor front-ends of the C ABI.
+
+torch is used for device memory and streams only; every byte of arithmetic happens in
+``csrc/*.cu``.  All tensors are contiguous uint8 NHWC on a CUDA device; kernels are enqueued on
+``torch.cuda.current_stream()``.  Names and argument meaning follow the reference's stages
+(/root/reference/diffuerase.py:26-31, :70-112) and SURVEY.md section 8b.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import VV_INTER_LINEAR, VV_INTER_NEAREST, lib
+
+INTER_NEAREST = VV_INTER_NEAREST      # same numeric values as cv2.INTER_NEAREST / cv2.INTER_LINEAR
+INTER_LINEAR = VV_INTER_LINEAR
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError("videovanish_b200.ops: expected a CUDA tensor (there is no CPU fallback)")
+        if not t.is_contiguous():
+            raise ValueError("videovanish_b200.ops: tensors must be contiguous")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def inference_size(h0, w0, max_img_size=960):
+    """(h, w) the model wrapper resizes to."""
+    h, w = ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.vv_inference_size(h0, w0, max_img_size, ctypes.byref(h), ctypes.byref(w)), "vv_inference_size")
+    return h.value, w.value
+
+
+def binarize_dilate(mask, iterations=8, lowres_size=None):
+    """K1.  mask u8 [T,H,W,C] (or [T,H,W]) -> u8 [T,H,W] in {0,255}   (diffuerase.py:28-31).
+    With ``lowres_size=(h, w)`` also returns the INTER_NEAREST down-sized mask [T,h,w]."""
+    if mask.dim() == 3:
+        mask = mask.unsqueeze(-1)
+    _require_cuda(mask)
+    if mask.dtype != torch.uint8 or mask.dim() != 4:
+        raise ValueError("binarize_dilate: mask must be uint8 [T,H,W,C]")
+    t, h, w, c = mask.shape
+    with torch.cuda.device(mask.device):
+        out = torch.empty((t, h, w), dtype=torch.uint8, device=mask.device)
+        low = None
+        lh = lw = 0
+        if lowres_size is not None:
+            lh, lw = int(lowres_size[0]), int(lowres_size[1])
+            low = torch.empty((t, lh, lw), dtype=torch.uint8, device=mask.device)
+        nbytes = lib.vv_binarize_dilate_workspace_bytes(t, h, w)
+        ws = _ws(nbytes, mask.device)
+        _lib.check(lib.vv_binarize_dilate(_ptr(mask), t, h, w, c, int(iterations), _ptr(out), _ptr(low), lh, lw,
+                                          _ptr(ws), nbytes, _stream()), "vv_binarize_dilate")
+    return out if low is None else (out, low)
+
+
+def resize(src, h, w, interpolation=INTER_LINEAR):
+    """K2.  u8 [T,H,W,C] -> u8 [T,h,w,C], cv2.resize semantics (bit-exact)."""
+    squeeze = src.dim() == 3
+    if squeeze:
+        src = src.unsqueeze(-1)
+    _require_cuda(src)
+    if src.dtype != torch.uint8 or src.dim() != 4:
+        raise ValueError("resize: src must be uint8 [T,H,W,C]")
+    t, hh, ww, c = src.shape
+    with torch.cuda.device(src.device):
+        dst = torch.empty((t, int(h), int(w), c), dtype=torch.uint8, device=src.device)
+        nbytes = lib.vv_resize_workspace_bytes(int(h), int(w))
+        ws = _ws(nbytes, src.device)
+        _lib.check(lib.vv_resize(_ptr(src), t, hh, ww, c, _ptr(dst), int(h), int(w), int(interpolation), _ptr(ws),
+                                 nbytes, _stream()), "vv_resize")
+    return dst.squeeze(-1) if squeeze else dst
+
+
+def upscale_feather_composite(inpainted, orig, mask, feather_px=3, keep_unmasked_original=True, out=None):
+    """K3.  inpainted u8 [T,h,w,3], orig u8 [T,H0,W0,3], mask u8 [T,H0,W0] -> u8 [T,H0,W0,3]
+    (diffuerase.py:70-112 applied to every frame)."""
+    _require_cuda(inpainted, orig, mask)
+    t, h, w, _ = inpainted.shape
+    if keep_unmasked_original:
+        if orig is None or mask is None:
+            raise ValueError("upscale_feather_composite: orig and mask are required when keep_unmasked_original")
+        h0, w0 = orig.shape[1:3]
+        if tuple(mask.shape) != (t, h0, w0) or orig.shape[0] != t:
+            raise ValueError("upscale_feather_composite: shape mismatch")
+    else:
+        h0, w0 = (orig.shape[1:3] if orig is not None else mask.shape[1:3])
+    with torch.cuda.device(inpainted.device):
+        if out is None:
+            out = torch.empty((t, h0, w0, 3), dtype=torch.uint8, device=inpainted.device)
+        nbytes = lib.vv_composite_workspace_bytes(h0, w0)
+        ws = _ws(nbytes, inpainted.device)
+        _lib.check(lib.vv_upscale_feather_composite(
+            _ptr(inpainted), t, h, w, _ptr(orig) if keep_unmasked_original else None,
+            _ptr(mask) if keep_unmasked_original else None, h0, w0, float(feather_px),
+            1 if keep_unmasked_original else 0, _ptr(out), _ptr(ws), nbytes, _stream()), "vv_upscale_feather_composite")
+    return out
+
+
+def subvideo_plan(video_length, subvideo_length=50, pad_len=10):
+    """Windows of propainter/inference.py's image-propagation loop: (s_f, e_f, pad_s, pad_e)."""
+    sub = min(100, subvideo_length)
+    if video_length <= sub:
+        return [(0, video_length, 0, 0)]
+    plan = []
+    for f in range(0, video_length, sub):
+        s_f = max(0, f - pad_len)
+        e_f = min(video_length, f + sub + pad_len)
+        plan.append((s_f, e_f, f - s_f, e_f - min(video_length, f + sub)))
+    return plan
+
+
+def propagate(frames, masks, flows_f, flows_b, subvideo_length=50, pad_len=10, keep_pads=False):
+    """K4.  frames u8 [N,h,w,3], masks u8 [N,h,w] (>0 = hole), flows f32 [N-1,h,w,2] ->
+    packed u32 [N,h,w] (R | G<<8 | B<<16 | state<<24) of the forward propagation pass, pad
+    frames of every sub-video window discarded (``keep_pads=True`` returns the raw windows)."""
+    _require_cuda(frames, masks, flows_f, flows_b)
+    n, h, w, _ = frames.shape
+    plan = subvideo_plan(n, subvideo_length, pad_len)
+    starts = (ctypes.c_int * len(plan))(*[p[0] for p in plan])
+    lens = (ctypes.c_int * len(plan))(*[p[1] - p[0] for p in plan])
+    total = sum(p[1] - p[0] for p in plan)
+    with torch.cuda.device(frames.device):
+        out = torch.empty((total, h, w), dtype=torch.int32, device=frames.device)
+        nbytes = lib.vv_propagate_workspace_bytes(total, h, w)
+        ws = _ws(nbytes, frames.device)
+        _lib.check(lib.vv_propagate(_ptr(frames), _ptr(masks), _ptr(flows_f) if n > 1 else None,
+                                    _ptr(flows_b) if n > 1 else None, n, h, w, starts, lens, len(plan), _ptr(out),
+                                    _ptr(ws), nbytes, _stream()), "vv_propagate")
+        if keep_pads or len(plan) == 1:
+            return out
+        keep, off = [], 0
+        for s_f, e_f, ps, pe in plan:
+            keep.append(out[off + ps: off + (e_f - s_f) - pe])
+            off += e_f - s_f
+        return torch.cat(keep)
+
+
+def propagate_unpack(packed, zero_level=127):
+    """packed u32 [N,h,w] -> (rgb u8 [N,h,w,3], hole mask u8 [N,h,w] in {0,255})."""
+    _require_cuda(packed)
+    n, h, w = packed.shape
+    with torch.cuda.device(packed.device):
+        rgb = torch.empty((n, h, w, 3), dtype=torch.uint8, device=packed.device)
+        hole = torch.empty((n, h, w), dtype=torch.uint8, device=packed.device)
+        _lib.check(lib.vv_propagate_unpack(_ptr(packed), n * h * w, int(zero_level), _ptr(rgb), _ptr(hole), _stream()),
+                   "vv_propagate_unpack")
+    return rgb, hole
+
+
+def chunk_blend(tail, head, k0=0, overlap_total=None, out=None):
+    """K5.  tail/head u8 [O,H,W,C] (earlier chunk's last O frames / later chunk's first O)
+    -> blended u8 [O,H,W,C].  Either input may be an ``int`` device address instead of a tensor:
+    a peer GPU's buffer mapped through CUDA IPC, read in place over NVLink."""
+    ref = tail if isinstance(tail, torch.Tensor) else head
+    if not isinstance(ref, torch.Tensor):
+        ref = out
+    _require_cuda(ref, out, *(x for x in (tail, head) if isinstance(x, torch.Tensor)))
+    o = ref.shape[0]
+    frame_bytes = ref[0].numel() * ref.element_size()
+    if overlap_total is None:
+        overlap_total = k0 + o
+    with torch.cuda.device(ref.device):
+        if out is None:
+            out = torch.empty_like(ref)
+        pa = tail if isinstance(tail, int) else tail.data_ptr()
+        pb = head if isinstance(head, int) else head.data_ptr()
+        _lib.check(lib.vv_chunk_blend(ctypes.c_void_p(pa), ctypes.c_void_p(pb), o, frame_bytes, int(k0),
+                                      int(overlap_total), _ptr(out), _stream()), "vv_chunk_blend")
+    return out
