@@ -283,12 +283,12 @@ def run_ours(args, rank, world, local_rank):
     inpainted_host = list(host["inpainted"].numpy())
     vvd.set_models(diffueraser=_StubModel())
     e2e_steps = max(1, min(args.steps, 3))
-    vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host, max_img_size=960 if HS == 536 else 961)
+    vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host, max_img_size=960)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host,
-                                       max_img_size=960 if HS == 536 else 961)
+                                       max_img_size=960)
     torch.cuda.synchronize()
     e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=device)
     if world > 1:

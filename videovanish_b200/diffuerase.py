@@ -15,7 +15,7 @@ Differences, all deliberate and documented in DESIGN.md:
 """
 import numpy as np
 
-from . import hostpipe, ops
+from . import hostpipe
 
 BUG_COMPAT = False           # True: reproduce the early return of diffuerase.py:114
 
@@ -36,12 +36,12 @@ def set_models(diffueraser=None, propainter_model=None):
         propainter = propainter_model
 
 
-def _get_pipeline(h0, w0, h, w):
+def _get_pipeline(h0, w0):
     global _pipeline
-    if _pipeline is None or _pipeline.geometry != (h0, w0, h, w):
+    if _pipeline is None or _pipeline.geometry != (h0, w0):
         if _pipeline is not None:
             _pipeline.close()
-        _pipeline = hostpipe.HostPipeline(h0, w0, h, w)
+        _pipeline = hostpipe.HostPipeline(h0, w0)
     return _pipeline
 
 
@@ -52,8 +52,7 @@ def run_infill_on_frames(frames_rgb, mask_frames, mask_dilation_iter=8, ckpt="2-
     global device, last_ckpt, video_inpainting_sd, propainter
 
     H0, W0 = frames_rgb[0].shape[:2]
-    h, w = ops.inference_size(H0, W0, max_img_size)
-    pipe = _get_pipeline(H0, W0, h, w)
+    pipe = _get_pipeline(H0, W0)
 
     if prog is not None: prog(5, "dilating frames")
     dilated_mask_frames = pipe.pre(mask_frames, mask_dilation_iter)                      # :27-31 (K1)
@@ -89,12 +88,10 @@ def run_infill_on_frames(frames_rgb, mask_frames, mask_dilation_iter=8, ckpt="2-
     fh, fw = inpainted_frames[0].shape[:2]
     if (fh, fw) == (H0, W0) and not keep_unmasked_original:
         return inpainted_frames                                                          # nothing to do (:72, :75)
-    resident = True
-    if (fh, fw) != (h, w):            # the model picked another size than row A9 predicts
-        pipe = _get_pipeline(H0, W0, fh, fw)
-        resident = False
-    out = pipe.post(inpainted_frames[:n], frames_rgb[:n], None if resident else dilated_mask_frames[:n],
-                    feather_px, keep_unmasked_original)                                  # :70-112 (K3)
+    if fh * fw > H0 * W0:             # never produced by the model wrapper (row A9 only shrinks)
+        raise ValueError("inpainted frames (%dx%d) larger than the originals (%dx%d)" % (fh, fw, H0, W0))
+    # the dilated masks are still on the device from `pre`
+    out = pipe.post(inpainted_frames[:n], frames_rgb[:n], None, feather_px, keep_unmasked_original)   # :70-112 (K3)
     for i in range(n):
         inpainted_frames[i] = out[i]
     return inpainted_frames

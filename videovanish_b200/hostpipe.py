@@ -39,13 +39,13 @@ def pinned_frames(t, shape):
 
 
 class HostPipeline:
-    def __init__(self, h0, w0, h, w, device=None, frames_per_batch=8, n_slots=3):
+    def __init__(self, h0, w0, device=None, frames_per_batch=8, n_slots=3):
         if not torch.cuda.is_available():
             raise RuntimeError("videovanish_b200: CUDA device required (there is no CPU fallback)")
         self.device = torch.cuda.current_device() if device is None else int(device)
-        self.geometry = (int(h0), int(w0), int(h), int(w))
+        self.geometry = (int(h0), int(w0))
         handle = ctypes.c_void_p()
-        _lib.check(lib.vv_pipeline_create(ctypes.byref(handle), self.device, int(h0), int(w0), int(h), int(w),
+        _lib.check(lib.vv_pipeline_create(ctypes.byref(handle), self.device, int(h0), int(w0),
                                           int(frames_per_batch), int(n_slots)), "vv_pipeline_create")
         self._h = handle
 
@@ -56,39 +56,46 @@ class HostPipeline:
 
     __del__ = close
 
-    def pre(self, mask_frames, iterations, want_lowres=False):
-        """diffuerase.py:28-31 over a list of HxWxC masks -> list of HxW u8 {0,255} (+ low-res)."""
-        h0, w0, h, w = self.geometry
+    def pre(self, mask_frames, iterations, lowres_size=None):
+        """diffuerase.py:28-31 over a list of HxWxC masks -> list of HxW u8 {0,255}; with
+        ``lowres_size=(h, w)`` also the INTER_NEAREST down-sized masks."""
+        h0, w0 = self.geometry
         c = 1 if mask_frames[0].ndim == 2 else mask_frames[0].shape[2]
         shape = (h0, w0) if mask_frames[0].ndim == 2 else (h0, w0, c)
         src, keep = _ptr_array(mask_frames, shape)
         t = len(mask_frames)
         dil = pinned_frames(t, (h0, w0))
         dptr, _ = _ptr_array(dil)
-        low = pinned_frames(t, (h, w)) if want_lowres else None
-        lptr = _ptr_array(low)[0] if want_lowres else None
-        _lib.check(lib.vv_pipeline_pre(self._h, src, t, c, int(iterations), dptr, lptr), "vv_pipeline_pre")
+        low, lptr, lh, lw = None, None, 0, 0
+        if lowres_size is not None:
+            lh, lw = int(lowres_size[0]), int(lowres_size[1])
+            low = pinned_frames(t, (lh, lw))
+            lptr = _ptr_array(low)[0]
+        _lib.check(lib.vv_pipeline_pre(self._h, src, t, c, int(iterations), dptr, lptr, lh, lw), "vv_pipeline_pre")
         del keep
-        return (dil, low) if want_lowres else dil
+        return dil if low is None else (dil, low)
 
-    def downsize(self, frames):
-        h0, w0, h, w = self.geometry
+    def downsize(self, frames, h, w):
+        """Row A9: list of H0xW0x3 frames -> list of hxwx3 frames (cv2 INTER_LINEAR semantics)."""
+        h0, w0 = self.geometry
         src, keep = _ptr_array(frames, (h0, w0, 3))
-        out = pinned_frames(len(frames), (h, w, 3))
-        _lib.check(lib.vv_pipeline_downsize(self._h, src, len(frames), _ptr_array(out)[0]), "vv_pipeline_downsize")
+        out = pinned_frames(len(frames), (int(h), int(w), 3))
+        _lib.check(lib.vv_pipeline_downsize(self._h, src, len(frames), int(h), int(w), _ptr_array(out)[0]),
+                   "vv_pipeline_downsize")
         del keep
         return out
 
     def post(self, inpainted, orig, dilated=None, feather_px=3, keep_unmasked_original=True):
         """diffuerase.py:70-112 over lists; ``dilated=None`` reuses the masks left on the device
         by the preceding ``pre`` call."""
-        h0, w0, h, w = self.geometry
+        h0, w0 = self.geometry
         t = len(inpainted)
+        h, w = inpainted[0].shape[:2]
         iptr, k1 = _ptr_array(inpainted, (h, w, 3))
         optr, k2 = _ptr_array(orig, (h0, w0, 3)) if keep_unmasked_original else (None, None)
         mptr, k3 = _ptr_array(dilated, (h0, w0)) if (dilated is not None and keep_unmasked_original) else (None, None)
         out = pinned_frames(t, (h0, w0, 3))
-        _lib.check(lib.vv_pipeline_post(self._h, iptr, optr, mptr, t, float(feather_px),
+        _lib.check(lib.vv_pipeline_post(self._h, iptr, int(h), int(w), optr, mptr, t, float(feather_px),
                                         1 if keep_unmasked_original else 0, _ptr_array(out)[0]), "vv_pipeline_post")
         del k1, k2, k3
         return out
