@@ -6,7 +6,7 @@ what=${1:-all}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit --format=csv > gpurun_out/gpu.csv 2>&1
 if [[ $what == all || $what == tests ]]; then
-  timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
+  timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
   tail -25 gpurun_out/pytest_gpu.log
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
@@ -21,7 +21,7 @@ fi
 if [[ $what == all || $what == ncu ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-  for k in k3_upscale k1a_binarize k1b_dilate k2_resize_linear_half k4_step k5_chunk; do
+  for k in k3_upscale k1a_binarize k1b_dilate k2_resize_linear_half k4_step; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 2 -f \
         -o gpurun_out/prof_$k python bench.py --steps 1 --warmup 3 --frames 120 --no-cpu-baseline > gpurun_out/ncu_$k.log 2>&1
   done
