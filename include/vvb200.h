@@ -51,6 +51,10 @@ VV_API int vv_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *t
  * bench.py reports it as `gpu_launches`. */
 VV_API unsigned long long vv_launch_count(void);
 VV_API void vv_reset_launch_count(void);
+/* Kernel-variant switches used for A/B measurements (defaults are the tuned choices):
+ *   "k1b_exact"  1 = fully unrolled 8-round dilation for the default radius, 0 = generic loop. */
+VV_API int vv_set_option(const char *name, int value);
+VV_API int vv_get_option(const char *name, int *value);
 
 /* ---------------------------------------------------------------------------------
  * K1  mask binarise + L1 dilation.                       Replaces diffuerase.py:28-31

@@ -62,3 +62,22 @@ def test_clip_level_model_matches_torch():
     g, gm = opp.decode_state(opp.model_propagate_clip(fr, m, ff, fb, subvideo_length=5, pad_len=2))
     assert u.shape == g.shape == (14, 3, 32, 40)
     assert (g != u).mean() <= MAX_MISMATCH_FRACTION and (gm != um).mean() <= MAX_MISMATCH_FRACTION
+
+
+def test_zero_padding_fill_state():
+    """A hole on the left border whose small outward flow samples the zero padding is filled
+    with the float 0.0 (state ZERO without HOLE), exactly as torch's grid_sample does."""
+    t, h, w = 3, 24, 32
+    fr = synth.frames(t, h, w, seed=5)
+    m = np.zeros((t, h, w), np.uint8)
+    m[1, 4:20, 0:2] = 255
+    ff = np.zeros((t - 1, h, w, 2), np.float32)
+    fb = np.zeros((t - 1, h, w, 2), np.float32)
+    ff[..., 0] = -0.61
+    fb[..., 0] = 0.58
+    p = opp.model_propagate(fr, m, ff, fb)
+    assert ((p >> 24) == opp.ZERO).sum() == 16 and ((p >> 24) & opp.HOLE).sum() == 0
+    rf, rm = opp.img_propagation_torch(fr, m, ff, fb)
+    gf, gm = opp.decode_state(p)
+    assert np.array_equal(gf, rf) and np.array_equal(gm, rm)
+    assert (rf[1, :, 4:20, 0] == 0).all()

@@ -1,11 +1,11 @@
 #!/bin/bash
-# One gpurun call: parity tests, smoke, bench, ncu launch list + full captures of the hot kernels.
-# Usage (from the repo root on the GPU box):  bash tools/gpu_check.sh [tests|bench|ncu|all]
+# One gpurun call: parity tests, smoke, bench, microbench, ncu launch list + full captures.
+# Usage (from the repo root on the GPU box):  bash tools/gpu_check.sh "tests bench micro ncu"
 set -u
-what=${1:-all}
+what=${1:-"tests bench micro ncu"}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit --format=csv > gpurun_out/gpu.csv 2>&1
-if [[ $what == all || $what == tests ]]; then
+if [[ $what == *tests* ]]; then
   timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
   tail -25 gpurun_out/pytest_gpu.log
@@ -13,17 +13,21 @@ if [[ $what == all || $what == tests ]]; then
   echo "smoke exit $?" >> gpurun_out/smoke.log
   tail -3 gpurun_out/smoke.log
 fi
-if [[ $what == all || $what == bench ]]; then
+if [[ $what == *micro* ]]; then
+  timeout 600 python tools/microbench.py > gpurun_out/micro.log 2>&1
+  cat gpurun_out/micro.log
+fi
+if [[ $what == *bench* ]]; then
   timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1
   echo "bench exit $?" >> gpurun_out/bench.log
   tail -5 gpurun_out/bench.log
 fi
-if [[ $what == all || $what == ncu ]]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
+if [[ $what == *ncu* ]]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
   for k in k3_upscale k1a_binarize k1b_dilate k2_resize_linear_half k4_step; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 2 -f \
-        -o gpurun_out/prof_$k python bench.py --steps 1 --warmup 3 --frames 120 --no-cpu-baseline > gpurun_out/ncu_$k.log 2>&1
+        -o gpurun_out/prof_$k python tools/microbench.py --frames 120 > gpurun_out/ncu_$k.log 2>&1
   done
   ls -la gpurun_out
 fi

@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""Per-operator timing at the BASELINE config-2 shape (CUDA events, device-resident inputs larger
+than L2).  Used for A/B-ing kernel variants in one GPU call:  python tools/microbench.py [--frames N]
+Prints one JSON object per line."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from videovanish_b200 import _lib, ops, synth  # noqa: E402
+
+H0, W0, HS, WS = 1080, 1920, 540, 960
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in ev]
+    return float(np.median(ts)), float(min(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=120)
+    ap.add_argument("--ops", default="all")
+    args = ap.parse_args()
+    t = args.frames
+    dev = torch.device("cuda", 0)
+    base = min(t, 16)
+    reps = (t + base - 1) // base
+    fr = torch.from_numpy(np.tile(synth.frames(base, H0, W0, seed=1), (reps, 1, 1, 1))[:t]).to(dev)
+    inp = torch.from_numpy(np.tile(synth.noise_frames(base, HS, WS, seed=2), (reps, 1, 1, 1))[:t]).to(dev)
+    mk = torch.from_numpy(synth.masks(t, H0, W0, seed=3)).to(dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    ff = torch.tensor([3.0, -1.5], device=dev) + 0.05 * torch.randn((t - 1, HS, WS, 2), device=dev, generator=g)
+    fb = -ff + 0.05 * torch.randn((t - 1, HS, WS, 2), device=dev, generator=g)
+    bad = torch.rand((t - 1, HS, WS), device=dev, generator=g) < 0.02
+    ff[bad] += (torch.rand((int(bad.sum()), 2), device=dev, generator=g) - 0.5) * 40.0
+    px, spx = H0 * W0, HS * WS
+    dil, low = ops.binarize_dilate(mk, 8, lowres_size=(HS, WS))
+    small = ops.resize(fr, HS, WS)
+    out = torch.empty_like(fr)
+    empty_mask = torch.zeros_like(dil)
+    full_mask = torch.full_like(dil, 255)
+    peak = 6545.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+
+    def report(name, alg_bytes, fn, **extra):
+        med, best = timeit(fn)
+        gbs = alg_bytes / (med * 1e-3) / 1e9
+        print(json.dumps(dict(op=name, frames=t, ms=med, ms_best=best, us_per_frame=med * 1e3 / t, GBps=gbs,
+                              frac=gbs / peak, **extra)), flush=True)
+
+    print(json.dumps(dict(mask_fraction=float((dil > 0).float().mean()))), flush=True)
+    for exact in (1, 0):
+        _lib.set_option("k1b_exact", exact)
+        report("K1 dilate8 + half-res mask", t * (4 * px + spx), lambda: ops.binarize_dilate(mk, 8, lowres_size=(HS, WS)),
+               k1b_exact=exact)
+        report("K1 dilate8", t * 4 * px, lambda: ops.binarize_dilate(mk, 8), k1b_exact=exact)
+    _lib.set_option("k1b_exact", 1)
+    report("K1 dilate8 + generic low-res (536)", t * (4 * px + 536 * 960),
+           lambda: ops.binarize_dilate(mk, 8, lowres_size=(536, 960)))
+    report("K1 dilate25", t * 4 * px, lambda: ops.binarize_dilate(mk, 25))
+    report("K2 resize 1080p->540p", t * (3 * px + 3 * spx), lambda: ops.resize(fr, HS, WS))
+    report("K2 resize 1080p->536p", t * (3 * px + 3 * 536 * 960), lambda: ops.resize(fr, 536, 960))
+    report("K2 nearest mask 1080p->540p", t * (px + spx), lambda: ops.resize(dil, HS, WS, ops.INTER_NEAREST))
+    report("K3 composite (synthetic mask)", t * (7 * px + 3 * spx),
+           lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out))
+    report("K3 composite (empty mask)", t * (7 * px + 3 * spx),
+           lambda: ops.upscale_feather_composite(inp, fr, empty_mask, 3, out=out))
+    report("K3 composite (full mask)", t * (7 * px + 3 * spx),
+           lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out))
+    report("K3 composite feather 5 (generic path)", t * (7 * px + 3 * spx),
+           lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
+    report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb))
+    report("K5 chunk blend 16 frames", 16 * 9 * px, lambda: ops.chunk_blend(fr[:16], fr[16:32], out=out[:16]))
+    report("copy (torch) 1080p frames", t * 6 * px, lambda: out.copy_(fr))
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,8 @@ _SIGNATURES = {
     "vv_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "vv_launch_count": (c_ulonglong, []),
     "vv_reset_launch_count": (None, []),
+    "vv_set_option": (c_int, [c_char_p, c_int]),
+    "vv_get_option": (c_int, [c_char_p, POINTER(c_int)]),
     "vv_binarize_dilate_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vv_binarize_dilate": (c_int, [_u8p, c_int, c_int, c_int, c_int, c_int, _u8p, _u8p, c_int, c_int, c_void_p,
                                    c_size_t, c_void_p]),
@@ -79,3 +81,13 @@ def launch_count():
 
 def reset_launch_count():
     lib.vv_reset_launch_count()
+
+
+def set_option(name, value):
+    check(lib.vv_set_option(name.encode(), int(value)), "vv_set_option")
+
+
+def get_option(name):
+    v = c_int()
+    check(lib.vv_get_option(name.encode(), ctypes.byref(v)), "vv_get_option")
+    return v.value

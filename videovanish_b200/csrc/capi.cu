@@ -9,6 +9,10 @@ namespace vv {
 
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_options[OPT_COUNT] = {{1}};
+static const char *const g_option_names[OPT_COUNT] = {"k1b_exact"};
+
+int get_option(int opt) { return g_options[opt].load(std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -22,6 +26,28 @@ void set_error(const char *fmt, ...) {
 using namespace vv;
 
 extern "C" int vv_version(void) { return 100; }
+
+extern "C" int vv_set_option(const char *name, int value) {
+    VV_CHECK_ARG(name, "vv_set_option: NULL name");
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (!strcmp(name, g_option_names[i])) {
+            g_options[i].store(value);
+            return VV_OK;
+        }
+    set_error("vv_set_option: unknown option '%s'", name);
+    return VV_ERR_INVALID;
+}
+
+extern "C" int vv_get_option(const char *name, int *value) {
+    VV_CHECK_ARG(name && value, "vv_get_option: NULL argument");
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (!strcmp(name, g_option_names[i])) {
+            *value = g_options[i].load();
+            return VV_OK;
+        }
+    set_error("vv_get_option: unknown option '%s'", name);
+    return VV_ERR_INVALID;
+}
 
 extern "C" const char *vv_last_error(void) { return g_err; }
 

@@ -11,6 +11,10 @@
 namespace vv {
 
 void set_error(const char *fmt, ...);
+
+// Tuning switches (vv_set_option): variants kept side by side so that one GPU run can A/B them.
+enum Option { OPT_K1B_EXACT = 0, OPT_COUNT };
+int get_option(int opt);
 extern std::atomic<unsigned long long> g_launches;
 
 inline int fail_cuda(cudaError_t e, const char *what) {

@@ -73,12 +73,41 @@ __global__ void __launch_bounds__(256) k1a_binarize_pack(const uint8_t *__restri
 
 // ------------------------------------------------------------------ k1b: dilate (+ expand)
 // Warp tile: lanes 1..30 own output word columns tx*30 + (lane-1); lanes 0 and 31 carry the
-// 32-pixel horizontal halo (enough for n_iter <= 32).  Register row i <-> frame row
-// y0 - NMAX + i.  After n_iter rounds rows [NMAX, NMAX+RB) of lanes 1..30 are exact.
-template <int NMAX, int RB>
+// 32-pixel horizontal halo (enough for n_iter <= 32; what they compute themselves is never used).
+// Register row i <-> frame row y0 - NMAX + i.  After n_iter rounds rows [NMAX, NMAX+RB) of lanes
+// 1..30 are exact.  EXACT (n_iter == NMAX at compile time) unrolls the rounds as well, which lets
+// the compiler drop the halo-row updates that can no longer reach an output row.
+// HALF: additionally write the exact x2 INTER_NEAREST down-size (source index 2*d) of the dilated
+// mask: even bits of even rows, 16 low-res pixels per word.
+__device__ __forceinline__ uint32_t even_bits(uint32_t x) {   // bits 0,2,4,...,30 -> bits 0..15
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    x = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+
+template <int NMAX, int ROWS>
+__device__ __forceinline__ void cross_round(uint32_t (&r)[ROWS]) {
+    uint32_t prev = 0;
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+        const uint32_t c = r[i];
+        const uint32_t l = __shfl_up_sync(0xffffffffu, c, 1);      // lane 0 / 31 receive their own word:
+        const uint32_t rt = __shfl_down_sync(0xffffffffu, c, 1);   // only halo lanes are affected
+        const uint32_t nxt = (i + 1 < ROWS) ? r[i + 1] : 0u;
+        // (c << 1 | l >> 31) | (c >> 1 | rt << 31) | c | up | down
+        r[i] = (__funnelshift_l(l, c, 1) | __funnelshift_r(c, rt, 1) | c) | (prev | nxt);
+        prev = c;
+    }
+}
+
+template <int NMAX, int RB, bool EXACT>
 __global__ void __launch_bounds__(128)
     k1b_dilate_expand(const uint32_t *__restrict__ bits_in, uint32_t *__restrict__ bits_out, uint8_t *__restrict__ out,
-                      int H, int W, int Wp, int n_iter, int tiles_x, int tiles_y, long long n_tiles, int vec_ok) {
+                      uint8_t *__restrict__ half_out, int H, int W, int Wp, int n_iter, int tiles_x, int tiles_y,
+                      long long n_tiles, int vec_ok) {
     constexpr int ROWS = RB + 2 * NMAX;
     const int lane = threadIdx.x & 31;
     const long long tile = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -91,6 +120,7 @@ __global__ void __launch_bounds__(128)
     const int y0 = ty * RB;
     const bool col_ok = wx >= 0 && wx < Wp;
     const uint32_t *src = bits_in + t * H * (long long)Wp + wx;
+    if (EXACT) n_iter = NMAX;
 
     uint32_t r[ROWS];
 #pragma unroll
@@ -100,26 +130,19 @@ __global__ void __launch_bounds__(128)
         r[i] = (col_ok && need && y >= 0 && y < H) ? __ldg(src + (long long)y * Wp) : 0u;
     }
 
-#pragma unroll 1
-    for (int it = 0; it < n_iter; ++it) {
-        uint32_t prev = 0;
+    if (EXACT) {
 #pragma unroll
-        for (int i = 0; i < ROWS; ++i) {
-            const uint32_t c = r[i];
-            uint32_t l = __shfl_up_sync(0xffffffffu, c, 1);
-            uint32_t rt = __shfl_down_sync(0xffffffffu, c, 1);
-            if (lane == 0) l = 0;
-            if (lane == 31) rt = 0;
-            const uint32_t nxt = (i + 1 < ROWS) ? r[i + 1] : 0u;
-            r[i] = c | (c << 1) | (c >> 1) | (l >> 31) | (rt << 31) | prev | nxt;
-            prev = c;
-        }
+        for (int it = 0; it < NMAX; ++it) cross_round<NMAX, ROWS>(r);
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < n_iter; ++it) cross_round<NMAX, ROWS>(r);
     }
 
     if (lane == 0 || lane == 31 || !col_ok) return;
     // bits beyond the frame edge may have been dilated into; clear them in the last word
     const int valid_bits = W - wx * 32;
     const uint32_t keep = valid_bits >= 32 ? 0xffffffffu : ((1u << valid_bits) - 1u);
+    const int lw = W >> 1;
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
         const int y = y0 + i;
@@ -137,7 +160,19 @@ __global__ void __launch_bounds__(128)
                 stg128_stream(o + 16, b);
             } else {
                 const int n = min(32, valid_bits);
+#pragma unroll 1
                 for (int k = 0; k < n; ++k) o[k] = ((v >> k) & 1u) ? 255 : 0;
+            }
+        }
+        if (half_out && !(i & 1)) {       // RB and y0 are even, so (y0 + i) is even iff i is
+            const uint32_t e = even_bits(v);
+            uint8_t *o = half_out + (t * (H >> 1) + (y >> 1)) * lw + wx * 16;
+            if (vec_ok && wx * 16 + 16 <= lw) {
+                stg128_stream(o, make_uint4(expand4(e), expand4(e >> 4), expand4(e >> 8), expand4(e >> 12)));
+            } else {
+                const int n = min(16, lw - wx * 16);
+#pragma unroll 1
+                for (int k = 0; k < n; ++k) o[k] = ((e >> k) & 1u) ? 255 : 0;
             }
         }
     }
@@ -177,19 +212,35 @@ __global__ void __launch_bounds__(256) k1c_fill(const uint32_t *__restrict__ fla
 // dilated bit plane so the full-resolution u8 mask is not re-read.
 __global__ void __launch_bounds__(256)
     k1d_lowres_from_bits(const uint32_t *__restrict__ bits, int H, int W, int Wp, uint8_t *__restrict__ low, int lh,
-                         int lw, long long T) {
-    const long long total = T * lh * (long long)lw;
-    const double sy = 1.0 / ((double)lh / (double)H), sx = 1.0 / ((double)lw / (double)W);
+                         int lw, long long T, int words_ok) {
+    const int groups = (lw + 3) >> 2;
+    const long long total = T * lh * (long long)groups;
+    const double sy = __ddiv_rn(1.0, __ddiv_rn((double)lh, (double)H));
+    const double sx = __ddiv_rn(1.0, __ddiv_rn((double)lw, (double)W));
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % lw);
-        const long long q = idx / lw;
+        const int g = (int)(idx % groups);
+        const long long q = idx / groups;
         const int y = (int)(q % lh);
         const long long t = q / lh;
         const int srcy = min((int)floor(__dmul_rn((double)y, sy)), H - 1);
-        const int srcx = min((int)floor(__dmul_rn((double)x, sx)), W - 1);
-        const uint32_t w = __ldg(bits + (t * H + srcy) * Wp + (srcx >> 5));
-        low[idx] = ((w >> (srcx & 31)) & 1u) ? 255 : 0;
+        const uint32_t *brow = bits + (t * H + srcy) * Wp;
+        const int x0 = g * 4, n = min(4, lw - x0);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < n) {
+                const int srcx = min((int)floor(__dmul_rn((double)(x0 + i), sx)), W - 1);
+                const uint32_t w = __ldg(brow + (srcx >> 5));
+                packed |= (((w >> (srcx & 31)) & 1u) * 0xffu) << (8 * i);
+            }
+        }
+        uint8_t *o = low + (t * lh + y) * (long long)lw + x0;
+        if (words_ok && n == 4) {
+            *reinterpret_cast<uint32_t *>(o) = packed;
+        } else {
+            for (int i = 0; i < n; ++i) o[i] = (uint8_t)(packed >> (8 * i));
+        }
     }
 }
 
@@ -204,24 +255,25 @@ static int launch_k1a(const uint8_t *mask, uint16_t *bits, int W, int Wp, long l
     return VV_OK;
 }
 
-template <int NMAX, int RB>
-static int launch_k1b(const uint32_t *in, uint32_t *bits_out, uint8_t *out, int T, int H, int W, int Wp, int n_iter,
-                      bool vec, cudaStream_t st) {
+template <int NMAX, int RB, bool EXACT>
+static int launch_k1b(const uint32_t *in, uint32_t *bits_out, uint8_t *out, uint8_t *half_out, int T, int H, int W,
+                      int Wp, int n_iter, bool vec, cudaStream_t st) {
     const int tiles_x = ceil_div(Wp, 30), tiles_y = ceil_div(H, RB);
     const long long n_tiles = (long long)T * tiles_x * tiles_y;
     const int grid = ceil_div(n_tiles, 4);
-    k1b_dilate_expand<NMAX, RB><<<grid, 128, 0, st>>>(in, bits_out, out, H, W, Wp, n_iter, tiles_x, tiles_y, n_tiles,
-                                                      vec ? 1 : 0);
+    k1b_dilate_expand<NMAX, RB, EXACT><<<grid, 128, 0, st>>>(in, bits_out, out, half_out, H, W, Wp, n_iter, tiles_x,
+                                                             tiles_y, n_tiles, vec ? 1 : 0);
     VV_POST_LAUNCH("k1b_dilate_expand");
     return VV_OK;
 }
 
-static int dilate_pass(const uint32_t *in, uint32_t *bits_out, uint8_t *out, int T, int H, int W, int Wp, int n,
-                       bool vec, cudaStream_t st) {
-    if (n <= 4) return launch_k1b<4, 32>(in, bits_out, out, T, H, W, Wp, n, vec, st);
-    if (n <= 8) return launch_k1b<8, 32>(in, bits_out, out, T, H, W, Wp, n, vec, st);
-    if (n <= 16) return launch_k1b<16, 32>(in, bits_out, out, T, H, W, Wp, n, vec, st);
-    return launch_k1b<32, 16>(in, bits_out, out, T, H, W, Wp, n, vec, st);
+static int dilate_pass(const uint32_t *in, uint32_t *bits_out, uint8_t *out, uint8_t *half_out, int T, int H, int W,
+                       int Wp, int n, bool vec, cudaStream_t st) {
+    if (n == 8 && get_option(OPT_K1B_EXACT)) return launch_k1b<8, 32, true>(in, bits_out, out, half_out, T, H, W, Wp, n, vec, st);   // GUI default
+    if (n <= 4) return launch_k1b<4, 32, false>(in, bits_out, out, half_out, T, H, W, Wp, n, vec, st);
+    if (n <= 8) return launch_k1b<8, 32, false>(in, bits_out, out, half_out, T, H, W, Wp, n, vec, st);
+    if (n <= 16) return launch_k1b<16, 32, false>(in, bits_out, out, half_out, T, H, W, Wp, n, vec, st);
+    return launch_k1b<32, 16, false>(in, bits_out, out, half_out, T, H, W, Wp, n, vec, st);
 }
 
 }  // namespace vv
@@ -281,18 +333,23 @@ extern "C" int vv_binarize_dilate(const uint8_t *mask, int T, int H, int W, int 
     uint32_t *cur = bits0, *nxt = bits1;
     int left = iterations;
     while (left > 32) {
-        rc = dilate_pass(cur, nxt, nullptr, T, H, W, Wp, 32, vec_out, st);
+        rc = dilate_pass(cur, nxt, nullptr, nullptr, T, H, W, Wp, 32, vec_out, st);
         if (rc) return rc;
         uint32_t *tmp = cur;
         cur = nxt, nxt = tmp;
         left -= 32;
     }
-    rc = dilate_pass(cur, lowres_out ? nxt : nullptr, out, T, H, W, Wp, left, vec_out, st);
+    // exact x2 down-size: the low-res mask is written by the dilation pass itself
+    const bool half = lowres_out && H == 2 * lh && W == 2 * lw;
+    const bool vec_half = vec_out && (lw % 16 == 0) && ((uintptr_t)lowres_out % 16 == 0);
+    rc = dilate_pass(cur, (lowres_out && !half) ? nxt : nullptr, out, half ? lowres_out : nullptr, T, H, W, Wp, left,
+                     half ? vec_half : vec_out, st);
     if (rc) return rc;
-    if (lowres_out) {
-        const long long total = (long long)T * lh * lw;
+    if (lowres_out && !half) {
+        const long long total = (long long)T * lh * ((lw + 3) / 4);
+        const int words_ok = (lw % 4 == 0) && ((uintptr_t)lowres_out % 4 == 0);
         k1d_lowres_from_bits<<<(int)min((long long)ceil_div(total, 256), (long long)148 * 32), 256, 0, st>>>(
-            nxt, H, W, Wp, lowres_out, lh, lw, T);
+            nxt, H, W, Wp, lowres_out, lh, lw, T, words_ok);
         VV_POST_LAUNCH("k1d_lowres_from_bits");
     }
     return VV_OK;

@@ -68,8 +68,34 @@ __device__ __forceinline__ uint32_t bit_window(const uint32_t *row, int col0) {
     return __funnelshift_r(row[k], row[k + 1], off);
 }
 
+// RGB of source pixels sx and min(sx+1, w-1) of one inference-resolution row (24-bit each).
+// Fast path: two aligned 64-bit loads cover the 6 contiguous bytes; byte loads near the row end
+// or when the row is not 8-byte aligned.
+__device__ __forceinline__ void load_pixel_pair(const uint8_t *__restrict__ row, int sx, int w, bool row_aligned8,
+                                                uint32_t &p0, uint32_t &p1) {
+    const int o = sx * 3, a8 = o & ~7;
+    if (row_aligned8 && a8 + 16 <= w * 3) {
+        const unsigned long long lo = __ldg(reinterpret_cast<const unsigned long long *>(row + a8));
+        const unsigned long long hi = __ldg(reinterpret_cast<const unsigned long long *>(row + a8 + 8));
+        const int sh = (o & 7) * 8;
+        const unsigned long long v = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+        p0 = (uint32_t)v & 0xffffffu;
+        p1 = (uint32_t)(v >> 24) & 0xffffffu;
+    } else {
+        const int o1 = min(sx + 1, w - 1) * 3;
+        p0 = __ldg(row + o) | (__ldg(row + o + 1) << 8) | (__ldg(row + o + 2) << 16);
+        p1 = __ldg(row + o1) | (__ldg(row + o1 + 1) << 8) | (__ldg(row + o1 + 2) << 16);
+    }
+}
+
+constexpr int K3_THREADS = 256;
+constexpr int K3_QUEUE = 512;     // work items per warp task: 32 lanes x 16 pixels
+
+// Work item: x (16 bits) | row in strip (4 bits) << 16 | alpha code (9 bits) << 20.
+// SMALL_R: code = LUT index (class | inside << 3); generic: code = (entry + 1, 0 = none) | inside << 8.
+
 template <bool VEC, bool SMALL_R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(K3_THREADS)
     k3_upscale_feather_composite(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig,
                                  const uint8_t *__restrict__ mask, uint8_t *__restrict__ out,
                                  const Tap *__restrict__ xt, const Tap *__restrict__ yt, int h, int w, int H0, int W0,
@@ -79,8 +105,10 @@ __global__ void __launch_bounds__(256)
     const int Wp = (W0 + 31) >> 5;
     const int row_words = Wp + 2;
     const int rows_s = K3_TH + 2 * R;
-    uint32_t *bits = smem;                                 // [rows_s][row_words]
+    uint32_t *bits = smem;                                               // [rows_s][row_words]
     float *lut = reinterpret_cast<float *>(smem + rows_s * row_words);   // [16] alpha levels (SMALL_R)
+    uint32_t *queue = smem + rows_s * row_words + 16 + (threadIdx.x >> 5) * K3_QUEUE;   // per-warp work queue
+    const int lane = threadIdx.x & 31;
 
     const long long t = blockIdx.x / strips_per_frame;
     const int y0 = (blockIdx.x % strips_per_frame) * K3_TH;
@@ -122,146 +150,181 @@ __global__ void __launch_bounds__(256)
     const uint8_t *orig_t = orig + t * H0 * (long long)W0 * 3;
     uint8_t *out_t = out + t * H0 * (long long)W0 * 3;
     const uint8_t *inp_t = inp + t * h * (long long)w * 3;
+    const bool inp_aligned8 = ((w * 3) % 8 == 0) && ((uintptr_t)inp_t % 8 == 0);
+    const bool hard = !SMALL_R && ft.n == 0;
+    // which LUT levels have alpha > 0 (SMALL_R): all inside levels, outside levels whose cost < F
+    uint32_t lut_pos = 0;
+    if (SMALL_R) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) lut_pos |= (uint32_t)(lut[k] > 0.f) << k;
+    }
 
-    for (int id = threadIdx.x; id < K3_TH * G; id += blockDim.x) {
+    const int n_tasks = K3_TH * G;
+    const int n_iters = (n_tasks + K3_THREADS - 1) / K3_THREADS;     // same trip count for the whole warp
+    for (int it = 0; it < n_iters; ++it) {
+        const int id = it * K3_THREADS + threadIdx.x;
         const int row = id / G, g = id - row * G;
         const int y = y0 + row;
-        if (y >= H0) break;
+        const bool active = id < n_tasks && y < H0;
         const int x0 = g * 16;
         const int npx = VEC ? 16 : min(16, W0 - x0);
         const long long pix_off = ((long long)y * W0 + x0) * 3;
+        uint32_t need = 0;                  // pixels (bit i) with alpha > 0
+        uint32_t L0 = 0, L1 = 0, L2 = 0, M2 = 0;
 
-        // original pixels (issued first: independent of the mask logic)
-        uint32_t o[12];
-        if (VEC) {
-            const uint4 a = ldg128(orig_t + pix_off), b = ldg128(orig_t + pix_off + 16), c = ldg128(orig_t + pix_off + 32);
-            o[0] = a.x, o[1] = a.y, o[2] = a.z, o[3] = a.w, o[4] = b.x, o[5] = b.y, o[6] = b.z, o[7] = b.w;
-            o[8] = c.x, o[9] = c.y, o[10] = c.z, o[11] = c.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 12; ++k) o[k] = 0;
-            for (int k = 0; k < npx * 3; ++k) o[k >> 2] |= (uint32_t)orig_t[pix_off + k] << (8 * (k & 3));
-        }
-
-        // window of valid columns: bit j <-> column x0 - 8 + j
-        const int c0 = x0 - 8;
-        const int lo = max(0, -c0), hi = min(32, W0 - c0);
-        const uint32_t colvalid = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-        const uint32_t *brow = bits + (row + R) * row_words;   // centre row of this pixel row
-        const uint32_t M2 = bit_window(brow, c0);
-        const uint32_t px_bits = ((npx >= 16 ? 0xffffu : ((1u << npx) - 1u)) << 8);
-
-        float alpha[16];
-        uint32_t need_up = 0;      // pixels (bit i) with alpha > 0
-        if (SMALL_R) {
-            uint32_t Mw[5], Zw[5];
-#pragma unroll
-            for (int d = 0; d < 5; ++d) {
-                const int yy = y + d - 2;
-                Mw[d] = bit_window(brow + (d - 2) * row_words, c0);
-                Zw[d] = (yy >= 0 && yy < H0) ? (~Mw[d] & colvalid) : 0u;
-            }
-            const uint32_t anyM = Mw[0] | Mw[1] | Mw[2] | Mw[3] | Mw[4];
-            // window of pixel i covers bits i+6 .. i+10, i.e. bits 6..25 for the whole group
-            if ((anyM & 0x03ffffc0u) == 0) {
-                need_up = 0;        // no masked pixel near this group: alpha == 0 everywhere
-#pragma unroll
-                for (int i = 0; i < 16; ++i) alpha[i] = 0.f;
+        if (active) {
+            // pass the original pixels through; pixels with alpha > 0 are overwritten below
+            if (VEC) {
+                const uint4 a = ldg128(orig_t + pix_off), b = ldg128(orig_t + pix_off + 16),
+                            c = ldg128(orig_t + pix_off + 32);
+                stg128_stream(out_t + pix_off, a);
+                stg128_stream(out_t + pix_off + 16, b);
+                stg128_stream(out_t + pix_off + 32, c);
             } else {
-                auto classes = [](const uint32_t *S, uint32_t *hc) {
-                    const uint32_t A1 = S[1] | S[3], A0 = S[0] | S[4];
-                    hc[0] = (S[2] << 1) | (S[2] >> 1) | A1;                                  // cost 1
-                    hc[1] = (A1 << 1) | (A1 >> 1);                                           // 1.4
-                    hc[2] = (S[2] << 2) | (S[2] >> 2) | A0;                                  // 2
-                    hc[3] = (A0 << 1) | (A0 >> 1) | (A1 << 2) | (A1 >> 2);                   // 2.1969
-                    hc[4] = (A0 << 2) | (A0 >> 2);                                           // 2.8
-                };
-                uint32_t hm[5], hz[5], hsel[5];
-                classes(Mw, hm);
-                classes(Zw, hz);
-#pragma unroll
-                for (int k = 0; k < 5; ++k) hsel[k] = (hz[k] & M2) | (hm[k] & ~M2);   // inside pixels look for zeros
-                // priority encode: level = first class hit (1..5), 0 if none
-                const uint32_t p1 = hsel[0];
-                const uint32_t p2 = hsel[1] & ~p1;
-                const uint32_t s12 = p1 | hsel[1];
-                const uint32_t p3 = hsel[2] & ~s12;
-                const uint32_t s123 = s12 | hsel[2];
-                const uint32_t p4 = hsel[3] & ~s123;
-                const uint32_t p5 = hsel[4] & ~(s123 | hsel[3]);
-                const uint32_t L0 = p1 | p3 | p5, L1 = p2 | p3, L2 = p4 | p5;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int b = i + 8;
-                    const uint32_t idx = ((L0 >> b) & 1u) | (((L1 >> b) & 1u) << 1) | (((L2 >> b) & 1u) << 2) |
-                                         (((M2 >> b) & 1u) << 3);
-                    alpha[i] = lut[idx];
-                }
-                need_up = 0;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) need_up |= (uint32_t)(alpha[i] > 0.f) << i;
+                for (int k = 0; k < npx * 3; ++k) out_t[pix_off + k] = orig_t[pix_off + k];
             }
-        } else {
-            // generic radius: first (cheapest) window offset whose opposite-class bit is set
-            const bool hard = ft.n == 0;
-#pragma unroll 1
-            for (int i = 0; i < 16; ++i) {
-                const bool inside = (M2 >> (i + 8)) & 1u;
-                float d = 8192.f;
-                if (!hard && i < npx) {
-                    for (int e = 0; e < ft.n; ++e) {
-                        const int yy = y + ft.dy[e], xx = x0 + i + ft.dx[e];
-                        if (yy < 0 || yy >= H0 || xx < 0 || xx >= W0) continue;
-                        const uint32_t wv = bits[(row + R + ft.dy[e]) * row_words + 1 + (xx >> 5)];
-                        const bool set = (wv >> (xx & 31)) & 1u;
-                        if (set != inside) {
-                            d = ft.cost[e];
-                            break;
+            // window of valid columns: bit j <-> column x0 - 8 + j
+            const int c0 = x0 - 8;
+            const int lo = max(0, -c0), hi = min(32, W0 - c0);
+            const uint32_t colvalid = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+            const uint32_t *brow = bits + (row + R) * row_words;   // centre row of this pixel row
+            M2 = bit_window(brow, c0);
+            const uint32_t pxmask = npx >= 16 ? 0xffffu : ((1u << npx) - 1u);
+            if (SMALL_R) {
+                uint32_t Mw[5], Zw[5];
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const int yy = y + d - 2;
+                    Mw[d] = bit_window(brow + (d - 2) * row_words, c0);
+                    Zw[d] = (yy >= 0 && yy < H0) ? (~Mw[d] & colvalid) : 0u;
+                }
+                const uint32_t anyM = Mw[0] | Mw[1] | Mw[2] | Mw[3] | Mw[4];
+                // the 5x5 window of pixel i covers bits i+6 .. i+10, i.e. bits 6..25 for the whole group
+                if (anyM & 0x03ffffc0u) {
+                    auto classes = [](const uint32_t *S, uint32_t *hc) {
+                        const uint32_t A1 = S[1] | S[3], A0 = S[0] | S[4];
+                        hc[0] = (S[2] << 1) | (S[2] >> 1) | A1;                                  // cost 1
+                        hc[1] = (A1 << 1) | (A1 >> 1);                                           // 1.4
+                        hc[2] = (S[2] << 2) | (S[2] >> 2) | A0;                                  // 2
+                        hc[3] = (A0 << 1) | (A0 >> 1) | (A1 << 2) | (A1 >> 2);                   // 2.1969
+                        hc[4] = (A0 << 2) | (A0 >> 2);                                           // 2.8
+                    };
+                    uint32_t hm[5], hz[5], hsel[5];
+                    classes(Mw, hm);
+                    classes(Zw, hz);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) hsel[k] = (hz[k] & M2) | (hm[k] & ~M2);   // inside pixels look for zeros
+                    // priority encode: level = first class hit (1..5), 0 if none -> 3 bit planes
+                    const uint32_t p1 = hsel[0];
+                    const uint32_t p2 = hsel[1] & ~p1;
+                    const uint32_t s12 = p1 | hsel[1];
+                    const uint32_t p3 = hsel[2] & ~s12;
+                    const uint32_t s123 = s12 | hsel[2];
+                    const uint32_t p4 = hsel[3] & ~s123;
+                    const uint32_t p5 = hsel[4] & ~(s123 | hsel[3]);
+                    L0 = p1 | p3 | p5, L1 = p2 | p3, L2 = p4 | p5;
+                    // alpha > 0: every inside pixel, and outside pixels whose first hit has alpha > 0
+                    uint32_t pos = M2;
+#pragma unroll
+                    for (int k = 1; k <= 5; ++k) {
+                        if ((lut_pos >> k) & 1u) {
+                            const uint32_t pk = k == 1 ? p1 : k == 2 ? p2 : k == 3 ? p3 : k == 4 ? p4 : p5;
+                            pos |= pk;
                         }
                     }
+                    need = (pos >> 8) & pxmask;
                 }
-                alpha[i] = hard ? (inside ? 1.f : 0.f) : (inside ? alpha_from(d, 0.f, ft.div) : alpha_from(0.f, d, ft.div));
+            } else {
+                // generic radius: decided per pixel by the workers; here only "inside, or some masked
+                // pixel within the window" (a superset of alpha > 0)
+                uint32_t anyM = 0;
+                for (int d = -R; d <= R; ++d) {
+                    // OR of the row window dilated horizontally by R
+                    const uint32_t m = bit_window(brow + d * row_words, c0);
+                    uint32_t acc = m;
+                    for (int k = 1; k <= R; ++k) acc |= (m << k) | (m >> k);
+                    anyM |= acc;
+                }
+                need = (hard ? (M2 >> 8) : (anyM >> 8)) & pxmask;
             }
-            need_up = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) need_up |= (uint32_t)(alpha[i] > 0.f) << i;
         }
-        need_up &= (px_bits >> 8);
 
-        if (need_up) {
-            const Tap ty = yt[y];
-            const int b0 = (short)(ty.w & 0xffff), b1 = ty.w >> 16;
-            const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
-            const uint8_t *r0 = inp_t + (long long)ya * w * 3;
-            const uint8_t *r1 = inp_t + (long long)yb * w * 3;
+        // ---- warp-level compaction: every pixel that needs blending becomes one work item
+        const uint32_t any_need = __ballot_sync(0xffffffffu, need != 0);
+        if (any_need == 0) continue;                     // warp-uniform
+        const int cnt = __popc(need);
+        int pre = cnt;                                   // inclusive scan over lanes
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if ((need_up >> i) & 1u) {
-                    const Tap tx = xt[x0 + i];
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pre, d);
+            if (lane >= d) pre += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        int pos = pre - cnt;
+        uint32_t nb = need;
+        while (nb) {
+            const int i = __ffs(nb) - 1;
+            nb &= nb - 1;
+            uint32_t code;
+            if (SMALL_R) {
+                const int b = i + 8;
+                code = ((L0 >> b) & 1u) | (((L1 >> b) & 1u) << 1) | (((L2 >> b) & 1u) << 2) | (((M2 >> b) & 1u) << 3);
+            } else {
+                code = ((M2 >> (i + 8)) & 1u) << 8;      // the worker fills in the table entry
+            }
+            queue[pos++] = (uint32_t)(x0 + i) | ((uint32_t)row << 16) | (code << 20);
+        }
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+            const int qi = base + lane;
+            if (qi < total) {
+                const uint32_t item = queue[qi];
+                const int x = item & 0xffff, r = (item >> 16) & 15;
+                const uint32_t code = item >> 20;
+                const int yy = y0 + r;
+                float a;
+                if (SMALL_R) {
+                    a = lut[code];
+                } else {
+                    const bool inside = code >> 8;
+                    if (hard) {
+                        a = inside ? 1.f : 0.f;
+                    } else {
+                        float d = 8192.f;   // first (cheapest) window offset whose opposite-class bit is set
+                        for (int e = 0; e < ft.n; ++e) {
+                            const int ey = yy + ft.dy[e], ex = x + ft.dx[e];
+                            if (ey < 0 || ey >= H0 || ex < 0 || ex >= W0) continue;
+                            const uint32_t wv = bits[(r + R + ft.dy[e]) * row_words + 1 + (ex >> 5)];
+                            if ((((wv >> (ex & 31)) & 1u) != 0) != inside) {
+                                d = ft.cost[e];
+                                break;
+                            }
+                        }
+                        a = inside ? alpha_from(d, 0.f, ft.div) : alpha_from(0.f, d, ft.div);
+                    }
+                }
+                if (a > 0.f) {
+                    const Tap ty = yt[yy], tx = xt[x];
+                    const int b0 = (short)(ty.w & 0xffff), b1 = ty.w >> 16;
                     const int a0 = (short)(tx.w & 0xffff), a1 = tx.w >> 16;
-                    const int s0 = tx.ofs * 3, s1 = min(tx.ofs + 1, w - 1) * 3;
-                    const float a = alpha[i], na = __fsub_rn(1.f, a);
+                    const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
+                    uint32_t s00, s01, s10, s11;
+                    load_pixel_pair(inp_t + (long long)ya * w * 3, tx.ofs, w, inp_aligned8, s00, s01);
+                    load_pixel_pair(inp_t + (long long)yb * w * 3, tx.ofs, w, inp_aligned8, s10, s11);
+                    const long long po = ((long long)yy * W0 + x) * 3;
+                    const float na = __fsub_rn(1.f, a);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const int h0 = __ldg(r0 + s0 + c) * a0 + __ldg(r0 + s1 + c) * a1;
-                        const int h1 = __ldg(r1 + s0 + c) * a0 + __ldg(r1 + s1 + c) * a1;
-                        const uint32_t up = (uint32_t)vlin3(b0, b1, h0, h1);
-                        const int ob = 3 * i + c;
-                        const uint32_t og = byte_of(o[ob >> 2], ob & 3);
-                        const uint32_t res = blend_u8(a, na, up, og);
-                        o[ob >> 2] = (o[ob >> 2] & ~(0xffu << (8 * (ob & 3)))) | (res << (8 * (ob & 3)));
+                        const int h0 = (int)byte_of(s00, c) * a0 + (int)byte_of(s01, c) * a1;
+                        const int h1 = (int)byte_of(s10, c) * a0 + (int)byte_of(s11, c) * a1;
+                        uint32_t res = (uint32_t)vlin3(b0, b1, h0, h1);
+                        if (a < 1.f) res = blend_u8(a, na, res, orig_t[po + c]);
+                        out_t[po + c] = (uint8_t)res;
                     }
                 }
             }
         }
-
-        if (VEC) {
-            stg128_stream(out_t + pix_off, make_uint4(o[0], o[1], o[2], o[3]));
-            stg128_stream(out_t + pix_off + 16, make_uint4(o[4], o[5], o[6], o[7]));
-            stg128_stream(out_t + pix_off + 32, make_uint4(o[8], o[9], o[10], o[11]));
-        } else {
-            for (int k = 0; k < npx * 3; ++k) out_t[pix_off + k] = (uint8_t)byte_of(o[k >> 2], k & 3);
-        }
+        __syncwarp();      // the queue is reused by the next iteration
     }
 }
 
@@ -346,7 +409,7 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
     const bool small_r = feather_px > 0.f && ft.radius <= 2;
     const int R = small_r ? 2 : ft.radius;
     const int Wp = ceil_div(W0, 32);
-    const size_t smem = (size_t)(K3_TH + 2 * R) * (Wp + 2) * 4 + 64;
+    const size_t smem = ((size_t)(K3_TH + 2 * R) * (Wp + 2) + 16 + (K3_THREADS / 32) * K3_QUEUE) * 4;
     const bool vec = (W0 % 16 == 0) && ((uintptr_t)orig % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                      ((uintptr_t)mask % 16 == 0);
     const int strips = ceil_div(H0, K3_TH);
@@ -360,7 +423,7 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
             if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(k3)");                              \
         }                                                                                                       \
-        kfn<<<(unsigned)grid, 256, smem, st>>>(inp, orig, mask, out, xt, yt, h, w, H0, W0, strips, ft);         \
+        kfn<<<(unsigned)grid, K3_THREADS, smem, st>>>(inp, orig, mask, out, xt, yt, h, w, H0, W0, strips, ft);         \
     } while (0)
     if (vec && small_r)
         VV_K3_LAUNCH(true, true);

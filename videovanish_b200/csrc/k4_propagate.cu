@@ -116,57 +116,78 @@ __global__ void __launch_bounds__(256)
     const uint8_t *mk = masks + gframe * npx;
     const bool first = step == 0;
 
+    // Every thread passes 4 pixels through; hole pixels become work items in a per-warp queue so
+    // that the long gather path runs on dense warps instead of diverging on a few lanes.
+    __shared__ uint32_t s_queue[256 / 32][128];
+    uint32_t *queue = s_queue[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
     const long long ngroups = (npx + 3) >> 2;
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < ngroups;
-         g += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long iters = (ngroups + stride - 1) / stride;            // same trip count for every thread
+    for (long long itn = 0; itn < iters; ++itn) {
+        const long long g = itn * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
         const long long p0 = g * 4;
-        uint32_t c[4];
-        int n = 4;
-        if (VEC) {
-            if (PASS2) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(cur_packed + p0);
-                c[0] = v.x, c[1] = v.y, c[2] = v.z, c[3] = v.w;
-            } else {
-                const uint32_t m4 = __ldg(reinterpret_cast<const uint32_t *>(mk + p0));
-                const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0 * 3);
-                const uint32_t a = __ldg(f3), b = __ldg(f3 + 1), d = __ldg(f3 + 2);
-                c[0] = a & 0x00ffffffu;
-                c[1] = (a >> 24) | ((b & 0x0000ffffu) << 8);
-                c[2] = (b >> 16) | ((d & 0x000000ffu) << 16);
-                c[3] = d >> 8;
+        uint32_t c[4] = {0, 0, 0, 0};
+        int n = 0;
+        if (g < ngroups) {
+            n = 4;
+            if (VEC) {
+                if (PASS2) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(cur_packed + p0);
+                    c[0] = v.x, c[1] = v.y, c[2] = v.z, c[3] = v.w;
+                } else {
+                    const uint32_t m4 = __ldg(reinterpret_cast<const uint32_t *>(mk + p0));
+                    const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0 * 3);
+                    const uint32_t a = __ldg(f3), b = __ldg(f3 + 1), d = __ldg(f3 + 2);
+                    c[0] = a & 0x00ffffffu;
+                    c[1] = (a >> 24) | ((b & 0x0000ffffu) << 8);
+                    c[2] = (b >> 16) | ((d & 0x000000ffu) << 16);
+                    c[3] = d >> 8;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (byte_of(m4, i)) c[i] = ST_HOLE | ST_ZERO;
-            }
-        } else {
-            n = (int)min(4LL, npx - p0);
-            for (int i = 0; i < 4; ++i) {
-                c[i] = 0;
-                if (i < n) {
+                    for (int i = 0; i < 4; ++i)
+                        if (byte_of(m4, i)) c[i] = ST_HOLE | ST_ZERO;
+                }
+                *reinterpret_cast<uint4 *>(dst + p0) = make_uint4(c[0], c[1], c[2], c[3]);
+            } else {
+                n = (int)min(4LL, npx - p0);
+                for (int i = 0; i < n; ++i) {
                     if (PASS2) {
                         c[i] = cur_packed[p0 + i];
                     } else {
                         const uint8_t *q = fr + (p0 + i) * 3;
                         c[i] = mk[p0 + i] ? (ST_HOLE | ST_ZERO) : (q[0] | (q[1] << 8) | ((uint32_t)q[2] << 16));
                     }
+                    dst[p0 + i] = c[i];
                 }
             }
         }
-        if (!first) {
+        if (first) continue;                              // uniform: step 0 only copies
+        uint32_t holes = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (i < n && (c[i] & ST_HOLE)) {
-                    const long long p = p0 + i;
-                    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
-                    c[i] = propagate_pixel(x, y, h, w, c[i], flow_prop, flow_check, prev);
-                }
+        for (int i = 0; i < 4; ++i) holes |= (uint32_t)(i < n && (c[i] & ST_HOLE)) << i;
+        if (__ballot_sync(0xffffffffu, holes != 0) == 0) continue;       // warp-uniform
+        const int cnt = __popc(holes);
+        int pre = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pre, d);
+            if (lane >= d) pre += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        int pos = pre - cnt;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if ((holes >> i) & 1u) queue[pos++] = (uint32_t)(p0 + i);
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+            if (base + lane < total) {
+                const uint32_t p = queue[base + lane];
+                const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
+                const uint32_t nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, flow_prop, flow_check, prev);
+                if (nv != (ST_HOLE | ST_ZERO)) dst[p] = nv;
             }
         }
-        if (VEC) {
-            *reinterpret_cast<uint4 *>(dst + p0) = make_uint4(c[0], c[1], c[2], c[3]);
-        } else {
-            for (int i = 0; i < n; ++i) dst[p0 + i] = c[i];
-        }
+        __syncwarp();
     }
 }
 
