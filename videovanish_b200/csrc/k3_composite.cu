@@ -399,6 +399,10 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
         set_error("vv_upscale_feather_composite: feather_px %.3f > supported maximum %.1f", feather_px, VV_MAX_FEATHER);
         return VV_ERR_UNSUPPORTED;
     }
+    if (W0 > 65535) {
+        set_error("vv_upscale_feather_composite: frames wider than 65535 pixels are not supported");
+        return VV_ERR_UNSUPPORTED;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const Tap *xt, *yt;
     int rc = build_linear_taps(workspace, h, w, H0, W0, &xt, &yt, st);
