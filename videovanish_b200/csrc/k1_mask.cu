@@ -138,41 +138,56 @@ __global__ void __launch_bounds__(128)
         for (int it = 0; it < n_iter; ++it) cross_round<NMAX, ROWS>(r);
     }
 
-    if (lane == 0 || lane == 31 || !col_ok) return;
-    // bits beyond the frame edge may have been dilated into; clear them in the last word
-    const int valid_bits = W - wx * 32;
-    const uint32_t keep = valid_bits >= 32 ? 0xffffffffu : ((1u << valid_bits) - 1u);
-    const int lw = W >> 1;
+    // ---- output stage.  The dilated words go through shared memory so that this part is a short
+    // rolled loop (fully unrolled it was ~4k instructions of straight-line code and the kernel
+    // stalled on instruction fetch) and so that every 128-bit store instruction of the warp writes
+    // one contiguous 512-byte run of the row.
+    __shared__ uint32_t s_rows[4][RB][32];
+    uint32_t(*my)[32] = s_rows[threadIdx.x >> 5];
+    {
+        const int valid_bits = W - wx * 32;     // bits beyond the frame edge may have been dilated into
+        const uint32_t keep = !col_ok ? 0u : valid_bits >= 32 ? 0xffffffffu : ((1u << valid_bits) - 1u);
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-        const int y = y0 + i;
-        if (y >= H) break;
-        const uint32_t v = r[NMAX + i] & keep;
-        const long long row = t * H + y;
-        if (bits_out) bits_out[row * Wp + wx] = v;
-        if (out) {
-            uint8_t *o = out + row * W + wx * 32;
-            if (vec_ok && valid_bits >= 32) {
-                uint4 a, b;
-                a.x = expand4(v), a.y = expand4(v >> 4), a.z = expand4(v >> 8), a.w = expand4(v >> 12);
-                b.x = expand4(v >> 16), b.y = expand4(v >> 20), b.z = expand4(v >> 24), b.w = expand4(v >> 28);
-                stg128_stream(o, a);
-                stg128_stream(o + 16, b);
-            } else {
-                const int n = min(32, valid_bits);
+        for (int i = 0; i < RB; ++i) my[i][lane] = r[NMAX + i] & keep;
+    }
+    __syncwarp();
+    const int lw = W >> 1;
+    const int x_tile = tx * 30 * 32;            // first pixel column of the tile's useful words
+    const int rows_here = min(RB, H - y0);
 #pragma unroll 1
-                for (int k = 0; k < n; ++k) o[k] = ((v >> k) & 1u) ? 255 : 0;
+    for (int i = 0; i < rows_here; ++i) {
+        const long long row = t * H + y0 + i;
+        if (bits_out && lane >= 1 && lane <= 30 && col_ok) bits_out[row * Wp + wx] = my[i][lane];
+        if (out) {
+            uint8_t *orow = out + row * W;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int k = pass * 32 + lane;          // 16-pixel chunk of the tile row (60 chunks)
+                const int px0 = x_tile + k * 16;
+                if (k < 60 && px0 < W) {
+                    const uint32_t v = (my[i][1 + (k >> 1)] >> (16 * (k & 1))) & 0xffffu;
+                    if (vec_ok && px0 + 16 <= W) {
+                        stg128_stream(orow + px0, make_uint4(expand4(v), expand4(v >> 4), expand4(v >> 8), expand4(v >> 12)));
+                    } else {
+                        const int n = min(16, W - px0);
+#pragma unroll 1
+                        for (int q = 0; q < n; ++q) orow[px0 + q] = ((v >> q) & 1u) ? 255 : 0;
+                    }
+                }
             }
         }
-        if (half_out && !(i & 1)) {       // RB and y0 are even, so (y0 + i) is even iff i is
-            const uint32_t e = even_bits(v);
-            uint8_t *o = half_out + (t * (H >> 1) + (y >> 1)) * lw + wx * 16;
-            if (vec_ok && wx * 16 + 16 <= lw) {
-                stg128_stream(o, make_uint4(expand4(e), expand4(e >> 4), expand4(e >> 8), expand4(e >> 12)));
-            } else {
-                const int n = min(16, lw - wx * 16);
+        if (half_out && !(i & 1) && lane < 30) {          // RB and y0 are even, so (y0 + i) is even iff i is
+            const int lx0 = (tx * 30 + lane) * 16;        // low-res column of this lane's 16 pixels
+            if (lx0 < lw) {
+                const uint32_t e = even_bits(my[i][1 + lane]);
+                uint8_t *o = half_out + (t * (H >> 1) + ((y0 + i) >> 1)) * lw + lx0;
+                if (vec_ok && lx0 + 16 <= lw) {
+                    stg128_stream(o, make_uint4(expand4(e), expand4(e >> 4), expand4(e >> 8), expand4(e >> 12)));
+                } else {
+                    const int n = min(16, lw - lx0);
 #pragma unroll 1
-                for (int k = 0; k < n; ++k) o[k] = ((e >> k) & 1u) ? 255 : 0;
+                    for (int q = 0; q < n; ++q) o[q] = ((e >> q) & 1u) ? 255 : 0;
+                }
             }
         }
     }

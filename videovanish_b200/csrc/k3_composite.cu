@@ -52,8 +52,8 @@ __device__ __forceinline__ float alpha_from(float d_in, float d_out, float div) 
 
 __device__ __forceinline__ uint32_t blend_u8(float a, float one_minus_a, uint32_t up, uint32_t orig) {
     const float v = __fadd_rn(__fmul_rn(a, (float)up), __fmul_rn(one_minus_a, (float)orig));
-    int r = __float2int_rn(v);                     // round-half-even, like np.rint
-    return (uint32_t)min(max(r, 0), 255);
+    // a in (0,1), both inputs in [0,255]: the sum is within half an ulp of [0,255], so np.clip is a no-op
+    return (uint32_t)__float2int_rn(v);            // round-half-even, like np.rint
 }
 
 __device__ __forceinline__ int vlin3(int b0, int b1, int h0, int h1) {
@@ -68,31 +68,38 @@ __device__ __forceinline__ uint32_t bit_window(const uint32_t *row, int col0) {
     return __funnelshift_r(row[k], row[k + 1], off);
 }
 
-// RGB of source pixels sx and min(sx+1, w-1) of one inference-resolution row (24-bit each).
-// Fast path: two aligned 64-bit loads cover the 6 contiguous bytes; byte loads near the row end
-// or when the row is not 8-byte aligned.
-__device__ __forceinline__ void load_pixel_pair(const uint8_t *__restrict__ row, int sx, int w, bool row_aligned8,
-                                                uint32_t &p0, uint32_t &p1) {
+// The 6 bytes (RGB of source pixel sx, RGB of sx+1) of one inference-resolution row as a 64-bit
+// value.  Fast path: two aligned 64-bit loads + funnel shift; byte loads near the row end (where
+// sx+1 is clamped to w-1; its weight is 0 there) or when the row is not 8-byte aligned.
+__device__ __forceinline__ unsigned long long load_pixel_pair(const uint8_t *__restrict__ row, int sx, int w,
+                                                              bool row_aligned8) {
     const int o = sx * 3, a8 = o & ~7;
     if (row_aligned8 && a8 + 16 <= w * 3) {
         const unsigned long long lo = __ldg(reinterpret_cast<const unsigned long long *>(row + a8));
         const unsigned long long hi = __ldg(reinterpret_cast<const unsigned long long *>(row + a8 + 8));
         const int sh = (o & 7) * 8;
-        const unsigned long long v = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
-        p0 = (uint32_t)v & 0xffffffu;
-        p1 = (uint32_t)(v >> 24) & 0xffffffu;
-    } else {
-        const int o1 = min(sx + 1, w - 1) * 3;
-        p0 = __ldg(row + o) | (__ldg(row + o + 1) << 8) | (__ldg(row + o + 2) << 16);
-        p1 = __ldg(row + o1) | (__ldg(row + o1 + 1) << 8) | (__ldg(row + o1 + 2) << 16);
+        return sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
     }
+    const int o1 = min(sx + 1, w - 1) * 3;
+    const uint32_t p0 = __ldg(row + o) | (__ldg(row + o + 1) << 8) | (__ldg(row + o + 2) << 16);
+    const uint32_t p1 = __ldg(row + o1) | (__ldg(row + o1 + 1) << 8) | (__ldg(row + o1 + 2) << 16);
+    return (unsigned long long)p0 | ((unsigned long long)p1 << 24);
+}
+
+// Horizontal pass for channel C of one source row: S[sx][C]*w0 + S[sx+1][C]*w1 as ONE dot product
+// (wts = w0 | w1 << 16, both u16; the two source bytes gathered by a byte permute).
+template <int C>
+__device__ __forceinline__ int hpass(unsigned long long pair, uint32_t wts) {
+    const uint32_t two = __byte_perm((uint32_t)pair, (uint32_t)(pair >> 32), 0x30 + 0x11 * C);   // bytes C, C+3
+    return (int)__dp2a_lo(wts, two, 0u);
 }
 
 constexpr int K3_THREADS = 256;
-constexpr int K3_QUEUE = 512;     // work items per warp task: 32 lanes x 16 pixels
+constexpr int K3_QUEUE = 128;     // work items (4-pixel quads) per warp task: 32 lanes x 4 quads
 
-// Work item: x (16 bits) | row in strip (4 bits) << 16 | alpha code (9 bits) << 20.
-// SMALL_R: code = LUT index (class | inside << 3); generic: code = (entry + 1, 0 = none) | inside << 8.
+// Work item = one 4-pixel quad (x aligned to 4) that contains at least one pixel with alpha > 0:
+//   .x = x | row-in-strip << 16 | need(4) << 20 | inside(4) << 24
+//   .y = level bit planes l0 | l1 << 4 | l2 << 8 (SMALL_R; per-pixel LUT index = l0 | l1<<1 | l2<<2 | inside<<3)
 
 template <bool VEC, bool SMALL_R>
 __global__ void __launch_bounds__(K3_THREADS)
@@ -107,7 +114,8 @@ __global__ void __launch_bounds__(K3_THREADS)
     const int rows_s = K3_TH + 2 * R;
     uint32_t *bits = smem;                                               // [rows_s][row_words]
     float *lut = reinterpret_cast<float *>(smem + rows_s * row_words);   // [16] alpha levels (SMALL_R)
-    uint32_t *queue = smem + rows_s * row_words + 16 + (threadIdx.x >> 5) * K3_QUEUE;   // per-warp work queue
+    uint2 *queue = reinterpret_cast<uint2 *>(smem + ((rows_s * row_words + 16 + 1) & ~1)) +
+                   (threadIdx.x >> 5) * K3_QUEUE;                        // per-warp work queue
     const int lane = threadIdx.x & 31;
 
     const long long t = blockIdx.x / strips_per_frame;
@@ -168,12 +176,12 @@ __global__ void __launch_bounds__(K3_THREADS)
         const bool active = id < n_tasks && y < H0;
         const int x0 = g * 16;
         const int npx = VEC ? 16 : min(16, W0 - x0);
-        const long long pix_off = ((long long)y * W0 + x0) * 3;
         uint32_t need = 0;                  // pixels (bit i) with alpha > 0
         uint32_t L0 = 0, L1 = 0, L2 = 0, M2 = 0;
 
         if (active) {
-            // pass the original pixels through; pixels with alpha > 0 are overwritten below
+            // pass the original pixels through; quads with alpha > 0 somewhere are rewritten below
+            const int pix_off = (y * W0 + x0) * 3;
             if (VEC) {
                 const uint4 a = ldg128(orig_t + pix_off), b = ldg128(orig_t + pix_off + 16),
                             c = ldg128(orig_t + pix_off + 32);
@@ -225,13 +233,11 @@ __global__ void __launch_bounds__(K3_THREADS)
                     L0 = p1 | p3 | p5, L1 = p2 | p3, L2 = p4 | p5;
                     // alpha > 0: every inside pixel, and outside pixels whose first hit has alpha > 0
                     uint32_t pos = M2;
-#pragma unroll
-                    for (int k = 1; k <= 5; ++k) {
-                        if ((lut_pos >> k) & 1u) {
-                            const uint32_t pk = k == 1 ? p1 : k == 2 ? p2 : k == 3 ? p3 : k == 4 ? p4 : p5;
-                            pos |= pk;
-                        }
-                    }
+                    if ((lut_pos >> 1) & 1u) pos |= p1;
+                    if ((lut_pos >> 2) & 1u) pos |= p2;
+                    if ((lut_pos >> 3) & 1u) pos |= p3;
+                    if ((lut_pos >> 4) & 1u) pos |= p4;
+                    if ((lut_pos >> 5) & 1u) pos |= p5;
                     need = (pos >> 8) & pxmask;
                 }
             } else {
@@ -239,7 +245,6 @@ __global__ void __launch_bounds__(K3_THREADS)
                 // pixel within the window" (a superset of alpha > 0)
                 uint32_t anyM = 0;
                 for (int d = -R; d <= R; ++d) {
-                    // OR of the row window dilated horizontally by R
                     const uint32_t m = bit_window(brow + d * row_words, c0);
                     uint32_t acc = m;
                     for (int k = 1; k <= R; ++k) acc |= (m << k) | (m >> k);
@@ -249,78 +254,114 @@ __global__ void __launch_bounds__(K3_THREADS)
             }
         }
 
-        // ---- warp-level compaction: every pixel that needs blending becomes one work item
-        const uint32_t any_need = __ballot_sync(0xffffffffu, need != 0);
-        if (any_need == 0) continue;                     // warp-uniform
-        const int cnt = __popc(need);
-        int pre = cnt;                                   // inclusive scan over lanes
+        // ---- warp-level compaction: every quad with a pixel to blend becomes one work item
+        if (__ballot_sync(0xffffffffu, need != 0) == 0) continue;        // warp-uniform
+        const uint32_t qn = ((need & 0x000fu) != 0) + ((need & 0x00f0u) != 0) + ((need & 0x0f00u) != 0) +
+                            ((need & 0xf000u) != 0);
+        int pre = (int)qn;                               // inclusive scan over lanes
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, pre, d);
             if (lane >= d) pre += v;
         }
         const int total = __shfl_sync(0xffffffffu, pre, 31);
-        int pos = pre - cnt;
-        uint32_t nb = need;
-        while (nb) {
-            const int i = __ffs(nb) - 1;
-            nb &= nb - 1;
-            uint32_t code;
-            if (SMALL_R) {
-                const int b = i + 8;
-                code = ((L0 >> b) & 1u) | (((L1 >> b) & 1u) << 1) | (((L2 >> b) & 1u) << 2) | (((M2 >> b) & 1u) << 3);
-            } else {
-                code = ((M2 >> (i + 8)) & 1u) << 8;      // the worker fills in the table entry
+        int pos = pre - (int)qn;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t n4 = (need >> (4 * q)) & 15u;
+            if (n4) {
+                const int b = 8 + 4 * q;
+                uint2 e;
+                e.x = (uint32_t)(x0 + 4 * q) | ((uint32_t)row << 16) | (n4 << 20) | (((M2 >> b) & 15u) << 24);
+                e.y = ((L0 >> b) & 15u) | (((L1 >> b) & 15u) << 4) | (((L2 >> b) & 15u) << 8);
+                queue[pos++] = e;
             }
-            queue[pos++] = (uint32_t)(x0 + i) | ((uint32_t)row << 16) | (code << 20);
         }
         __syncwarp();
         for (int base = 0; base < total; base += 32) {
             const int qi = base + lane;
             if (qi < total) {
-                const uint32_t item = queue[qi];
-                const int x = item & 0xffff, r = (item >> 16) & 15;
-                const uint32_t code = item >> 20;
+                const uint2 item = queue[qi];
+                const int xq = item.x & 0xffff, r = (item.x >> 16) & 15;
+                const uint32_t n4 = (item.x >> 20) & 15u, in4 = (item.x >> 24) & 15u;
                 const int yy = y0 + r;
-                float a;
-                if (SMALL_R) {
-                    a = lut[code];
+                const Tap ty = yt[yy];
+                const int b0 = (short)(ty.w & 0xffff), b1 = ty.w >> 16;
+                const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
+                const uint8_t *r0 = inp_t + ya * w * 3;
+                const uint8_t *r1 = inp_t + yb * w * 3;
+                const int po = (yy * W0 + xq) * 3;
+                int ofs[4];
+                uint32_t wts[4], o[3];
+                if (VEC) {                                   // W0 % 16 == 0: the quad is whole and 4-byte aligned
+                    const uint4 t01 = ldg128(xt + xq), t23 = ldg128(xt + xq + 2);
+                    ofs[0] = t01.x, wts[0] = t01.y, ofs[1] = t01.z, wts[1] = t01.w;
+                    ofs[2] = t23.x, wts[2] = t23.y, ofs[3] = t23.z, wts[3] = t23.w;
+                    const uint32_t *op = reinterpret_cast<const uint32_t *>(orig_t + po);
+                    o[0] = __ldg(op), o[1] = __ldg(op + 1), o[2] = __ldg(op + 2);
                 } else {
-                    const bool inside = code >> 8;
-                    if (hard) {
-                        a = inside ? 1.f : 0.f;
-                    } else {
-                        float d = 8192.f;   // first (cheapest) window offset whose opposite-class bit is set
-                        for (int e = 0; e < ft.n; ++e) {
-                            const int ey = yy + ft.dy[e], ex = x + ft.dx[e];
-                            if (ey < 0 || ey >= H0 || ex < 0 || ex >= W0) continue;
-                            const uint32_t wv = bits[(r + R + ft.dy[e]) * row_words + 1 + (ex >> 5)];
-                            if ((((wv >> (ex & 31)) & 1u) != 0) != inside) {
-                                d = ft.cost[e];
-                                break;
-                            }
+                    o[0] = o[1] = o[2] = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        ofs[i] = 0, wts[i] = 0;
+                        if (xq + i < W0) {
+                            const Tap tx = xt[xq + i];
+                            ofs[i] = tx.ofs, wts[i] = (uint32_t)tx.w;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                o[(3 * i + c) >> 2] |= (uint32_t)orig_t[po + 3 * i + c] << (8 * ((3 * i + c) & 3));
                         }
-                        a = inside ? alpha_from(d, 0.f, ft.div) : alpha_from(0.f, d, ft.div);
                     }
                 }
-                if (a > 0.f) {
-                    const Tap ty = yt[yy], tx = xt[x];
-                    const int b0 = (short)(ty.w & 0xffff), b1 = ty.w >> 16;
-                    const int a0 = (short)(tx.w & 0xffff), a1 = tx.w >> 16;
-                    const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
-                    uint32_t s00, s01, s10, s11;
-                    load_pixel_pair(inp_t + (long long)ya * w * 3, tx.ofs, w, inp_aligned8, s00, s01);
-                    load_pixel_pair(inp_t + (long long)yb * w * 3, tx.ofs, w, inp_aligned8, s10, s11);
-                    const long long po = ((long long)yy * W0 + x) * 3;
-                    const float na = __fsub_rn(1.f, a);
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int h0 = (int)byte_of(s00, c) * a0 + (int)byte_of(s01, c) * a1;
-                        const int h1 = (int)byte_of(s10, c) * a0 + (int)byte_of(s11, c) * a1;
-                        uint32_t res = (uint32_t)vlin3(b0, b1, h0, h1);
-                        if (a < 1.f) res = blend_u8(a, na, res, orig_t[po + c]);
-                        out_t[po + c] = (uint8_t)res;
+                for (int i = 0; i < 4; ++i) {
+                    if ((n4 >> i) & 1u) {
+                        float a;
+                        if (SMALL_R) {
+                            a = lut[((item.y >> i) & 1u) | (((item.y >> (4 + i)) & 1u) << 1) |
+                                    (((item.y >> (8 + i)) & 1u) << 2) | (((in4 >> i) & 1u) << 3)];
+                        } else {
+                            const bool inside = (in4 >> i) & 1u;
+                            if (hard) {
+                                a = inside ? 1.f : 0.f;
+                            } else {
+                                float d = 8192.f;   // first (cheapest) window offset whose opposite-class bit is set
+                                for (int e = 0; e < ft.n; ++e) {
+                                    const int ey = yy + ft.dy[e], ex = xq + i + ft.dx[e];
+                                    if (ey < 0 || ey >= H0 || ex < 0 || ex >= W0) continue;
+                                    const uint32_t wv = bits[(r + R + ft.dy[e]) * row_words + 1 + (ex >> 5)];
+                                    if ((((wv >> (ex & 31)) & 1u) != 0) != inside) {
+                                        d = ft.cost[e];
+                                        break;
+                                    }
+                                }
+                                a = inside ? alpha_from(d, 0.f, ft.div) : alpha_from(0.f, d, ft.div);
+                            }
+                        }
+                        if (a > 0.f) {
+                            const unsigned long long pr0 = load_pixel_pair(r0, ofs[i], w, inp_aligned8);
+                            const unsigned long long pr1 = load_pixel_pair(r1, ofs[i], w, inp_aligned8);
+                            const float na = __fsub_rn(1.f, a);
+                            uint32_t res[3];
+                            res[0] = (uint32_t)vlin3(b0, b1, hpass<0>(pr0, wts[i]), hpass<0>(pr1, wts[i]));
+                            res[1] = (uint32_t)vlin3(b0, b1, hpass<1>(pr0, wts[i]), hpass<1>(pr1, wts[i]));
+                            res[2] = (uint32_t)vlin3(b0, b1, hpass<2>(pr0, wts[i]), hpass<2>(pr1, wts[i]));
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const int ob = 3 * i + c;
+                                if (a < 1.f) res[c] = blend_u8(a, na, res[c], byte_of(o[ob >> 2], ob & 3));
+                                o[ob >> 2] = (o[ob >> 2] & ~(0xffu << (8 * (ob & 3)))) | (res[c] << (8 * (ob & 3)));
+                            }
+                        }
                     }
+                }
+                if (VEC) {
+                    uint32_t *dp = reinterpret_cast<uint32_t *>(out_t + po);
+                    dp[0] = o[0], dp[1] = o[1], dp[2] = o[2];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                        if (xq + k / 3 < W0 && ((n4 >> (k / 3)) & 1u)) out_t[po + k] = (uint8_t)byte_of(o[k >> 2], k & 3);
                 }
             }
         }
@@ -413,7 +454,7 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
     const bool small_r = feather_px > 0.f && ft.radius <= 2;
     const int R = small_r ? 2 : ft.radius;
     const int Wp = ceil_div(W0, 32);
-    const size_t smem = ((size_t)(K3_TH + 2 * R) * (Wp + 2) + 16 + (K3_THREADS / 32) * K3_QUEUE) * 4;
+    const size_t smem = ((size_t)(K3_TH + 2 * R) * (Wp + 2) + 16 + 2 + (K3_THREADS / 32) * K3_QUEUE * 2) * 4;
     const bool vec = (W0 % 16 == 0) && ((uintptr_t)orig % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                      ((uintptr_t)mask % 16 == 0);
     const int strips = ceil_div(H0, K3_TH);

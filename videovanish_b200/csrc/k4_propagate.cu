@@ -15,10 +15,12 @@
 // masked frame's 0.0").  The four bilinear taps of the previous state give both the mask warp and
 // the nearest pixel, so one 4-word gather serves both.
 //
-// The scan is serial in time; parallelism comes from the frame (one thread = 4 pixels) and from
-// advancing up to 32 independent sub-videos (propainter/inference.py windows: 50 frames + 10 pad
-// each side) in lock step, one launch per time step and direction.  Only hole pixels touch the
-// flows; known pixels are a 16-byte pass-through.
+// Structure: k4_pack turns frames + masks into the packed state ONCE (fully parallel over all
+// frames, streaming) and records each frame's hole pixels in a list.  The scan itself is serial in
+// time but touches hole pixels only: every step launch walks the hole list of one frame per
+// sub-video, in place on the state buffer (backward pass, then forward pass over the same buffer).
+// Up to 32 independent sub-videos (propainter/inference.py windows: 50 frames + 10 pad each side)
+// advance in lock step, so the chain is 2*(window length - 1) short launches whatever the clip length.
 #include "common.cuh"
 
 namespace vv {
@@ -92,76 +94,56 @@ __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, 
     return inb ? (src & ~ST_HOLE) : ST_ZERO;
 }
 
-// One time step of one direction for every sub-video of the batch.  blockIdx.y = sub-video.
-//   PASS2 == false (backward pass, t = len-1 .. 0): current = input frame + mask, prev = ws[idx+1]
-//   PASS2 == true  (forward pass,  t = 0 .. len-1): current = ws[idx],          prev = out[idx-1]
-template <bool PASS2, bool VEC>
+// ---- k4_pack: frames + masks -> packed state, and the per-frame list of hole pixels ------------
+// One launch for every frame of every window of the batch (blockIdx.y = output frame).  Each warp
+// compacts the hole pixels of its 128-pixel span and appends them to the frame's list with one
+// atomicAdd (the order inside a list is irrelevant: items of a step are independent).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
-    k4_step(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, const float2 *__restrict__ flows_f,
-            const float2 *__restrict__ flows_b, uint32_t *__restrict__ ws, uint32_t *__restrict__ out, int h, int w,
-            int step, const __grid_constant__ SubBatch batch) {
-    const SubDesc sd = batch.sub[blockIdx.y];
-    if (step >= sd.len) return;
+    k4_pack(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, uint32_t *__restrict__ state,
+            uint32_t *__restrict__ lists, uint32_t *__restrict__ counts, int h, int w, long long first_out_frame,
+            const __grid_constant__ SubBatch batch) {
+    const long long of = first_out_frame + blockIdx.y;          // output frame handled by this CTA row
+    int s = 0;
+    while (s + 1 < batch.n && batch.sub[s + 1].out_frame <= of) ++s;
+    const long long gframe = batch.sub[s].start + (of - batch.sub[s].out_frame);
     const long long npx = (long long)h * w;
-    const int idx = PASS2 ? step : sd.len - 1 - step;
-    const long long gframe = sd.start + idx;
-    // flows: backward pass uses flow index idx (prop = forward flow), forward pass idx-1 (prop = backward flow)
-    const long long fi = PASS2 ? gframe - 1 : gframe;
-    const float2 *flow_prop = (PASS2 ? flows_b : flows_f) + fi * npx;
-    const float2 *flow_check = (PASS2 ? flows_f : flows_b) + fi * npx;
-    uint32_t *dst = (PASS2 ? out : ws) + (sd.out_frame + idx) * npx;
-    const uint32_t *prev = PASS2 ? out + (sd.out_frame + idx - 1) * npx : ws + (sd.out_frame + idx + 1) * npx;
-    const uint32_t *cur_packed = ws + (sd.out_frame + idx) * npx;
     const uint8_t *fr = frames + gframe * npx * 3;
     const uint8_t *mk = masks + gframe * npx;
-    const bool first = step == 0;
-
-    // Every thread passes 4 pixels through; hole pixels become work items in a per-warp queue so
-    // that the long gather path runs on dense warps instead of diverging on a few lanes.
-    __shared__ uint32_t s_queue[256 / 32][128];
-    uint32_t *queue = s_queue[threadIdx.x >> 5];
+    uint32_t *dst = state + of * npx;
+    uint32_t *list = lists + of * npx;
     const int lane = threadIdx.x & 31;
     const long long ngroups = (npx + 3) >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long iters = (ngroups + stride - 1) / stride;            // same trip count for every thread
+    const long long iters = (ngroups + stride - 1) / stride;
     for (long long itn = 0; itn < iters; ++itn) {
         const long long g = itn * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
         const long long p0 = g * 4;
         uint32_t c[4] = {0, 0, 0, 0};
         int n = 0;
         if (g < ngroups) {
-            n = 4;
             if (VEC) {
-                if (PASS2) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(cur_packed + p0);
-                    c[0] = v.x, c[1] = v.y, c[2] = v.z, c[3] = v.w;
-                } else {
-                    const uint32_t m4 = __ldg(reinterpret_cast<const uint32_t *>(mk + p0));
-                    const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0 * 3);
-                    const uint32_t a = __ldg(f3), b = __ldg(f3 + 1), d = __ldg(f3 + 2);
-                    c[0] = a & 0x00ffffffu;
-                    c[1] = (a >> 24) | ((b & 0x0000ffffu) << 8);
-                    c[2] = (b >> 16) | ((d & 0x000000ffu) << 16);
-                    c[3] = d >> 8;
+                n = 4;
+                const uint32_t m4 = __ldg(reinterpret_cast<const uint32_t *>(mk + p0));
+                const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0 * 3);
+                const uint32_t a = __ldg(f3), b = __ldg(f3 + 1), d = __ldg(f3 + 2);
+                c[0] = a & 0x00ffffffu;
+                c[1] = (a >> 24) | ((b & 0x0000ffffu) << 8);
+                c[2] = (b >> 16) | ((d & 0x000000ffu) << 16);
+                c[3] = d >> 8;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (byte_of(m4, i)) c[i] = ST_HOLE | ST_ZERO;
-                }
+                for (int i = 0; i < 4; ++i)
+                    if (byte_of(m4, i)) c[i] = ST_HOLE | ST_ZERO;
                 *reinterpret_cast<uint4 *>(dst + p0) = make_uint4(c[0], c[1], c[2], c[3]);
             } else {
                 n = (int)min(4LL, npx - p0);
                 for (int i = 0; i < n; ++i) {
-                    if (PASS2) {
-                        c[i] = cur_packed[p0 + i];
-                    } else {
-                        const uint8_t *q = fr + (p0 + i) * 3;
-                        c[i] = mk[p0 + i] ? (ST_HOLE | ST_ZERO) : (q[0] | (q[1] << 8) | ((uint32_t)q[2] << 16));
-                    }
+                    const uint8_t *q = fr + (p0 + i) * 3;
+                    c[i] = mk[p0 + i] ? (ST_HOLE | ST_ZERO) : (q[0] | (q[1] << 8) | ((uint32_t)q[2] << 16));
                     dst[p0 + i] = c[i];
                 }
             }
         }
-        if (first) continue;                              // uniform: step 0 only copies
         uint32_t holes = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) holes |= (uint32_t)(i < n && (c[i] & ST_HOLE)) << i;
@@ -174,20 +156,49 @@ __global__ void __launch_bounds__(256)
             if (lane >= d) pre += v;
         }
         const int total = __shfl_sync(0xffffffffu, pre, 31);
-        int pos = pre - cnt;
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(counts + of, (uint32_t)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t pos = base + (uint32_t)(pre - cnt);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if ((holes >> i) & 1u) queue[pos++] = (uint32_t)(p0 + i);
-        __syncwarp();
-        for (int base = 0; base < total; base += 32) {
-            if (base + lane < total) {
-                const uint32_t p = queue[base + lane];
-                const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
-                const uint32_t nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, flow_prop, flow_check, prev);
-                if (nv != (ST_HOLE | ST_ZERO)) dst[p] = nv;
-            }
-        }
-        __syncwarp();
+            if ((holes >> i) & 1u) list[pos++] = (uint32_t)(p0 + i);
+    }
+}
+
+// ---- k4_step: one time step of one direction, in place, over the hole lists -------------------
+// blockIdx.y = sub-video.  The state buffer holds the input frames after k4_pack, the backward
+// result after pass 1 and the forward result after pass 2:
+//   PASS2 == false (backward, t = len-2 .. 0):  frame idx is updated from frame idx+1
+//   PASS2 == true  (forward,  t = 1 .. len-1):  frame idx (backward result) is updated from frame
+//                                               idx-1 (already the forward result)
+// Frame len-1 / frame 0 are the first step of their pass and stay as they are.
+template <bool PASS2>
+__global__ void __launch_bounds__(256)
+    k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state,
+            const uint32_t *__restrict__ lists, const uint32_t *__restrict__ counts, int h, int w, int step,
+            const __grid_constant__ SubBatch batch) {
+    const SubDesc sd = batch.sub[blockIdx.y];
+    if (step >= sd.len) return;
+    const long long npx = (long long)h * w;
+    const int idx = PASS2 ? step : sd.len - 1 - step;
+    const long long gframe = sd.start + idx;
+    // flows: backward pass uses flow index idx (prop = forward flow), forward pass idx-1 (prop = backward flow)
+    const long long fi = PASS2 ? gframe - 1 : gframe;
+    const float2 *flow_prop = (PASS2 ? flows_b : flows_f) + fi * npx;
+    const float2 *flow_check = (PASS2 ? flows_f : flows_b) + fi * npx;
+    const long long of = sd.out_frame + idx;
+    uint32_t *cur = state + of * npx;
+    const uint32_t *prev = state + (PASS2 ? of - 1 : of + 1) * npx;
+    const uint32_t *list = lists + of * npx;
+    const uint32_t n = counts[of];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t p = list[i];
+        if (PASS2 && !(cur[p] & ST_HOLE)) continue;              // filled by the backward pass
+        const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
+        const uint32_t nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, flow_prop, flow_check, prev);
+        if (nv != (ST_HOLE | ST_ZERO)) cur[p] = nv;
     }
 }
 
@@ -212,7 +223,8 @@ using namespace vv;
 
 extern "C" size_t vv_propagate_workspace_bytes(int n_out_frames, int h, int w) {
     if (n_out_frames <= 0 || h <= 0 || w <= 0) return 0;
-    return align_up((size_t)n_out_frames * h * w * 4, 256);
+    // hole-pixel lists (one u32 per pixel, worst case) + one counter per frame
+    return align_up((size_t)n_out_frames * h * w * 4, 256) + align_up((size_t)n_out_frames * 4, 256);
 }
 
 extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const float *flows_f, const float *flows_b,
@@ -220,29 +232,33 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
                             uint32_t *out, void *workspace, size_t workspace_bytes, void *stream) {
     VV_CHECK_ARG(frames && masks && out && workspace && sub_start && sub_len, "vv_propagate: NULL pointer");
     VV_CHECK_ARG(n_frames > 0 && h > 0 && w > 0 && n_sub > 0, "vv_propagate: bad shape");
+    VV_CHECK_ARG((long long)h * w < (1LL << 31), "vv_propagate: frame too large");
     VV_CHECK_ARG(n_frames == 1 || (flows_f && flows_b), "vv_propagate: flows required when there is more than one frame");
     long long total = 0;
-    int maxlen = 0;
     for (int s = 0; s < n_sub; ++s) {
         VV_CHECK_ARG(sub_len[s] > 0 && sub_start[s] >= 0 && sub_start[s] + sub_len[s] <= n_frames,
                      "vv_propagate: sub-video %d [%d,+%d) outside the clip of %d frames", s, sub_start[s], sub_len[s],
                      n_frames);
         total += sub_len[s];
-        if (sub_len[s] > maxlen) maxlen = sub_len[s];
     }
+    VV_CHECK_ARG(total < (1LL << 31), "vv_propagate: too many frames");
     VV_CHECK_ARG(workspace_bytes >= vv_propagate_workspace_bytes((int)total, h, w), "vv_propagate: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const long long npx = (long long)h * w;
     const bool vec = (npx % 4 == 0) && ((uintptr_t)frames % 4 == 0) && ((uintptr_t)masks % 4 == 0) &&
-                     ((uintptr_t)out % 16 == 0) && ((uintptr_t)workspace % 16 == 0);
-    uint32_t *ws = (uint32_t *)workspace;
+                     ((uintptr_t)out % 16 == 0);
+    uint32_t *lists = (uint32_t *)workspace;
+    uint32_t *counts = (uint32_t *)((uint8_t *)workspace + align_up((size_t)total * npx * 4, 256));
     const float2 *ff = (const float2 *)flows_f, *fb = (const float2 *)flows_b;
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)total * 4, st);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
 
     long long out_frame = 0;
     for (int base = 0; base < n_sub; base += K4_MAX_SUB) {
         SubBatch b;
         b.n = min(K4_MAX_SUB, n_sub - base);
         int blen = 0;
+        const long long first = out_frame;
         for (int s = 0; s < b.n; ++s) {
             b.sub[s].start = sub_start[base + s];
             b.sub[s].len = sub_len[base + s];
@@ -250,22 +266,25 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             out_frame += sub_len[base + s];
             blen = max(blen, sub_len[base + s]);
         }
-        // enough CTAs to fill 148 SMs a few times, split over the sub-videos of the batch
-        const int gx = max(1, min(ceil_div((npx + 3) / 4, 256), ceil_div(148 * 8, b.n)));
-        dim3 grid(gx, b.n);
+        const long long bframes = out_frame - first;
+        // pack: all frames of the batch at once (grid.y <= 65535 frames per launch)
+        for (long long f0 = 0; f0 < bframes; f0 += 32768) {
+            const int ny = (int)min(32768LL, bframes - f0);
+            const int gx = max(1, min(ceil_div((npx + 3) / 4, 256), ceil_div(148 * 16, ny)));
+            if (vec)
+                k4_pack<true><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, lists, counts, h, w, first + f0, b);
+            else
+                k4_pack<false><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, lists, counts, h, w, first + f0, b);
+            VV_POST_LAUNCH("k4_pack");
+        }
+        // the serial scans touch hole pixels only; a few CTAs per SM, split over the windows
+        dim3 grid(max(1, ceil_div(148 * 4, b.n)), b.n);
         for (int pass = 0; pass < 2; ++pass)
-            for (int step = 0; step < blen; ++step) {
-                if (pass == 0) {
-                    if (vec)
-                        k4_step<false, true><<<grid, 256, 0, st>>>(frames, masks, ff, fb, ws, out, h, w, step, b);
-                    else
-                        k4_step<false, false><<<grid, 256, 0, st>>>(frames, masks, ff, fb, ws, out, h, w, step, b);
-                } else {
-                    if (vec)
-                        k4_step<true, true><<<grid, 256, 0, st>>>(frames, masks, ff, fb, ws, out, h, w, step, b);
-                    else
-                        k4_step<true, false><<<grid, 256, 0, st>>>(frames, masks, ff, fb, ws, out, h, w, step, b);
-                }
+            for (int step = 1; step < blen; ++step) {
+                if (pass == 0)
+                    k4_step<false><<<grid, 256, 0, st>>>(ff, fb, out, lists, counts, h, w, step, b);
+                else
+                    k4_step<true><<<grid, 256, 0, st>>>(ff, fb, out, lists, counts, h, w, step, b);
                 VV_POST_LAUNCH("k4_step");
             }
     }
