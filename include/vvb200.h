@@ -52,7 +52,10 @@ VV_API int vv_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *t
 VV_API unsigned long long vv_launch_count(void);
 VV_API void vv_reset_launch_count(void);
 /* Kernel-variant switches used for A/B measurements (defaults are the tuned choices):
- *   "k1b_exact"  1 = fully unrolled 8-round dilation for the default radius, 0 = generic loop. */
+ *   "k1b_exact"  1 = fully unrolled 8-round dilation for the default radius, 0 = generic loop.
+ *   "k3_nt"      16-pixel groups per thread and iteration in K3 (1 or 2).
+ *   "k3_tma"     1 = K3 stages the original strip through shared memory with bulk async copies
+ *                (TMA) when the frame is 16-byte aligned, 0 = register pass-through kernel. */
 VV_API int vv_set_option(const char *name, int value);
 VV_API int vv_get_option(const char *name, int *value);
 

@@ -134,8 +134,30 @@ def test_k3_feather_values(ops, f):
         assert d.max() == 0
 
 
+@pytest.mark.parametrize("variant", [dict(k3_tma=1), dict(k3_tma=0, k3_nt=1), dict(k3_tma=0, k3_nt=2)],
+                         ids=["tma", "regs-nt1", "regs-nt2"])
+def test_k3_kernel_variants(ops, variant):
+    """Every K3 variant (TMA-staged strip / register pass-through) gives the same bytes."""
+    from videovanish_b200 import _lib
+    fr = synth.frames(3, 200, 320, seed=41)
+    inp = synth.noise_frames(3, 96, 160, seed=42)
+    dil = np.stack(op.model_binarize_dilate(list(synth.masks(3, 200, 320, seed=43, salt=0.003)), 4))
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, 3) for i in range(3)])
+    ref5 = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, 5) for i in range(3)])
+    try:
+        for k, v in variant.items():
+            _lib.set_option(k, v)
+        got = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=3))
+        got5 = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=5))
+    finally:
+        _lib.set_option("k3_tma", 1)
+        _lib.set_option("k3_nt", 2)
+    assert np.array_equal(got, ref)
+    assert np.abs(got5.astype(int) - ref5.astype(int)).max() <= 1
+
+
 @pytest.mark.parametrize("h0,w0,h,w", [(97, 131, 40, 56), (360, 640, 176, 320), (72, 128, 72, 128), (50, 1040, 24, 520),
-                                        (35, 16, 70, 32), (1, 16, 1, 8)])
+                                        (35, 16, 70, 32), (1, 16, 1, 8), (20, 4096, 10, 2048)])
 def test_k3_shapes(ops, h0, w0, h, w):
     fr = synth.frames(2, h0, w0, seed=h0)
     inp = synth.noise_frames(2, h, w, seed=w0)

@@ -13,7 +13,7 @@ namespace vv {
 void set_error(const char *fmt, ...);
 
 // Tuning switches (vv_set_option): variants kept side by side so that one GPU run can A/B them.
-enum Option { OPT_K1B_EXACT = 0, OPT_COUNT };
+enum Option { OPT_K1B_EXACT = 0, OPT_K3_NT, OPT_K3_TMA, OPT_COUNT };
 int get_option(int opt);
 extern std::atomic<unsigned long long> g_launches;
 
@@ -69,5 +69,47 @@ __device__ __forceinline__ uint32_t nonzero_bits16(const uint4 &v) {
     };
     return nz4(v.x) | (nz4(v.y) << 4) | (nz4(v.z) << 8) | (nz4(v.w) << 12);
 }
+
+// ---- TMA (bulk async copy) + mbarrier wrappers, sm_90+ PTX -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// global -> shared bulk copy; completion is signalled on `bar` (complete_tx of `bytes`).
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion).
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// make generic-proxy writes to shared memory visible to the async proxy (before a bulk store)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace vv

@@ -33,7 +33,7 @@ struct Tap {
 };
 int build_linear_taps(void *workspace, int H, int W, int h, int w, const Tap **xt, const Tap **yt, cudaStream_t st);
 
-constexpr int K3_TH = 16;          // output rows per CTA strip
+constexpr int K3_TH = 16;          // maximum output rows per CTA strip
 constexpr int K3_MAX_ENTRIES = 224;   // window offsets with cost < feather_px, radius <= 7
 
 struct FeatherTable {      // passed by value as a kernel parameter (constant bank, uniform reads)
@@ -94,39 +94,63 @@ __device__ __forceinline__ int hpass(unsigned long long pair, uint32_t wts) {
     return (int)__dp2a_lo(wts, two, 0u);
 }
 
-constexpr int K3_THREADS = 256;
-constexpr int K3_QUEUE = 128;     // work items (4-pixel quads) per warp task: 32 lanes x 4 quads
+constexpr int K3_THREADS = 256;    // register pass-through kernel
+constexpr int K3_THREADS_TMA = 384;   // TMA-staged kernel: the strip occupies shared memory, 2 CTAs per SM
+constexpr int K3_QUEUE1 = 128;    // work items (4-pixel quads) per warp iteration and group: 32 lanes x 4 quads
 
 // Work item = one 4-pixel quad (x aligned to 4) that contains at least one pixel with alpha > 0:
 //   .x = x | row-in-strip << 16 | need(4) << 20 | inside(4) << 24
 //   .y = level bit planes l0 | l1 << 4 | l2 << 8 (SMALL_R; per-pixel LUT index = l0 | l1<<1 | l2<<2 | inside<<3)
 
-template <bool VEC, bool SMALL_R>
-__global__ void __launch_bounds__(K3_THREADS)
+// K3_NT = 16-pixel groups per thread and iteration.
+// TMA: the strip of original pixels is brought into shared memory by bulk async copies (one
+// elected thread, mbarrier completion), the blended quads are patched into it there, and the whole
+// strip leaves with a bulk store - the 6 B/px pass-through never touches registers.  Requires VEC.
+template <bool VEC, bool SMALL_R, int K3_NT, bool TMA>
+__global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4)
     k3_upscale_feather_composite(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig,
                                  const uint8_t *__restrict__ mask, uint8_t *__restrict__ out,
                                  const Tap *__restrict__ xt, const Tap *__restrict__ yt, int h, int w, int H0, int W0,
-                                 int strips_per_frame, const __grid_constant__ FeatherTable ft) {
-    extern __shared__ uint32_t smem[];
+                                 int strips_per_frame, int th, const __grid_constant__ FeatherTable ft) {
+    extern __shared__ __align__(128) uint32_t smem_base[];
+    const int nthreads = TMA ? K3_THREADS_TMA : K3_THREADS;
+    // TMA: [strip th*W0*3 bytes][mbarrier 16 B] then the common part
+    const int strip_words = TMA ? (th * W0 * 3) / 4 : 0;
+    uint8_t *strip = reinterpret_cast<uint8_t *>(smem_base);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_base + strip_words);
+    uint32_t *smem = smem_base + strip_words + (TMA ? 4 : 0);
     const int R = SMALL_R ? 2 : ft.radius;
     const int Wp = (W0 + 31) >> 5;
     const int row_words = Wp + 2;
-    const int rows_s = K3_TH + 2 * R;
+    const int rows_s = th + 2 * R;
     uint32_t *bits = smem;                                               // [rows_s][row_words]
     float *lut = reinterpret_cast<float *>(smem + rows_s * row_words);   // [16] alpha levels (SMALL_R)
     uint2 *queue = reinterpret_cast<uint2 *>(smem + ((rows_s * row_words + 16 + 1) & ~1)) +
-                   (threadIdx.x >> 5) * K3_QUEUE;                        // per-warp work queue
+                   (threadIdx.x >> 5) * (K3_QUEUE1 * K3_NT);                        // per-warp work queue
     const int lane = threadIdx.x & 31;
 
     const long long t = blockIdx.x / strips_per_frame;
-    const int y0 = (blockIdx.x % strips_per_frame) * K3_TH;
+    const int y0 = (blockIdx.x % strips_per_frame) * th;
     const uint8_t *mask_t = mask + t * H0 * (long long)W0;
+    const uint8_t *orig_t = orig + t * H0 * (long long)W0 * 3;
+    uint8_t *out_t = out + t * H0 * (long long)W0 * 3;
+    const uint32_t strip_bytes = (uint32_t)(min(th, H0 - y0) * W0 * 3);
+    if (TMA) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(bar, strip_bytes);
+            const uint8_t *src = orig_t + (long long)y0 * W0 * 3;
+            for (uint32_t off = 0; off < strip_bytes; off += 32768u)
+                bulk_g2s(strip + off, src + off, min(32768u, strip_bytes - off), bar);
+        }
+    }
 
     // ---------------- phase 1: mask strip -> bit rows
     {
         uint16_t *b16 = reinterpret_cast<uint16_t *>(bits);
         const int halves = 2 * row_words;
-        for (int id = threadIdx.x; id < rows_s * halves; id += blockDim.x) {
+        for (int id = threadIdx.x; id < rows_s * halves; id += nthreads) {
             const int i = id / halves, hw = id - i * halves;
             const int y = y0 - R + i, x0 = (hw - 2) * 16;
             uint32_t v = 0;
@@ -155,8 +179,6 @@ __global__ void __launch_bounds__(K3_THREADS)
 
     // ---------------- phase 2: 16-pixel groups
     const int G = (W0 + 15) >> 4;
-    const uint8_t *orig_t = orig + t * H0 * (long long)W0 * 3;
-    uint8_t *out_t = out + t * H0 * (long long)W0 * 3;
     const uint8_t *inp_t = inp + t * h * (long long)w * 3;
     const bool inp_aligned8 = ((w * 3) % 8 == 0) && ((uintptr_t)inp_t % 8 == 0);
     const bool hard = !SMALL_R && ft.n == 0;
@@ -167,36 +189,51 @@ __global__ void __launch_bounds__(K3_THREADS)
         for (int k = 0; k < 16; ++k) lut_pos |= (uint32_t)(lut[k] > 0.f) << k;
     }
 
-    const int n_tasks = K3_TH * G;
-    const int n_iters = (n_tasks + K3_THREADS - 1) / K3_THREADS;     // same trip count for the whole warp
+    const int n_tasks = th * G;
+    bool landed = false;       // TMA: the strip has arrived in shared memory
+    // K3_NT tasks (16-pixel groups) per thread and iteration: all their loads are issued before the
+    // first store, which keeps enough bytes in flight to cover HBM latency; same trip count for the
+    // whole warp.
+    const int n_iters = (n_tasks + nthreads * K3_NT - 1) / (nthreads * K3_NT);
     for (int it = 0; it < n_iters; ++it) {
-        const int id = it * K3_THREADS + threadIdx.x;
-        const int row = id / G, g = id - row * G;
-        const int y = y0 + row;
-        const bool active = id < n_tasks && y < H0;
-        const int x0 = g * 16;
-        const int npx = VEC ? 16 : min(16, W0 - x0);
-        uint32_t need = 0;                  // pixels (bit i) with alpha > 0
-        uint32_t L0 = 0, L1 = 0, L2 = 0, M2 = 0;
-
-        if (active) {
+        int row[K3_NT], x0[K3_NT];
+        bool active[K3_NT];
+        uint4 pa[K3_NT], pb[K3_NT], pc[K3_NT];
+#pragma unroll
+        for (int k = 0; k < K3_NT; ++k) {
+            const int id = (it * K3_NT + k) * nthreads + threadIdx.x;
+            row[k] = id / G;
+            x0[k] = (id - row[k] * G) * 16;
+            active[k] = id < n_tasks && y0 + row[k] < H0;
+            if (VEC && !TMA && active[k]) {
+                const int pix_off = ((y0 + row[k]) * W0 + x0[k]) * 3;
+                pa[k] = ldg128(orig_t + pix_off), pb[k] = ldg128(orig_t + pix_off + 16), pc[k] = ldg128(orig_t + pix_off + 32);
+            }
+        }
+        uint32_t need[K3_NT], L0[K3_NT], L1[K3_NT], L2[K3_NT], M2[K3_NT];
+#pragma unroll
+        for (int k = 0; k < K3_NT; ++k) {
+            need[k] = L0[k] = L1[k] = L2[k] = M2[k] = 0;
+            if (!active[k]) continue;
+            const int y = y0 + row[k];
+            const int npx = VEC ? 16 : min(16, W0 - x0[k]);
             // pass the original pixels through; quads with alpha > 0 somewhere are rewritten below
-            const int pix_off = (y * W0 + x0) * 3;
-            if (VEC) {
-                const uint4 a = ldg128(orig_t + pix_off), b = ldg128(orig_t + pix_off + 16),
-                            c = ldg128(orig_t + pix_off + 32);
-                stg128_stream(out_t + pix_off, a);
-                stg128_stream(out_t + pix_off + 16, b);
-                stg128_stream(out_t + pix_off + 32, c);
+            const int pix_off = (y * W0 + x0[k]) * 3;
+            if (TMA) {
+                // the strip travels by bulk copy
+            } else if (VEC) {
+                stg128_stream(out_t + pix_off, pa[k]);
+                stg128_stream(out_t + pix_off + 16, pb[k]);
+                stg128_stream(out_t + pix_off + 32, pc[k]);
             } else {
-                for (int k = 0; k < npx * 3; ++k) out_t[pix_off + k] = orig_t[pix_off + k];
+                for (int q = 0; q < npx * 3; ++q) out_t[pix_off + q] = orig_t[pix_off + q];
             }
             // window of valid columns: bit j <-> column x0 - 8 + j
-            const int c0 = x0 - 8;
+            const int c0 = x0[k] - 8;
             const int lo = max(0, -c0), hi = min(32, W0 - c0);
             const uint32_t colvalid = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-            const uint32_t *brow = bits + (row + R) * row_words;   // centre row of this pixel row
-            M2 = bit_window(brow, c0);
+            const uint32_t *brow = bits + (row[k] + R) * row_words;   // centre row of this pixel row
+            M2[k] = bit_window(brow, c0);
             const uint32_t pxmask = npx >= 16 ? 0xffffu : ((1u << npx) - 1u);
             if (SMALL_R) {
                 uint32_t Mw[5], Zw[5];
@@ -221,7 +258,7 @@ __global__ void __launch_bounds__(K3_THREADS)
                     classes(Mw, hm);
                     classes(Zw, hz);
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) hsel[k] = (hz[k] & M2) | (hm[k] & ~M2);   // inside pixels look for zeros
+                    for (int j = 0; j < 5; ++j) hsel[j] = (hz[j] & M2[k]) | (hm[j] & ~M2[k]);   // inside pixels look for zeros
                     // priority encode: level = first class hit (1..5), 0 if none -> 3 bit planes
                     const uint32_t p1 = hsel[0];
                     const uint32_t p2 = hsel[1] & ~p1;
@@ -230,15 +267,15 @@ __global__ void __launch_bounds__(K3_THREADS)
                     const uint32_t s123 = s12 | hsel[2];
                     const uint32_t p4 = hsel[3] & ~s123;
                     const uint32_t p5 = hsel[4] & ~(s123 | hsel[3]);
-                    L0 = p1 | p3 | p5, L1 = p2 | p3, L2 = p4 | p5;
+                    L0[k] = p1 | p3 | p5, L1[k] = p2 | p3, L2[k] = p4 | p5;
                     // alpha > 0: every inside pixel, and outside pixels whose first hit has alpha > 0
-                    uint32_t pos = M2;
+                    uint32_t pos = M2[k];
                     if ((lut_pos >> 1) & 1u) pos |= p1;
                     if ((lut_pos >> 2) & 1u) pos |= p2;
                     if ((lut_pos >> 3) & 1u) pos |= p3;
                     if ((lut_pos >> 4) & 1u) pos |= p4;
                     if ((lut_pos >> 5) & 1u) pos |= p5;
-                    need = (pos >> 8) & pxmask;
+                    need[k] = (pos >> 8) & pxmask;
                 }
             } else {
                 // generic radius: decided per pixel by the workers; here only "inside, or some masked
@@ -247,17 +284,22 @@ __global__ void __launch_bounds__(K3_THREADS)
                 for (int d = -R; d <= R; ++d) {
                     const uint32_t m = bit_window(brow + d * row_words, c0);
                     uint32_t acc = m;
-                    for (int k = 1; k <= R; ++k) acc |= (m << k) | (m >> k);
+                    for (int j = 1; j <= R; ++j) acc |= (m << j) | (m >> j);
                     anyM |= acc;
                 }
-                need = (hard ? (M2 >> 8) : (anyM >> 8)) & pxmask;
+                need[k] = (hard ? (M2[k] >> 8) : (anyM >> 8)) & pxmask;
             }
         }
 
         // ---- warp-level compaction: every quad with a pixel to blend becomes one work item
-        if (__ballot_sync(0xffffffffu, need != 0) == 0) continue;        // warp-uniform
-        const uint32_t qn = ((need & 0x000fu) != 0) + ((need & 0x00f0u) != 0) + ((need & 0x0f00u) != 0) +
-                            ((need & 0xf000u) != 0);
+        uint32_t any_need = 0, qn = 0;
+#pragma unroll
+        for (int k = 0; k < K3_NT; ++k) {
+            any_need |= need[k];
+            qn += ((need[k] & 0x000fu) != 0) + ((need[k] & 0x00f0u) != 0) + ((need[k] & 0x0f00u) != 0) +
+                  ((need[k] & 0xf000u) != 0);
+        }
+        if (__ballot_sync(0xffffffffu, any_need != 0) == 0) continue;        // warp-uniform
         int pre = (int)qn;                               // inclusive scan over lanes
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -267,17 +309,24 @@ __global__ void __launch_bounds__(K3_THREADS)
         const int total = __shfl_sync(0xffffffffu, pre, 31);
         int pos = pre - (int)qn;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t n4 = (need >> (4 * q)) & 15u;
-            if (n4) {
-                const int b = 8 + 4 * q;
-                uint2 e;
-                e.x = (uint32_t)(x0 + 4 * q) | ((uint32_t)row << 16) | (n4 << 20) | (((M2 >> b) & 15u) << 24);
-                e.y = ((L0 >> b) & 15u) | (((L1 >> b) & 15u) << 4) | (((L2 >> b) & 15u) << 8);
-                queue[pos++] = e;
+        for (int k = 0; k < K3_NT; ++k) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t n4 = (need[k] >> (4 * q)) & 15u;
+                if (n4) {
+                    const int b = 8 + 4 * q;
+                    uint2 e;
+                    e.x = (uint32_t)(x0[k] + 4 * q) | ((uint32_t)row[k] << 16) | (n4 << 20) | (((M2[k] >> b) & 15u) << 24);
+                    e.y = ((L0[k] >> b) & 15u) | (((L1[k] >> b) & 15u) << 4) | (((L2[k] >> b) & 15u) << 8);
+                    queue[pos++] = e;
+                }
             }
         }
         __syncwarp();
+        if (TMA && !landed) {
+            mbar_wait(bar, 0);
+            landed = true;
+        }
         for (int base = 0; base < total; base += 32) {
             const int qi = base + lane;
             if (qi < total) {
@@ -290,15 +339,20 @@ __global__ void __launch_bounds__(K3_THREADS)
                 const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
                 const uint8_t *r0 = inp_t + ya * w * 3;
                 const uint8_t *r1 = inp_t + yb * w * 3;
-                const int po = (yy * W0 + xq) * 3;
+                const int po = TMA ? (r * W0 + xq) * 3 : (yy * W0 + xq) * 3;   // offset in the strip / in the frame
                 int ofs[4];
                 uint32_t wts[4], o[3];
                 if (VEC) {                                   // W0 % 16 == 0: the quad is whole and 4-byte aligned
                     const uint4 t01 = ldg128(xt + xq), t23 = ldg128(xt + xq + 2);
                     ofs[0] = t01.x, wts[0] = t01.y, ofs[1] = t01.z, wts[1] = t01.w;
                     ofs[2] = t23.x, wts[2] = t23.y, ofs[3] = t23.z, wts[3] = t23.w;
-                    const uint32_t *op = reinterpret_cast<const uint32_t *>(orig_t + po);
-                    o[0] = __ldg(op), o[1] = __ldg(op + 1), o[2] = __ldg(op + 2);
+                    if (TMA) {
+                        const uint32_t *op = reinterpret_cast<const uint32_t *>(strip + po);
+                        o[0] = op[0], o[1] = op[1], o[2] = op[2];
+                    } else {
+                        const uint32_t *op = reinterpret_cast<const uint32_t *>(orig_t + po);
+                        o[0] = __ldg(op), o[1] = __ldg(op + 1), o[2] = __ldg(op + 2);
+                    }
                 } else {
                     o[0] = o[1] = o[2] = 0;
 #pragma unroll
@@ -356,7 +410,7 @@ __global__ void __launch_bounds__(K3_THREADS)
                     }
                 }
                 if (VEC) {
-                    uint32_t *dp = reinterpret_cast<uint32_t *>(out_t + po);
+                    uint32_t *dp = TMA ? reinterpret_cast<uint32_t *>(strip + po) : reinterpret_cast<uint32_t *>(out_t + po);
                     dp[0] = o[0], dp[1] = o[1], dp[2] = o[2];
                 } else {
 #pragma unroll
@@ -366,6 +420,17 @@ __global__ void __launch_bounds__(K3_THREADS)
             }
         }
         __syncwarp();      // the queue is reused by the next iteration
+    }
+    if (TMA) {
+        if (!landed) mbar_wait(bar, 0);
+        fence_proxy_async();                 // the patched quads must be visible to the bulk store
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint8_t *dst = out_t + (long long)y0 * W0 * 3;
+            for (uint32_t off = 0; off < strip_bytes; off += 32768u)
+                bulk_s2g(dst + off, strip + off, min(32768u, strip_bytes - off));
+            bulk_commit_and_wait_read();     // shared memory must outlive the reads of the store
+        }
     }
 }
 
@@ -454,30 +519,60 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
     const bool small_r = feather_px > 0.f && ft.radius <= 2;
     const int R = small_r ? 2 : ft.radius;
     const int Wp = ceil_div(W0, 32);
-    const size_t smem = ((size_t)(K3_TH + 2 * R) * (Wp + 2) + 16 + 2 + (K3_THREADS / 32) * K3_QUEUE * 2) * 4;
     const bool vec = (W0 % 16 == 0) && ((uintptr_t)orig % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                      ((uintptr_t)mask % 16 == 0);
-    const int strips = ceil_div(H0, K3_TH);
+    // TMA-staged variant: strip rows chosen so that strip + bit rows + queues fit twice per SM
+    int th = K3_TH;
+    bool tma = vec && get_option(OPT_K3_TMA) != 0;
+    const size_t common_words = 16 + 2;
+    size_t smem = 0;
+    if (tma) {
+        for (th = 16; th >= 2; th >>= 1) {
+            smem = (size_t)th * W0 * 3 + 16 +
+                   ((size_t)(th + 2 * R) * (Wp + 2) + common_words + (K3_THREADS_TMA / 32) * K3_QUEUE1 * 2) * 4;
+            if (smem <= 110 * 1024) break;
+        }
+        if (th < 2) tma = false;
+    }
+    const int nt = tma ? 1 : (get_option(OPT_K3_NT) == 1 ? 1 : 2);
+    if (!tma) {
+        th = K3_TH;
+        smem = ((size_t)(th + 2 * R) * (Wp + 2) + common_words + (K3_THREADS / 32) * K3_QUEUE1 * nt * 2) * 4;
+    }
+    const int strips = ceil_div(H0, th);
     const long long grid = (long long)T * strips;
     VV_CHECK_ARG(grid < 2147483647LL, "vv_upscale_feather_composite: too many strips");
 
-#define VV_K3_LAUNCH(V, S)                                                                                      \
+#define VV_K3_LAUNCH(V, S, N, M)                                                                                \
     do {                                                                                                        \
-        auto kfn = k3_upscale_feather_composite<V, S>;                                                          \
+        auto kfn = k3_upscale_feather_composite<V, S, N, M>;                                                    \
         if (smem > 48 * 1024) {                                                                                 \
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
             if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(k3)");                              \
         }                                                                                                       \
-        kfn<<<(unsigned)grid, K3_THREADS, smem, st>>>(inp, orig, mask, out, xt, yt, h, w, H0, W0, strips, ft);         \
+        kfn<<<(unsigned)grid, (M) ? K3_THREADS_TMA : K3_THREADS, smem, st>>>(inp, orig, mask, out, xt, yt, h, w, H0,   \
+                                                                            W0, strips, th, ft);                \
     } while (0)
-    if (vec && small_r)
-        VV_K3_LAUNCH(true, true);
+#define VV_K3_DISPATCH(V, S)            \
+    do {                                \
+        if (nt == 1)                    \
+            VV_K3_LAUNCH(V, S, 1, false); \
+        else                            \
+            VV_K3_LAUNCH(V, S, 2, false); \
+    } while (0)
+    if (tma && small_r)
+        VV_K3_LAUNCH(true, true, 1, true);
+    else if (tma)
+        VV_K3_LAUNCH(true, false, 1, true);
+    else if (vec && small_r)
+        VV_K3_DISPATCH(true, true);
     else if (vec)
-        VV_K3_LAUNCH(true, false);
+        VV_K3_DISPATCH(true, false);
     else if (small_r)
-        VV_K3_LAUNCH(false, true);
+        VV_K3_DISPATCH(false, true);
     else
-        VV_K3_LAUNCH(false, false);
+        VV_K3_DISPATCH(false, false);
+#undef VV_K3_DISPATCH
 #undef VV_K3_LAUNCH
     VV_POST_LAUNCH("k3_upscale_feather_composite");
     return VV_OK;

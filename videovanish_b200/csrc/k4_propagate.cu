@@ -195,10 +195,11 @@ __global__ void __launch_bounds__(256)
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t p = list[i];
-        if (PASS2 && !(cur[p] & ST_HOLE)) continue;              // filled by the backward pass
+        const uint32_t cv = PASS2 ? cur[p] : (ST_HOLE | ST_ZERO);   // issued together with the flow load below
         const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
         const uint32_t nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, flow_prop, flow_check, prev);
-        if (nv != (ST_HOLE | ST_ZERO)) cur[p] = nv;
+        // pixels already filled by the backward pass keep their value
+        if ((cv & ST_HOLE) && nv != (ST_HOLE | ST_ZERO)) cur[p] = nv;
     }
 }
 
@@ -278,7 +279,9 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             VV_POST_LAUNCH("k4_pack");
         }
         // the serial scans touch hole pixels only; a few CTAs per SM, split over the windows
-        dim3 grid(max(1, ceil_div(148 * 4, b.n)), b.n);
+        // (the hole counts live on the device: the grid is sized for ~1 item per thread at a 25 % hole
+        // fraction and strides over the list otherwise)
+        dim3 grid(max(1, min(ceil_div(npx / 4, 256), ceil_div(148 * 16, b.n))), b.n);
         for (int pass = 0; pass < 2; ++pass)
             for (int step = 1; step < blen; ++step) {
                 if (pass == 0)
