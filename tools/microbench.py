@@ -33,7 +33,7 @@ def timeit(fn, reps=5, warm=2):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=120)
+    ap.add_argument("--frames", type=int, default=240)
     ap.add_argument("--ops", default="all")
     args = ap.parse_args()
     t = args.frames
@@ -80,17 +80,22 @@ def main():
     report("K2 resize 1080p->540p", t * (3 * px + 3 * spx), lambda: ops.resize(fr, HS, WS))
     report("K2 resize 1080p->536p", t * (3 * px + 3 * 536 * 960), lambda: ops.resize(fr, 536, 960))
     report("K2 nearest mask 1080p->540p", t * (px + spx), lambda: ops.resize(dil, HS, WS, ops.INTER_NEAREST))
-    for tma, nt in ((1, 1), (0, 1), (0, 2)):
+    for tma, nt, rows, thr in ((1, 1, 16, 512), (1, 1, 16, 384), (1, 1, 8, 512), (1, 1, 8, 256), (0, 2, 16, 512)):
         _lib.set_option("k3_tma", tma)
         _lib.set_option("k3_nt", nt)
+        _lib.set_option("k3_tma_rows", rows)
+        _lib.set_option("k3_tma_threads", thr)
+        kw = dict(k3_tma=tma, k3_nt=nt, rows=rows, threads=thr)
         report("K3 composite (synthetic mask)", t * (7 * px + 3 * spx),
-               lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out), k3_tma=tma, k3_nt=nt)
+               lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out), **kw)
         report("K3 composite (empty mask)", t * (7 * px + 3 * spx),
-               lambda: ops.upscale_feather_composite(inp, fr, empty_mask, 3, out=out), k3_tma=tma, k3_nt=nt)
+               lambda: ops.upscale_feather_composite(inp, fr, empty_mask, 3, out=out), **kw)
         report("K3 composite (full mask)", t * (7 * px + 3 * spx),
-               lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out), k3_tma=tma, k3_nt=nt)
+               lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out), **kw)
     _lib.set_option("k3_tma", 1)
     _lib.set_option("k3_nt", 2)
+    _lib.set_option("k3_tma_rows", 16)
+    _lib.set_option("k3_tma_threads", 512)
     report("K3 composite feather 5 (generic path)", t * (7 * px + 3 * spx),
            lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
     report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb))

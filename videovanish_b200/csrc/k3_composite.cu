@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <mutex>
 #include <queue>
 #include <tuple>
 #include <vector>
@@ -95,7 +96,7 @@ __device__ __forceinline__ int hpass(unsigned long long pair, uint32_t wts) {
 }
 
 constexpr int K3_THREADS = 256;    // register pass-through kernel
-constexpr int K3_THREADS_TMA = 384;   // TMA-staged kernel: the strip occupies shared memory, 2 CTAs per SM
+constexpr int K3_THREADS_TMA = 512;   // TMA-staged kernel (maximum; chosen at launch): the strip occupies shared memory, 2 CTAs per SM
 constexpr int K3_QUEUE1 = 128;    // work items (4-pixel quads) per warp iteration and group: 32 lanes x 4 quads
 
 // Work item = one 4-pixel quad (x aligned to 4) that contains at least one pixel with alpha > 0:
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                                  const Tap *__restrict__ xt, const Tap *__restrict__ yt, int h, int w, int H0, int W0,
                                  int strips_per_frame, int th, const __grid_constant__ FeatherTable ft) {
     extern __shared__ __align__(128) uint32_t smem_base[];
-    const int nthreads = TMA ? K3_THREADS_TMA : K3_THREADS;
+    const int nthreads = TMA ? (int)blockDim.x : K3_THREADS;
     // TMA: [strip th*W0*3 bytes][mbarrier 16 B] then the common part
     const int strip_words = TMA ? (th * W0 * 3) / 4 : 0;
     uint8_t *strip = reinterpret_cast<uint8_t *>(smem_base);
@@ -514,8 +515,19 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
     int rc = build_linear_taps(workspace, h, w, H0, W0, &xt, &yt, st);
     if (rc) return rc;
 
+    // the table only depends on feather_px: keep the last one (the GUI never changes it from 3)
+    static std::mutex ft_mu;
+    static FeatherTable ft_cache;
+    static float ft_cache_key = -12345.f;
     FeatherTable ft;
-    build_feather_table(feather_px, &ft);
+    {
+        std::lock_guard<std::mutex> g(ft_mu);
+        if (ft_cache_key != feather_px) {
+            build_feather_table(feather_px, &ft_cache);
+            ft_cache_key = feather_px;
+        }
+        ft = ft_cache;
+    }
     const bool small_r = feather_px > 0.f && ft.radius <= 2;
     const int R = small_r ? 2 : ft.radius;
     const int Wp = ceil_div(W0, 32);
@@ -524,13 +536,16 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
     // TMA-staged variant: strip rows chosen so that strip + bit rows + queues fit twice per SM
     int th = K3_TH;
     bool tma = vec && get_option(OPT_K3_TMA) != 0;
+    int tma_threads = K3_THREADS_TMA;
     const size_t common_words = 16 + 2;
     size_t smem = 0;
     if (tma) {
-        for (th = 16; th >= 2; th >>= 1) {
+        const int th_max = min(16, max(2, get_option(OPT_K3_TMA_ROWS)));
+        tma_threads = get_option(OPT_K3_TMA_THREADS) >= 512 ? 512 : get_option(OPT_K3_TMA_THREADS) >= 384 ? 384 : 256;
+        for (th = th_max; th >= 2; --th) {      // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
             smem = (size_t)th * W0 * 3 + 16 +
-                   ((size_t)(th + 2 * R) * (Wp + 2) + common_words + (K3_THREADS_TMA / 32) * K3_QUEUE1 * 2) * 4;
-            if (smem <= 110 * 1024) break;
+                   ((size_t)(th + 2 * R) * (Wp + 2) + common_words + (tma_threads / 32) * K3_QUEUE1 * 2) * 4;
+            if (smem <= 113 * 1024) break;
         }
         if (th < 2) tma = false;
     }
@@ -546,11 +561,13 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
 #define VV_K3_LAUNCH(V, S, N, M)                                                                                \
     do {                                                                                                        \
         auto kfn = k3_upscale_feather_composite<V, S, N, M>;                                                    \
-        if (smem > 48 * 1024) {                                                                                 \
+        static std::atomic<size_t> smem_set{48 * 1024};                                                        \
+        if (smem > smem_set.load()) {                                                                           \
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
             if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(k3)");                              \
+            smem_set.store(smem);                                                                               \
         }                                                                                                       \
-        kfn<<<(unsigned)grid, (M) ? K3_THREADS_TMA : K3_THREADS, smem, st>>>(inp, orig, mask, out, xt, yt, h, w, H0,   \
+        kfn<<<(unsigned)grid, (M) ? tma_threads : K3_THREADS, smem, st>>>(inp, orig, mask, out, xt, yt, h, w, H0,   \
                                                                             W0, strips, th, ft);                \
     } while (0)
 #define VV_K3_DISPATCH(V, S)            \
