@@ -61,7 +61,11 @@ def main():
     except Exception:
         pass
 
+    wanted = None if args.ops == "all" else [w.strip().lower() for w in args.ops.split(",")]
+
     def report(name, alg_bytes, fn, **extra):
+        if wanted is not None and not any(w in name.lower() for w in wanted):
+            return
         med, best = timeit(fn)
         gbs = alg_bytes / (med * 1e-3) / 1e9
         print(json.dumps(dict(op=name, frames=t, ms=med, ms_best=best, us_per_frame=med * 1e3 / t, GBps=gbs,
