@@ -173,31 +173,89 @@ __global__ void __launch_bounds__(256)
 //   PASS2 == true  (forward,  t = 1 .. len-1):  frame idx (backward result) is updated from frame
 //                                               idx-1 (already the forward result)
 // Frame len-1 / frame 0 are the first step of their pass and stay as they are.
+//
+// The chain of ~2*(len-1) dependent launches is latency bound (per item: list -> flow -> 8 taps),
+// so every launch also WARMS L2 FOR THE NEXT STEP: it walks the next frame's hole list, loads the
+// flow vector of each hole and prefetches the sectors its taps will touch.  That part does not
+// depend on the previous step, so with programmatic dependent launch it runs while the previous
+// step is still executing; `griddepcontrol.wait` then fences the part that needs its results.
+struct StepView {
+    const float2 *flow_prop, *flow_check;
+    long long of;          // frame index in the state / list buffers
+    bool valid;
+};
+
 template <bool PASS2>
-__global__ void __launch_bounds__(256)
-    k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state,
-            const uint32_t *__restrict__ lists, const uint32_t *__restrict__ counts, int h, int w, int step,
-            const __grid_constant__ SubBatch batch) {
-    const SubDesc sd = batch.sub[blockIdx.y];
-    if (step >= sd.len) return;
-    const long long npx = (long long)h * w;
+__device__ __forceinline__ StepView step_view(const SubDesc &sd, int step, const float2 *flows_f, const float2 *flows_b,
+                                              long long npx) {
+    StepView v;
+    v.valid = step >= 1 && step < sd.len;
     const int idx = PASS2 ? step : sd.len - 1 - step;
     const long long gframe = sd.start + idx;
     // flows: backward pass uses flow index idx (prop = forward flow), forward pass idx-1 (prop = backward flow)
     const long long fi = PASS2 ? gframe - 1 : gframe;
-    const float2 *flow_prop = (PASS2 ? flows_b : flows_f) + fi * npx;
-    const float2 *flow_check = (PASS2 ? flows_f : flows_b) + fi * npx;
-    const long long of = sd.out_frame + idx;
-    uint32_t *cur = state + of * npx;
-    const uint32_t *prev = state + (PASS2 ? of - 1 : of + 1) * npx;
-    const uint32_t *list = lists + of * npx;
-    const uint32_t n = counts[of];
+    v.flow_prop = (PASS2 ? flows_b : flows_f) + fi * npx;
+    v.flow_check = (PASS2 ? flows_f : flows_b) + fi * npx;
+    v.of = sd.out_frame + idx;
+    return v;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Touch what `propagate_pixel` will read for hole pixel p of a future step.
+__device__ __forceinline__ void warm_pixel(uint32_t p, int h, int w, const StepView &v, const uint32_t *state_frame) {
+    const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
+    const float2 f = __ldg(v.flow_prop + p);
+    const float ix = unnormalized(__fadd_rn((float)x, f.x), w);
+    const float iy = unnormalized(__fadd_rn((float)y, f.y), h);
+    const int x0 = (int)fminf(fmaxf(floorf(ix), 0.f), (float)(w - 1));
+    const int y0 = (int)fminf(fmaxf(floorf(iy), 0.f), (float)(h - 1));
+    const long long i00 = (long long)y0 * w + x0;
+    const long long i10 = (long long)min(y0 + 1, h - 1) * w + x0;
+    prefetch_l2(v.flow_check + i00);
+    prefetch_l2(v.flow_check + i00 + 1);
+    prefetch_l2(v.flow_check + i10);
+    prefetch_l2(v.flow_check + i10 + 1);
+    prefetch_l2(state_frame + p);
+}
+
+template <bool PASS2>
+__global__ void __launch_bounds__(256)
+    k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state,
+            const uint32_t *__restrict__ lists, const uint32_t *__restrict__ counts, int h, int w, int step,
+            int warm_next, const __grid_constant__ SubBatch batch) {
+    asm volatile("griddepcontrol.launch_dependents;");      // the next step may start its warm-up part
+    const SubDesc sd = batch.sub[blockIdx.y];
+    const long long npx = (long long)h * w;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+
+    if (warm_next) {
+        // next step: step+1 of this pass, or step 1 of the forward pass after the last backward step
+        StepView nv;
+        if (PASS2 || step + 1 < sd.len)
+            nv = step_view<PASS2>(sd, step + 1, flows_f, flows_b, npx);
+        else
+            nv = step_view<true>(sd, 1, flows_f, flows_b, npx);
+        if (nv.valid) {
+            const uint32_t *nlist = lists + nv.of * npx;
+            const uint32_t nn = counts[nv.of];
+            for (uint32_t i = tid; i < nn; i += stride) warm_pixel(nlist[i], h, w, nv, state + nv.of * npx);
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // results of the previous step are visible
+
+    const StepView v = step_view<PASS2>(sd, step, flows_f, flows_b, npx);
+    if (!v.valid) return;
+    uint32_t *cur = state + v.of * npx;
+    const uint32_t *prev = state + (PASS2 ? v.of - 1 : v.of + 1) * npx;
+    const uint32_t *list = lists + v.of * npx;
+    const uint32_t n = counts[v.of];
+    for (uint32_t i = tid; i < n; i += stride) {
         const uint32_t p = list[i];
         const uint32_t cv = PASS2 ? cur[p] : (ST_HOLE | ST_ZERO);   // issued together with the flow load below
         const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
-        const uint32_t nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, flow_prop, flow_check, prev);
+        const uint32_t nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, v.flow_prop, v.flow_check, prev);
         // pixels already filled by the backward pass keep their value
         if ((cv & ST_HOLE) && nv != (ST_HOLE | ST_ZERO)) cur[p] = nv;
     }
@@ -282,12 +340,27 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
         // (the hole counts live on the device: the grid is sized for ~1 item per thread at a 25 % hole
         // fraction and strides over the list otherwise)
         dim3 grid(max(1, min(ceil_div(npx / 4, 256), ceil_div(148 * 16, b.n))), b.n);
+        const int warm = get_option(OPT_K4_WARM) != 0;
+        const int pdl = get_option(OPT_K4_PDL) != 0;
         for (int pass = 0; pass < 2; ++pass)
             for (int step = 1; step < blen; ++step) {
-                if (pass == 0)
-                    k4_step<false><<<grid, 256, 0, st>>>(ff, fb, out, lists, counts, h, w, step, b);
-                else
-                    k4_step<true><<<grid, 256, 0, st>>>(ff, fb, out, lists, counts, h, w, step, b);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid;
+                cfg.blockDim = dim3(256);
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr;
+                // the first step after k4_pack is an ordinary launch: its warm-up part reads the lists
+                // that k4_pack wrote, and only a full stream dependency makes those visible
+                cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
+                const int warm_next = warm && !(pass == 1 && step == blen - 1);
+                cudaError_t le = pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step<false>, ff, fb, out, (const uint32_t *)lists,
+                                                                (const uint32_t *)counts, h, w, step, warm_next, b)
+                                           : cudaLaunchKernelEx(&cfg, k4_step<true>, ff, fb, out, (const uint32_t *)lists,
+                                                                (const uint32_t *)counts, h, w, step, warm_next, b);
+                if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step)");
                 VV_POST_LAUNCH("k4_step");
             }
     }
