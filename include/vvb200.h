@@ -57,7 +57,6 @@ VV_API void vv_reset_launch_count(void);
  *   "k3_tma"     1 = K3 stages the original strip through shared memory with bulk async copies
  *                (TMA) when the frame is 16-byte aligned, 0 = register pass-through kernel.
  *   "k3_tma_rows" maximum rows per staged strip (2..16);  "k3_tma_threads" 256, 384 or 512.
- *   "k4_warm"    1 = every propagation step prefetches the next step's flow/tap sectors into L2.
  *   "k4_pdl"     1 = propagation steps use programmatic dependent launch. */
 VV_API int vv_set_option(const char *name, int value);
 VV_API int vv_get_option(const char *name, int *value);

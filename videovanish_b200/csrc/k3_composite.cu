@@ -69,30 +69,42 @@ __device__ __forceinline__ uint32_t bit_window(const uint32_t *row, int col0) {
     return __funnelshift_r(row[k], row[k + 1], off);
 }
 
-// The 6 bytes (RGB of source pixel sx, RGB of sx+1) of one inference-resolution row as a 64-bit
-// value.  Fast path: two aligned 64-bit loads + funnel shift; byte loads near the row end (where
-// sx+1 is clamped to w-1; its weight is 0 there) or when the row is not 8-byte aligned.
-__device__ __forceinline__ unsigned long long load_pixel_pair(const uint8_t *__restrict__ row, int sx, int w,
-                                                              bool row_aligned8) {
-    const int o = sx * 3, a8 = o & ~7;
-    if (row_aligned8 && a8 + 16 <= w * 3) {
-        const unsigned long long lo = __ldg(reinterpret_cast<const unsigned long long *>(row + a8));
-        const unsigned long long hi = __ldg(reinterpret_cast<const unsigned long long *>(row + a8 + 8));
-        const int sh = (o & 7) * 8;
-        return sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+// The 6 bytes (RGB of source pixel sx, RGB of sx+1) of one inference-resolution row as two words
+// (lo = bytes 0..3, hi = bytes 4..7 from the pair's first byte).  Fast path: three aligned 32-bit
+// loads + two byte permutes; byte loads near the row end (where sx+1 is clamped to w-1; its weight
+// is 0 there) or when the row is not 4-byte aligned.
+struct PixelPair {
+    uint32_t lo, hi;
+};
+__device__ __forceinline__ PixelPair load_pixel_pair(const uint8_t *__restrict__ row, int sx, int w, bool row_aligned4) {
+    const int o = sx * 3, a4 = o & ~3;
+    PixelPair r;
+    if (row_aligned4 && a4 + 12 <= w * 3) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + a4);
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(o & 3);
+        r.lo = __byte_perm(w0, w1, sel);
+        r.hi = __byte_perm(w1, w2, sel);
+    } else {
+        const int o1 = min(sx + 1, w - 1) * 3;
+        r.lo = __ldg(row + o) | (__ldg(row + o + 1) << 8) | (__ldg(row + o + 2) << 16) | (__ldg(row + o1) << 24);
+        r.hi = __ldg(row + o1 + 1) | (__ldg(row + o1 + 2) << 8);
     }
-    const int o1 = min(sx + 1, w - 1) * 3;
-    const uint32_t p0 = __ldg(row + o) | (__ldg(row + o + 1) << 8) | (__ldg(row + o + 2) << 16);
-    const uint32_t p1 = __ldg(row + o1) | (__ldg(row + o1 + 1) << 8) | (__ldg(row + o1 + 2) << 16);
-    return (unsigned long long)p0 | ((unsigned long long)p1 << 24);
+    return r;
 }
 
 // Horizontal pass for channel C of one source row: S[sx][C]*w0 + S[sx+1][C]*w1 as ONE dot product
 // (wts = w0 | w1 << 16, both u16; the two source bytes gathered by a byte permute).
 template <int C>
-__device__ __forceinline__ int hpass(unsigned long long pair, uint32_t wts) {
-    const uint32_t two = __byte_perm((uint32_t)pair, (uint32_t)(pair >> 32), 0x30 + 0x11 * C);   // bytes C, C+3
-    return (int)__dp2a_lo(wts, two, 0u);
+__device__ __forceinline__ uint32_t hpass(const PixelPair &pair, uint32_t wts) {
+    const uint32_t two = __byte_perm(pair.lo, pair.hi, 0x30 + 0x11 * C);   // bytes C, C+3
+    return __dp2a_lo(wts, two, 0u);
+}
+
+// Vertical pass (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2 with the weights pre-shifted by 16,
+// so that each product-and-shift is one multiply-high.
+__device__ __forceinline__ uint32_t vpass(uint32_t b0s, uint32_t b1s, uint32_t h0, uint32_t h1) {
+    return (__umulhi(b0s, h0 >> 4) + __umulhi(b1s, h1 >> 4) + 2u) >> 2;
 }
 
 constexpr int K3_THREADS = 256;    // register pass-through kernel
@@ -101,7 +113,7 @@ constexpr int K3_QUEUE1 = 128;    // work items (4-pixel quads) per warp iterati
 
 // Work item = one 4-pixel quad (x aligned to 4) that contains at least one pixel with alpha > 0:
 //   .x = x | row-in-strip << 16 | need(4) << 20 | inside(4) << 24
-//   .y = level bit planes l0 | l1 << 4 | l2 << 8 (SMALL_R; per-pixel LUT index = l0 | l1<<1 | l2<<2 | inside<<3)
+//   .y = one LUT index nibble per pixel (SMALL_R): class | inside << 3 for pixel i at bits 4i..4i+3
 
 // K3_NT = 16-pixel groups per thread and iteration.
 // TMA: the strip of original pixels is brought into shared memory by bulk async copies (one
@@ -181,7 +193,7 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
     // ---------------- phase 2: 16-pixel groups
     const int G = (W0 + 15) >> 4;
     const uint8_t *inp_t = inp + t * h * (long long)w * 3;
-    const bool inp_aligned8 = ((w * 3) % 8 == 0) && ((uintptr_t)inp_t % 8 == 0);
+    const bool inp_aligned4 = ((w * 3) % 4 == 0) && ((uintptr_t)inp_t % 4 == 0);
     const bool hard = !SMALL_R && ft.n == 0;
     // which LUT levels have alpha > 0 (SMALL_R): all inside levels, outside levels whose cost < F
     uint32_t lut_pos = 0;
@@ -318,7 +330,14 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                     const int b = 8 + 4 * q;
                     uint2 e;
                     e.x = (uint32_t)(x0[k] + 4 * q) | ((uint32_t)row[k] << 16) | (n4 << 20) | (((M2[k] >> b) & 15u) << 24);
-                    e.y = ((L0[k] >> b) & 15u) | (((L1[k] >> b) & 15u) << 4) | (((L2[k] >> b) & 15u) << 8);
+                    // 4x4 bit transpose: planes (l0, l1, l2, inside) x pixels -> one LUT index nibble per pixel
+                    uint32_t x4 = ((L0[k] >> b) & 15u) | (((L1[k] >> b) & 15u) << 4) | (((L2[k] >> b) & 15u) << 8) |
+                                  (((M2[k] >> b) & 15u) << 12);
+                    uint32_t tt = (x4 ^ (x4 >> 3)) & 0x0a0au;
+                    x4 ^= tt ^ (tt << 3);
+                    tt = (x4 ^ (x4 >> 6)) & 0x00ccu;
+                    x4 ^= tt ^ (tt << 6);
+                    e.y = x4;
                     queue[pos++] = e;
                 }
             }
@@ -336,7 +355,7 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                 const uint32_t n4 = (item.x >> 20) & 15u, in4 = (item.x >> 24) & 15u;
                 const int yy = y0 + r;
                 const Tap ty = yt[yy];
-                const int b0 = (short)(ty.w & 0xffff), b1 = ty.w >> 16;
+                const uint32_t b0s = (uint32_t)(ty.w & 0xffff) << 16, b1s = (uint32_t)ty.w & 0xffff0000u;
                 const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
                 const uint8_t *r0 = inp_t + ya * w * 3;
                 const uint8_t *r1 = inp_t + yb * w * 3;
@@ -373,8 +392,7 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                     if ((n4 >> i) & 1u) {
                         float a;
                         if (SMALL_R) {
-                            a = lut[((item.y >> i) & 1u) | (((item.y >> (4 + i)) & 1u) << 1) |
-                                    (((item.y >> (8 + i)) & 1u) << 2) | (((in4 >> i) & 1u) << 3)];
+                            a = lut[(item.y >> (4 * i)) & 15u];      // > 0 by construction of `need`
                         } else {
                             const bool inside = (in4 >> i) & 1u;
                             if (hard) {
@@ -393,19 +411,30 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                                 a = inside ? alpha_from(d, 0.f, ft.div) : alpha_from(0.f, d, ft.div);
                             }
                         }
-                        if (a > 0.f) {
-                            const unsigned long long pr0 = load_pixel_pair(r0, ofs[i], w, inp_aligned8);
-                            const unsigned long long pr1 = load_pixel_pair(r1, ofs[i], w, inp_aligned8);
-                            const float na = __fsub_rn(1.f, a);
-                            uint32_t res[3];
-                            res[0] = (uint32_t)vlin3(b0, b1, hpass<0>(pr0, wts[i]), hpass<0>(pr1, wts[i]));
-                            res[1] = (uint32_t)vlin3(b0, b1, hpass<1>(pr0, wts[i]), hpass<1>(pr1, wts[i]));
-                            res[2] = (uint32_t)vlin3(b0, b1, hpass<2>(pr0, wts[i]), hpass<2>(pr1, wts[i]));
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const int ob = 3 * i + c;
-                                if (a < 1.f) res[c] = blend_u8(a, na, res[c], byte_of(o[ob >> 2], ob & 3));
-                                o[ob >> 2] = (o[ob >> 2] & ~(0xffu << (8 * (ob & 3)))) | (res[c] << (8 * (ob & 3)));
+                        if (SMALL_R || a > 0.f) {
+                            const PixelPair pr0 = load_pixel_pair(r0, ofs[i], w, inp_aligned4);
+                            const PixelPair pr1 = load_pixel_pair(r1, ofs[i], w, inp_aligned4);
+                            uint32_t cr = vpass(b0s, b1s, hpass<0>(pr0, wts[i]), hpass<0>(pr1, wts[i]));
+                            uint32_t cg = vpass(b0s, b1s, hpass<1>(pr0, wts[i]), hpass<1>(pr1, wts[i]));
+                            uint32_t cb = vpass(b0s, b1s, hpass<2>(pr0, wts[i]), hpass<2>(pr1, wts[i]));
+                            if (a < 1.f) {
+                                const float na = __fsub_rn(1.f, a);
+                                cr = blend_u8(a, na, cr, byte_of(o[(3 * i) >> 2], (3 * i) & 3));
+                                cg = blend_u8(a, na, cg, byte_of(o[(3 * i + 1) >> 2], (3 * i + 1) & 3));
+                                cb = blend_u8(a, na, cb, byte_of(o[(3 * i + 2) >> 2], (3 * i + 2) & 3));
+                            }
+                            const uint32_t rgb = cr | (cg << 8) | (cb << 16);
+                            // write the 3 bytes at byte offset 3*i of the 12-byte quad with byte permutes
+                            if (i == 0) {
+                                o[0] = __byte_perm(o[0], rgb, 0x3654);
+                            } else if (i == 1) {
+                                o[0] = __byte_perm(o[0], rgb, 0x4210);
+                                o[1] = __byte_perm(o[1], rgb, 0x3265);
+                            } else if (i == 2) {
+                                o[1] = __byte_perm(o[1], rgb, 0x5410);
+                                o[2] = __byte_perm(o[2], rgb, 0x3216);
+                            } else {
+                                o[2] = __byte_perm(o[2], rgb, 0x6540);
                             }
                         }
                     }

@@ -46,11 +46,9 @@ __device__ __forceinline__ float unnormalized(float pos, int size) {
 }
 
 // One hole pixel: returns the new packed state.
-__device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, uint32_t cur,
-                                                    const float2 *__restrict__ flow_prop,
+__device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, uint32_t cur, const float2 f,
                                                     const float2 *__restrict__ flow_check,
                                                     const uint32_t *__restrict__ prev) {
-    const float2 f = __ldg(flow_prop + (long long)y * w + x);
     const float ix = unnormalized(__fadd_rn((float)x, f.x), w);
     const float iy = unnormalized(__fadd_rn((float)y, f.y), h);
     const float x0f = floorf(ix), y0f = floorf(iy);
@@ -101,7 +99,9 @@ __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
     k4_pack(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, uint32_t *__restrict__ state,
-            uint32_t *__restrict__ lists, uint32_t *__restrict__ counts, int h, int w, long long first_out_frame,
+            const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, int n_frames,
+            uint32_t *__restrict__ lists, float2 *__restrict__ list_ff, float2 *__restrict__ list_fb,
+            uint32_t *__restrict__ counts, int h, int w, long long first_out_frame,
             const __grid_constant__ SubBatch batch) {
     const long long of = first_out_frame + blockIdx.y;          // output frame handled by this CTA row
     int s = 0;
@@ -112,6 +112,10 @@ __global__ void __launch_bounds__(256)
     const uint8_t *mk = masks + gframe * npx;
     uint32_t *dst = state + of * npx;
     uint32_t *list = lists + of * npx;
+    // flow used to propagate INTO this frame: backward pass flows_f[gframe], forward pass flows_b[gframe-1]
+    const float2 *pf = (gframe + 1 < n_frames) ? flows_f + gframe * npx : nullptr;
+    const float2 *pb = (gframe >= 1) ? flows_b + (gframe - 1) * npx : nullptr;
+    float2 *lff = list_ff + of * npx, *lfb = list_fb + of * npx;
     const int lane = threadIdx.x & 31;
     const long long ngroups = (npx + 3) >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -162,7 +166,12 @@ __global__ void __launch_bounds__(256)
         uint32_t pos = base + (uint32_t)(pre - cnt);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if ((holes >> i) & 1u) list[pos++] = (uint32_t)(p0 + i);
+            if ((holes >> i) & 1u) {
+                list[pos] = (uint32_t)(p0 + i);
+                lff[pos] = pf ? __ldg(pf + p0 + i) : make_float2(0.f, 0.f);
+                lfb[pos] = pb ? __ldg(pb + p0 + i) : make_float2(0.f, 0.f);
+                ++pos;
+            }
     }
 }
 
@@ -174,88 +183,42 @@ __global__ void __launch_bounds__(256)
 //                                               idx-1 (already the forward result)
 // Frame len-1 / frame 0 are the first step of their pass and stay as they are.
 //
-// The chain of ~2*(len-1) dependent launches is latency bound (per item: list -> flow -> 8 taps),
-// so every launch also WARMS L2 FOR THE NEXT STEP: it walks the next frame's hole list, loads the
-// flow vector of each hole and prefetches the sectors its taps will touch.  That part does not
-// depend on the previous step, so with programmatic dependent launch it runs while the previous
-// step is still executing; `griddepcontrol.wait` then fences the part that needs its results.
-struct StepView {
-    const float2 *flow_prop, *flow_check;
-    long long of;          // frame index in the state / list buffers
-    bool valid;
-};
-
-template <bool PASS2>
-__device__ __forceinline__ StepView step_view(const SubDesc &sd, int step, const float2 *flows_f, const float2 *flows_b,
-                                              long long npx) {
-    StepView v;
-    v.valid = step >= 1 && step < sd.len;
-    const int idx = PASS2 ? step : sd.len - 1 - step;
-    const long long gframe = sd.start + idx;
-    // flows: backward pass uses flow index idx (prop = forward flow), forward pass idx-1 (prop = backward flow)
-    const long long fi = PASS2 ? gframe - 1 : gframe;
-    v.flow_prop = (PASS2 ? flows_b : flows_f) + fi * npx;
-    v.flow_check = (PASS2 ? flows_f : flows_b) + fi * npx;
-    v.of = sd.out_frame + idx;
-    return v;
-}
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Touch what `propagate_pixel` will read for hole pixel p of a future step.
-__device__ __forceinline__ void warm_pixel(uint32_t p, int h, int w, const StepView &v, const uint32_t *state_frame) {
-    const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
-    const float2 f = __ldg(v.flow_prop + p);
-    const float ix = unnormalized(__fadd_rn((float)x, f.x), w);
-    const float iy = unnormalized(__fadd_rn((float)y, f.y), h);
-    const int x0 = (int)fminf(fmaxf(floorf(ix), 0.f), (float)(w - 1));
-    const int y0 = (int)fminf(fmaxf(floorf(iy), 0.f), (float)(h - 1));
-    const long long i00 = (long long)y0 * w + x0;
-    const long long i10 = (long long)min(y0 + 1, h - 1) * w + x0;
-    prefetch_l2(v.flow_check + i00);
-    prefetch_l2(v.flow_check + i00 + 1);
-    prefetch_l2(v.flow_check + i10);
-    prefetch_l2(v.flow_check + i10 + 1);
-    prefetch_l2(state_frame + p);
-}
-
+// The chain of 2*(len-1) dependent launches is latency bound, so the per-item dependency chain is
+// kept at two memory round trips: the list entry carries the pixel index AND its propagation flow
+// vector (recorded by k4_pack), then come the 8 taps.  With programmatic dependent launch the next
+// step's CTAs are resident and have their list entries loaded before the previous step retires.
 template <bool PASS2>
 __global__ void __launch_bounds__(256)
     k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state,
-            const uint32_t *__restrict__ lists, const uint32_t *__restrict__ counts, int h, int w, int step,
-            int warm_next, const __grid_constant__ SubBatch batch) {
-    asm volatile("griddepcontrol.launch_dependents;");      // the next step may start its warm-up part
+            const uint32_t *__restrict__ lists, const float2 *__restrict__ list_ff, const float2 *__restrict__ list_fb,
+            const uint32_t *__restrict__ counts, int h, int w, int step, const __grid_constant__ SubBatch batch) {
+    asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
     const SubDesc sd = batch.sub[blockIdx.y];
+    if (step >= sd.len) return;
     const long long npx = (long long)h * w;
+    const int idx = PASS2 ? step : sd.len - 1 - step;
+    const long long gframe = sd.start + idx;
+    // check flow: backward pass flows_b[idx] (prop = flows_f[idx]), forward pass flows_f[idx-1] (prop = flows_b[idx-1])
+    const float2 *flow_check = (PASS2 ? flows_f + (gframe - 1) * npx : flows_b + gframe * npx);
+    const long long of = sd.out_frame + idx;
+    uint32_t *cur = state + of * npx;
+    const uint32_t *prev = state + (PASS2 ? of - 1 : of + 1) * npx;
+    const uint32_t *list = lists + of * npx;
+    const float2 *lflow = (PASS2 ? list_fb : list_ff) + of * npx;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-
-    if (warm_next) {
-        // next step: step+1 of this pass, or step 1 of the forward pass after the last backward step
-        StepView nv;
-        if (PASS2 || step + 1 < sd.len)
-            nv = step_view<PASS2>(sd, step + 1, flows_f, flows_b, npx);
-        else
-            nv = step_view<true>(sd, 1, flows_f, flows_b, npx);
-        if (nv.valid) {
-            const uint32_t *nlist = lists + nv.of * npx;
-            const uint32_t nn = counts[nv.of];
-            for (uint32_t i = tid; i < nn; i += stride) warm_pixel(nlist[i], h, w, nv, state + nv.of * npx);
-        }
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");       // results of the previous step are visible
-
-    const StepView v = step_view<PASS2>(sd, step, flows_f, flows_b, npx);
-    if (!v.valid) return;
-    uint32_t *cur = state + v.of * npx;
-    const uint32_t *prev = state + (PASS2 ? v.of - 1 : v.of + 1) * npx;
-    const uint32_t *list = lists + v.of * npx;
-    const uint32_t n = counts[v.of];
+    // everything above and these first loads only touch what k4_pack wrote (completed before the
+    // first step was launched); the previous step's results are needed from here on
+    const uint32_t n = counts[of];
+    uint32_t p = 0;
+    float2 f = make_float2(0.f, 0.f);
+    if (tid < n) p = list[tid], f = lflow[tid];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (uint32_t i = tid; i < n; i += stride) {
-        const uint32_t p = list[i];
-        const uint32_t cv = PASS2 ? cur[p] : (ST_HOLE | ST_ZERO);   // issued together with the flow load below
+        if (i != tid) p = list[i], f = lflow[i];
+        const uint32_t cv = PASS2 ? cur[p] : (ST_HOLE | ST_ZERO);
         const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
-        const uint32_t nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, v.flow_prop, v.flow_check, prev);
+        const uint32_t nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, f, flow_check, prev);
         // pixels already filled by the backward pass keep their value
         if ((cv & ST_HOLE) && nv != (ST_HOLE | ST_ZERO)) cur[p] = nv;
     }
@@ -282,8 +245,9 @@ using namespace vv;
 
 extern "C" size_t vv_propagate_workspace_bytes(int n_out_frames, int h, int w) {
     if (n_out_frames <= 0 || h <= 0 || w <= 0) return 0;
-    // hole-pixel lists (one u32 per pixel, worst case) + one counter per frame
-    return align_up((size_t)n_out_frames * h * w * 4, 256) + align_up((size_t)n_out_frames * 4, 256);
+    // hole lists, worst case one entry per pixel: u32 index + two float2 flows; one counter per frame
+    return align_up((size_t)n_out_frames * h * w * 4, 256) + 2 * align_up((size_t)n_out_frames * h * w * 8, 256) +
+           align_up((size_t)n_out_frames * 4, 256);
 }
 
 extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const float *flows_f, const float *flows_b,
@@ -307,7 +271,10 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
     const bool vec = (npx % 4 == 0) && ((uintptr_t)frames % 4 == 0) && ((uintptr_t)masks % 4 == 0) &&
                      ((uintptr_t)out % 16 == 0);
     uint32_t *lists = (uint32_t *)workspace;
-    uint32_t *counts = (uint32_t *)((uint8_t *)workspace + align_up((size_t)total * npx * 4, 256));
+    const size_t l4 = align_up((size_t)total * npx * 4, 256), l8 = align_up((size_t)total * npx * 8, 256);
+    float2 *list_ff = (float2 *)((uint8_t *)workspace + l4);
+    float2 *list_fb = (float2 *)((uint8_t *)workspace + l4 + l8);
+    uint32_t *counts = (uint32_t *)((uint8_t *)workspace + l4 + 2 * l8);
     const float2 *ff = (const float2 *)flows_f, *fb = (const float2 *)flows_b;
     cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)total * 4, st);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
@@ -331,16 +298,17 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             const int ny = (int)min(32768LL, bframes - f0);
             const int gx = max(1, min(ceil_div((npx + 3) / 4, 256), ceil_div(148 * 16, ny)));
             if (vec)
-                k4_pack<true><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, lists, counts, h, w, first + f0, b);
+                k4_pack<true><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, n_frames, lists, list_ff, list_fb, counts, h, w,
+                                                            first + f0, b);
             else
-                k4_pack<false><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, lists, counts, h, w, first + f0, b);
+                k4_pack<false><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, n_frames, lists, list_ff, list_fb, counts, h, w,
+                                                             first + f0, b);
             VV_POST_LAUNCH("k4_pack");
         }
         // the serial scans touch hole pixels only; a few CTAs per SM, split over the windows
         // (the hole counts live on the device: the grid is sized for ~1 item per thread at a 25 % hole
         // fraction and strides over the list otherwise)
         dim3 grid(max(1, min(ceil_div(npx / 4, 256), ceil_div(148 * 16, b.n))), b.n);
-        const int warm = get_option(OPT_K4_WARM) != 0;
         const int pdl = get_option(OPT_K4_PDL) != 0;
         for (int pass = 0; pass < 2; ++pass)
             for (int step = 1; step < blen; ++step) {
@@ -352,14 +320,16 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 attr[0].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = attr;
-                // the first step after k4_pack is an ordinary launch: its warm-up part reads the lists
-                // that k4_pack wrote, and only a full stream dependency makes those visible
+                // the first step after k4_pack is an ordinary launch: steps read the lists k4_pack wrote
+                // BEFORE their griddepcontrol.wait, and only a full stream dependency makes those visible
                 cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
-                const int warm_next = warm && !(pass == 1 && step == blen - 1);
-                cudaError_t le = pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step<false>, ff, fb, out, (const uint32_t *)lists,
-                                                                (const uint32_t *)counts, h, w, step, warm_next, b)
-                                           : cudaLaunchKernelEx(&cfg, k4_step<true>, ff, fb, out, (const uint32_t *)lists,
-                                                                (const uint32_t *)counts, h, w, step, warm_next, b);
+                cudaError_t le =
+                    pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step<false>, ff, fb, out, (const uint32_t *)lists,
+                                                   (const float2 *)list_ff, (const float2 *)list_fb,
+                                                   (const uint32_t *)counts, h, w, step, b)
+                              : cudaLaunchKernelEx(&cfg, k4_step<true>, ff, fb, out, (const uint32_t *)lists,
+                                                   (const float2 *)list_ff, (const float2 *)list_fb,
+                                                   (const uint32_t *)counts, h, w, step, b);
                 if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step)");
                 VV_POST_LAUNCH("k4_step");
             }
