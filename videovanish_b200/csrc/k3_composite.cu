@@ -387,6 +387,30 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                         }
                     }
                 }
+                // Source pixels for all four output pixels are fetched up front (one L2 round trip per
+                // quad instead of one per pixel).  ofs[] is non-decreasing, so the aligned fast path is
+                // valid for the whole quad when it is valid for the last pixel.
+                PixelPair pr0[4], pr1[4];
+                const bool fast = inp_aligned4 && (((ofs[3] * 3) & ~3) + 12 <= w * 3);
+                if (fast) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int o3 = ofs[i] * 3, a4 = o3 & ~3;
+                        const uint32_t *q0 = reinterpret_cast<const uint32_t *>(r0 + a4);
+                        const uint32_t *q1 = reinterpret_cast<const uint32_t *>(r1 + a4);
+                        const uint32_t u0 = __ldg(q0), u1 = __ldg(q0 + 1), u2 = __ldg(q0 + 2);
+                        const uint32_t v0 = __ldg(q1), v1 = __ldg(q1 + 1), v2 = __ldg(q1 + 2);
+                        const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(o3 & 3);
+                        pr0[i].lo = __byte_perm(u0, u1, sel), pr0[i].hi = __byte_perm(u1, u2, sel);
+                        pr1[i].lo = __byte_perm(v0, v1, sel), pr1[i].hi = __byte_perm(v1, v2, sel);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        pr0[i] = load_pixel_pair(r0, ofs[i], w, false);
+                        pr1[i] = load_pixel_pair(r1, ofs[i], w, false);
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if ((n4 >> i) & 1u) {
@@ -412,11 +436,9 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                             }
                         }
                         if (SMALL_R || a > 0.f) {
-                            const PixelPair pr0 = load_pixel_pair(r0, ofs[i], w, inp_aligned4);
-                            const PixelPair pr1 = load_pixel_pair(r1, ofs[i], w, inp_aligned4);
-                            uint32_t cr = vpass(b0s, b1s, hpass<0>(pr0, wts[i]), hpass<0>(pr1, wts[i]));
-                            uint32_t cg = vpass(b0s, b1s, hpass<1>(pr0, wts[i]), hpass<1>(pr1, wts[i]));
-                            uint32_t cb = vpass(b0s, b1s, hpass<2>(pr0, wts[i]), hpass<2>(pr1, wts[i]));
+                            uint32_t cr = vpass(b0s, b1s, hpass<0>(pr0[i], wts[i]), hpass<0>(pr1[i], wts[i]));
+                            uint32_t cg = vpass(b0s, b1s, hpass<1>(pr0[i], wts[i]), hpass<1>(pr1[i], wts[i]));
+                            uint32_t cb = vpass(b0s, b1s, hpass<2>(pr0[i], wts[i]), hpass<2>(pr1[i], wts[i]));
                             if (a < 1.f) {
                                 const float na = __fsub_rn(1.f, a);
                                 cr = blend_u8(a, na, cr, byte_of(o[(3 * i) >> 2], (3 * i) & 3));
