@@ -92,31 +92,54 @@ __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, 
     return inb ? (src & ~ST_HOLE) : ST_ZERO;
 }
 
-// ---- k4_pack: frames + masks -> packed state, and the per-frame list of hole pixels ------------
-// One launch for every frame of every window of the batch (blockIdx.y = output frame).  Each warp
-// compacts the hole pixels of its 128-pixel span and appends them to the frame's list with one
-// atomicAdd (the order inside a list is irrelevant: items of a step are independent).
+// Hole lists.  One entry per hole pixel: position (x | y << 16) and the flow vector that will
+// propagate INTO that pixel, so that a step's dependency chain is two memory round trips (entry,
+// then the 8 taps).  Two sets per frame: `l1` drives the backward pass (flow = flows_f[frame]),
+// `l2` the forward pass (flow = flows_b[frame-1]) and only holds the holes the backward pass left.
+struct HoleLists {
+    uint32_t *xy;        // [frames][npx]
+    float2 *flow;        // [frames][npx]
+    uint32_t *count;     // [frames]
+};
+
+// Appends the lanes with `take` set to list `of` (one atomicAdd per warp).  All 32 lanes must call.
+__device__ __forceinline__ void warp_append(const HoleLists &l, long long of, long long npx, bool take, uint32_t xy,
+                                            float2 flow) {
+    const uint32_t m = __ballot_sync(0xffffffffu, take);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(l.count + of, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) {
+        const long long pos = of * npx + base + __popc(m & ((1u << lane) - 1u));
+        l.xy[pos] = xy;
+        l.flow[pos] = flow;
+    }
+}
+
+// ---- k4_pack: frames + masks -> packed state, and the per-frame lists of hole pixels -----------
+// One launch for every frame of every window of the batch (blockIdx.y = output frame).  Holes of
+// the last frame of a window are never touched by the backward pass, so they go straight to `l2`.
 template <bool VEC>
 __global__ void __launch_bounds__(256)
     k4_pack(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, uint32_t *__restrict__ state,
-            const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, int n_frames,
-            uint32_t *__restrict__ lists, float2 *__restrict__ list_ff, float2 *__restrict__ list_fb,
-            uint32_t *__restrict__ counts, int h, int w, long long first_out_frame,
-            const __grid_constant__ SubBatch batch) {
+            const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, HoleLists l1, HoleLists l2, int h,
+            int w, long long first_out_frame, const __grid_constant__ SubBatch batch) {
     const long long of = first_out_frame + blockIdx.y;          // output frame handled by this CTA row
     int s = 0;
     while (s + 1 < batch.n && batch.sub[s + 1].out_frame <= of) ++s;
-    const long long gframe = batch.sub[s].start + (of - batch.sub[s].out_frame);
+    const int idx = (int)(of - batch.sub[s].out_frame), len = batch.sub[s].len;
+    const long long gframe = batch.sub[s].start + idx;
     const long long npx = (long long)h * w;
     const uint8_t *fr = frames + gframe * npx * 3;
     const uint8_t *mk = masks + gframe * npx;
     uint32_t *dst = state + of * npx;
-    uint32_t *list = lists + of * npx;
-    // flow used to propagate INTO this frame: backward pass flows_f[gframe], forward pass flows_b[gframe-1]
-    const float2 *pf = (gframe + 1 < n_frames) ? flows_f + gframe * npx : nullptr;
-    const float2 *pb = (gframe >= 1) ? flows_b + (gframe - 1) * npx : nullptr;
-    float2 *lff = list_ff + of * npx, *lfb = list_fb + of * npx;
-    const int lane = threadIdx.x & 31;
+    const bool last = idx == len - 1;
+    const bool listed = len > 1;                                // a single-frame window has no steps at all
+    // flow that propagates INTO this frame: backward pass flows_f[gframe], forward pass flows_b[gframe-1]
+    const float2 *pflow = last ? flows_b + (gframe - 1) * npx : flows_f + gframe * npx;
+    const HoleLists &dl = last ? l2 : l1;
     const long long ngroups = (npx + 3) >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long iters = (ngroups + stride - 1) / stride;
@@ -148,50 +171,37 @@ __global__ void __launch_bounds__(256)
                 }
             }
         }
+        if (!listed) continue;
         uint32_t holes = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) holes |= (uint32_t)(i < n && (c[i] & ST_HOLE)) << i;
         if (__ballot_sync(0xffffffffu, holes != 0) == 0) continue;       // warp-uniform
-        const int cnt = __popc(holes);
-        int pre = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, pre, d);
-            if (lane >= d) pre += v;
+        for (int i = 0; i < 4; ++i) {
+            const bool take = (holes >> i) & 1u;
+            const long long p = p0 + i;
+            const uint32_t y = take ? (uint32_t)(p / w) : 0u, x = take ? (uint32_t)(p - (long long)y * w) : 0u;
+            warp_append(dl, of, npx, take, x | (y << 16), take ? __ldg(pflow + p) : make_float2(0.f, 0.f));
         }
-        const int total = __shfl_sync(0xffffffffu, pre, 31);
-        uint32_t base = 0;
-        if (lane == 31) base = atomicAdd(counts + of, (uint32_t)total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        uint32_t pos = base + (uint32_t)(pre - cnt);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if ((holes >> i) & 1u) {
-                list[pos] = (uint32_t)(p0 + i);
-                lff[pos] = pf ? __ldg(pf + p0 + i) : make_float2(0.f, 0.f);
-                lfb[pos] = pb ? __ldg(pb + p0 + i) : make_float2(0.f, 0.f);
-                ++pos;
-            }
     }
 }
 
 // ---- k4_step: one time step of one direction, in place, over the hole lists -------------------
 // blockIdx.y = sub-video.  The state buffer holds the input frames after k4_pack, the backward
 // result after pass 1 and the forward result after pass 2:
-//   PASS2 == false (backward, t = len-2 .. 0):  frame idx is updated from frame idx+1
+//   PASS2 == false (backward, t = len-2 .. 0):  frame idx is updated from frame idx+1; holes that
+//                                               stay holes are appended to the frame's forward list
 //   PASS2 == true  (forward,  t = 1 .. len-1):  frame idx (backward result) is updated from frame
 //                                               idx-1 (already the forward result)
 // Frame len-1 / frame 0 are the first step of their pass and stay as they are.
 //
 // The chain of 2*(len-1) dependent launches is latency bound, so the per-item dependency chain is
-// kept at two memory round trips: the list entry carries the pixel index AND its propagation flow
-// vector (recorded by k4_pack), then come the 8 taps.  With programmatic dependent launch the next
-// step's CTAs are resident and have their list entries loaded before the previous step retires.
+// kept at two memory round trips and the forward pass only visits what the backward pass left.
+// With programmatic dependent launch the next step's CTAs are resident before this one retires.
 template <bool PASS2>
 __global__ void __launch_bounds__(256)
-    k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state,
-            const uint32_t *__restrict__ lists, const float2 *__restrict__ list_ff, const float2 *__restrict__ list_fb,
-            const uint32_t *__restrict__ counts, int h, int w, int step, const __grid_constant__ SubBatch batch) {
+    k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state, HoleLists l1,
+            HoleLists l2, int h, int w, int step, const __grid_constant__ SubBatch batch) {
     asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
     const SubDesc sd = batch.sub[blockIdx.y];
     if (step >= sd.len) return;
@@ -200,27 +210,41 @@ __global__ void __launch_bounds__(256)
     const long long gframe = sd.start + idx;
     // check flow: backward pass flows_b[idx] (prop = flows_f[idx]), forward pass flows_f[idx-1] (prop = flows_b[idx-1])
     const float2 *flow_check = (PASS2 ? flows_f + (gframe - 1) * npx : flows_b + gframe * npx);
+    const float2 *next_flow = flows_b + (gframe - 1) * npx;       // forward-pass flow into this frame (idx >= 1)
     const long long of = sd.out_frame + idx;
     uint32_t *cur = state + of * npx;
     const uint32_t *prev = state + (PASS2 ? of - 1 : of + 1) * npx;
-    const uint32_t *list = lists + of * npx;
-    const float2 *lflow = (PASS2 ? list_fb : list_ff) + of * npx;
+    const HoleLists &li = PASS2 ? l2 : l1;
+    const uint32_t *lxy = li.xy + of * npx;
+    const float2 *lflow = li.flow + of * npx;
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    // everything above and these first loads only touch what k4_pack wrote (completed before the
-    // first step was launched); the previous step's results are needed from here on
-    const uint32_t n = counts[of];
-    uint32_t p = 0;
+    const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);    // warp-uniform loop bounds
+    const uint32_t lane = threadIdx.x & 31u;
+    // The backward pass reads what k4_pack wrote (complete before the first step was launched) and
+    // may load its first entry early; the forward lists are produced by the preceding launches.
+    uint32_t xy = 0;
     float2 f = make_float2(0.f, 0.f);
-    if (tid < n) p = list[tid], f = lflow[tid];
+    uint32_t n = 0;
+    if (!PASS2) {
+        n = li.count[of];
+        if (first + lane < n) xy = lxy[first + lane], f = lflow[first + lane];
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (uint32_t i = tid; i < n; i += stride) {
-        if (i != tid) p = list[i], f = lflow[i];
-        const uint32_t cv = PASS2 ? cur[p] : (ST_HOLE | ST_ZERO);
-        const int y = (int)(p / (uint32_t)w), x = (int)(p - (uint32_t)y * (uint32_t)w);
-        const uint32_t nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, f, flow_check, prev);
-        // pixels already filled by the backward pass keep their value
-        if ((cv & ST_HOLE) && nv != (ST_HOLE | ST_ZERO)) cur[p] = nv;
+    if (PASS2) n = li.count[of];
+    for (uint32_t base = first; base < n; base += stride) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        if (valid && (PASS2 || base != first)) xy = lxy[i], f = lflow[i];
+        const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+        uint32_t nv = ST_HOLE | ST_ZERO;
+        if (valid) {
+            nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, f, flow_check, prev);
+            if (nv != (ST_HOLE | ST_ZERO)) cur[(long long)y * w + x] = nv;
+        }
+        if (!PASS2 && idx >= 1) {       // still a hole: the forward pass gets another chance
+            const bool remains = valid && nv == (ST_HOLE | ST_ZERO);
+            warp_append(l2, of, npx, remains, xy, remains ? __ldg(next_flow + (long long)y * w + x) : f);
+        }
     }
 }
 
@@ -245,9 +269,9 @@ using namespace vv;
 
 extern "C" size_t vv_propagate_workspace_bytes(int n_out_frames, int h, int w) {
     if (n_out_frames <= 0 || h <= 0 || w <= 0) return 0;
-    // hole lists, worst case one entry per pixel: u32 index + two float2 flows; one counter per frame
-    return align_up((size_t)n_out_frames * h * w * 4, 256) + 2 * align_up((size_t)n_out_frames * h * w * 8, 256) +
-           align_up((size_t)n_out_frames * 4, 256);
+    // two hole-list sets, worst case one entry per pixel: u32 position + float2 flow; counters per frame
+    const size_t n = (size_t)n_out_frames * h * w;
+    return 2 * (align_up(n * 4, 256) + align_up(n * 8, 256)) + align_up((size_t)n_out_frames * 8, 256);
 }
 
 extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const float *flows_f, const float *flows_b,
@@ -255,7 +279,7 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
                             uint32_t *out, void *workspace, size_t workspace_bytes, void *stream) {
     VV_CHECK_ARG(frames && masks && out && workspace && sub_start && sub_len, "vv_propagate: NULL pointer");
     VV_CHECK_ARG(n_frames > 0 && h > 0 && w > 0 && n_sub > 0, "vv_propagate: bad shape");
-    VV_CHECK_ARG((long long)h * w < (1LL << 31), "vv_propagate: frame too large");
+    VV_CHECK_ARG(h <= 65535 && w <= 65535, "vv_propagate: frame too large");
     VV_CHECK_ARG(n_frames == 1 || (flows_f && flows_b), "vv_propagate: flows required when there is more than one frame");
     long long total = 0;
     for (int s = 0; s < n_sub; ++s) {
@@ -270,13 +294,15 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
     const long long npx = (long long)h * w;
     const bool vec = (npx % 4 == 0) && ((uintptr_t)frames % 4 == 0) && ((uintptr_t)masks % 4 == 0) &&
                      ((uintptr_t)out % 16 == 0);
-    uint32_t *lists = (uint32_t *)workspace;
     const size_t l4 = align_up((size_t)total * npx * 4, 256), l8 = align_up((size_t)total * npx * 8, 256);
-    float2 *list_ff = (float2 *)((uint8_t *)workspace + l4);
-    float2 *list_fb = (float2 *)((uint8_t *)workspace + l4 + l8);
-    uint32_t *counts = (uint32_t *)((uint8_t *)workspace + l4 + 2 * l8);
+    uint8_t *wsp = (uint8_t *)workspace;
+    HoleLists l1, l2;
+    l1.xy = (uint32_t *)wsp, l1.flow = (float2 *)(wsp + l4);
+    l2.xy = (uint32_t *)(wsp + l4 + l8), l2.flow = (float2 *)(wsp + 2 * l4 + l8);
+    l1.count = (uint32_t *)(wsp + 2 * (l4 + l8));
+    l2.count = l1.count + total;
     const float2 *ff = (const float2 *)flows_f, *fb = (const float2 *)flows_b;
-    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)total * 4, st);
+    cudaError_t e = cudaMemsetAsync(l1.count, 0, (size_t)total * 8, st);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
 
     long long out_frame = 0;
@@ -298,16 +324,13 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             const int ny = (int)min(32768LL, bframes - f0);
             const int gx = max(1, min(ceil_div((npx + 3) / 4, 256), ceil_div(148 * 16, ny)));
             if (vec)
-                k4_pack<true><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, n_frames, lists, list_ff, list_fb, counts, h, w,
-                                                            first + f0, b);
+                k4_pack<true><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, l1, l2, h, w, first + f0, b);
             else
-                k4_pack<false><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, n_frames, lists, list_ff, list_fb, counts, h, w,
-                                                             first + f0, b);
+                k4_pack<false><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, l1, l2, h, w, first + f0, b);
             VV_POST_LAUNCH("k4_pack");
         }
-        // the serial scans touch hole pixels only; a few CTAs per SM, split over the windows
-        // (the hole counts live on the device: the grid is sized for ~1 item per thread at a 25 % hole
-        // fraction and strides over the list otherwise)
+        // The serial scans touch hole pixels only.  The hole counts live on the device: the grid is
+        // sized for ~1 item per thread at a 25 % hole fraction and strides over the list otherwise.
         dim3 grid(max(1, min(ceil_div(npx / 4, 256), ceil_div(148 * 16, b.n))), b.n);
         const int pdl = get_option(OPT_K4_PDL) != 0;
         for (int pass = 0; pass < 2; ++pass)
@@ -320,16 +343,11 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 attr[0].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = attr;
-                // the first step after k4_pack is an ordinary launch: steps read the lists k4_pack wrote
-                // BEFORE their griddepcontrol.wait, and only a full stream dependency makes those visible
+                // the first step after k4_pack is an ordinary launch: backward steps read the lists k4_pack
+                // wrote BEFORE their griddepcontrol.wait, and only a full stream dependency makes those visible
                 cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
-                cudaError_t le =
-                    pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step<false>, ff, fb, out, (const uint32_t *)lists,
-                                                   (const float2 *)list_ff, (const float2 *)list_fb,
-                                                   (const uint32_t *)counts, h, w, step, b)
-                              : cudaLaunchKernelEx(&cfg, k4_step<true>, ff, fb, out, (const uint32_t *)lists,
-                                                   (const float2 *)list_ff, (const float2 *)list_fb,
-                                                   (const uint32_t *)counts, h, w, step, b);
+                cudaError_t le = pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step<false>, ff, fb, out, l1, l2, h, w, step, b)
+                                           : cudaLaunchKernelEx(&cfg, k4_step<true>, ff, fb, out, l1, l2, h, w, step, b);
                 if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step)");
                 VV_POST_LAUNCH("k4_step");
             }
