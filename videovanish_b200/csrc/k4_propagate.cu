@@ -102,20 +102,44 @@ struct HoleLists {
     uint32_t *count;     // [frames]
 };
 
-// Appends the lanes with `take` set to list `of` (one atomicAdd per warp).  All 32 lanes must call.
-__device__ __forceinline__ void warp_append(const HoleLists &l, long long of, long long npx, bool take, uint32_t xy,
-                                            float2 flow) {
+// Block-level append.  Hole entries are first collected in a shared-memory queue (one shared
+// atomic per warp and call), then the block reserves its range of the frame's list with ONE global
+// atomic and writes it out coalesced - a per-warp global atomic on the single per-frame counter
+// serialises in L2 and dominated the first version of this stage.
+constexpr int K4_BLOCK = 256;
+struct BlockQueue {
+    uint32_t xy[K4_BLOCK * 4];
+    uint32_t count, base;
+};
+
+__device__ __forceinline__ void queue_push(BlockQueue &q, bool take, uint32_t xy) {   // all 32 lanes must call
     const uint32_t m = __ballot_sync(0xffffffffu, take);
     if (m == 0) return;
     const int lane = threadIdx.x & 31;
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(l.count + of, (uint32_t)__popc(m));
+    if (lane == 0) base = atomicAdd(&q.count, (uint32_t)__popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (take) {
-        const long long pos = of * npx + base + __popc(m & ((1u << lane) - 1u));
-        l.xy[pos] = xy;
-        l.flow[pos] = flow;
+    if (take) q.xy[base + __popc(m & ((1u << lane) - 1u))] = xy;
+}
+
+// All threads of the block must call (contains barriers).  `flow_frame` is gathered for each entry.
+__device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, long long of, long long npx, int w,
+                                            const float2 *__restrict__ flow_frame) {
+    __syncthreads();
+    const uint32_t n = q.count;
+    if (n) {
+        if (threadIdx.x == 0) q.base = atomicAdd(l.count + of, n);
+        __syncthreads();
+        const long long dst = of * npx + q.base;
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+            const uint32_t xy = q.xy[j];
+            l.xy[dst + j] = xy;
+            l.flow[dst + j] = __ldg(flow_frame + (long long)(xy >> 16) * w + (xy & 0xffffu));
+        }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) q.count = 0;
+    __syncthreads();
 }
 
 // ---- k4_pack: frames + masks -> packed state, and the per-frame lists of hole pixels -----------
@@ -140,6 +164,9 @@ __global__ void __launch_bounds__(256)
     // flow that propagates INTO this frame: backward pass flows_f[gframe], forward pass flows_b[gframe-1]
     const float2 *pflow = last ? flows_b + (gframe - 1) * npx : flows_f + gframe * npx;
     const HoleLists &dl = last ? l2 : l1;
+    __shared__ BlockQueue q;
+    if (threadIdx.x == 0) q.count = 0;
+    __syncthreads();
     const long long ngroups = (npx + 3) >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long iters = (ngroups + stride - 1) / stride;
@@ -171,18 +198,20 @@ __global__ void __launch_bounds__(256)
                 }
             }
         }
-        if (!listed) continue;
+        if (!listed) continue;                                 // block-uniform
         uint32_t holes = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) holes |= (uint32_t)(i < n && (c[i] & ST_HOLE)) << i;
-        if (__ballot_sync(0xffffffffu, holes != 0) == 0) continue;       // warp-uniform
+        if (__ballot_sync(0xffffffffu, holes != 0)) {          // warp-uniform
+            const uint32_t y0 = (uint32_t)(p0 / w), x0 = (uint32_t)(p0 - (long long)y0 * w);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool take = (holes >> i) & 1u;
-            const long long p = p0 + i;
-            const uint32_t y = take ? (uint32_t)(p / w) : 0u, x = take ? (uint32_t)(p - (long long)y * w) : 0u;
-            warp_append(dl, of, npx, take, x | (y << 16), take ? __ldg(pflow + p) : make_float2(0.f, 0.f));
+            for (int i = 0; i < 4; ++i) {
+                uint32_t x = x0 + i, y = y0;
+                while (x >= (uint32_t)w) x -= w, ++y;          // a group may straddle a row end when w % 4 != 0
+                queue_push(q, (holes >> i) & 1u, x | (y << 16));
+            }
         }
+        queue_flush(q, dl, of, npx, w, pflow);                 // same trip count for every thread of the block
     }
 }
 
@@ -220,6 +249,11 @@ __global__ void __launch_bounds__(256)
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);    // warp-uniform loop bounds
     const uint32_t lane = threadIdx.x & 31u;
+    __shared__ BlockQueue q;
+    if (!PASS2) {
+        if (threadIdx.x == 0) q.count = 0;
+        __syncthreads();
+    }
     // The backward pass reads what k4_pack wrote (complete before the first step was launched) and
     // may load its first entry early; the forward lists are produced by the preceding launches.
     uint32_t xy = 0;
@@ -231,7 +265,9 @@ __global__ void __launch_bounds__(256)
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (PASS2) n = li.count[of];
-    for (uint32_t base = first; base < n; base += stride) {
+    // backward pass: block-uniform trip count (the queue flush has barriers)
+    const uint32_t n_loop = PASS2 ? n : min(n + (K4_BLOCK - 1), 0xffffff00u) / K4_BLOCK * K4_BLOCK;
+    for (uint32_t base = first; base < n_loop; base += stride) {
         const uint32_t i = base + lane;
         const bool valid = i < n;
         if (valid && (PASS2 || base != first)) xy = lxy[i], f = lflow[i];
@@ -242,8 +278,8 @@ __global__ void __launch_bounds__(256)
             if (nv != (ST_HOLE | ST_ZERO)) cur[(long long)y * w + x] = nv;
         }
         if (!PASS2 && idx >= 1) {       // still a hole: the forward pass gets another chance
-            const bool remains = valid && nv == (ST_HOLE | ST_ZERO);
-            warp_append(l2, of, npx, remains, xy, remains ? __ldg(next_flow + (long long)y * w + x) : f);
+            queue_push(q, valid && nv == (ST_HOLE | ST_ZERO), xy);
+            queue_flush(q, l2, of, npx, w, next_flow);
         }
     }
 }
