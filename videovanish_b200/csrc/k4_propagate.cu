@@ -107,8 +107,9 @@ struct HoleLists {
 // atomic and writes it out coalesced - a per-warp global atomic on the single per-frame counter
 // serialises in L2 and dominated the first version of this stage.
 constexpr int K4_BLOCK = 256;
+constexpr int K4_QCAP = 4096;                 // queue entries; one push round adds at most 4 * K4_BLOCK
 struct BlockQueue {
-    uint32_t xy[K4_BLOCK * 4];
+    uint32_t xy[K4_QCAP];
     uint32_t count, base;
 };
 
@@ -123,10 +124,13 @@ __device__ __forceinline__ void queue_push(BlockQueue &q, bool take, uint32_t xy
 }
 
 // All threads of the block must call (contains barriers).  `flow_frame` is gathered for each entry.
+// With `force == false` the queue is only written out when another push round might overflow it.
 __device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, long long of, long long npx, int w,
-                                            const float2 *__restrict__ flow_frame) {
+                                            const float2 *__restrict__ flow_frame, bool force) {
     __syncthreads();
     const uint32_t n = q.count;
+    __syncthreads();                                            // everyone has read the count before it can change
+    if (!force && n + 4 * K4_BLOCK <= K4_QCAP) return;          // block-uniform
     if (n) {
         if (threadIdx.x == 0) q.base = atomicAdd(l.count + of, n);
         __syncthreads();
@@ -211,8 +215,9 @@ __global__ void __launch_bounds__(256)
                 queue_push(q, (holes >> i) & 1u, x | (y << 16));
             }
         }
-        queue_flush(q, dl, of, npx, w, pflow);                 // same trip count for every thread of the block
+        queue_flush(q, dl, of, npx, w, pflow, false);          // same trip count for every thread of the block
     }
+    if (listed) queue_flush(q, dl, of, npx, w, pflow, true);
 }
 
 // ---- k4_step: one time step of one direction, in place, over the hole lists -------------------
@@ -279,9 +284,10 @@ __global__ void __launch_bounds__(256)
         }
         if (!PASS2 && idx >= 1) {       // still a hole: the forward pass gets another chance
             queue_push(q, valid && nv == (ST_HOLE | ST_ZERO), xy);
-            queue_flush(q, l2, of, npx, w, next_flow);
+            queue_flush(q, l2, of, npx, w, next_flow, false);
         }
     }
+    if (!PASS2 && idx >= 1) queue_flush(q, l2, of, npx, w, next_flow, true);
 }
 
 __global__ void __launch_bounds__(256)
