@@ -207,12 +207,29 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int i = 0; i < 4; ++i) holes |= (uint32_t)(i < n && (c[i] & ST_HOLE)) << i;
         if (__ballot_sync(0xffffffffu, holes != 0)) {          // warp-uniform
-            const uint32_t y0 = (uint32_t)(p0 / w), x0 = (uint32_t)(p0 - (long long)y0 * w);
+            // one shared-memory atomic per warp: scan the per-lane hole counts
+            const int lane = threadIdx.x & 31;
+            const int cnt = __popc(holes);
+            int pre = cnt;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint32_t x = x0 + i, y = y0;
-                while (x >= (uint32_t)w) x -= w, ++y;          // a group may straddle a row end when w % 4 != 0
-                queue_push(q, (holes >> i) & 1u, x | (y << 16));
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += v;
+            }
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&q.count, (uint32_t)pre);
+            base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(pre - cnt);
+            if (holes) {
+                const uint32_t p32 = (uint32_t)p0;             // h*w < 2^32 (both <= 65535)
+                const uint32_t y0 = p32 / (uint32_t)w, x0 = p32 - y0 * (uint32_t)w;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if ((holes >> i) & 1u) {
+                        uint32_t x = x0 + i, y = y0;
+                        while (x >= (uint32_t)w) x -= w, ++y;  // a group may straddle a row end when w % 4 != 0
+                        q.xy[base++] = x | (y << 16);
+                    }
+                }
             }
         }
         queue_flush(q, dl, of, npx, w, pflow, false);          // same trip count for every thread of the block
