@@ -170,7 +170,8 @@ VV_API int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted, int
                             float feather_px, int keep_unmasked, uint8_t *const *out);
 
 /* Peer-memory helpers for the multi-GPU halo blend (one process per GPU). */
-VV_API int vv_ipc_get_handle(const void *dev_ptr, void *handle_out_64B);
+/* handle of the allocation that contains dev_ptr + the offset of dev_ptr inside it */
+VV_API int vv_ipc_get_handle(const void *dev_ptr, void *handle_out_64B, size_t *offset_out);
 VV_API int vv_ipc_open_handle(const void *handle_64B, void **mapped_ptr);
 VV_API int vv_ipc_close_handle(void *mapped_ptr);
 

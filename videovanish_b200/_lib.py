@@ -52,7 +52,7 @@ _SIGNATURES = {
     "vv_pipeline_pre": (c_int, [c_void_p, _pp, c_int, c_int, c_int, _pp, _pp, c_int, c_int]),
     "vv_pipeline_downsize": (c_int, [c_void_p, _pp, c_int, c_int, c_int, _pp]),
     "vv_pipeline_post": (c_int, [c_void_p, _pp, c_int, c_int, _pp, _pp, c_int, c_float, c_int, _pp]),
-    "vv_ipc_get_handle": (c_int, [c_void_p, c_void_p]),
+    "vv_ipc_get_handle": (c_int, [c_void_p, c_void_p, POINTER(c_size_t)]),
     "vv_ipc_open_handle": (c_int, [c_void_p, POINTER(c_void_p)]),
     "vv_ipc_close_handle": (c_int, [c_void_p]),
 }

@@ -76,10 +76,10 @@ class PeerWindow:
         self.group = group
         self.tensor = tensor
         handle = (ctypes.c_ubyte * 64)()
-        _lib.check(_lib.lib.vv_ipc_get_handle(ctypes.c_void_p(tensor.untyped_storage().data_ptr()), handle),
+        offset = ctypes.c_size_t()
+        _lib.check(_lib.lib.vv_ipc_get_handle(ctypes.c_void_p(tensor.data_ptr()), handle, ctypes.byref(offset)),
                    "vv_ipc_get_handle")
-        offset = tensor.data_ptr() - tensor.untyped_storage().data_ptr()
-        mine = (bytes(handle), offset)
+        mine = (bytes(handle), int(offset.value))
         everyone = [None] * dist.get_world_size(group)
         dist.all_gather_object(everyone, mine, group=group)
         self.rank = dist.get_rank(group)

@@ -69,13 +69,31 @@ extern "C" int vv_device_info(int *sm_count, int *cc_major, int *cc_minor, size_
     return VV_OK;
 }
 
-extern "C" int vv_ipc_get_handle(const void *dev_ptr, void *handle_out_64B) {
-    VV_CHECK_ARG(dev_ptr && handle_out_64B, "vv_ipc_get_handle: NULL pointer");
+extern "C" int vv_ipc_get_handle(const void *dev_ptr, void *handle_out_64B, size_t *offset_out) {
+    VV_CHECK_ARG(dev_ptr && handle_out_64B && offset_out, "vv_ipc_get_handle: NULL pointer");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    // An IPC handle always denotes a whole allocation; `dev_ptr` may sit inside a block of a caching
+    // allocator, so report its offset from the allocation base (driver API, resolved at run time).
+    typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+    static GetRange get_range = nullptr;
+    if (!get_range) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr);
+        if (e != cudaSuccess || !fn) return fail_cuda(e, "cudaGetDriverEntryPoint(cuMemGetAddressRange)");
+        get_range = (GetRange)fn;
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (get_range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0) {
+        set_error("vv_ipc_get_handle: cuMemGetAddressRange failed");
+        return VV_ERR_CUDA;
+    }
     cudaIpcMemHandle_t h;
-    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr));
+    cudaError_t e = cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base);
     if (e != cudaSuccess) return fail_cuda(e, "cudaIpcGetMemHandle");
     memcpy(handle_out_64B, &h, 64);
+    *offset_out = (size_t)((unsigned long long)(uintptr_t)dev_ptr - base);
     return VV_OK;
 }
 
