@@ -43,6 +43,19 @@ def algorithmic_bytes(t):
     }
 
 
+def measured_traffic(stage, frames):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of a stage's kernels from the committed
+    ncu capture of this same command (profiles/ncu_traffic.json, written by tools/ncu_traffic.py)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("frames") == frames and stage in d["stages"]:
+            return float(d["stages"][stage]["dram_bytes"])
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -219,6 +232,10 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         stages.append("K5_halo_blend")
     out_buf = torch.empty((t, H0, W0, 3), dtype=torch.uint8, device=device)
+    # N > 1: the neighbours' overlap frames are read in place over NVLink by the blend kernel (CUDA-IPC
+    # mapping of every rank's output buffer); VV_HALO_MODE=nccl switches to explicit send/recv + blend
+    halo_mode = os.environ.get("VV_HALO_MODE", "peer")
+    window = chunking.PeerWindow(out_buf) if (world > 1 and halo_mode == "peer") else None
 
     def step(ev=None):
         def mark(i):
@@ -234,7 +251,7 @@ def run_ours(args, rank, world, local_rank):
         out = ops.upscale_feather_composite(dev["inpainted"], dev["frames"], dil, FEATHER, out=out_buf)
         mark(4)
         if world > 1:
-            chunking.blend_rank_boundaries(out, OVERLAP, mode="nccl")
+            chunking.blend_rank_boundaries(out, OVERLAP, mode=halo_mode, window=window)
             mark(5)
         return out, packed
 
@@ -309,9 +326,10 @@ def run_ours(args, rank, world, local_rank):
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu": t, "l2": "inputs (>4 GB/step) larger than L2",
-                       "halo_overlap": OVERLAP if world > 1 else 0},
+                       "halo_overlap": OVERLAP if world > 1 else 0,
+                       "halo_mode": (halo_mode if world > 1 else None)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic(dom, t), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom]},
             "stages": {s: {"ms": stage_ms[s], "GBps": (alg[s] / (stage_ms[s] * 1e-3) / 1e9) if s in alg else None,
                            "frac": (alg[s] / (stage_ms[s] * 1e-3) / 1e9 / peak) if s in alg else None} for s in stages},
