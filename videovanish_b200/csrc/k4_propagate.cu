@@ -107,20 +107,50 @@ struct HoleLists {
 // atomic and writes it out coalesced - a per-warp global atomic on the single per-frame counter
 // serialises in L2 and dominated the first version of this stage.
 constexpr int K4_BLOCK = 256;
-constexpr int K4_QCAP = 4096;                 // queue entries; one push round adds at most 4 * K4_BLOCK
+constexpr int K4_PACK_UNROLL = 4;             // 4-pixel groups per thread and round in k4_pack
+constexpr int K4_QCAP = 2 * 4 * K4_BLOCK * K4_PACK_UNROLL;   // queue entries: two k4_pack push rounds
 struct BlockQueue {
     uint32_t xy[K4_QCAP];
     uint32_t count, base;
 };
+struct FlowQueue {                            // k4_step: entries carry their flow (loaded speculatively)
+    uint32_t xy[2 * K4_BLOCK];
+    float2 flow[2 * K4_BLOCK];
+    uint32_t count, base;
+};
 
-__device__ __forceinline__ void queue_push(BlockQueue &q, bool take, uint32_t xy) {   // all 32 lanes must call
+__device__ __forceinline__ void queue_push(FlowQueue &q, bool take, uint32_t xy, float2 flow) {   // all 32 lanes must call
     const uint32_t m = __ballot_sync(0xffffffffu, take);
     if (m == 0) return;
     const int lane = threadIdx.x & 31;
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&q.count, (uint32_t)__popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (take) q.xy[base + __popc(m & ((1u << lane) - 1u))] = xy;
+    if (take) {
+        const uint32_t j = base + __popc(m & ((1u << lane) - 1u));
+        q.xy[j] = xy;
+        q.flow[j] = flow;
+    }
+}
+
+// k4_step flavour: entries already carry their flow.  All threads of the block must call.
+__device__ __forceinline__ void queue_flush(FlowQueue &q, const HoleLists &l, long long of, long long npx, bool force) {
+    __syncthreads();
+    const uint32_t n = q.count;
+    __syncthreads();                                            // everyone has read the count before it can change
+    if (!force && n + K4_BLOCK <= 2 * K4_BLOCK) return;         // block-uniform
+    if (n) {
+        if (threadIdx.x == 0) q.base = atomicAdd(l.count + of, n);
+        __syncthreads();
+        const long long dst = of * npx + q.base;
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+            l.xy[dst + j] = q.xy[j];
+            l.flow[dst + j] = q.flow[j];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) q.count = 0;
+    __syncthreads();
 }
 
 // All threads of the block must call (contains barriers).  `flow_frame` is gathered for each entry.
@@ -130,7 +160,7 @@ __device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, l
     __syncthreads();
     const uint32_t n = q.count;
     __syncthreads();                                            // everyone has read the count before it can change
-    if (!force && n + 4 * K4_BLOCK <= K4_QCAP) return;          // block-uniform
+    if (!force && n + 4 * K4_BLOCK * K4_PACK_UNROLL <= K4_QCAP) return;   // block-uniform
     if (n) {
         if (threadIdx.x == 0) q.base = atomicAdd(l.count + of, n);
         __syncthreads();
@@ -173,42 +203,54 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     const long long ngroups = (npx + 3) >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long iters = (ngroups + stride - 1) / stride;
+    const long long iters = (ngroups + stride * K4_PACK_UNROLL - 1) / (stride * K4_PACK_UNROLL);
+    const int lane = threadIdx.x & 31;
     for (long long itn = 0; itn < iters; ++itn) {
-        const long long g = itn * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-        const long long p0 = g * 4;
-        uint32_t c[4] = {0, 0, 0, 0};
-        int n = 0;
-        if (g < ngroups) {
+        // K4_PACK_UNROLL groups per thread: all loads first (memory-level parallelism), one flush check per round
+        uint32_t c[K4_PACK_UNROLL][4];
+        uint32_t m4[K4_PACK_UNROLL], fa[K4_PACK_UNROLL], fb2[K4_PACK_UNROLL], fd[K4_PACK_UNROLL];
+        long long p0[K4_PACK_UNROLL];
+        int n[K4_PACK_UNROLL];
+#pragma unroll
+        for (int u = 0; u < K4_PACK_UNROLL; ++u) {
+            const long long g = (itn * K4_PACK_UNROLL + u) * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+            p0[u] = g * 4;
+            n[u] = g < ngroups ? (VEC ? 4 : (int)min(4LL, npx - p0[u])) : 0;
+            if (VEC && n[u]) {
+                m4[u] = __ldg(reinterpret_cast<const uint32_t *>(mk + p0[u]));
+                const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0[u] * 3);
+                fa[u] = __ldg(f3), fb2[u] = __ldg(f3 + 1), fd[u] = __ldg(f3 + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < K4_PACK_UNROLL; ++u) {
+            c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0;
+            if (!n[u]) continue;
             if (VEC) {
-                n = 4;
-                const uint32_t m4 = __ldg(reinterpret_cast<const uint32_t *>(mk + p0));
-                const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0 * 3);
-                const uint32_t a = __ldg(f3), b = __ldg(f3 + 1), d = __ldg(f3 + 2);
-                c[0] = a & 0x00ffffffu;
-                c[1] = (a >> 24) | ((b & 0x0000ffffu) << 8);
-                c[2] = (b >> 16) | ((d & 0x000000ffu) << 16);
-                c[3] = d >> 8;
+                c[u][0] = fa[u] & 0x00ffffffu;
+                c[u][1] = (fa[u] >> 24) | ((fb2[u] & 0x0000ffffu) << 8);
+                c[u][2] = (fb2[u] >> 16) | ((fd[u] & 0x000000ffu) << 16);
+                c[u][3] = fd[u] >> 8;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (byte_of(m4, i)) c[i] = ST_HOLE | ST_ZERO;
-                *reinterpret_cast<uint4 *>(dst + p0) = make_uint4(c[0], c[1], c[2], c[3]);
+                    if (byte_of(m4[u], i)) c[u][i] = ST_HOLE | ST_ZERO;
+                *reinterpret_cast<uint4 *>(dst + p0[u]) = make_uint4(c[u][0], c[u][1], c[u][2], c[u][3]);
             } else {
-                n = (int)min(4LL, npx - p0);
-                for (int i = 0; i < n; ++i) {
-                    const uint8_t *q = fr + (p0 + i) * 3;
-                    c[i] = mk[p0 + i] ? (ST_HOLE | ST_ZERO) : (q[0] | (q[1] << 8) | ((uint32_t)q[2] << 16));
-                    dst[p0 + i] = c[i];
+                for (int i = 0; i < n[u]; ++i) {
+                    const uint8_t *q8 = fr + (p0[u] + i) * 3;
+                    c[u][i] = mk[p0[u] + i] ? (ST_HOLE | ST_ZERO) : (q8[0] | (q8[1] << 8) | ((uint32_t)q8[2] << 16));
+                    dst[p0[u] + i] = c[u][i];
                 }
             }
         }
         if (!listed) continue;                                 // block-uniform
-        uint32_t holes = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) holes |= (uint32_t)(i < n && (c[i] & ST_HOLE)) << i;
-        if (__ballot_sync(0xffffffffu, holes != 0)) {          // warp-uniform
+        for (int u = 0; u < K4_PACK_UNROLL; ++u) {
+            uint32_t holes = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) holes |= (uint32_t)(i < n[u] && (c[u][i] & ST_HOLE)) << i;
+            if (__ballot_sync(0xffffffffu, holes != 0) == 0) continue;   // warp-uniform
             // one shared-memory atomic per warp: scan the per-lane hole counts
-            const int lane = threadIdx.x & 31;
             const int cnt = __popc(holes);
             int pre = cnt;
 #pragma unroll
@@ -220,7 +262,7 @@ __global__ void __launch_bounds__(256)
             if (lane == 31) base = atomicAdd(&q.count, (uint32_t)pre);
             base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(pre - cnt);
             if (holes) {
-                const uint32_t p32 = (uint32_t)p0;             // h*w < 2^32 (both <= 65535)
+                const uint32_t p32 = (uint32_t)p0[u];          // h*w < 2^32 (both <= 65535)
                 const uint32_t y0 = p32 / (uint32_t)w, x0 = p32 - y0 * (uint32_t)w;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -271,11 +313,12 @@ __global__ void __launch_bounds__(256)
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);    // warp-uniform loop bounds
     const uint32_t lane = threadIdx.x & 31u;
-    __shared__ BlockQueue q;
+    __shared__ FlowQueue q;
     if (!PASS2) {
         if (threadIdx.x == 0) q.count = 0;
         __syncthreads();
     }
+    const bool relist = !PASS2 && idx >= 1;      // holes that stay holes go to the forward list
     // The backward pass reads what k4_pack wrote (complete before the first step was launched) and
     // may load its first entry early; the forward lists are produced by the preceding launches.
     uint32_t xy = 0;
@@ -295,16 +338,19 @@ __global__ void __launch_bounds__(256)
         if (valid && (PASS2 || base != first)) xy = lxy[i], f = lflow[i];
         const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
         uint32_t nv = ST_HOLE | ST_ZERO;
+        float2 nf = make_float2(0.f, 0.f);
         if (valid) {
+            // the forward-pass flow is fetched speculatively, in the same round trip as the taps
+            if (relist) nf = __ldg(next_flow + (long long)y * w + x);
             nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, f, flow_check, prev);
             if (nv != (ST_HOLE | ST_ZERO)) cur[(long long)y * w + x] = nv;
         }
-        if (!PASS2 && idx >= 1) {       // still a hole: the forward pass gets another chance
-            queue_push(q, valid && nv == (ST_HOLE | ST_ZERO), xy);
-            queue_flush(q, l2, of, npx, w, next_flow, false);
+        if (relist) {                   // still a hole: the forward pass gets another chance
+            queue_push(q, valid && nv == (ST_HOLE | ST_ZERO), xy, nf);
+            queue_flush(q, l2, of, npx, false);
         }
     }
-    if (!PASS2 && idx >= 1) queue_flush(q, l2, of, npx, w, next_flow, true);
+    if (relist) queue_flush(q, l2, of, npx, true);
 }
 
 __global__ void __launch_bounds__(256)
