@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
     uint32_t *bits = smem;                                               // [rows_s][row_words]
     float *lut = reinterpret_cast<float *>(smem + rows_s * row_words);   // [16] alpha levels (SMALL_R)
     uint2 *queue = reinterpret_cast<uint2 *>(smem + ((rows_s * row_words + 16 + 1) & ~1)) +
-                   (threadIdx.x >> 5) * (K3_QUEUE1 * K3_NT);                        // per-warp work queue
+                   (threadIdx.x >> 5) * (K3_QUEUE1 * K3_NT + 32);                  // + carried-over items                        // per-warp work queue
     const int lane = threadIdx.x & 31;
 
     const long long t = blockIdx.x / strips_per_frame;
@@ -208,7 +208,11 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
     // first store, which keeps enough bytes in flight to cover HBM latency; same trip count for the
     // whole warp.
     const int n_iters = (n_tasks + nthreads * K3_NT - 1) / (nthreads * K3_NT);
-    for (int it = 0; it < n_iters; ++it) {
+    // Work items are carried over between iterations so that the worker rounds below always run
+    // with all 32 lanes busy; one extra iteration (no new tasks) drains the remainder.
+    int qcount = 0;
+    for (int it = 0; it <= n_iters; ++it) {
+        const bool drain = it == n_iters;
         int row[K3_NT], x0[K3_NT];
         bool active[K3_NT];
         uint4 pa[K3_NT], pb[K3_NT], pc[K3_NT];
@@ -312,15 +316,15 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
             qn += ((need[k] & 0x000fu) != 0) + ((need[k] & 0x00f0u) != 0) + ((need[k] & 0x0f00u) != 0) +
                   ((need[k] & 0xf000u) != 0);
         }
-        if (__ballot_sync(0xffffffffu, any_need != 0) == 0) continue;        // warp-uniform
+        if (__ballot_sync(0xffffffffu, any_need != 0)) {                     // warp-uniform
         int pre = (int)qn;                               // inclusive scan over lanes
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, pre, d);
             if (lane >= d) pre += v;
         }
-        const int total = __shfl_sync(0xffffffffu, pre, 31);
-        int pos = pre - (int)qn;
+        int pos = qcount + pre - (int)qn;
+        qcount += __shfl_sync(0xffffffffu, pre, 31);
 #pragma unroll
         for (int k = 0; k < K3_NT; ++k) {
 #pragma unroll
@@ -342,14 +346,18 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                 }
             }
         }
+        }
         __syncwarp();
+        if (qcount < 32 && !(drain && qcount > 0)) continue;                 // warp-uniform
         if (TMA && !landed) {
             mbar_wait(bar, 0);
             landed = true;
         }
-        for (int base = 0; base < total; base += 32) {
-            const int qi = base + lane;
-            if (qi < total) {
+        while (qcount >= 32 || (drain && qcount > 0)) {
+            const int take = min(qcount, 32);
+            const int qi = qcount - take + lane;
+            qcount -= take;
+            if (lane < take) {
                 const uint2 item = queue[qi];
                 const int xq = item.x & 0xffff, r = (item.x >> 16) & 15;
                 const uint32_t n4 = (item.x >> 20) & 15u, in4 = (item.x >> 24) & 15u;
@@ -595,7 +603,7 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
         tma_threads = get_option(OPT_K3_TMA_THREADS) >= 512 ? 512 : get_option(OPT_K3_TMA_THREADS) >= 384 ? 384 : 256;
         for (th = th_max; th >= 2; --th) {      // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2
             smem = (size_t)th * W0 * 3 + 16 +
-                   ((size_t)(th + 2 * R) * (Wp + 2) + common_words + (tma_threads / 32) * K3_QUEUE1 * 2) * 4;
+                   ((size_t)(th + 2 * R) * (Wp + 2) + common_words + (tma_threads / 32) * (K3_QUEUE1 + 32) * 2) * 4;
             if (smem <= 113 * 1024) break;
         }
         if (th < 2) tma = false;
@@ -603,7 +611,7 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
     const int nt = tma ? 1 : (get_option(OPT_K3_NT) == 1 ? 1 : 2);
     if (!tma) {
         th = K3_TH;
-        smem = ((size_t)(th + 2 * R) * (Wp + 2) + common_words + (K3_THREADS / 32) * K3_QUEUE1 * nt * 2) * 4;
+        smem = ((size_t)(th + 2 * R) * (Wp + 2) + common_words + (K3_THREADS / 32) * (K3_QUEUE1 * nt + 32) * 2) * 4;
     }
     const int strips = ceil_div(H0, th);
     const long long grid = (long long)T * strips;
