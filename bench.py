@@ -237,22 +237,35 @@ def run_ours(args, rank, world, local_rank):
     halo_mode = os.environ.get("VV_HALO_MODE", "peer")
     window = chunking.PeerWindow(out_buf) if (world > 1 and halo_mode == "peer") else None
 
+    # Two streams: the propagation prior (K2 -> K4) is a chain of ~140 short dependent launches that
+    # leaves most of the machine idle, while the post stage (K3, + halo blend) is throughput bound and
+    # only depends on K1 - so K3 runs on a second stream next to K4 (VV_BENCH_OVERLAP=0: one stream).
+    overlap = os.environ.get("VV_BENCH_OVERLAP", "1") != "0"
+    main_stream = torch.cuda.current_stream()
+    post_stream = torch.cuda.Stream(device=device) if overlap else main_stream
+
     def step(ev=None):
-        def mark(i):
-            if ev is not None:
-                ev[i].record()
-        mark(0)
-        dil, low = ops.binarize_dilate(dev["masks"], DILATE, lowres_size=(HS, WS))
-        mark(1)
-        small = ops.resize(dev["frames"], HS, WS)
-        mark(2)
-        packed = ops.propagate(small, low, dev["flows_f"], dev["flows_b"])
-        mark(3)
-        out = ops.upscale_feather_composite(dev["inpainted"], dev["frames"], dil, FEATHER, out=out_buf)
-        mark(4)
+        # ev[i] = (start, end) events of stage i, recorded on the stream that stage runs on
+        def timed(i, fn, stream):
+            with torch.cuda.stream(stream):
+                if ev is not None:
+                    ev[i][0].record()
+                r = fn()
+                if ev is not None:
+                    ev[i][1].record()
+            return r
+        dil, low = timed(0, lambda: ops.binarize_dilate(dev["masks"], DILATE, lowres_size=(HS, WS)), main_stream)
+        if overlap:
+            post_stream.wait_stream(main_stream)              # K3 needs the dilated masks (and the previous step's K4 is done)
+            dil.record_stream(post_stream)
+        small = timed(1, lambda: ops.resize(dev["frames"], HS, WS), main_stream)
+        packed = timed(2, lambda: ops.propagate(small, low, dev["flows_f"], dev["flows_b"]), main_stream)
+        out = timed(3, lambda: ops.upscale_feather_composite(dev["inpainted"], dev["frames"], dil, FEATHER, out=out_buf),
+                    post_stream)
         if world > 1:
-            chunking.blend_rank_boundaries(out, OVERLAP, mode=halo_mode, window=window)
-            mark(5)
+            timed(4, lambda: chunking.blend_rank_boundaries(out, OVERLAP, mode=halo_mode, window=window), post_stream)
+        if overlap:
+            main_stream.wait_stream(post_stream)              # the step ends when both streams are done
         return out, packed
 
     def sync_all():
@@ -267,8 +280,8 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    n_marks = len(stages) + 1
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in stages]
+           for _ in range(args.steps)]
     _lib.reset_launch_count()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -284,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_step = float(tm.item()) / args.steps
-    stage_ms = {s: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
+    stage_ms = {s: float(np.mean([evs[k][i][0].elapsed_time(evs[k][i][1]) for k in range(args.steps)]))
                 for i, s in enumerate(stages)}
 
     # ---- end to end through the reference-facing call, host buffers in, host buffers out
@@ -326,6 +339,7 @@ def run_ours(args, rank, world, local_rank):
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu": t, "l2": "inputs (>4 GB/step) larger than L2",
+                       "streams": ("2: K1,K2,K4 | K3" + (",K5" if world > 1 else "")) if overlap else "1",
                        "halo_overlap": OVERLAP if world > 1 else 0,
                        "halo_mode": (halo_mode if world > 1 else None)},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
