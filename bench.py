@@ -241,8 +241,16 @@ def run_ours(args, rank, world, local_rank):
     # leaves most of the machine idle, while the post stage (K3, + halo blend) is throughput bound and
     # only depends on K1 - so K3 runs on a second stream next to K4 (VV_BENCH_OVERLAP=0: one stream).
     overlap = os.environ.get("VV_BENCH_OVERLAP", "1") != "0"
-    main_stream = torch.cuda.current_stream()
-    post_stream = torch.cuda.Stream(device=device) if overlap else main_stream
+    for kv in filter(None, os.environ.get("VV_OPTS", "").split(",")):      # e.g. VV_OPTS=k3_tma_rows=8,k3_tma_threads=256
+        k, v = kv.split("=")
+        _lib.set_option(k.strip(), int(v))
+    if overlap:
+        # the latency-bound chain gets the high-priority stream so that its short kernels are scheduled
+        # ahead of the post stage's CTAs as soon as resources free up
+        main_stream = torch.cuda.Stream(device=device, priority=-1)
+        post_stream = torch.cuda.Stream(device=device, priority=0)
+    else:
+        main_stream = post_stream = torch.cuda.current_stream()
 
     def step(ev=None):
         # ev[i] = (start, end) events of stage i, recorded on the stream that stage runs on
@@ -285,10 +293,10 @@ def run_ours(args, rank, world, local_rank):
     _lib.reset_launch_count()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(main_stream)
     for k in range(args.steps):
         step(evs[k])
-    e1.record()
+    e1.record(main_stream)
     sync_all()
     launches = _lib.launch_count()
     clocks = sampler.stop() if rank == 0 else None
