@@ -324,16 +324,21 @@ def run_ours(args, rank, world, local_rank):
         res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host, max_img_size=960)
         del res
     sync_all()
+    marks = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         res = None              # the caller drops the previous result before asking for the next one
         res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host,
-                                       max_img_size=960)
+                                       max_img_size=960, prog=lambda p, s: marks.append((p, time.perf_counter())))
+        marks.append((100, time.perf_counter()))
     torch.cuda.synchronize()
     e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=device)
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_fps = world * t / float(e2e_dt.item())
+    # phases of the last call, from the progress milestones: 5 -> 10 = pre (K1), 90 -> end = post (K3)
+    last = dict(marks[-5:]) if len(marks) >= 5 else {}
+    e2e_phases = {"pre_ms": (last[10] - last[5]) * 1e3, "post_ms": (last[100] - last[90]) * 1e3} if 90 in last else None
     fh, fw = res[0].shape[:2]
     px, spx = H0 * W0, inpainted_host[0].shape[0] * inpainted_host[0].shape[1]
     h2d = t * (3 * px + 3 * spx + 3 * px)           # masks (pre) + inpainted + originals (post)
@@ -358,6 +363,7 @@ def run_ours(args, rank, world, local_rank):
             "stages": {s: {"ms": stage_ms[s], "GBps": (alg[s] / (stage_ms[s] * 1e-3) / 1e9) if s in alg else None,
                            "frac": (alg[s] / (stage_ms[s] * 1e-3) / 1e9 / peak) if s in alg else None} for s in stages},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "phases": e2e_phases,
                     "path": "diffuerase.run_infill_on_frames(list of pinned host frames), stub models, K1 + K3 via "
                             "the host pipeline; result %dx%d" % (fh, fw)},
             "gpu_launches": int(launches), "clocks": clocks,
