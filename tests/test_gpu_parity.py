@@ -337,3 +337,61 @@ def test_full_size_1080p_properties(ops):
     # linearity check of the box filter: resize(255 - x) == 255 - resize(x) up to rounding
     inv = host(ops.resize(255 - dfr, h, w)).astype(int)
     assert np.abs((255 - inv) - host(small).astype(int)).max() <= 1
+
+
+# ------------------------------------------------------------------------------- remaining BASELINE configs
+def test_config3_720p_propagation_slice(ops):
+    """BASELINE config 3 shape (720p, bidirectional flow): an 8-frame slice against the explicit model,
+    plus size-independent properties (holes only shrink; known pixels never change)."""
+    t, h, w = 8, 720, 1280
+    fr, m, ff, fb = prop_clip(t, h, w, seed=33)
+    got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb))).view(np.uint32)
+    assert np.array_equal(got, opp.model_propagate(fr, m, ff, fb))
+    hole_after = (got >> 24) & 1
+    assert np.all(hole_after <= (m > 0)) and hole_after.sum() < (m > 0).sum()
+    known = m == 0
+    assert np.array_equal(got[known], opp.pack_state(fr, m)[known])
+
+
+def test_config4_chunked_stitch(ops):
+    """BASELINE config 4 scheme (chunk 80 / overlap 16, here 20 / 6 on a small clip): per-chunk outputs
+    stitched with K5 == the oracle's stitch."""
+    from videovanish_b200 import chunking
+    rng = np.random.default_rng(4)
+    plan = chunking.chunk_plan(50, 20, 6)
+    outs = [rng.integers(0, 256, (e - s, 36, 64, 3), dtype=np.uint8) for s, e in plan]
+    got = host(chunking.stitch_chunks([dev(o) for o in outs], plan))
+    assert np.array_equal(got, ocb.stitch_chunks(outs, plan, 6))
+
+
+def test_config5_long_clip_streams_through_pipeline(ops):
+    """BASELINE config 5 idea (a clip much longer than one batch): 70 frames through the host pipeline
+    in batches of 8 over 3 slots, pageable inputs (staging ring) - same bytes as the oracle."""
+    from videovanish_b200 import hostpipe
+    t, h0, w0, h, w = 70, 72, 128, 32, 64
+    fr, mk, inp = synth.frames(t, h0, w0, seed=51), synth.masks(t, h0, w0, seed=52), synth.noise_frames(t, h, w, seed=53)
+    pipe = hostpipe.HostPipeline(h0, w0)
+    dil = pipe.pre([m.copy() for m in mk], 4)
+    ref_dil = op.ref_binarize_dilate(list(mk), 4)
+    assert np.array_equal(np.stack(dil), np.stack(ref_dil))
+    out = pipe.post([x.copy() for x in inp], [f.copy() for f in fr])
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], ref_dil[i], True, 3) for i in range(t)])
+    assert np.array_equal(np.stack(out), ref)
+    pipe.close()
+
+
+def test_empty_and_degenerate_inputs(ops):
+    """Ragged / degenerate shapes the reference would accept: single pixel rows, 1-frame clips,
+    all-masked and unmasked frames mixed in one batch."""
+    fr = synth.frames(3, 2, 16, seed=1)
+    inp = synth.noise_frames(3, 1, 8, seed=2)
+    dil = np.zeros((3, 2, 16), np.uint8)
+    dil[1] = 255
+    dil[2, 0, 3] = 255
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, 3) for i in range(3)])
+    assert np.array_equal(host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), 3)), ref)
+    one = synth.masks(1, 1, 1, seed=3, salt=0)
+    one[...] = 7
+    assert host(ops.binarize_dilate(dev(one), 8)).tolist() == [[[255]]]
+    with pytest.raises(RuntimeError):
+        ops.binarize_dilate(dev(np.zeros((0, 4, 4, 3), np.uint8)), 1)

@@ -244,14 +244,17 @@ __global__ void __launch_bounds__(256)
             }
         }
         if (!listed) continue;                                 // block-uniform
+        uint32_t holes[K4_PACK_UNROLL];
+        int cnt = 0;
 #pragma unroll
         for (int u = 0; u < K4_PACK_UNROLL; ++u) {
-            uint32_t holes = 0;
+            holes[u] = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) holes |= (uint32_t)(i < n[u] && (c[u][i] & ST_HOLE)) << i;
-            if (__ballot_sync(0xffffffffu, holes != 0) == 0) continue;   // warp-uniform
-            // one shared-memory atomic per warp: scan the per-lane hole counts
-            const int cnt = __popc(holes);
+            for (int i = 0; i < 4; ++i) holes[u] |= (uint32_t)(i < n[u] && (c[u][i] & ST_HOLE)) << i;
+            cnt += __popc(holes[u]);
+        }
+        if (__ballot_sync(0xffffffffu, cnt != 0)) {            // warp-uniform
+            // one scan and one shared-memory atomic per warp and round
             int pre = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -261,15 +264,18 @@ __global__ void __launch_bounds__(256)
             uint32_t base = 0;
             if (lane == 31) base = atomicAdd(&q.count, (uint32_t)pre);
             base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(pre - cnt);
-            if (holes) {
-                const uint32_t p32 = (uint32_t)p0[u];          // h*w < 2^32 (both <= 65535)
-                const uint32_t y0 = p32 / (uint32_t)w, x0 = p32 - y0 * (uint32_t)w;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if ((holes >> i) & 1u) {
-                        uint32_t x = x0 + i, y = y0;
-                        while (x >= (uint32_t)w) x -= w, ++y;  // a group may straddle a row end when w % 4 != 0
-                        q.xy[base++] = x | (y << 16);
+            for (int u = 0; u < K4_PACK_UNROLL; ++u) {
+                if (holes[u]) {
+                    const uint32_t p32 = (uint32_t)p0[u];      // h*w < 2^32 (both <= 65535)
+                    const uint32_t y0 = p32 / (uint32_t)w, x0 = p32 - y0 * (uint32_t)w;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if ((holes[u] >> i) & 1u) {
+                            uint32_t x = x0 + i, y = y0;
+                            while (x >= (uint32_t)w) x -= w, ++y;   // a group may straddle a row end when w % 4 != 0
+                            q.xy[base++] = x | (y << 16);
+                        }
                     }
                 }
             }
