@@ -57,7 +57,9 @@ VV_API void vv_reset_launch_count(void);
  *   "k3_tma"     1 = K3 stages the original strip through shared memory with bulk async copies
  *                (TMA) when the frame is 16-byte aligned, 0 = register pass-through kernel.
  *   "k3_tma_rows" maximum rows per staged strip (2..16);  "k3_tma_threads" 256, 384 or 512.
- *   "k4_pdl"     1 = propagation steps use programmatic dependent launch. */
+ *   "k4_pdl"     1 = propagation steps use programmatic dependent launch (multi-launch mode).
+ *   "k4_persistent" 1 = the whole propagation scan runs in one cooperative launch with per-window
+ *                barriers, 0 = one launch per time step. */
 VV_API int vv_set_option(const char *name, int value);
 VV_API int vv_get_option(const char *name, int *value);
 

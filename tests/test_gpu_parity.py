@@ -224,6 +224,23 @@ def test_k4_zero_padding_fill(ops):
     assert np.array_equal(gf, rf) and np.array_equal(gm, rm)
 
 
+@pytest.mark.parametrize("variant", [dict(k4_persistent=1), dict(k4_persistent=0, k4_pdl=1), dict(k4_persistent=0, k4_pdl=0)],
+                         ids=["persistent", "launch-per-step-pdl", "launch-per-step"])
+def test_k4_kernel_variants(ops, variant):
+    """The cooperative persistent scan and the launch-per-step fallback give identical states."""
+    from videovanish_b200 import _lib
+    fr, m, ff, fb = prop_clip(26, 96, 160, seed=91)
+    want = opp.model_propagate_clip(fr, m, ff, fb, subvideo_length=8, pad_len=3)
+    try:
+        for k, v in variant.items():
+            _lib.set_option(k, v)
+        got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb), subvideo_length=8, pad_len=3)).view(np.uint32)
+    finally:
+        _lib.set_option("k4_persistent", 1)
+        _lib.set_option("k4_pdl", 1)
+    assert np.array_equal(got, want)
+
+
 def test_k4_subvideo_windows(ops):
     fr, m, ff, fb = prop_clip(23, 32, 48, seed=77)
     got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb), subvideo_length=6, pad_len=2)).view(np.uint32)

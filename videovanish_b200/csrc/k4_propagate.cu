@@ -46,9 +46,11 @@ __device__ __forceinline__ float unnormalized(float pos, int size) {
 }
 
 // One hole pixel: returns the new packed state.
+// COHERENT: the previous frame's state was written by other CTAs of the SAME (persistent) kernel, so it
+// is read with ld.global.cg (L2), never from a possibly stale L1 line.
+template <bool COHERENT>
 __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, uint32_t cur, const float2 f,
-                                                    const float2 *__restrict__ flow_check,
-                                                    const uint32_t *__restrict__ prev) {
+                                                    const float2 *__restrict__ flow_check, const uint32_t *prev) {
     const float ix = unnormalized(__fadd_rn((float)x, f.x), w);
     const float iy = unnormalized(__fadd_rn((float)y, f.y), h);
     const float x0f = floorf(ix), y0f = floorf(iy);
@@ -64,10 +66,11 @@ __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, 
 
     float2 c00 = make_float2(0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
     uint32_t p00 = 0, p01 = 0, p10 = 0, p11 = 0;          // out-of-frame taps: not a hole
-    if (ya && xa) c00 = __ldg(flow_check + i00), p00 = prev[i00];
-    if (ya && xb) c01 = __ldg(flow_check + i00 + 1), p01 = prev[i00 + 1];
-    if (yb && xa) c10 = __ldg(flow_check + i00 + w), p10 = prev[i00 + w];
-    if (yb && xb) c11 = __ldg(flow_check + i00 + w + 1), p11 = prev[i00 + w + 1];
+    auto ld_state = [&](long long i) { return COHERENT ? __ldcg(prev + i) : prev[i]; };
+    if (ya && xa) c00 = __ldg(flow_check + i00), p00 = ld_state(i00);
+    if (ya && xb) c01 = __ldg(flow_check + i00 + 1), p01 = ld_state(i00 + 1);
+    if (yb && xa) c10 = __ldg(flow_check + i00 + w), p10 = ld_state(i00 + w);
+    if (yb && xb) c11 = __ldg(flow_check + i00 + w + 1), p11 = ld_state(i00 + w + 1);
 
     // bilinear, torch CPU order: r = a*nw; r = fma(b, ne, r); r = fma(c, sw, r); r = fma(d, se, r)
     const float bwx = __fmaf_rn(c11.x, se, __fmaf_rn(c10.x, sw, __fmaf_rn(c01.x, ne, __fmul_rn(c00.x, nw))));
@@ -297,13 +300,10 @@ __global__ void __launch_bounds__(256)
 // The chain of 2*(len-1) dependent launches is latency bound, so the per-item dependency chain is
 // kept at two memory round trips and the forward pass only visits what the backward pass left.
 // With programmatic dependent launch the next step's CTAs are resident before this one retires.
-template <bool PASS2>
-__global__ void __launch_bounds__(256)
-    k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state, HoleLists l1,
-            HoleLists l2, int h, int w, int step, const __grid_constant__ SubBatch batch) {
-    asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
-    const SubDesc sd = batch.sub[blockIdx.y];
-    if (step >= sd.len) return;
+template <bool PASS2, bool PERSIST>
+__device__ __forceinline__ void step_body(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b,
+                                          uint32_t *state, const HoleLists &l1, const HoleLists &l2, int h, int w, int step,
+                                          const SubDesc &sd, FlowQueue &q) {
     const long long npx = (long long)h * w;
     const int idx = PASS2 ? step : sd.len - 1 - step;
     const long long gframe = sd.start + idx;
@@ -319,36 +319,40 @@ __global__ void __launch_bounds__(256)
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);    // warp-uniform loop bounds
     const uint32_t lane = threadIdx.x & 31u;
-    __shared__ FlowQueue q;
-    if (!PASS2) {
-        if (threadIdx.x == 0) q.count = 0;
-        __syncthreads();
-    }
     const bool relist = !PASS2 && idx >= 1;      // holes that stay holes go to the forward list
-    // The backward pass reads what k4_pack wrote (complete before the first step was launched) and
-    // may load its first entry early; the forward lists are produced by the preceding launches.
+    // Multi-launch mode: the backward pass reads what k4_pack wrote (complete before the first step was
+    // launched) and may load its first entry before the grid dependency resolves; the forward lists are
+    // produced by the preceding launches.  Persistent mode: forward lists come from other CTAs of this
+    // kernel -> L2-coherent loads.
     uint32_t xy = 0;
     float2 f = make_float2(0.f, 0.f);
     uint32_t n = 0;
-    if (!PASS2) {
-        n = li.count[of];
-        if (first + lane < n) xy = lxy[first + lane], f = lflow[first + lane];
+    if (!PERSIST) {
+        if (!PASS2) {
+            n = li.count[of];
+            if (first + lane < n) xy = lxy[first + lane], f = lflow[first + lane];
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (PASS2) n = li.count[of];
+    } else {
+        n = __ldcg(li.count + of);
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (PASS2) n = li.count[of];
     // backward pass: block-uniform trip count (the queue flush has barriers)
     const uint32_t n_loop = PASS2 ? n : min(n + (K4_BLOCK - 1), 0xffffff00u) / K4_BLOCK * K4_BLOCK;
     for (uint32_t base = first; base < n_loop; base += stride) {
         const uint32_t i = base + lane;
         const bool valid = i < n;
-        if (valid && (PASS2 || base != first)) xy = lxy[i], f = lflow[i];
+        if (valid && (PERSIST || PASS2 || base != first)) {
+            xy = PERSIST ? __ldcg(lxy + i) : lxy[i];
+            f = PERSIST ? __ldcg(lflow + i) : lflow[i];
+        }
         const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
         uint32_t nv = ST_HOLE | ST_ZERO;
         float2 nf = make_float2(0.f, 0.f);
         if (valid) {
             // the forward-pass flow is fetched speculatively, in the same round trip as the taps
             if (relist) nf = __ldg(next_flow + (long long)y * w + x);
-            nv = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, f, flow_check, prev);
+            nv = propagate_pixel<PERSIST>(x, y, h, w, ST_HOLE | ST_ZERO, f, flow_check, prev);
             if (nv != (ST_HOLE | ST_ZERO)) cur[(long long)y * w + x] = nv;
         }
         if (relist) {                   // still a hole: the forward pass gets another chance
@@ -357,6 +361,60 @@ __global__ void __launch_bounds__(256)
         }
     }
     if (relist) queue_flush(q, l2, of, npx, true);
+}
+
+// One launch per step (fallback, and the variant the ncu launch lists show step by step).
+template <bool PASS2>
+__global__ void __launch_bounds__(256)
+    k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state, HoleLists l1,
+            HoleLists l2, int h, int w, int step, const __grid_constant__ SubBatch batch) {
+    asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
+    const SubDesc sd = batch.sub[blockIdx.y];
+    if (step >= sd.len) return;
+    __shared__ FlowQueue q;
+    if (threadIdx.x == 0) q.count = 0;
+    __syncthreads();
+    step_body<PASS2, false>(flows_f, flows_b, state, l1, l2, h, w, step, sd, q);
+}
+
+// Barrier among the CTAs of one window (blockIdx.y): monotonic arrival counter in global memory.
+// `target` = arrivals expected so far.  The spin is bounded so that a broken launch cannot hang the GPU.
+__device__ __forceinline__ void window_barrier(unsigned int *ctr, unsigned int target, int *failed) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // this CTA's state / list writes are visible device-wide
+        atomicAdd(ctr, 1u);
+        unsigned int seen, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        } while (seen < target && ++spins < (1u << 22));
+        if (seen < target) *failed = 1;
+    }
+    __syncthreads();
+}
+
+// The whole scan of a batch of windows in ONE cooperative launch: every CTA stays resident, walks its
+// share of the hole list of each step and meets the other CTAs of its window at a barrier.  A step then
+// costs two memory round trips + one barrier (~5 us) instead of a kernel launch + ramp-up (~11-16 us).
+__global__ void __launch_bounds__(256)
+    k4_scan_persistent(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state,
+                       HoleLists l1, HoleLists l2, int h, int w, unsigned int *barriers, int *failed,
+                       const __grid_constant__ SubBatch batch) {
+    const SubDesc sd = batch.sub[blockIdx.y];
+    __shared__ FlowQueue q;
+    if (threadIdx.x == 0) q.count = 0;
+    __syncthreads();
+    unsigned int arrivals = 0;
+    for (int step = 1; step < sd.len; ++step) {
+        step_body<false, true>(flows_f, flows_b, state, l1, l2, h, w, step, sd, q);
+        arrivals += gridDim.x;
+        window_barrier(barriers + blockIdx.y, arrivals, failed);
+    }
+    for (int step = 1; step < sd.len; ++step) {
+        step_body<true, true>(flows_f, flows_b, state, l1, l2, h, w, step, sd, q);
+        arrivals += gridDim.x;
+        if (step + 1 < sd.len) window_barrier(barriers + blockIdx.y, arrivals, failed);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -382,7 +440,7 @@ extern "C" size_t vv_propagate_workspace_bytes(int n_out_frames, int h, int w) {
     if (n_out_frames <= 0 || h <= 0 || w <= 0) return 0;
     // two hole-list sets, worst case one entry per pixel: u32 position + float2 flow; counters per frame
     const size_t n = (size_t)n_out_frames * h * w;
-    return 2 * (align_up(n * 4, 256) + align_up(n * 8, 256)) + align_up((size_t)n_out_frames * 8, 256);
+    return 2 * (align_up(n * 4, 256) + align_up(n * 8, 256)) + align_up((size_t)n_out_frames * 8, 256) + 256;
 }
 
 extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const float *flows_f, const float *flows_b,
@@ -412,6 +470,8 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
     l2.xy = (uint32_t *)(wsp + l4 + l8), l2.flow = (float2 *)(wsp + 2 * l4 + l8);
     l1.count = (uint32_t *)(wsp + 2 * (l4 + l8));
     l2.count = l1.count + total;
+    unsigned int *barriers = (unsigned int *)(wsp + 2 * (l4 + l8) + align_up((size_t)total * 8, 256));   // 32 + failure flag
+    int *failed = (int *)(barriers + K4_MAX_SUB);
     const float2 *ff = (const float2 *)flows_f, *fb = (const float2 *)flows_b;
     cudaError_t e = cudaMemsetAsync(l1.count, 0, (size_t)total * 8, st);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
@@ -443,6 +503,30 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
         // The serial scans touch hole pixels only.  The hole counts live on the device: the grid is
         // sized for ~1 item per thread at a 25 % hole fraction and strides over the list otherwise.
         dim3 grid(max(1, min(ceil_div(npx / 4, 256), ceil_div(148 * 16, b.n))), b.n);
+        if (get_option(OPT_K4_PERSISTENT) != 0 && blen > 1) {
+            // persistent scan: as many co-resident CTAs per window as the device can hold
+            static int max_blocks_per_sm = 0, sm_count = 0, coop = -1;
+            if (coop < 0) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+                cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, k4_scan_persistent, 256, 0);
+            }
+            const int resident = max_blocks_per_sm * sm_count;
+            const int gpw = min(resident / b.n, ceil_div(npx / 4, 256));     // CTAs per window
+            if (coop > 0 && gpw >= 1) {
+                cudaError_t me = cudaMemsetAsync(barriers, 0, (K4_MAX_SUB + 1) * sizeof(unsigned int), st);
+                if (me != cudaSuccess) return fail_cuda(me, "cudaMemsetAsync");
+                void *args[] = {(void *)&ff, (void *)&fb, (void *)&out, (void *)&l1, (void *)&l2, (void *)&h, (void *)&w,
+                                (void *)&barriers, (void *)&failed, (void *)&b};
+                cudaError_t le = cudaLaunchCooperativeKernel((const void *)k4_scan_persistent, dim3(gpw, b.n), dim3(256),
+                                                             args, 0, st);
+                if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchCooperativeKernel(k4_scan_persistent)");
+                VV_POST_LAUNCH("k4_scan_persistent");
+                continue;
+            }
+        }
         const int pdl = get_option(OPT_K4_PDL) != 0;
         for (int pass = 0; pass < 2; ++pass)
             for (int step = 1; step < blen; ++step) {
