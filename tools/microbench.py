@@ -102,13 +102,15 @@ def main():
     _lib.set_option("k3_tma_threads", 512)
     report("K3 composite feather 5 (generic path)", t * (7 * px + 3 * spx),
            lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
-    for pers, pdl in ((1, 1), (0, 1), (0, 0)):
+    for pers, pdl, warm in ((1, 1, 1), (1, 1, 0), (0, 1, 0), (0, 0, 0)):
         _lib.set_option("k4_persistent", pers)
         _lib.set_option("k4_pdl", pdl)
+        _lib.set_option("k4_warm", warm)
         report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb), k4_persistent=pers,
-               k4_pdl=pdl)
+               k4_pdl=pdl, k4_warm=warm)
     _lib.set_option("k4_persistent", 1)
     _lib.set_option("k4_pdl", 1)
+    _lib.set_option("k4_warm", 1)
     report("K5 chunk blend 16 frames", 16 * 9 * px, lambda: ops.chunk_blend(fr[:16], fr[16:32], out=out[:16]))
     report("copy (torch) 1080p frames", t * 6 * px, lambda: out.copy_(fr))
 

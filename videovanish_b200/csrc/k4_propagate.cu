@@ -300,6 +300,75 @@ __global__ void __launch_bounds__(256)
 // The chain of 2*(len-1) dependent launches is latency bound, so the per-item dependency chain is
 // kept at two memory round trips and the forward pass only visits what the backward pass left.
 // With programmatic dependent launch the next step's CTAs are resident before this one retires.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Frame / list / flow pointers of one step of one window.
+struct StepView {
+    long long of;                 // frame index in the state / list buffers
+    const float2 *flow_check;
+    const uint32_t *lxy;
+    const float2 *lflow;
+    const uint32_t *count;
+    bool valid;
+};
+template <bool PASS2>
+__device__ __forceinline__ StepView step_view(const SubDesc &sd, int step, const float2 *flows_f, const float2 *flows_b,
+                                              const HoleLists &l1, const HoleLists &l2, long long npx) {
+    StepView v;
+    v.valid = step >= 1 && step < sd.len;
+    const int idx = PASS2 ? step : sd.len - 1 - step;
+    const long long gframe = sd.start + idx;
+    v.flow_check = (PASS2 ? flows_f + (gframe - 1) * npx : flows_b + gframe * npx);
+    v.of = sd.out_frame + idx;
+    const HoleLists &li = PASS2 ? l2 : l1;
+    v.lxy = li.xy + v.of * npx;
+    v.lflow = li.flow + v.of * npx;
+    v.count = li.count + v.of;
+    return v;
+}
+
+// Persistent mode, software pipelining across steps: while a step runs, each thread already loads the
+// list entries it will own in the NEXT step and prefetches the flow_check sectors their taps will touch
+// into L2, so that the next step's dependency chain runs out of L2 instead of DRAM.
+constexpr int K4_WARM = 4;        // entries per thread warmed ahead
+struct WarmSet {
+    uint32_t xy[K4_WARM];
+    float2 f[K4_WARM];
+    int n;
+};
+__device__ __forceinline__ void warm_load(WarmSet &ws, const StepView &nv, uint32_t first, uint32_t lane, uint32_t stride) {
+    ws.n = 0;
+    if (!nv.valid) return;
+    const uint32_t n = __ldcg(nv.count);
+#pragma unroll
+    for (int k = 0; k < K4_WARM; ++k) {
+        const uint32_t i = first + lane + (uint32_t)k * stride;
+        if (i < n) {
+            ws.xy[k] = __ldcg(nv.lxy + i);
+            ws.f[k] = __ldcg(nv.lflow + i);
+            ws.n = k + 1;
+        }
+    }
+}
+__device__ __forceinline__ void warm_taps(const WarmSet &ws, const StepView &nv, int h, int w) {
+#pragma unroll
+    for (int k = 0; k < K4_WARM; ++k) {
+        if (k < ws.n) {
+            const int x = (int)(ws.xy[k] & 0xffffu), y = (int)(ws.xy[k] >> 16);
+            const float ix = unnormalized(__fadd_rn((float)x, ws.f[k].x), w);
+            const float iy = unnormalized(__fadd_rn((float)y, ws.f[k].y), h);
+            const int x0 = (int)fminf(fmaxf(floorf(ix), 0.f), (float)(w - 1));
+            const int y0 = (int)fminf(fmaxf(floorf(iy), 0.f), (float)(h - 1));
+            const float2 *r0 = nv.flow_check + (long long)y0 * w + x0;
+            const float2 *r1 = nv.flow_check + (long long)min(y0 + 1, h - 1) * w + x0;
+            prefetch_l2(r0);
+            prefetch_l2(r0 + 1);
+            prefetch_l2(r1);
+            prefetch_l2(r1 + 1);
+        }
+    }
+}
+
 template <bool PASS2, bool PERSIST>
 __device__ __forceinline__ void step_body(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b,
                                           uint32_t *state, const HoleLists &l1, const HoleLists &l2, int h, int w, int step,
@@ -398,20 +467,33 @@ __device__ __forceinline__ void window_barrier(unsigned int *ctr, unsigned int t
 // costs two memory round trips + one barrier (~5 us) instead of a kernel launch + ramp-up (~11-16 us).
 __global__ void __launch_bounds__(256)
     k4_scan_persistent(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state,
-                       HoleLists l1, HoleLists l2, int h, int w, unsigned int *barriers, int *failed,
+                       HoleLists l1, HoleLists l2, int h, int w, unsigned int *barriers, int *failed, int warm,
                        const __grid_constant__ SubBatch batch) {
     const SubDesc sd = batch.sub[blockIdx.y];
     __shared__ FlowQueue q;
     if (threadIdx.x == 0) q.count = 0;
     __syncthreads();
+    const long long npx = (long long)h * w;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u), lane = threadIdx.x & 31u;
     unsigned int arrivals = 0;
+    WarmSet ws;
     for (int step = 1; step < sd.len; ++step) {
+        // next step: step+1 of the backward pass, or step 1 of the forward pass after the last one (its
+        // list is complete by then only for frames the backward pass has already left: frame 1 is
+        // written in this very step, so the forward pass's first step is not warmed)
+        const StepView nv = step_view<false>(sd, step + 1, flows_f, flows_b, l1, l2, npx);
+        if (warm) warm_load(ws, nv, first, lane, stride);
         step_body<false, true>(flows_f, flows_b, state, l1, l2, h, w, step, sd, q);
+        if (warm) warm_taps(ws, nv, h, w);
         arrivals += gridDim.x;
         window_barrier(barriers + blockIdx.y, arrivals, failed);
     }
     for (int step = 1; step < sd.len; ++step) {
+        const StepView nv = step_view<true>(sd, step + 1, flows_f, flows_b, l1, l2, npx);
+        if (warm) warm_load(ws, nv, first, lane, stride);
         step_body<true, true>(flows_f, flows_b, state, l1, l2, h, w, step, sd, q);
+        if (warm) warm_taps(ws, nv, h, w);
         arrivals += gridDim.x;
         if (step + 1 < sd.len) window_barrier(barriers + blockIdx.y, arrivals, failed);
     }
@@ -518,8 +600,9 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             if (coop > 0 && gpw >= 1) {
                 cudaError_t me = cudaMemsetAsync(barriers, 0, (K4_MAX_SUB + 1) * sizeof(unsigned int), st);
                 if (me != cudaSuccess) return fail_cuda(me, "cudaMemsetAsync");
+                int warm = get_option(OPT_K4_WARM) != 0;
                 void *args[] = {(void *)&ff, (void *)&fb, (void *)&out, (void *)&l1, (void *)&l2, (void *)&h, (void *)&w,
-                                (void *)&barriers, (void *)&failed, (void *)&b};
+                                (void *)&barriers, (void *)&failed, (void *)&warm, (void *)&b};
                 cudaError_t le = cudaLaunchCooperativeKernel((const void *)k4_scan_persistent, dim3(gpw, b.n), dim3(256),
                                                              args, 0, st);
                 if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchCooperativeKernel(k4_scan_persistent)");
