@@ -224,8 +224,9 @@ def test_k4_zero_padding_fill(ops):
     assert np.array_equal(gf, rf) and np.array_equal(gm, rm)
 
 
-@pytest.mark.parametrize("variant", [dict(k4_persistent=1), dict(k4_persistent=0, k4_pdl=1), dict(k4_persistent=0, k4_pdl=0)],
-                         ids=["persistent", "launch-per-step-pdl", "launch-per-step"])
+@pytest.mark.parametrize("variant", [dict(k4_persistent=1, k4_warm=1), dict(k4_persistent=1, k4_warm=0),
+                                     dict(k4_persistent=0, k4_pdl=1), dict(k4_persistent=0, k4_pdl=0)],
+                         ids=["persistent-warm", "persistent", "launch-per-step-pdl", "launch-per-step"])
 def test_k4_kernel_variants(ops, variant):
     """The cooperative persistent scan and the launch-per-step fallback give identical states."""
     from videovanish_b200 import _lib
@@ -236,8 +237,9 @@ def test_k4_kernel_variants(ops, variant):
             _lib.set_option(k, v)
         got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb), subvideo_length=8, pad_len=3)).view(np.uint32)
     finally:
-        _lib.set_option("k4_persistent", 1)
+        _lib.set_option("k4_persistent", 0)
         _lib.set_option("k4_pdl", 1)
+        _lib.set_option("k4_warm", 0)
     assert np.array_equal(got, want)
 
 

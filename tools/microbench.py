@@ -108,9 +108,9 @@ def main():
         _lib.set_option("k4_warm", warm)
         report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb), k4_persistent=pers,
                k4_pdl=pdl, k4_warm=warm)
-    _lib.set_option("k4_persistent", 1)
+    _lib.set_option("k4_persistent", 0)
     _lib.set_option("k4_pdl", 1)
-    _lib.set_option("k4_warm", 1)
+    _lib.set_option("k4_warm", 0)
     report("K5 chunk blend 16 frames", 16 * 9 * px, lambda: ops.chunk_blend(fr[:16], fr[16:32], out=out[:16]))
     report("copy (torch) 1080p frames", t * 6 * px, lambda: out.copy_(fr))
 
