@@ -114,6 +114,23 @@ def main():
     report("K5 chunk blend 16 frames", 16 * 9 * px, lambda: ops.chunk_blend(fr[:16], fr[16:32], out=out[:16]))
     report("copy (torch) 1080p frames", t * 6 * px, lambda: out.copy_(fr))
 
+    # BASELINE config 4 shape: 4K frames, inference 960x536 (x ratio exactly 4, y ratio 4.03)
+    if wanted is None or any("4k" in w_ for w_ in wanted):
+        del fr, inp, mk, dil, low, small, out, empty_mask, full_mask, ff, fb
+        torch.cuda.empty_cache()
+        t4, H4, W4, h4, w4 = 48, 2160, 3840, 536, 960
+        fr4 = torch.from_numpy(np.tile(synth.frames(4, H4, W4, seed=5), (12, 1, 1, 1))).to(dev)
+        mk4 = torch.from_numpy(synth.masks(t4, H4, W4, seed=6)).to(dev)
+        inp4 = torch.from_numpy(np.tile(synth.noise_frames(4, h4, w4, seed=7), (12, 1, 1, 1))).to(dev)
+        px4, spx4 = H4 * W4, h4 * w4
+        dil4 = ops.binarize_dilate(mk4, 8)
+        out4 = torch.empty_like(fr4)
+        report("4K K1 dilate8 + low-res 960x536", t4 * (4 * px4 + spx4), lambda: ops.binarize_dilate(mk4, 8, lowres_size=(h4, w4)), frames_4k=t4)
+        report("4K K2 resize ->960x536", t4 * (3 * px4 + 3 * spx4), lambda: ops.resize(fr4, h4, w4), frames_4k=t4)
+        report("4K K3 composite (synthetic mask)", t4 * (7 * px4 + 3 * spx4),
+               lambda: ops.upscale_feather_composite(inp4, fr4, dil4, 3, out=out4), frames_4k=t4)
+        report("4K K5 chunk blend 16 frames", 16 * 9 * px4, lambda: ops.chunk_blend(fr4[:16], fr4[16:32], out=out4[:16]), frames_4k=t4)
+
 
 if __name__ == "__main__":
     main()

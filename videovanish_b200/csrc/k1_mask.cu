@@ -227,8 +227,9 @@ __global__ void __launch_bounds__(256) k1c_fill(const uint32_t *__restrict__ fla
 // dilated bit plane so the full-resolution u8 mask is not re-read.
 __global__ void __launch_bounds__(256)
     k1d_lowres_from_bits(const uint32_t *__restrict__ bits, int H, int W, int Wp, uint8_t *__restrict__ low, int lh,
-                         int lw, long long T, int words_ok) {
-    const int groups = (lw + 3) >> 2;
+                         int lw, long long T, int vec_ok) {
+    // one thread = 16 consecutive low-res pixels of one row -> one 128-bit store
+    const int groups = (lw + 15) >> 4;
     const long long total = T * lh * (long long)groups;
     const double sy = __ddiv_rn(1.0, __ddiv_rn((double)lh, (double)H));
     const double sx = __ddiv_rn(1.0, __ddiv_rn((double)lw, (double)W));
@@ -240,21 +241,21 @@ __global__ void __launch_bounds__(256)
         const long long t = q / lh;
         const int srcy = min((int)floor(__dmul_rn((double)y, sy)), H - 1);
         const uint32_t *brow = bits + (t * H + srcy) * Wp;
-        const int x0 = g * 4, n = min(4, lw - x0);
-        uint32_t packed = 0;
+        const int x0 = g * 16, n = min(16, lw - x0);
+        uint32_t m16 = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 16; ++i) {
             if (i < n) {
                 const int srcx = min((int)floor(__dmul_rn((double)(x0 + i), sx)), W - 1);
-                const uint32_t w = __ldg(brow + (srcx >> 5));
-                packed |= (((w >> (srcx & 31)) & 1u) * 0xffu) << (8 * i);
+                m16 |= ((__ldg(brow + (srcx >> 5)) >> (srcx & 31)) & 1u) << i;
             }
         }
         uint8_t *o = low + (t * lh + y) * (long long)lw + x0;
-        if (words_ok && n == 4) {
-            *reinterpret_cast<uint32_t *>(o) = packed;
+        if (vec_ok && n == 16) {
+            stg128_stream(o, make_uint4(expand4(m16), expand4(m16 >> 4), expand4(m16 >> 8), expand4(m16 >> 12)));
         } else {
-            for (int i = 0; i < n; ++i) o[i] = (uint8_t)(packed >> (8 * i));
+#pragma unroll 1
+            for (int i = 0; i < n; ++i) o[i] = ((m16 >> i) & 1u) ? 255 : 0;
         }
     }
 }
@@ -344,15 +345,18 @@ extern "C" int vv_binarize_dilate(const uint8_t *mask, int T, int H, int W, int 
         return VV_OK;
     }
 
-    // chains of <= 32 rounds (diamond_a (+) diamond_b == diamond_{a+b}); the last pass expands to bytes
+    // Chains of <= 16 rounds on the bit planes (diamond_a (+) diamond_b == diamond_{a+b}); the last pass
+    // expands to bytes.  16 keeps the register tile at 32 output rows + 2x16 halo rows: a single pass of
+    // radius 25 would recompute a 50-row halo for every 16 output rows.
     uint32_t *cur = bits0, *nxt = bits1;
     int left = iterations;
-    while (left > 32) {
-        rc = dilate_pass(cur, nxt, nullptr, nullptr, T, H, W, Wp, 32, vec_out, st);
+    while (left > 16) {
+        const int step_n = left > 32 ? 16 : (left + 1) / 2;      // split the tail evenly (25 -> 13 + 12)
+        rc = dilate_pass(cur, nxt, nullptr, nullptr, T, H, W, Wp, step_n, vec_out, st);
         if (rc) return rc;
         uint32_t *tmp = cur;
         cur = nxt, nxt = tmp;
-        left -= 32;
+        left -= step_n;
     }
     // exact x2 down-size: the low-res mask is written by the dilation pass itself
     const bool half = lowres_out && H == 2 * lh && W == 2 * lw;
@@ -361,10 +365,10 @@ extern "C" int vv_binarize_dilate(const uint8_t *mask, int T, int H, int W, int 
                      half ? vec_half : vec_out, st);
     if (rc) return rc;
     if (lowres_out && !half) {
-        const long long total = (long long)T * lh * ((lw + 3) / 4);
-        const int words_ok = (lw % 4 == 0) && ((uintptr_t)lowres_out % 4 == 0);
+        const long long total = (long long)T * lh * ((lw + 15) / 16);
+        const int vec_low = (lw % 16 == 0) && ((uintptr_t)lowres_out % 16 == 0);
         k1d_lowres_from_bits<<<(int)min((long long)ceil_div(total, 256), (long long)148 * 32), 256, 0, st>>>(
-            nxt, H, W, Wp, lowres_out, lh, lw, T, words_ok);
+            nxt, H, W, Wp, lowres_out, lh, lw, T, vec_low);
         VV_POST_LAUNCH("k1d_lowres_from_bits");
     }
     return VV_OK;

@@ -163,6 +163,30 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// NEAREST for single-channel images (masks): 16 destination pixels per thread, one 128-bit store.
+__global__ void __launch_bounds__(256)
+    k2_resize_nearest_c1_x16(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const int *__restrict__ xo,
+                             const int *__restrict__ yo, int H, int W, int h, int w, long long T) {
+    const int groups = w >> 4;
+    const long long total = T * h * (long long)groups;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % groups);
+        const long long q = idx / groups;
+        const int y = (int)(q % h);
+        const long long t = q / h;
+        const uint8_t *s = src + (t * H + yo[y]) * (long long)W;
+        const int4 *xq = reinterpret_cast<const int4 *>(xo + g * 16);
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int4 xi = __ldg(xq + k);
+            o[k] = __ldg(s + xi.x) | (__ldg(s + xi.y) << 8) | (__ldg(s + xi.z) << 16) | ((uint32_t)__ldg(s + xi.w) << 24);
+        }
+        stg128_stream(dst + (t * h + y) * (long long)w + g * 16, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
 }  // namespace vv
 
 using namespace vv;
@@ -222,7 +246,10 @@ extern "C" int vv_resize(const uint8_t *src, int T, int H, int W, int C, uint8_t
         k2_make_nearest_taps<<<ceil_div(h, 256), 256, 0, st>>>(yo, h, H);
         VV_POST_LAUNCH("k2_make_nearest_taps(y)");
         const int grid = (int)min((long long)ceil_div((long long)T * h * w, 256), (long long)max_grid);
-        if (C == 1)
+        if (C == 1 && w % 16 == 0 && (uintptr_t)dst % 16 == 0) {
+            const int g16 = (int)min((long long)ceil_div((long long)T * h * (w / 16), 256), (long long)max_grid);
+            k2_resize_nearest_c1_x16<<<g16, 256, 0, st>>>(src, dst, xo, yo, H, W, h, w, T);
+        } else if (C == 1)
             k2_resize_nearest<1><<<grid, 256, 0, st>>>(src, dst, xo, yo, H, W, h, w, T);
         else if (C == 3)
             k2_resize_nearest<3><<<grid, 256, 0, st>>>(src, dst, xo, yo, H, W, h, w, T);
