@@ -148,6 +148,23 @@ VV_API int vv_chunk_blend(const uint8_t *A, const uint8_t *B, int O, size_t fram
                    int O_total, uint8_t *out, void *stream);
 
 /* ---------------------------------------------------------------------------------
+ * "Next" rows: the pixel glue immediately either side of the hot path.
+ * N3  SAM2 mask colour painter.                        Replaces sam2_masker.py:151-175
+ *   masks: u8 (non-zero = set) or f32 logits (> 0 = set) [T,K,mh,mw], object k in paint order
+ *   (ascending object id: the LAST one wins where masks overlap, :159-173); NEAREST-resized to
+ *   the canvas when (mh,mw) != (H0,W0) (:167).  colors: HOST u8 [K,3], written as given (the
+ *   reference stores its (B,G,R) tuples).  out: u8 [T,H0,W0,3], black where no object is set.
+ * N2  K4 packed state -> f32 [n_frames,3,h,w] in [-1,1] (`to_tensors()*2-1`, 0.0 for state bit 1)
+ *   and the f32 hole mask [n_frames,h,w] (may be NULL): what the ProPainter network consumes.
+ * --------------------------------------------------------------------------------- */
+VV_API size_t vv_paint_masks_workspace_bytes(int H0, int W0);
+VV_API int vv_paint_masks(const void *masks, int mask_is_f32, int T, int K, int mh, int mw,
+                          const uint8_t *colors_host, uint8_t *out, int H0, int W0, void *workspace,
+                          size_t workspace_bytes, void *stream);
+VV_API int vv_propagate_to_float(const uint32_t *packed, int n_frames, int h, int w, float *rgb_chw,
+                                 float *hole_mask, void *stream);
+
+/* ---------------------------------------------------------------------------------
  * Host-buffer pipeline (the path the Python drop-in takes for lists of numpy frames, i.e. the
  * whole of diffuerase.py:26-31 and :69-114 with per-frame HOST pointers in and out).
  * A context owns device buffers, streams and (lazily) pinned staging rings for one original

@@ -60,5 +60,28 @@ def main():
         print(name, "dilated px", int(np.stack(dil).astype(bool).sum()), "out", np.stack(outs).shape)
 
 
+def main_paint():
+    """tests/golden/paint.npz: the UNMODIFIED sam2_masker.run_sam2_on_frames (stub SAM2 predictor that
+    replays seeded logits) -> colour-painted mask frames (SURVEY next row N3)."""
+    from oracle import painter
+    rng = np.random.default_rng(5)
+    t, k, mh, mw, h0, w0 = 4, 3, 45, 80, 90, 160
+    obj_ids = [1, 2, 7]
+    frames = [np.zeros((h0, w0, 3), np.uint8) for _ in range(t)]
+    logits = {i: (rng.normal(size=(k, 1, mh, mw)) - 0.8).astype(np.float32) for i in range(t)}
+    for i in range(t):
+        logits[i][0, 0, 5:30, 10:50] = 2.0
+        logits[i][1, 0, 20:40, 30:70] = 1.0
+        logits[i][2, 0, 25:35, 40:45] = 3.0
+    out, _ = painter.reference_paint(frames, logits, obj_ids)
+    logits2 = {i: (rng.normal(size=(k, 1, h0, w0)) - 1.0).astype(np.float32) for i in range(2)}
+    out2, _ = painter.reference_paint(frames[:2], logits2, obj_ids)
+    np.savez_compressed(os.path.join(OUT, "paint.npz"), logits=np.stack([logits[i] for i in range(t)]),
+                        obj_ids=np.array(obj_ids), out=np.stack(out),
+                        logits_same=np.stack([logits2[i] for i in range(2)]), out_same=np.stack(out2))
+    print("paint", np.stack(out).shape)
+
+
 if __name__ == "__main__":
     main()
+    main_paint()

@@ -20,7 +20,8 @@ from tests.golden.make_golden import inputs as golden_inputs
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if os.path.basename(p) != "paint.npz")
 
 
 @pytest.fixture(scope="module")
@@ -414,3 +415,36 @@ def test_empty_and_degenerate_inputs(ops):
     assert host(ops.binarize_dilate(dev(one), 8)).tolist() == [[[255]]]
     with pytest.raises(RuntimeError):
         ops.binarize_dilate(dev(np.zeros((0, 4, 4, 3), np.uint8)), 1)
+
+
+# ------------------------------------------------------------------------------- next rows N3 / N2
+def test_n3_painter_matches_reference_golden(ops):
+    from oracle import painter
+    from videovanish_b200 import sam2_masker as vsm
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "paint.npz"))
+    ids = [int(v) for v in z["obj_ids"]]
+    h0, w0 = z["out"].shape[1:3]
+    assert [vsm.color_for_obj(o) for o in ids] == [painter.color_for_obj(o) for o in ids]
+    # float logits straight from the model (T,K,1,mh,mw), resized by the kernel
+    got = host(ops.paint_masks(dev(z["logits"][:, :, 0]), [painter.color_for_obj(o) for o in ids], out_size=(h0, w0)))
+    assert np.array_equal(got, z["out"])
+    got_same = host(ops.paint_masks(dev((z["logits_same"][:, :, 0] > 0).astype(np.uint8)),
+                                    [painter.color_for_obj(o) for o in ids]))
+    assert np.array_equal(got_same, z["out_same"])
+    # the dict-of-dicts front-end, with a missing object on one frame and odd sizes
+    rng = np.random.default_rng(9)
+    segs = {i: {o: rng.random((33, 47)) < 0.2 for o in (3, 1, 12)} for i in range(3)}
+    del segs[1][12]
+    want = painter.ref_paint(segs, 4, 67, 95)
+    have = vsm.paint_mask_frames(segs, 4, 67, 95)
+    assert all(np.array_equal(a, b) for a, b in zip(want, have))
+
+
+def test_n2_state_to_float(ops):
+    fr, m, ff, fb = prop_clip(5, 36, 52, seed=61)
+    packed = ops.propagate(dev(fr), dev(m), dev(ff), dev(fb))
+    rgb, hole = ops.propagate_to_float(packed)
+    want_rgb, want_hole = opp.decode_state(host(packed).view(np.uint32))
+    assert np.array_equal(host(rgb), want_rgb) and np.array_equal(host(hole), want_hole)
+    ref_rgb, ref_hole = opp.img_propagation_torch(fr, m, ff, fb)
+    assert np.array_equal(host(rgb), ref_rgb) and np.array_equal(host(hole), ref_hole)

@@ -46,6 +46,10 @@ _SIGNATURES = {
     "vv_propagate": (c_int, [_u8p, _u8p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int,
                              c_void_p, c_void_p, c_size_t, c_void_p]),
     "vv_propagate_unpack": (c_int, [c_void_p, c_size_t, c_ubyte, _u8p, _u8p, c_void_p]),
+    "vv_paint_masks_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "vv_paint_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, _u8p, c_int, c_int, c_void_p,
+                               c_size_t, c_void_p]),
+    "vv_propagate_to_float": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vv_chunk_blend": (c_int, [_u8p, _u8p, c_int, c_size_t, c_int, c_int, _u8p, c_void_p]),
     "vv_pipeline_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int]),
     "vv_pipeline_destroy": (None, [c_void_p]),

@@ -182,3 +182,35 @@ def chunk_blend(tail, head, k0=0, overlap_total=None, out=None):
         _lib.check(lib.vv_chunk_blend(ctypes.c_void_p(pa), ctypes.c_void_p(pb), o, frame_bytes, int(k0),
                                       int(overlap_total), _ptr(out), _stream()), "vv_chunk_blend")
     return out
+
+
+def paint_masks(masks, colors, out_size=None):
+    """N3.  masks u8 / f32-logits [T,K,mh,mw] (object k in ascending id order), colors K x 3 ints ->
+    u8 [T,H0,W0,3] colour-painted mask frames (sam2_masker.py:151-175; highest object wins)."""
+    _require_cuda(masks)
+    if masks.dim() != 4 or masks.dtype not in (torch.uint8, torch.float32, torch.bool):
+        raise ValueError("paint_masks: masks must be uint8 / bool / float32 [T,K,mh,mw]")
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    t, k, mh, mw = masks.shape
+    h0, w0 = (mh, mw) if out_size is None else (int(out_size[0]), int(out_size[1]))
+    cols = (ctypes.c_ubyte * (3 * k))(*[int(v) & 255 for c in colors for v in c])
+    with torch.cuda.device(masks.device):
+        out = torch.empty((t, h0, w0, 3), dtype=torch.uint8, device=masks.device)
+        nbytes = lib.vv_paint_masks_workspace_bytes(h0, w0)
+        ws = _ws(nbytes, masks.device)
+        _lib.check(lib.vv_paint_masks(_ptr(masks), 1 if masks.dtype == torch.float32 else 0, t, k, mh, mw, cols, _ptr(out),
+                                      h0, w0, _ptr(ws), nbytes, _stream()), "vv_paint_masks")
+    return out
+
+
+def propagate_to_float(packed, want_mask=True):
+    """N2.  K4's packed state [N,h,w] -> (f32 [N,3,h,w] in [-1,1], f32 hole mask [N,h,w])."""
+    _require_cuda(packed)
+    n, h, w = packed.shape
+    with torch.cuda.device(packed.device):
+        rgb = torch.empty((n, 3, h, w), dtype=torch.float32, device=packed.device)
+        hole = torch.empty((n, h, w), dtype=torch.float32, device=packed.device) if want_mask else None
+        _lib.check(lib.vv_propagate_to_float(_ptr(packed), n, h, w, _ptr(rgb), _ptr(hole), _stream()),
+                   "vv_propagate_to_float")
+    return (rgb, hole) if want_mask else rgb
