@@ -113,6 +113,14 @@ def main():
     _lib.set_option("k4_warm", 0)
     report("K5 chunk blend 16 frames", 16 * 9 * px, lambda: ops.chunk_blend(fr[:16], fr[16:32], out=out[:16]))
     report("copy (torch) 1080p frames", t * 6 * px, lambda: out.copy_(fr))
+    # next rows: N3 painter (3 objects at inference resolution painted onto the 1080p canvas), N2 state -> float
+    if wanted is None or any(w_ in ("n3", "n2", "next") for w_ in wanted):
+        tn = min(t, 60)
+        logits = torch.randn((tn, 3, HS, WS), device=dev, generator=g) - 1.0
+        report("N3 paint 3 objects 540p -> 1080p", tn * (3 * 4 * spx + 3 * px),
+               lambda: ops.paint_masks(logits, [(55, 255, 208), (148, 255, 55), (182, 255, 55)], out_size=(H0, W0)), frames_n=tn)
+        packed = ops.propagate(small[:tn], low[:tn], ff[:tn - 1], fb[:tn - 1])
+        report("N2 state -> float CHW", tn * (4 + 16) * spx, lambda: ops.propagate_to_float(packed), frames_n=tn)
 
     # BASELINE config 4 shape: 4K frames, inference 960x536 (x ratio exactly 4, y ratio 4.03)
     if wanted is None or any("4k" in w_ for w_ in wanted):
