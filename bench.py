@@ -310,6 +310,33 @@ def run_ours(args, rank, world, local_rank):
     stage_ms = {s: float(np.mean([evs[k][i][0].elapsed_time(evs[k][i][1]) for k in range(args.steps)]))
                 for i, s in enumerate(stages)}
 
+    # ---- K3 against mask density (outside the timed region): the post kernel is HBM bound on sparse
+    # masks and issue bound on the dense synthetic one, so its roofline fraction is reported for three
+    # masks: none, the moving box only (5 % of the frame), and the bench mask (box + dilated salt, 18 %)
+    k3_density = None
+    if rank == 0:
+        from videovanish_b200 import synth as _synth
+        box_only = torch.from_numpy(_synth.masks(t, H0, W0, seed=10 + rank + 1, salt=0.0)).to(device)
+        masks_k3 = {"empty": torch.zeros((t, H0, W0), dtype=torch.uint8, device=device),
+                    "box_only_dilated": ops.binarize_dilate(box_only, DILATE),
+                    "bench_mask": ops.binarize_dilate(dev["masks"], DILATE)}
+        del box_only
+        k3_density = {}
+        alg_k3 = algorithmic_bytes(t)["K3_upscale_feather_composite"]
+        for name, mk in masks_k3.items():
+            for _ in range(2):
+                ops.upscale_feather_composite(dev["inpainted"], dev["frames"], mk, FEATHER, out=out_buf)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                ops.upscale_feather_composite(dev["inpainted"], dev["frames"], mk, FEATHER, out=out_buf)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 3
+            k3_density[name] = {"masked_fraction": float((mk > 0).float().mean()), "ms": ms,
+                                "GBps": alg_k3 / (ms * 1e-3) / 1e9, "frac": alg_k3 / (ms * 1e-3) / 1e9 / peaks()[0]}
+        del masks_k3
+
     # ---- end to end through the reference-facing call, host buffers in, host buffers out
     class _StubModel:                       # stands in for DiffuEraser / ProPainter (out of scope)
         def forward(self, frames, masks, priors, **kw):
@@ -366,6 +393,7 @@ def run_ours(args, rank, world, local_rank):
                     "phases": e2e_phases,
                     "path": "diffuerase.run_infill_on_frames(list of pinned host frames), stub models, K1 + K3 via "
                             "the host pipeline; result %dx%d" % (fh, fw)},
+            "k3_vs_mask_density": k3_density,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
