@@ -250,38 +250,53 @@ __global__ void __launch_bounds__(K4_BLOCK)
     // flow that propagates INTO this frame: backward pass flows_f[gframe], forward pass flows_b[gframe-1]
     const float2 *pflow = last ? flows_b + (gframe - 1) * npx : flows_f + gframe * npx;
     const HoleLists &dl = last ? l2 : l1;
-    const long long p0 = (long long)blockIdx.x * K4_CHUNK + threadIdx.x * 16;
-    const uint32_t holes = hole_bits16<VEC>(masks + gframe * npx, p0, npx);
-
-    // packed state of this thread's 16 pixels
-    if (p0 < npx) {
-        if (VEC) {
-            const uint4 a = ldg128(fr + p0 * 3), b = ldg128(fr + p0 * 3 + 16), c = ldg128(fr + p0 * 3 + 32);
-            const uint32_t wds[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    // Each warp owns 512 consecutive pixels; lane L handles the 4-pixel groups L, L+32, L+64, L+96 of that
+    // span, so every load / store instruction of the warp touches consecutive addresses.
+    const uint8_t *mk = masks + gframe * npx;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long span0 = (long long)blockIdx.x * K4_CHUNK + wid * 512;
+    uint32_t holes = 0;                                         // bit 4k+i: pixel i of group k is a hole
+    if (VEC) {
+        uint32_t m4[4], fa[4], fb2[4], fd[4];
+        bool ok[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                uint32_t c4[4];
-                c4[0] = wds[3 * g] & 0x00ffffffu;
-                c4[1] = (wds[3 * g] >> 24) | ((wds[3 * g + 1] & 0x0000ffffu) << 8);
-                c4[2] = (wds[3 * g + 1] >> 16) | ((wds[3 * g + 2] & 0x000000ffu) << 16);
-                c4[3] = wds[3 * g + 2] >> 8;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if ((holes >> (4 * g + i)) & 1u) c4[i] = ST_HOLE | ST_ZERO;
-                *reinterpret_cast<uint4 *>(dst + p0 + 4 * g) = make_uint4(c4[0], c4[1], c4[2], c4[3]);
+        for (int k = 0; k < 4; ++k) {
+            const long long p0 = span0 + (lane + 32 * k) * 4;
+            ok[k] = p0 < npx;
+            if (ok[k]) {
+                m4[k] = __ldg(reinterpret_cast<const uint32_t *>(mk + p0));
+                const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0 * 3);
+                fa[k] = __ldg(f3), fb2[k] = __ldg(f3 + 1), fd[k] = __ldg(f3 + 2);
             }
-        } else {
-            const int n = (int)min(16LL, npx - p0);
-            for (int i = 0; i < n; ++i) {
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!ok[k]) continue;
+            const long long p0 = span0 + (lane + 32 * k) * 4;
+            uint32_t c4[4];
+            c4[0] = fa[k] & 0x00ffffffu;
+            c4[1] = (fa[k] >> 24) | ((fb2[k] & 0x0000ffffu) << 8);
+            c4[2] = (fb2[k] >> 16) | ((fd[k] & 0x000000ffu) << 16);
+            c4[3] = fd[k] >> 8;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (byte_of(m4[k], i)) c4[i] = ST_HOLE | ST_ZERO, holes |= 1u << (4 * k + i);
+            *reinterpret_cast<uint4 *>(dst + p0) = make_uint4(c4[0], c4[1], c4[2], c4[3]);
+        }
+    } else {
+        for (int k = 0; k < 4; ++k) {
+            const long long p0 = span0 + (lane + 32 * k) * 4;
+            for (int i = 0; i < 4 && p0 + i < npx; ++i) {
                 const uint8_t *q8 = fr + (p0 + i) * 3;
-                dst[p0 + i] = ((holes >> i) & 1u) ? (ST_HOLE | ST_ZERO) : (q8[0] | (q8[1] << 8) | ((uint32_t)q8[2] << 16));
+                const bool hole = mk[p0 + i] != 0;
+                dst[p0 + i] = hole ? (ST_HOLE | ST_ZERO) : (q8[0] | (q8[1] << 8) | ((uint32_t)q8[2] << 16));
+                if (hole) holes |= 1u << (4 * k + i);
             }
         }
     }
     if (!listed) return;                                        // block-uniform
 
     // position of this thread's holes inside the chunk: warp scan + per-warp totals
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cnt = __popc(holes);
     int incl = cnt;
 #pragma unroll
@@ -296,32 +311,26 @@ __global__ void __launch_bounds__(K4_BLOCK)
     for (int k = 0; k < wid; ++k) woff += s_warp[k];
     if (holes) {
         long long pos = of * npx + chunk_offsets[of * chunks + blockIdx.x] + woff + incl - cnt;
-        const uint32_t p32 = (uint32_t)p0;                      // h*w < 2^32 (both <= 65535)
-        uint32_t y = p32 / (uint32_t)w, x = p32 - y * (uint32_t)w;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if ((holes >> i) & 1u) {
-                dl.xy[pos] = x | (y << 16);
-                dl.flow[pos] = __ldg(pflow + p0 + i);
-                ++pos;
+        for (int k = 0; k < 4; ++k) {
+            if ((holes >> (4 * k)) & 15u) {
+                const long long p0 = span0 + (lane + 32 * k) * 4;
+                const uint32_t p32 = (uint32_t)p0;              // h*w < 2^32 (both <= 65535)
+                uint32_t y = p32 / (uint32_t)w, x = p32 - y * (uint32_t)w;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if ((holes >> (4 * k + i)) & 1u) {
+                        dl.xy[pos] = x | (y << 16);
+                        dl.flow[pos] = __ldg(pflow + p0 + i);
+                        ++pos;
+                    }
+                    if (++x == (uint32_t)w) x = 0, ++y;
+                }
             }
-            if (++x == (uint32_t)w) x = 0, ++y;
         }
     }
 }
 
-// ---- k4_step: one time step of one direction, in place, over the hole lists -------------------
-// blockIdx.y = sub-video.  The state buffer holds the input frames after k4_pack, the backward
-// result after pass 1 and the forward result after pass 2:
-//   PASS2 == false (backward, t = len-2 .. 0):  frame idx is updated from frame idx+1; holes that
-//                                               stay holes are appended to the frame's forward list
-//   PASS2 == true  (forward,  t = 1 .. len-1):  frame idx (backward result) is updated from frame
-//                                               idx-1 (already the forward result)
-// Frame len-1 / frame 0 are the first step of their pass and stay as they are.
-//
-// The chain of 2*(len-1) dependent launches is latency bound, so the per-item dependency chain is
-// kept at two memory round trips and the forward pass only visits what the backward pass left.
-// With programmatic dependent launch the next step's CTAs are resident before this one retires.
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Frame / list / flow pointers of one step of one window.
