@@ -15,7 +15,7 @@
 // masked frame's 0.0").  The four bilinear taps of the previous state give both the mask warp and
 // the nearest pixel, so one 4-word gather serves both.
 //
-// Structure: k4_count / k4_offsets / k4_pack turn frames + masks into the packed state ONCE (fully parallel over all
+// Structure: k4_pack turns frames + masks into the packed state ONCE (fully parallel over all
 // frames, streaming) and records each frame's hole pixels in a list.  The scan itself is serial in
 // time but touches hole pixels only: every step launch walks the hole list of one frame per
 // sub-video, in place on the state buffer (backward pass, then forward pass over the same buffer).
@@ -105,12 +105,17 @@ struct HoleLists {
     uint32_t *count;     // [frames]
 };
 
-// Block-level append (backward steps re-listing the holes they could not fill).  Entries are first
-// collected in a shared-memory queue (one shared atomic per warp and call), then the block reserves its
-// range of the frame's list with ONE global atomic and writes it out coalesced - a per-warp global
-// atomic on the single per-frame counter serialises in L2 and dominated the first version.
+// Block-level append.  Hole entries are first collected in a shared-memory queue (one shared
+// atomic per warp and call), then the block reserves its range of the frame's list with ONE global
+// atomic and writes it out coalesced - a per-warp global atomic on the single per-frame counter
+// serialises in L2 and dominated the first version of this stage.
 constexpr int K4_BLOCK = 256;
-constexpr int K4_CHUNK = K4_BLOCK * 16;       // pixels per CTA in the count / pack kernels (16 per thread)
+constexpr int K4_PACK_UNROLL = 4;             // 4-pixel groups per thread and round in k4_pack
+constexpr int K4_QCAP = 2 * 4 * K4_BLOCK * K4_PACK_UNROLL;   // queue entries: two k4_pack push rounds
+struct BlockQueue {
+    uint32_t xy[K4_QCAP];
+    uint32_t count, base;
+};
 struct FlowQueue {                            // k4_step: entries carry their flow (loaded speculatively)
     uint32_t xy[2 * K4_BLOCK];
     float2 flow[2 * K4_BLOCK];
@@ -151,186 +156,150 @@ __device__ __forceinline__ void queue_flush(FlowQueue &q, const HoleLists &l, lo
     __syncthreads();
 }
 
-// ---- k4_count / k4_offsets / k4_pack: frames + masks -> packed state + per-frame hole lists ----------
-// The lists are built without atomics and in pixel order: k4_count counts the holes of every
-// 4096-pixel chunk, k4_offsets turns the counts of a frame into chunk offsets (and the frame total),
-// k4_pack then writes state and list entries at their final positions.  One launch each for all frames
-// of all windows of the batch (blockIdx.y = output frame).  Holes of the last frame of a window are never
-// touched by the backward pass, so they go straight to the forward list `l2`.
-__device__ __forceinline__ long long frame_of(const SubBatch &batch, long long of, int &idx, int &len) {
+// All threads of the block must call (contains barriers).  `flow_frame` is gathered for each entry.
+// With `force == false` the queue is only written out when another push round might overflow it.
+__device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, long long of, long long npx, int w,
+                                            const float2 *__restrict__ flow_frame, bool force) {
+    __syncthreads();
+    const uint32_t n = q.count;
+    __syncthreads();                                            // everyone has read the count before it can change
+    if (!force && n + 4 * K4_BLOCK * K4_PACK_UNROLL <= K4_QCAP) return;   // block-uniform
+    if (n) {
+        if (threadIdx.x == 0) q.base = atomicAdd(l.count + of, n);
+        __syncthreads();
+        const long long dst = of * npx + q.base;
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+            const uint32_t xy = q.xy[j];
+            l.xy[dst + j] = xy;
+            l.flow[dst + j] = __ldg(flow_frame + (long long)(xy >> 16) * w + (xy & 0xffffu));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) q.count = 0;
+    __syncthreads();
+}
+
+// ---- k4_pack: frames + masks -> packed state, and the per-frame lists of hole pixels -----------
+// One launch for every frame of every window of the batch (blockIdx.y = output frame).  Holes of
+// the last frame of a window are never touched by the backward pass, so they go straight to `l2`.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+    k4_pack(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, uint32_t *__restrict__ state,
+            const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, HoleLists l1, HoleLists l2, int h,
+            int w, long long first_out_frame, const __grid_constant__ SubBatch batch) {
+    const long long of = first_out_frame + blockIdx.y;          // output frame handled by this CTA row
     int s = 0;
     while (s + 1 < batch.n && batch.sub[s + 1].out_frame <= of) ++s;
-    idx = (int)(of - batch.sub[s].out_frame);
-    len = batch.sub[s].len;
-    return batch.sub[s].start + idx;
-}
-
-// 16 mask bytes of one thread -> 16 hole bits.
-template <bool VEC>
-__device__ __forceinline__ uint32_t hole_bits16(const uint8_t *__restrict__ mk, long long p0, long long npx) {
-    if (p0 >= npx) return 0;
-    if (VEC) return nonzero_bits16(ldg128(mk + p0));
-    uint32_t m = 0;
-    const int n = (int)min(16LL, npx - p0);
-    for (int i = 0; i < n; ++i) m |= (uint32_t)(mk[p0 + i] != 0) << i;
-    return m;
-}
-
-template <bool VEC>
-__global__ void __launch_bounds__(K4_BLOCK)
-    k4_count(const uint8_t *__restrict__ masks, uint32_t *__restrict__ chunk_counts, int h, int w, long long first_out_frame,
-             int chunks, const __grid_constant__ SubBatch batch) {
-    const long long of = first_out_frame + blockIdx.y;
-    int idx, len;
-    const long long gframe = frame_of(batch, of, idx, len);
-    const long long npx = (long long)h * w;
-    const long long p0 = (long long)blockIdx.x * K4_CHUNK + threadIdx.x * 16;
-    int cnt = __popc(hole_bits16<VEC>(masks + gframe * npx, p0, npx));
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    __shared__ int s_cnt[K4_BLOCK / 32];
-    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-#pragma unroll
-        for (int k = 0; k < K4_BLOCK / 32; ++k) tot += s_cnt[k];
-        chunk_counts[of * chunks + blockIdx.x] = (uint32_t)tot;
-    }
-}
-
-// One CTA per frame: exclusive scan of the chunk counts in place, frame total -> list count.
-__global__ void __launch_bounds__(K4_BLOCK)
-    k4_offsets(uint32_t *__restrict__ chunk_counts, HoleLists l1, HoleLists l2, long long first_out_frame, int chunks,
-               const __grid_constant__ SubBatch batch) {
-    const long long of = first_out_frame + blockIdx.x;
-    int idx, len;
-    frame_of(batch, of, idx, len);
-    uint32_t *c = chunk_counts + of * chunks;
-    __shared__ uint32_t s_warp[K4_BLOCK / 32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < chunks; base += K4_BLOCK) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = i < chunks ? c[i] : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += u;
-        }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        uint32_t woff = 0;
-        for (int k = 0; k < wid; ++k) woff += s_warp[k];
-        const uint32_t carry = s_carry;
-        if (i < chunks) c[i] = carry + woff + incl - v;          // exclusive offset of chunk i
-        __syncthreads();
-        if (threadIdx.x == K4_BLOCK - 1) s_carry = carry + woff + incl;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && len > 1) (idx == len - 1 ? l2 : l1).count[of] = s_carry;
-}
-
-template <bool VEC>
-__global__ void __launch_bounds__(K4_BLOCK)
-    k4_pack(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, uint32_t *__restrict__ state,
-            const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, HoleLists l1, HoleLists l2,
-            const uint32_t *__restrict__ chunk_offsets, int h, int w, long long first_out_frame, int chunks,
-            const __grid_constant__ SubBatch batch) {
-    const long long of = first_out_frame + blockIdx.y;          // output frame handled by this CTA row
-    int idx, len;
-    const long long gframe = frame_of(batch, of, idx, len);
+    const int idx = (int)(of - batch.sub[s].out_frame), len = batch.sub[s].len;
+    const long long gframe = batch.sub[s].start + idx;
     const long long npx = (long long)h * w;
     const uint8_t *fr = frames + gframe * npx * 3;
+    const uint8_t *mk = masks + gframe * npx;
     uint32_t *dst = state + of * npx;
     const bool last = idx == len - 1;
     const bool listed = len > 1;                                // a single-frame window has no steps at all
     // flow that propagates INTO this frame: backward pass flows_f[gframe], forward pass flows_b[gframe-1]
     const float2 *pflow = last ? flows_b + (gframe - 1) * npx : flows_f + gframe * npx;
     const HoleLists &dl = last ? l2 : l1;
-    // Each warp owns 512 consecutive pixels; lane L handles the 4-pixel groups L, L+32, L+64, L+96 of that
-    // span, so every load / store instruction of the warp touches consecutive addresses.
-    const uint8_t *mk = masks + gframe * npx;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long span0 = (long long)blockIdx.x * K4_CHUNK + wid * 512;
-    uint32_t holes = 0;                                         // bit 4k+i: pixel i of group k is a hole
-    if (VEC) {
-        uint32_t m4[4], fa[4], fb2[4], fd[4];
-        bool ok[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long p0 = span0 + (lane + 32 * k) * 4;
-            ok[k] = p0 < npx;
-            if (ok[k]) {
-                m4[k] = __ldg(reinterpret_cast<const uint32_t *>(mk + p0));
-                const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0 * 3);
-                fa[k] = __ldg(f3), fb2[k] = __ldg(f3 + 1), fd[k] = __ldg(f3 + 2);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!ok[k]) continue;
-            const long long p0 = span0 + (lane + 32 * k) * 4;
-            uint32_t c4[4];
-            c4[0] = fa[k] & 0x00ffffffu;
-            c4[1] = (fa[k] >> 24) | ((fb2[k] & 0x0000ffffu) << 8);
-            c4[2] = (fb2[k] >> 16) | ((fd[k] & 0x000000ffu) << 16);
-            c4[3] = fd[k] >> 8;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (byte_of(m4[k], i)) c4[i] = ST_HOLE | ST_ZERO, holes |= 1u << (4 * k + i);
-            *reinterpret_cast<uint4 *>(dst + p0) = make_uint4(c4[0], c4[1], c4[2], c4[3]);
-        }
-    } else {
-        for (int k = 0; k < 4; ++k) {
-            const long long p0 = span0 + (lane + 32 * k) * 4;
-            for (int i = 0; i < 4 && p0 + i < npx; ++i) {
-                const uint8_t *q8 = fr + (p0 + i) * 3;
-                const bool hole = mk[p0 + i] != 0;
-                dst[p0 + i] = hole ? (ST_HOLE | ST_ZERO) : (q8[0] | (q8[1] << 8) | ((uint32_t)q8[2] << 16));
-                if (hole) holes |= 1u << (4 * k + i);
-            }
-        }
-    }
-    if (!listed) return;                                        // block-uniform
-
-    // position of this thread's holes inside the chunk: warp scan + per-warp totals
-    const int cnt = __popc(holes);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-    }
-    __shared__ int s_warp[K4_BLOCK / 32];
-    if (lane == 31) s_warp[wid] = incl;
+    __shared__ BlockQueue q;
+    if (threadIdx.x == 0) q.count = 0;
     __syncthreads();
-    int woff = 0;
-    for (int k = 0; k < wid; ++k) woff += s_warp[k];
-    if (holes) {
-        long long pos = of * npx + chunk_offsets[of * chunks + blockIdx.x] + woff + incl - cnt;
+    const long long ngroups = (npx + 3) >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long iters = (ngroups + stride * K4_PACK_UNROLL - 1) / (stride * K4_PACK_UNROLL);
+    const int lane = threadIdx.x & 31;
+    for (long long itn = 0; itn < iters; ++itn) {
+        // K4_PACK_UNROLL groups per thread: all loads first (memory-level parallelism), one flush check per round
+        uint32_t c[K4_PACK_UNROLL][4];
+        uint32_t m4[K4_PACK_UNROLL], fa[K4_PACK_UNROLL], fb2[K4_PACK_UNROLL], fd[K4_PACK_UNROLL];
+        long long p0[K4_PACK_UNROLL];
+        int n[K4_PACK_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if ((holes >> (4 * k)) & 15u) {
-                const long long p0 = span0 + (lane + 32 * k) * 4;
-                const uint32_t p32 = (uint32_t)p0;              // h*w < 2^32 (both <= 65535)
-                uint32_t y = p32 / (uint32_t)w, x = p32 - y * (uint32_t)w;
+        for (int u = 0; u < K4_PACK_UNROLL; ++u) {
+            const long long g = (itn * K4_PACK_UNROLL + u) * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+            p0[u] = g * 4;
+            n[u] = g < ngroups ? (VEC ? 4 : (int)min(4LL, npx - p0[u])) : 0;
+            if (VEC && n[u]) {
+                m4[u] = __ldg(reinterpret_cast<const uint32_t *>(mk + p0[u]));
+                const uint32_t *f3 = reinterpret_cast<const uint32_t *>(fr + p0[u] * 3);
+                fa[u] = __ldg(f3), fb2[u] = __ldg(f3 + 1), fd[u] = __ldg(f3 + 2);
+            }
+        }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if ((holes >> (4 * k + i)) & 1u) {
-                        dl.xy[pos] = x | (y << 16);
-                        dl.flow[pos] = __ldg(pflow + p0 + i);
-                        ++pos;
-                    }
-                    if (++x == (uint32_t)w) x = 0, ++y;
+        for (int u = 0; u < K4_PACK_UNROLL; ++u) {
+            c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0;
+            if (!n[u]) continue;
+            if (VEC) {
+                c[u][0] = fa[u] & 0x00ffffffu;
+                c[u][1] = (fa[u] >> 24) | ((fb2[u] & 0x0000ffffu) << 8);
+                c[u][2] = (fb2[u] >> 16) | ((fd[u] & 0x000000ffu) << 16);
+                c[u][3] = fd[u] >> 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (byte_of(m4[u], i)) c[u][i] = ST_HOLE | ST_ZERO;
+                *reinterpret_cast<uint4 *>(dst + p0[u]) = make_uint4(c[u][0], c[u][1], c[u][2], c[u][3]);
+            } else {
+                for (int i = 0; i < n[u]; ++i) {
+                    const uint8_t *q8 = fr + (p0[u] + i) * 3;
+                    c[u][i] = mk[p0[u] + i] ? (ST_HOLE | ST_ZERO) : (q8[0] | (q8[1] << 8) | ((uint32_t)q8[2] << 16));
+                    dst[p0[u] + i] = c[u][i];
                 }
             }
         }
+        if (!listed) continue;                                 // block-uniform
+        uint32_t holes[K4_PACK_UNROLL];
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < K4_PACK_UNROLL; ++u) {
+            holes[u] = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) holes[u] |= (uint32_t)(i < n[u] && (c[u][i] & ST_HOLE)) << i;
+            cnt += __popc(holes[u]);
+        }
+        if (__ballot_sync(0xffffffffu, cnt != 0)) {            // warp-uniform
+            // one scan and one shared-memory atomic per warp and round
+            int pre = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += v;
+            }
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&q.count, (uint32_t)pre);
+            base = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(pre - cnt);
+#pragma unroll
+            for (int u = 0; u < K4_PACK_UNROLL; ++u) {
+                if (holes[u]) {
+                    const uint32_t p32 = (uint32_t)p0[u];      // h*w < 2^32 (both <= 65535)
+                    const uint32_t y0 = p32 / (uint32_t)w, x0 = p32 - y0 * (uint32_t)w;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if ((holes[u] >> i) & 1u) {
+                            uint32_t x = x0 + i, y = y0;
+                            while (x >= (uint32_t)w) x -= w, ++y;   // a group may straddle a row end when w % 4 != 0
+                            q.xy[base++] = x | (y << 16);
+                        }
+                    }
+                }
+            }
+        }
+        queue_flush(q, dl, of, npx, w, pflow, false);          // same trip count for every thread of the block
     }
+    if (listed) queue_flush(q, dl, of, npx, w, pflow, true);
 }
 
+// ---- k4_step: one time step of one direction, in place, over the hole lists -------------------
+// blockIdx.y = sub-video.  The state buffer holds the input frames after k4_pack, the backward
+// result after pass 1 and the forward result after pass 2:
+//   PASS2 == false (backward, t = len-2 .. 0):  frame idx is updated from frame idx+1; holes that
+//                                               stay holes are appended to the frame's forward list
+//   PASS2 == true  (forward,  t = 1 .. len-1):  frame idx (backward result) is updated from frame
+//                                               idx-1 (already the forward result)
+// Frame len-1 / frame 0 are the first step of their pass and stay as they are.
+//
+// The chain of 2*(len-1) dependent launches is latency bound, so the per-item dependency chain is
+// kept at two memory round trips and the forward pass only visits what the backward pass left.
+// With programmatic dependent launch the next step's CTAs are resident before this one retires.
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Frame / list / flow pointers of one step of one window.
@@ -553,9 +522,7 @@ extern "C" size_t vv_propagate_workspace_bytes(int n_out_frames, int h, int w) {
     if (n_out_frames <= 0 || h <= 0 || w <= 0) return 0;
     // two hole-list sets, worst case one entry per pixel: u32 position + float2 flow; counters per frame
     const size_t n = (size_t)n_out_frames * h * w;
-    const size_t chunks = ((size_t)h * w + K4_CHUNK - 1) / K4_CHUNK;
-    return 2 * (align_up(n * 4, 256) + align_up(n * 8, 256)) + align_up((size_t)n_out_frames * 8, 256) + 256 +
-           align_up((size_t)n_out_frames * chunks * 4, 256);
+    return 2 * (align_up(n * 4, 256) + align_up(n * 8, 256)) + align_up((size_t)n_out_frames * 8, 256) + 256;
 }
 
 extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const float *flows_f, const float *flows_b,
@@ -587,8 +554,6 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
     l2.count = l1.count + total;
     unsigned int *barriers = (unsigned int *)(wsp + 2 * (l4 + l8) + align_up((size_t)total * 8, 256));   // 32 + failure flag
     int *failed = (int *)(barriers + K4_MAX_SUB);
-    uint32_t *chunk_counts = (uint32_t *)((uint8_t *)barriers + 256);
-    const int chunks = ceil_div(npx, K4_CHUNK);
     const float2 *ff = (const float2 *)flows_f, *fb = (const float2 *)flows_b;
     cudaError_t e = cudaMemsetAsync(l1.count, 0, (size_t)total * 8, st);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
@@ -607,23 +572,14 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             blen = max(blen, sub_len[base + s]);
         }
         const long long bframes = out_frame - first;
-        // count -> offsets -> pack: all frames of the batch at once (grid.y <= 65535 frames per launch)
-        const bool vec16 = vec && (npx % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)masks % 16 == 0);
+        // pack: all frames of the batch at once (grid.y <= 65535 frames per launch)
         for (long long f0 = 0; f0 < bframes; f0 += 32768) {
             const int ny = (int)min(32768LL, bframes - f0);
-            if (vec16)
-                k4_count<true><<<dim3(chunks, ny), K4_BLOCK, 0, st>>>(masks, chunk_counts, h, w, first + f0, chunks, b);
+            const int gx = max(1, min(ceil_div((npx + 3) / 4, 256), ceil_div(148 * 16, ny)));
+            if (vec)
+                k4_pack<true><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, l1, l2, h, w, first + f0, b);
             else
-                k4_count<false><<<dim3(chunks, ny), K4_BLOCK, 0, st>>>(masks, chunk_counts, h, w, first + f0, chunks, b);
-            VV_POST_LAUNCH("k4_count");
-            k4_offsets<<<ny, K4_BLOCK, 0, st>>>(chunk_counts, l1, l2, first + f0, chunks, b);
-            VV_POST_LAUNCH("k4_offsets");
-            if (vec16)
-                k4_pack<true><<<dim3(chunks, ny), K4_BLOCK, 0, st>>>(frames, masks, out, ff, fb, l1, l2, chunk_counts, h, w,
-                                                                     first + f0, chunks, b);
-            else
-                k4_pack<false><<<dim3(chunks, ny), K4_BLOCK, 0, st>>>(frames, masks, out, ff, fb, l1, l2, chunk_counts, h, w,
-                                                                      first + f0, chunks, b);
+                k4_pack<false><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, l1, l2, h, w, first + f0, b);
             VV_POST_LAUNCH("k4_pack");
         }
         // The serial scans touch hole pixels only.  The hole counts live on the device: the grid is
