@@ -89,18 +89,25 @@ class ClockSampler:
         except Exception:
             self.handle = None
 
-    def _loop(self):
+    def sample(self):
+        """One sample now (also called from the timed loop right after a step has been enqueued, i.e.
+        while the GPU is executing it, so short timed regions still get one sample per step)."""
+        if self.handle is None:
+            return
         nv = self.nv
-        while not self._stop:
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
             try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
-                try:
-                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                except Exception:
-                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
             except Exception:
-                pass
-            time.sleep(0.004)
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop:
+            self.sample()
+            time.sleep(0.002)
 
     def start(self):
         if self.handle is None:
@@ -298,6 +305,8 @@ def run_ours(args, rank, world, local_rank):
     e0.record(main_stream)
     for k in range(args.steps):
         step(evs[k])
+        if rank == 0:
+            sampler.sample()
     e1.record(main_stream)
     sync_all()
     launches = _lib.launch_count()
