@@ -448,3 +448,22 @@ def test_n2_state_to_float(ops):
     assert np.array_equal(host(rgb), want_rgb) and np.array_equal(host(hole), want_hole)
     ref_rgb, ref_hole = opp.img_propagation_torch(fr, m, ff, fb)
     assert np.array_equal(host(rgb), ref_rgb) and np.array_equal(host(hole), ref_hole)
+
+
+def test_pageable_results_when_pinned_budget_exceeded(ops):
+    """Results above the pinned budget are returned in ordinary host memory and still match."""
+    from videovanish_b200 import hostpipe
+    t, h0, w0, h, w = 9, 64, 96, 32, 48
+    fr, mk, inp = synth.frames(t, h0, w0, seed=71), synth.masks(t, h0, w0, seed=72), synth.noise_frames(t, h, w, seed=73)
+    old = hostpipe.PINNED_RESULT_LIMIT
+    hostpipe.PINNED_RESULT_LIMIT = 0
+    try:
+        pipe = hostpipe.HostPipeline(h0, w0, frames_per_batch=4, n_slots=2)
+        dil = pipe.pre(list(mk), 2)
+        out = pipe.post(list(inp), list(fr))
+        pipe.close()
+    finally:
+        hostpipe.PINNED_RESULT_LIMIT = old
+    ref_dil = op.ref_binarize_dilate(list(mk), 2)
+    assert np.array_equal(np.stack(dil), np.stack(ref_dil))
+    assert np.array_equal(np.stack(out), np.stack([op.ref_post_frame(inp[i], fr[i], ref_dil[i], True, 3) for i in range(t)]))

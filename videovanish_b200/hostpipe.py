@@ -13,6 +13,10 @@ from . import _lib
 from ._lib import lib
 
 
+# results larger than this are returned in pageable memory (page-locking tens of GB starves the host)
+PINNED_RESULT_LIMIT = 8 << 30
+
+
 def _ptr_array(frames, shape=None):
     """Per-frame host pointers.  Returns (ctypes array, keep-alive list)."""
     keep = []
@@ -33,8 +37,17 @@ def pinned_frames(t, shape):
     kept alive by the views themselves)."""
     if not torch.cuda.is_available():
         raise RuntimeError("videovanish_b200: CUDA device required (there is no CPU fallback)")
-    block = torch.empty((t,) + tuple(shape), dtype=torch.uint8, pin_memory=True)
-    whole = block.numpy()
+    nbytes = t * int(np.prod(shape))
+    whole = None
+    if nbytes <= PINNED_RESULT_LIMIT:
+        try:
+            whole = torch.empty((t,) + tuple(shape), dtype=torch.uint8, pin_memory=True).numpy()
+        except RuntimeError:
+            whole = None        # page-locking refused (ulimit / memory pressure)
+    if whole is None:
+        # very long clips (BASELINE config 5: 5 000 frames = 31 GB per stream): ordinary host memory; the
+        # native pipeline then copies results out of its pinned ring with its memcpy pool
+        whole = np.empty((t,) + tuple(shape), np.uint8)
     return [whole[i] for i in range(t)]
 
 
