@@ -40,12 +40,21 @@ __global__ void __launch_bounds__(256)
         for (int i = 0; i < 4; ++i) {
             if (i < n) {
                 const int sx = xo[x0 + i];
-                for (int k = K - 1; k >= 0; --k) {
-                    if (frame[k * plane + sx] > (MaskT)0) {
-                        px[i] = colors.rgb[3 * k] | (colors.rgb[3 * k + 1] << 8) | (colors.rgb[3 * k + 2] << 16);
-                        break;
-                    }
+                int top = -1;                         // highest object whose mask is set here
+                if (K <= 8) {                         // all object planes loaded at once (independent loads)
+                    uint32_t hit = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < K) hit |= (uint32_t)(frame[k * plane + sx] > (MaskT)0) << k;
+                    top = 31 - __clz((int)hit);       // -1 when nothing is set
+                } else {
+                    for (int k = K - 1; k >= 0; --k)
+                        if (frame[k * plane + sx] > (MaskT)0) {
+                            top = k;
+                            break;
+                        }
                 }
+                if (top >= 0) px[i] = colors.rgb[3 * top] | (colors.rgb[3 * top + 1] << 8) | (colors.rgb[3 * top + 2] << 16);
             }
         }
         uint8_t *o = out + ((t * H0 + y) * (long long)W0 + x0) * 3;
