@@ -9,13 +9,23 @@
 // The two full-frame distance transforms are never materialised: alpha only leaves {0,1}
 // where the chamfer distance is < feather_px, and a 5x5-chamfer distance < F is decided by
 // the mask bits within Chebyshev radius ceil(F)-1 (oracle/prepost.py model_feather_alpha,
-// bit-exact against cv2 4.13).  One CTA owns a strip of TH full-width output rows:
+// bit-exact against cv2 4.13).  One CTA owns a strip of up to 16 full-width output rows:
+//   staging  (TMA variant) one thread brings the strip of `orig` into shared memory with bulk async
+//            copies (cp.async.bulk + mbarrier); after the fix-ups the strip leaves with a bulk store,
+//            so the 6 B/px pass-through never touches registers.  The register variant (widths that
+//            are not multiples of 16) streams orig -> out through 128-bit loads / stores instead.
 //   phase 1  mask rows [y0-R, y0+TH+R) -> bit rows in shared memory (128-bit loads, 1 bit/px)
-//   phase 2  each thread takes 16-pixel groups: 5 (or 2R+1) bit-row windows -> per-pixel chamfer
-//            class by bit-parallel shifts -> alpha level; groups with alpha == 0 everywhere are a
-//            straight 48-byte copy of `orig`; only pixels with alpha > 0 fetch bilinear taps.
+//   phase 2  each thread classifies 16-pixel groups: 5 (or 2R+1) bit-row windows -> per-pixel
+//            chamfer class by bit-parallel shifts -> alpha level (12 levels at feather 3)
+//   phase 3  every 4-pixel quad with alpha > 0 somewhere becomes a work item in a per-warp queue
+//            (warp-scan compaction, items carried over between iterations so worker rounds run
+//            with 32 busy lanes); a worker fetches the 8 source-pixel pairs of its quad up front,
+//            runs OpenCV's fixed-point bilinear (dp2a horizontal pass, multiply-high vertical
+//            pass), blends in non-FMA fp32 and patches the quad in the staged strip.
 // HBM traffic per frame: orig 3 + mask 1 (x (TH+2R)/TH from L2) + out 3 B/px, plus the small
-// inference-resolution frame, i.e. the algorithmic 7*H0*W0 + 3*h*w of SURVEY section 8d.
+// inference-resolution frame, i.e. the algorithmic 7*H0*W0 + 3*h*w of SURVEY section 8d
+// (ncu: 4.75 GB per 300 frames = 0.98 x algorithmic).  On dense masks the kernel is bound by the
+// issue slots of phase 3 (~98 instructions per blended pixel), on sparse masks by HBM.
 #include <math.h>
 
 #include <algorithm>
