@@ -57,7 +57,6 @@ VV_API void vv_reset_launch_count(void);
  *   "k3_tma"     1 = K3 stages the original strip through shared memory with bulk async copies
  *                (TMA) when the frame is 16-byte aligned, 0 = register pass-through kernel.
  *   "k3_tma_rows" maximum rows per staged strip (2..16);  "k3_tma_threads" 256, 384 or 512.
- *   "k3_pixel_items" 1 = K3 work items are single pixels, 0 = 4-pixel quads.
  *   "k4_pdl"     1 = propagation steps use programmatic dependent launch (multi-launch mode).
  *   "k4_persistent" 1 = the whole propagation scan runs in one cooperative launch with per-window
  *                barriers, 0 (default; measured equal on B200: the steps are bound by their DRAM

@@ -84,14 +84,12 @@ def main():
     report("K2 resize 1080p->540p", t * (3 * px + 3 * spx), lambda: ops.resize(fr, HS, WS))
     report("K2 resize 1080p->536p", t * (3 * px + 3 * 536 * 960), lambda: ops.resize(fr, 536, 960))
     report("K2 nearest mask 1080p->540p", t * (px + spx), lambda: ops.resize(dil, HS, WS, ops.INTER_NEAREST))
-    for tma, nt, rows, thr, pxi in ((1, 1, 16, 512, 1), (1, 1, 16, 512, 0), (1, 1, 16, 384, 1), (1, 1, 8, 256, 1), (0, 2, 16, 512, 1),
-                                    (0, 2, 16, 512, 0)):
+    for tma, nt, rows, thr in ((1, 1, 16, 512), (1, 1, 16, 384), (1, 1, 8, 512), (1, 1, 8, 256), (0, 2, 16, 512)):
         _lib.set_option("k3_tma", tma)
         _lib.set_option("k3_nt", nt)
         _lib.set_option("k3_tma_rows", rows)
         _lib.set_option("k3_tma_threads", thr)
-        _lib.set_option("k3_pixel_items", pxi)
-        kw = dict(k3_tma=tma, k3_nt=nt, rows=rows, threads=thr, pxi=pxi)
+        kw = dict(k3_tma=tma, k3_nt=nt, rows=rows, threads=thr)
         report("K3 composite (synthetic mask)", t * (7 * px + 3 * spx),
                lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out), **kw)
         report("K3 composite (empty mask)", t * (7 * px + 3 * spx),
@@ -102,7 +100,6 @@ def main():
     _lib.set_option("k3_nt", 2)
     _lib.set_option("k3_tma_rows", 16)
     _lib.set_option("k3_tma_threads", 512)
-    _lib.set_option("k3_pixel_items", 1)
     report("K3 composite feather 5 (generic path)", t * (7 * px + 3 * spx),
            lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
     for pers, pdl, warm in ((1, 1, 1), (1, 1, 0), (0, 1, 0), (0, 0, 0)):

@@ -129,10 +129,7 @@ constexpr int K3_QUEUE1 = 128;    // work items (4-pixel quads) per warp iterati
 // TMA: the strip of original pixels is brought into shared memory by bulk async copies (one
 // elected thread, mbarrier completion), the blended quads are patched into it there, and the whole
 // strip leaves with a bulk store - the 6 B/px pass-through never touches registers.  Requires VEC.
-// PXI: work items are single pixels (u32 entries) instead of 4-pixel quads: with the strip staged in shared
-// memory byte-granular patches are cheap, and ragged masks (1-2 blended pixels per quad) no longer pay for
-// the source loads of the whole quad.
-template <bool VEC, bool SMALL_R, int K3_NT, bool TMA, bool PXI>
+template <bool VEC, bool SMALL_R, int K3_NT, bool TMA>
 __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4)
     k3_upscale_feather_composite(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig,
                                  const uint8_t *__restrict__ mask, uint8_t *__restrict__ out,
@@ -321,108 +318,6 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
             }
         }
 
-        if constexpr (PXI) {
-            // ---- pixel items: entry = x | row << 16 | code << 20 (code: LUT index, or inside << 3 on the generic path)
-            uint32_t *q32 = reinterpret_cast<uint32_t *>(queue);
-            auto process = [&](uint32_t e) {
-                const int x = e & 0xffff, r = (e >> 16) & 15;
-                const uint32_t code = (e >> 20) & 15u;
-                const int yy = y0 + r;
-                float a;
-                if (SMALL_R) {
-                    a = lut[code];                       // > 0 by construction of `need`
-                } else {
-                    const bool inside = code >> 3;
-                    if (hard) {
-                        a = inside ? 1.f : 0.f;
-                    } else {
-                        float d = 8192.f;   // first (cheapest) window offset whose opposite-class bit is set
-                        for (int en = 0; en < ft.n; ++en) {
-                            const int ey = yy + ft.dy[en], ex = x + ft.dx[en];
-                            if (ey < 0 || ey >= H0 || ex < 0 || ex >= W0) continue;
-                            const uint32_t wv = bits[(r + R + ft.dy[en]) * row_words + 1 + (ex >> 5)];
-                            if ((((wv >> (ex & 31)) & 1u) != 0) != inside) {
-                                d = ft.cost[en];
-                                break;
-                            }
-                        }
-                        a = inside ? alpha_from(d, 0.f, ft.div) : alpha_from(0.f, d, ft.div);
-                    }
-                    if (!(a > 0.f)) return;
-                }
-                const Tap ty = yt[yy], tx = xt[x];
-                const uint32_t b0s = (uint32_t)(ty.w & 0xffff) << 16, b1s = (uint32_t)ty.w & 0xffff0000u;
-                const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
-                const PixelPair pr0 = load_pixel_pair(inp_t + ya * w * 3, tx.ofs, w, inp_aligned4);
-                const PixelPair pr1 = load_pixel_pair(inp_t + yb * w * 3, tx.ofs, w, inp_aligned4);
-                const uint32_t wts = (uint32_t)tx.w;
-                uint32_t cr = vpass(b0s, b1s, hpass<0>(pr0, wts), hpass<0>(pr1, wts));
-                uint32_t cg = vpass(b0s, b1s, hpass<1>(pr0, wts), hpass<1>(pr1, wts));
-                uint32_t cb = vpass(b0s, b1s, hpass<2>(pr0, wts), hpass<2>(pr1, wts));
-                const int po = TMA ? (r * W0 + x) * 3 : (yy * W0 + x) * 3;   // offset in the strip / in the frame
-                if (a < 1.f) {
-                    const float na = __fsub_rn(1.f, a);
-                    const uint8_t *ob = TMA ? strip + po : orig_t + po;
-                    cr = blend_u8(a, na, cr, ob[0]);
-                    cg = blend_u8(a, na, cg, ob[1]);
-                    cb = blend_u8(a, na, cb, ob[2]);
-                }
-                uint8_t *dp = TMA ? strip + po : out_t + po;
-                dp[0] = (uint8_t)cr, dp[1] = (uint8_t)cg, dp[2] = (uint8_t)cb;
-            };
-#pragma unroll
-            for (int k = 0; k < K3_NT; ++k) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t n4 = (need[k] >> (4 * q)) & 15u;
-                    if (__ballot_sync(0xffffffffu, n4 != 0) == 0) continue;        // warp-uniform
-                    const int cnt = __popc(n4);
-                    int pre = cnt;                               // inclusive scan over lanes
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, pre, d);
-                        if (lane >= d) pre += v;
-                    }
-                    int pos = qcount + pre - cnt;
-                    qcount += __shfl_sync(0xffffffffu, pre, 31);
-                    if (n4) {
-                        const int b = 8 + 4 * q;
-                        // 4x4 bit transpose: planes (l0, l1, l2, inside) x pixels -> one code nibble per pixel
-                        uint32_t x4 = ((L0[k] >> b) & 15u) | (((L1[k] >> b) & 15u) << 4) | (((L2[k] >> b) & 15u) << 8) |
-                                      (((M2[k] >> b) & 15u) << 12);
-                        uint32_t tt = (x4 ^ (x4 >> 3)) & 0x0a0au;
-                        x4 ^= tt ^ (tt << 3);
-                        tt = (x4 ^ (x4 >> 6)) & 0x00ccu;
-                        x4 ^= tt ^ (tt << 6);
-                        const uint32_t base_e = (uint32_t)(x0[k] + 4 * q) | ((uint32_t)row[k] << 16);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if ((n4 >> i) & 1u) q32[pos++] = (base_e + i) | (((x4 >> (4 * i)) & 15u) << 20);
-                    }
-                    __syncwarp();
-                    if (qcount >= 32) {
-                        if (TMA && !landed) {
-                            mbar_wait(bar, 0);
-                            landed = true;
-                        }
-                        while (qcount >= 32) {
-                            qcount -= 32;
-                            process(q32[qcount + lane]);
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            if (drain && qcount > 0) {
-                if (TMA && !landed) {
-                    mbar_wait(bar, 0);
-                    landed = true;
-                }
-                if (lane < qcount) process(q32[lane]);
-                qcount = 0;
-            }
-            continue;
-        }
         // ---- warp-level compaction: every quad with a pixel to blend becomes one work item
         uint32_t any_need = 0, qn = 0;
 #pragma unroll
@@ -728,14 +623,13 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
         th = K3_TH;
         smem = ((size_t)(th + 2 * R) * (Wp + 2) + common_words + (K3_THREADS / 32) * (K3_QUEUE1 * nt + 32) * 2) * 4;
     }
-    const bool pxi = get_option(OPT_K3_PIXEL_ITEMS) != 0;
     const int strips = ceil_div(H0, th);
     const long long grid = (long long)T * strips;
     VV_CHECK_ARG(grid < 2147483647LL, "vv_upscale_feather_composite: too many strips");
 
-#define VV_K3_LAUNCH_(V, S, N, M, P)                                                                            \
+#define VV_K3_LAUNCH(V, S, N, M)                                                                                \
     do {                                                                                                        \
-        auto kfn = k3_upscale_feather_composite<V, S, N, M, P>;                                                    \
+        auto kfn = k3_upscale_feather_composite<V, S, N, M>;                                                    \
         static std::atomic<size_t> smem_set{48 * 1024};                                                        \
         if (smem > smem_set.load()) {                                                                           \
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
@@ -744,13 +638,6 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
         }                                                                                                       \
         kfn<<<(unsigned)grid, (M) ? tma_threads : K3_THREADS, smem, st>>>(inp, orig, mask, out, xt, yt, h, w, H0,   \
                                                                             W0, strips, th, ft);                \
-    } while (0)
-#define VV_K3_LAUNCH(V, S, N, M)          \
-    do {                                  \
-        if (pxi)                          \
-            VV_K3_LAUNCH_(V, S, N, M, true);  \
-        else                              \
-            VV_K3_LAUNCH_(V, S, N, M, false); \
     } while (0)
 #define VV_K3_DISPATCH(V, S)            \
     do {                                \
