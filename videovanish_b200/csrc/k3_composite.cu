@@ -413,7 +413,6 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                 if (fast) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        if (!((n4 >> i) & 1u)) continue;         // ragged masks: ~1.7 of 4 pixels per quad are blended
                         const int o3 = ofs[i] * 3, a4 = o3 & ~3;
                         const uint32_t *q0 = reinterpret_cast<const uint32_t *>(r0 + a4);
                         const uint32_t *q1 = reinterpret_cast<const uint32_t *>(r1 + a4);
@@ -426,7 +425,6 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        if (!((n4 >> i) & 1u)) continue;
                         pr0[i] = load_pixel_pair(r0, ofs[i], w, false);
                         pr1[i] = load_pixel_pair(r1, ofs[i], w, false);
                     }
