@@ -221,6 +221,28 @@ def make_workload(t, device, seed):
     return host, dev
 
 
+def bind_to_gpu_numa_node(torch_index):
+    """Pin this process to the CPUs NVML reports as local to its GPU.  With one rank per GPU on a
+    multi-socket host the pinned staging memory of the end-to-end path otherwise lands on whatever
+    socket the rank happens to run on, and half of the host<->device traffic crosses the socket link."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        if cpus:
+            os.sched_setaffinity(0, cpus & set(os.sched_getaffinity(0)) or cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -228,6 +250,7 @@ def run_ours(args, rank, world, local_rank):
         raise RuntimeError("bench.py: no CUDA device - the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)        # before any pinned allocation: first touch places it locally
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     from videovanish_b200 import _lib, chunking, ops
