@@ -1,7 +1,11 @@
-"""Drop-in for the reference's ``tools`` module (/root/reference/tools.py:4-45): same two
-functions, same arguments and return values.  Decoding / encoding stays with OpenCV (frame I/O is
-SURVEY "next" row N1); what changes is where the frames land: decoded RGB frames are written
-straight into page-locked blocks, so ``run_infill_on_frames`` can DMA them without a staging copy.
+"""Frame I/O with the call surface of the reference's ``tools`` module
+(/root/reference/tools.py:4 ``load_video_frames_from_path``, :30 ``write_video_frames_to_path``):
+same arguments, same return values, same container / codec, same asserts.
+
+Decoding and encoding stay with OpenCV (device-side codecs are SURVEY "next" row N1).  What this
+module changes is where decoded frames land: RGB frames are written straight into page-locked
+blocks, ``_BLOCK_FRAMES`` at a time, so ``run_infill_on_frames`` can DMA them to the GPU without a
+staging copy.  Without a CUDA device the blocks are ordinary host memory (this is I/O, not compute).
 """
 import cv2
 import numpy as np
@@ -9,50 +13,76 @@ import numpy as np
 _BLOCK_FRAMES = 32
 
 
-def _new_block(shape):
-    try:
-        import torch
-        if torch.cuda.is_available():
-            return torch.empty((_BLOCK_FRAMES,) + tuple(shape), dtype=torch.uint8, pin_memory=True).numpy()
-    except Exception:
-        pass
-    return np.empty((_BLOCK_FRAMES,) + tuple(shape), np.uint8)      # plain host memory: I/O only, no compute
+class _FramePool:
+    """Hands out HxWx3 uint8 slots carved from page-locked blocks."""
+
+    def __init__(self):
+        self._block = None
+        self._used = 0
+
+    @staticmethod
+    def _allocate(shape):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.empty((_BLOCK_FRAMES,) + tuple(shape), dtype=torch.uint8, pin_memory=True).numpy()
+        except Exception:
+            pass
+        return np.empty((_BLOCK_FRAMES,) + tuple(shape), np.uint8)
+
+    def slot(self, shape):
+        exhausted = self._block is None or self._used == _BLOCK_FRAMES or self._block.shape[1:] != tuple(shape)
+        if exhausted:
+            self._block, self._used = self._allocate(shape), 0
+        view = self._block[self._used]
+        self._used += 1
+        return view
+
+
+def _decoded_frames(capture):
+    """Yield (index, BGR frame) until the stream ends."""
+    index = 0
+    while True:
+        ok, bgr = capture.read()
+        if not ok:
+            return
+        yield index, bgr
+        index += 1
 
 
 def load_video_frames_from_path(video_path, start_frame=0, max_frames=-1):
-    """tools.py:4-28.  Returns (list of RGB uint8 HxWx3 arrays, fps)."""
-    cap = cv2.VideoCapture(video_path)
-    assert cap.isOpened(), f"Failed to open video: {video_path}"
-    fps = cap.get(cv2.CAP_PROP_FPS)
-    frames = []
-    block, used = None, 0
-    idx = 0
-    while True:
-        ok, frame = cap.read()
-        if not ok:
-            break
-        if idx >= start_frame:
-            if block is None or used == _BLOCK_FRAMES or block.shape[1:] != frame.shape:
-                block, used = _new_block(frame.shape), 0
-            cv2.cvtColor(frame, cv2.COLOR_BGR2RGB, dst=block[used])              # tools.py:21
-            frames.append(block[used])
-            used += 1
-            if max_frames > 0 and len(frames) >= max_frames:
+    """Decode ``video_path`` and return ``(frames, fps)``: RGB uint8 HxWx3 arrays from
+    ``start_frame`` on, at most ``max_frames`` of them when that is positive (tools.py:4-28)."""
+    capture = cv2.VideoCapture(video_path)
+    assert capture.isOpened(), f"Failed to open video: {video_path}"
+    fps = capture.get(cv2.CAP_PROP_FPS)
+    pool, frames = _FramePool(), []
+    try:
+        for index, bgr in _decoded_frames(capture):
+            if index < start_frame:
+                continue
+            rgb = pool.slot(bgr.shape)
+            cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB, dst=rgb)          # channel swap of tools.py:21, in place
+            frames.append(rgb)
+            if 0 < max_frames <= len(frames):
                 break
-        idx += 1
-    cap.release()
+    finally:
+        capture.release()
     assert len(frames) > 0, "No frames read"
     return frames, fps
 
 
 def write_video_frames_to_path(out_video, mask_frames, fps, H0, W0):
-    """tools.py:30-45 (FFV1 / MKV, RGB->BGR, NEAREST fix-up of off-size frames)."""
-    writer = cv2.VideoWriter(out_video, cv2.VideoWriter_fourcc(*"FFV1"), fps, (W0, H0))
-    assert writer.isOpened(), "Failed to open VideoWriter (FFV1/MKV). Try MJPG or mp4v if needed."
-    for f in mask_frames:
-        f = cv2.cvtColor(f, cv2.COLOR_RGB2BGR)
-        if f.shape[0] != H0 or f.shape[1] != W0:
-            f = cv2.resize(f, (W0, H0), interpolation=cv2.INTER_NEAREST)         # tools.py:41-42
-        writer.write(f)
-    writer.release()
-    print(f"[ok] wrote {len(mask_frames)} frames to {out_video}")
+    """Encode RGB frames as lossless FFV1 (tools.py:30-45); frames of another size are brought to
+    (W0, H0) with NEAREST first, exactly like the reference's writer (:41-42)."""
+    sink = cv2.VideoWriter(out_video, cv2.VideoWriter_fourcc(*"FFV1"), fps, (W0, H0))
+    assert sink.isOpened(), "Failed to open VideoWriter (FFV1/MKV). Try MJPG or mp4v if needed."
+    count = 0
+    for rgb in mask_frames:
+        bgr = cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR)
+        if bgr.shape[:2] != (H0, W0):
+            bgr = cv2.resize(bgr, (W0, H0), interpolation=cv2.INTER_NEAREST)
+        sink.write(bgr)
+        count += 1
+    sink.release()
+    print(f"[ok] wrote {count} frames to {out_video}")
