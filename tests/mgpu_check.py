@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU check, run under torchrun (one rank per GPU):
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
 Verifies the rank-boundary halo blend (NCCL send/recv and CUDA-IPC peer reads inside K5) against the
 oracle, and times both."""
 import os
