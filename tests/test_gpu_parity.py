@@ -467,3 +467,18 @@ def test_pageable_results_when_pinned_budget_exceeded(ops):
     ref_dil = op.ref_binarize_dilate(list(mk), 2)
     assert np.array_equal(np.stack(dil), np.stack(ref_dil))
     assert np.array_equal(np.stack(out), np.stack([op.ref_post_frame(inp[i], fr[i], ref_dil[i], True, 3) for i in range(t)]))
+
+
+def test_multigpu_halo_blend_on_real_gpus(ops):
+    """Rank-boundary halo blend over NCCL and over CUDA-IPC peer reads (tests/mgpu_check.py), when the
+    box has at least two GPUs."""
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "mgpu_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0 and "MGPU CHECK PASS" in r.stdout, (r.stdout + r.stderr)[-3000:]
