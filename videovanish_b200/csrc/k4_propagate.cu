@@ -434,7 +434,7 @@ __device__ __forceinline__ void step_body(const float2 *__restrict__ flows_f, co
 
 // One launch per step (fallback, and the variant the ncu launch lists show step by step).
 template <bool PASS2>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
     k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state, HoleLists l1,
             HoleLists l2, int h, int w, int step, const __grid_constant__ SubBatch batch) {
     asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
