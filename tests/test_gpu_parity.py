@@ -482,3 +482,31 @@ def test_multigpu_halo_blend_on_real_gpus(ops):
                         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "mgpu_check.py")],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0 and "MGPU CHECK PASS" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+@pytest.mark.parametrize("keep,feather", [(False, 3), (True, 0), (True, 2.5)])
+def test_dropin_option_combinations(ops, keep, feather):
+    from videovanish_b200 import diffuerase as vvd
+    t, h0, w0, h, w = 5, 96, 160, 40, 72
+    fr, mk, inp = synth.frames(t, h0, w0, seed=81), synth.masks(t, h0, w0, seed=82), synth.noise_frames(t, h, w, seed=83)
+    vvd.set_models(diffueraser=_StubDiffuEraser(list(inp)))
+    out = vvd.run_infill_on_frames(list(fr), list(mk), mask_dilation_iter=3, propainer_frames=list(fr),
+                                   keep_unmasked_original=keep, feather_px=feather)
+    ref = op.ref_run_infill_on_frames(list(fr), list(mk), lambda *a, **k: [x.copy() for x in inp], mask_dilation_iter=3,
+                                      propainer_frames=list(fr), keep_unmasked_original=keep, feather_px=feather)
+    assert np.array_equal(np.stack(out), np.stack(ref))
+
+
+def test_dropin_same_size_model_output(ops):
+    """Model output already at the original size: the reference skips cv2.resize (:72) but still composites."""
+    from videovanish_b200 import diffuerase as vvd
+    t, h0, w0 = 4, 72, 128
+    fr, mk, inp = synth.frames(t, h0, w0, seed=91), synth.masks(t, h0, w0, seed=92), synth.noise_frames(t, h0, w0, seed=93)
+    vvd.set_models(diffueraser=_StubDiffuEraser(list(inp)))
+    out = vvd.run_infill_on_frames(list(fr), list(mk), mask_dilation_iter=2, propainer_frames=list(fr))
+    ref = op.ref_run_infill_on_frames(list(fr), list(mk), lambda *a, **k: [x.copy() for x in inp], mask_dilation_iter=2,
+                                      propainer_frames=list(fr))
+    assert np.array_equal(np.stack(out), np.stack(ref))
+    raw = vvd.run_infill_on_frames(list(fr), list(mk), mask_dilation_iter=2, propainer_frames=list(fr),
+                                   keep_unmasked_original=False)
+    assert np.array_equal(np.stack(raw), inp)

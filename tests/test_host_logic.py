@@ -123,3 +123,16 @@ def test_tools_roundtrip(tmp_path):
     got, fps = tools.load_video_frames_from_path(path, start_frame=1, max_frames=3)
     assert len(got) == 3 and abs(fps - 25.0) < 1e-6
     assert all(np.array_equal(g, f) for g, f in zip(got, frames[1:4]))          # FFV1 is lossless
+
+
+def test_dropin_imports_models_lazily_like_the_reference(monkeypatch):
+    """Without injected models the drop-in imports the un-vendored packages exactly where the reference
+    does (diffuerase.py:8-9); their absence surfaces as ImportError, not as a silent fallback."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("the pre stage needs a GPU before the model import is reached")
+    monkeypatch.setattr(diffuerase, "video_inpainting_sd", None)
+    monkeypatch.setattr(diffuerase, "last_ckpt", None)
+    z = np.zeros((16, 16, 3), np.uint8)
+    with pytest.raises(ImportError):
+        diffuerase.run_infill_on_frames([z], [z])
