@@ -510,3 +510,32 @@ def test_dropin_same_size_model_output(ops):
     raw = vvd.run_infill_on_frames(list(fr), list(mk), mask_dilation_iter=2, propainer_frames=list(fr),
                                    keep_unmasked_original=False)
     assert np.array_equal(np.stack(raw), inp)
+
+
+def test_chunked_driver_blends_overlaps(ops):
+    """run_infill_on_frames_chunked == per-chunk oracle outputs stitched by the oracle's blend (row A11)."""
+    from videovanish_b200 import chunking
+    from videovanish_b200 import diffuerase as vvd
+    t, h0, w0, h, w, chunk, ov = 23, 72, 128, 32, 64, 10, 4
+    fr, mk = synth.frames(t, h0, w0, seed=101), synth.masks(t, h0, w0, seed=102)
+    plan = chunking.chunk_plan(t, chunk, ov)
+
+    class _PerChunkModel:                       # a model whose output depends on the chunk it is called with
+        def __init__(self):
+            self.calls = 0
+
+        def forward(self, frames, masks, priors, **kw):
+            self.calls += 1
+            return list(synth.noise_frames(len(frames), h, w, seed=200 + self.calls))
+
+    model = _PerChunkModel()
+    vvd.set_models(diffueraser=model)
+    got = vvd.run_infill_on_frames_chunked(list(fr), list(mk), chunk=chunk, overlap=ov, mask_dilation_iter=2,
+                                           propainer_frames=list(fr))
+    assert model.calls == len(plan) and len(got) == t
+    per_chunk = []
+    for ci, (s, e) in enumerate(plan):
+        inp = list(synth.noise_frames(e - s, h, w, seed=201 + ci))
+        per_chunk.append(np.stack(op.ref_run_infill_on_frames(list(fr[s:e]), list(mk[s:e]), lambda *a, **k: inp,
+                                                              mask_dilation_iter=2, propainer_frames=list(fr[s:e]))))
+    assert np.array_equal(np.stack(got), ocb.stitch_chunks(per_chunk, plan, ov))
