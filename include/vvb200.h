@@ -62,7 +62,9 @@ VV_API void vv_reset_launch_count(void);
  *                barriers, 0 (default; measured equal on B200: the steps are bound by their DRAM
  *                gathers, not by launch latency) = one launch per time step.
  *   "k4_warm"    1 = the persistent scan pre-loads the next step's list entries and prefetches their
- *                flow sectors into L2 while the current step runs. */
+ *                flow sectors into L2 while the current step runs.
+ *   "k3_x2"      1 = K3 uses the closed-form worker for exact x2 up-scales (W0 == 2w, H0 == 2h, TMA
+ *                variant); 0 = the generic tap-table worker for every ratio. */
 VV_API int vv_set_option(const char *name, int value);
 VV_API int vv_get_option(const char *name, int *value);
 

@@ -157,6 +157,31 @@ def test_k3_kernel_variants(ops, variant):
     assert np.abs(got5.astype(int) - ref5.astype(int)).max() <= 1
 
 
+@pytest.mark.parametrize("h,w", [(60, 88), (8, 8), (33, 40), (540, 960)])
+@pytest.mark.parametrize("f", [3, 2.5, 1.5, 0.5])
+def test_k3_exact_x2_worker(ops, h, w, f):
+    """W0 == 2w and H0 == 2h takes the closed-form x2 worker: same bytes as the oracle and as the generic
+    tap-table worker, including the clamped border columns / rows (masks that touch all four borders)."""
+    from videovanish_b200 import _lib
+    h0, w0, t = 2 * h, 2 * w, 3
+    fr = synth.frames(t, h0, w0, seed=61)
+    inp = synth.noise_frames(t, h, w, seed=62)
+    dil = np.stack(op.model_binarize_dilate(list(synth.masks(t, h0, w0, seed=63, salt=0.004)), 2))
+    dil[1] = 255                                             # everything inside: every quad, all borders
+    dil[2, :3] = dil[2, -2:] = 255
+    dil[2, :, :5] = dil[2, :, -3:] = 255
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, f) for i in range(t)])
+    assert _lib.get_option("k3_x2") == 1
+    got = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=f))
+    try:
+        _lib.set_option("k3_x2", 0)
+        generic = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=f))
+    finally:
+        _lib.set_option("k3_x2", 1)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(generic, ref)
+
+
 @pytest.mark.parametrize("h0,w0,h,w", [(97, 131, 40, 56), (360, 640, 176, 320), (72, 128, 72, 128), (50, 1040, 24, 520),
                                         (35, 16, 70, 32), (1, 16, 1, 8), (20, 4096, 10, 2048)])
 def test_k3_shapes(ops, h0, w0, h, w):

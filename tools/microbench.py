@@ -100,6 +100,12 @@ def main():
     _lib.set_option("k3_nt", 2)
     _lib.set_option("k3_tma_rows", 16)
     _lib.set_option("k3_tma_threads", 512)
+    _lib.set_option("k3_x2", 0)
+    report("K3 composite (synthetic mask)", t * (7 * px + 3 * spx),
+           lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out), k3_x2=0)
+    report("K3 composite (full mask)", t * (7 * px + 3 * spx),
+           lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out), k3_x2=0)
+    _lib.set_option("k3_x2", 1)
     report("K3 composite feather 5 (generic path)", t * (7 * px + 3 * spx),
            lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
     for pers, pdl, warm in ((1, 1, 1), (1, 1, 0), (0, 1, 0), (0, 0, 0)):

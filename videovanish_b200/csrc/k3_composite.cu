@@ -117,6 +117,57 @@ __device__ __forceinline__ uint32_t vpass(uint32_t b0s, uint32_t b1s, uint32_t h
     return (__umulhi(b0s, h0 >> 4) + __umulhi(b1s, h1 >> 4) + 2u) >> 2;
 }
 
+// ---- exact x2 up-scale (W0 == 2w, H0 == 2h: 1080p <-> 960x540, the headline configuration) -------
+// OpenCV's taps are then the constants 512 / 1536 (of 2048) on both axes and its fixed-point arithmetic
+// collapses to small integers:  horizontal  m = far + 3*near  (exact: (s0*c0 + s1*c1) >> 4 == 32*m),
+// vertical  out = ((m_a >> 2) + ((3*m_b) >> 2) + 2) >> 2  with m_a from the source row of weight 1/4
+// and m_b from the row of weight 3/4.  Border columns / rows use clamped indices, which reproduces
+// OpenCV's coefficient clamp on x (4*s >> 2 == s) and its index clip on y.  The 12 channel values of
+// a quad are computed as 6 words of two 16-bit lanes.
+//
+// The 12 source bytes P[i-1], P[i], P[i+1], P[i+2] (i = xq/2, indices clamped) of one row, as 3 words.
+__device__ __forceinline__ void x2_load_row(const uint8_t *__restrict__ rowp, int xq, int W0, int w, uint32_t &r0,
+                                            uint32_t &r1, uint32_t &r2) {
+    if (xq == 0) {                                   // P[-1] -> P[0]
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(rowp);
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        r0 = __byte_perm(w0, w0, 0x0210), r1 = __byte_perm(w0, w1, 0x4321), r2 = __byte_perm(w1, w2, 0x4321);
+    } else if (xq == W0 - 4) {                       // P[w] -> P[w-1]
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(rowp + 3 * w - 12);
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        r0 = __byte_perm(w0, w1, 0x6543), r1 = __byte_perm(w1, w2, 0x6543), r2 = __byte_perm(w2, w2, 0x3213);
+    } else {
+        const int bo = 3 * (xq >> 1) - 3;            // odd, so the 12 bytes always span four words
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(rowp + (bo & ~3));
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
+        const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(bo & 3);
+        r0 = __byte_perm(w0, w1, sel), r1 = __byte_perm(w1, w2, sel), r2 = __byte_perm(w2, w3, sel);
+    }
+}
+// Horizontal pass of a quad: m[j] holds channel values 2j (low lane) and 2j+1 (high lane) of the
+// 12 output values (pixel k/3, channel k%3); near = the source pixel of weight 3/4.
+__device__ __forceinline__ void x2_hpass(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t m[6]) {
+    const uint32_t e0 = __byte_perm(r0, 0, 0x4140), e1 = __byte_perm(r0, 0, 0x4342);   // bytes (0,1), (2,3)
+    const uint32_t e2 = __byte_perm(r1, 0, 0x4140), e3 = __byte_perm(r1, 0, 0x4342);   // (4,5), (6,7)
+    const uint32_t e4 = __byte_perm(r2, 0, 0x4140), e5 = __byte_perm(r2, 0, 0x4342);   // (8,9), (10,11)
+    const uint32_t b34 = __byte_perm(e1, e2, 0x5432), b78 = __byte_perm(e3, e4, 0x5432);
+    m[0] = b34 * 3u + e0;                                                    // near (3,4)  far (0,1)
+    m[1] = __byte_perm(e2, e1, 0x7632) * 3u + __byte_perm(e1, e3, 0x5410);   // near (5,3)  far (2,6)
+    m[2] = e2 * 3u + b78;                                                    // near (4,5)  far (7,8)
+    m[3] = e3 * 3u + b34;                                                    // near (6,7)  far (3,4)
+    m[4] = __byte_perm(e4, e3, 0x5410) * 3u + __byte_perm(e2, e4, 0x7632);   // near (8,6)  far (5,9)
+    m[5] = b78 * 3u + e5;                                                    // near (7,8)  far (10,11)
+}
+// Vertical pass on both lanes at once.  Only the low byte of each lane of the result is meaningful:
+// the bits the word shifts leak between lanes stay above bit 11 of the low lane and never carry.
+__device__ __forceinline__ uint32_t x2_vpass(uint32_t m_a, uint32_t m_b) {
+    return ((m_a >> 2) + (((m_b * 3u) >> 2) & 0x3fff3fffu) + 0x00020002u) >> 2;
+}
+// byte `sel_byte` (PRMT index 0..3 of `v`) as an exact float: 2^23 + b, minus 2^23
+__device__ __forceinline__ float u8_to_float(uint32_t v, uint32_t sel_byte) {
+    return __fsub_rn(__uint_as_float(__byte_perm(v, 0x4b000000u, 0x7540u | sel_byte)), 8388608.f);
+}
+
 constexpr int K3_THREADS = 256;    // register pass-through kernel
 constexpr int K3_THREADS_TMA = 512;   // TMA-staged kernel (maximum; chosen at launch): the strip occupies shared memory, 2 CTAs per SM
 constexpr int K3_QUEUE1 = 128;    // work items (4-pixel quads) per warp iteration and group: 32 lanes x 4 quads
@@ -129,7 +180,8 @@ constexpr int K3_QUEUE1 = 128;    // work items (4-pixel quads) per warp iterati
 // TMA: the strip of original pixels is brought into shared memory by bulk async copies (one
 // elected thread, mbarrier completion), the blended quads are patched into it there, and the whole
 // strip leaves with a bulk store - the 6 B/px pass-through never touches registers.  Requires VEC.
-template <bool VEC, bool SMALL_R, int K3_NT, bool TMA>
+// X2: exact x2 up-scale worker (requires VEC, SMALL_R, TMA and 4-byte aligned source rows).
+template <bool VEC, bool SMALL_R, int K3_NT, bool TMA, bool X2 = false>
 __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4)
     k3_upscale_feather_composite(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig,
                                  const uint8_t *__restrict__ mask, uint8_t *__restrict__ out,
@@ -372,6 +424,47 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                 const int xq = item.x & 0xffff, r = (item.x >> 16) & 15;
                 const uint32_t n4 = (item.x >> 20) & 15u, in4 = (item.x >> 24) & 15u;
                 const int yy = y0 + r;
+                if constexpr (X2) {
+                    const int j = yy >> 1;                               // source row of weight 3/4
+                    const int ja = (yy & 1) ? min(j + 1, h - 1) : max(j - 1, 0);   // source row of weight 1/4
+                    uint32_t a0, a1, a2, b0, b1, b2;
+                    x2_load_row(inp_t + ja * w * 3, xq, W0, w, a0, a1, a2);
+                    x2_load_row(inp_t + j * w * 3, xq, W0, w, b0, b1, b2);
+                    uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
+                    uint32_t o[3] = {sp[0], sp[1], sp[2]};
+                    uint32_t ma[6], mb[6], up[6];
+                    x2_hpass(a0, a1, a2, ma);
+                    x2_hpass(b0, b1, b2, mb);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) up[k] = x2_vpass(ma[k], mb[k]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if ((n4 >> i) & 1u) {
+                            const float a = lut[(item.y >> (4 * i)) & 15u];      // > 0 by construction of `need`
+                            const float na = __fsub_rn(1.f, a);
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const int k = 3 * i + c;                          // byte k of the 12-byte quad
+                                const uint32_t upw = up[k >> 1];
+                                const uint32_t ub = (k & 1) * 2;                  // its byte in upw
+                                // nibble (k & 3) of the selector takes the new byte, the rest keep o[]
+                                const uint32_t keep = 0x3210u & ~(0xfu << (4 * (k & 3)));
+                                if (a < 1.f) {
+                                    const float v = __fadd_rn(__fmul_rn(a, u8_to_float(upw, ub)),
+                                                              __fmul_rn(na, u8_to_float(o[k >> 2], k & 3)));
+                                    // round-half-even like np.rint: the sum is in [0, 255], so adding 1.5 * 2^23
+                                    // leaves the rounded integer in the low mantissa byte
+                                    const uint32_t rb = __float_as_uint(__fadd_rn(v, 12582912.f));
+                                    o[k >> 2] = __byte_perm(o[k >> 2], rb, keep | (4u << (4 * (k & 3))));
+                                } else {
+                                    o[k >> 2] = __byte_perm(o[k >> 2], upw, keep | ((4u + ub) << (4 * (k & 3))));
+                                }
+                            }
+                        }
+                    }
+                    sp[0] = o[0], sp[1] = o[1], sp[2] = o[2];
+                    continue;
+                }
                 const Tap ty = yt[yy];
                 const uint32_t b0s = (uint32_t)(ty.w & 0xffff) << 16, b1s = (uint32_t)ty.w & 0xffff0000u;
                 const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
@@ -627,9 +720,9 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
     const long long grid = (long long)T * strips;
     VV_CHECK_ARG(grid < 2147483647LL, "vv_upscale_feather_composite: too many strips");
 
-#define VV_K3_LAUNCH(V, S, N, M)                                                                                \
+#define VV_K3_LAUNCH(V, S, N, M, ...)                                                                                \
     do {                                                                                                        \
-        auto kfn = k3_upscale_feather_composite<V, S, N, M>;                                                    \
+        auto kfn = k3_upscale_feather_composite<V, S, N, M, ##__VA_ARGS__>;                                                    \
         static std::atomic<size_t> smem_set{48 * 1024};                                                        \
         if (smem > smem_set.load()) {                                                                           \
             cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
@@ -646,7 +739,11 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
         else                            \
             VV_K3_LAUNCH(V, S, 2, false); \
     } while (0)
-    if (tma && small_r)
+    const bool x2 = tma && small_r && W0 == 2 * w && H0 == 2 * h && ((uintptr_t)inp % 4 == 0) &&
+                    get_option(OPT_K3_X2) != 0;
+    if (x2)
+        VV_K3_LAUNCH(true, true, 1, true, true);
+    else if (tma && small_r)
         VV_K3_LAUNCH(true, true, 1, true);
     else if (tma)
         VV_K3_LAUNCH(true, false, 1, true);

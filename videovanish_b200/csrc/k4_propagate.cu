@@ -168,10 +168,21 @@ __device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, l
         if (threadIdx.x == 0) q.base = atomicAdd(l.count + of, n);
         __syncthreads();
         const long long dst = of * npx + q.base;
-        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-            const uint32_t xy = q.xy[j];
-            l.xy[dst + j] = xy;
-            l.flow[dst + j] = __ldg(flow_frame + (long long)(xy >> 16) * w + (xy & 0xffffu));
+        // four entries per thread and trip: the flow gathers of a batch are in flight together
+        for (uint32_t j0 = threadIdx.x; j0 < n; j0 += 4 * blockDim.x) {
+            uint32_t xy[4];
+            float2 f[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + u * blockDim.x;
+                xy[u] = j < n ? q.xy[j] : 0u;
+                f[u] = __ldg(flow_frame + (long long)(xy[u] >> 16) * w + (xy[u] & 0xffffu));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + u * blockDim.x;
+                if (j < n) l.xy[dst + j] = xy[u], l.flow[dst + j] = f[u];
+            }
         }
     }
     __syncthreads();
@@ -200,7 +211,7 @@ __global__ void __launch_bounds__(256)
     const bool listed = len > 1;                                // a single-frame window has no steps at all
     // flow that propagates INTO this frame: backward pass flows_f[gframe], forward pass flows_b[gframe-1]
     const float2 *pflow = last ? flows_b + (gframe - 1) * npx : flows_f + gframe * npx;
-    const HoleLists &dl = last ? l2 : l1;
+    const HoleLists dl = {last ? l2.xy : l1.xy, last ? l2.flow : l1.flow, last ? l2.count : l1.count};   // selected member-wise: stays in registers
     __shared__ BlockQueue q;
     if (threadIdx.x == 0) q.count = 0;
     __syncthreads();
