@@ -126,23 +126,19 @@ __device__ __forceinline__ uint32_t vpass(uint32_t b0s, uint32_t b1s, uint32_t h
 // a quad are computed as 6 words of two 16-bit lanes.
 //
 // The 12 source bytes P[i-1], P[i], P[i+1], P[i+2] (i = xq/2, indices clamped) of one row, as 3 words.
-__device__ __forceinline__ void x2_load_row(const uint8_t *__restrict__ rowp, int xq, int W0, int w, uint32_t &r0,
-                                            uint32_t &r1, uint32_t &r2) {
-    if (xq == 0) {                                   // P[-1] -> P[0]
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(rowp);
-        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-        r0 = __byte_perm(w0, w0, 0x0210), r1 = __byte_perm(w0, w1, 0x4321), r2 = __byte_perm(w1, w2, 0x4321);
-    } else if (xq == W0 - 4) {                       // P[w] -> P[w-1]
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(rowp + 3 * w - 12);
-        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-        r0 = __byte_perm(w0, w1, 0x6543), r1 = __byte_perm(w1, w2, 0x6543), r2 = __byte_perm(w2, w2, 0x3213);
-    } else {
-        const int bo = 3 * (xq >> 1) - 3;            // odd, so the 12 bytes always span four words
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(rowp + (bo & ~3));
-        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
-        const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(bo & 3);
-        r0 = __byte_perm(w0, w1, sel), r1 = __byte_perm(w1, w2, sel), r2 = __byte_perm(w2, w3, sel);
-    }
+__device__ __forceinline__ void x2_load_row(const uint8_t *__restrict__ rowp, int xq, int W0, uint32_t &r0, uint32_t &r1,
+                                            uint32_t &r2) {
+    // byte offset 3*(i-1) is odd, so the 12 bytes always span four words.  At the two border quads the
+    // outermost word would lie outside the row: its load is redirected to a neighbour word and the
+    // clamped pixel (P[-1] -> P[0], P[w] -> P[w-1]) is patched in with one byte permute.
+    const bool left = xq == 0, right = xq == W0 - 4;
+    const int bo = 3 * (xq >> 1) - 3;
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(rowp + (bo & ~3));
+    const uint32_t w0 = __ldg(p + (left ? 1 : 0)), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + (right ? 2 : 3));
+    const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(bo & 3);
+    r0 = __byte_perm(w0, w1, sel), r1 = __byte_perm(w1, w2, sel), r2 = __byte_perm(w2, w3, sel);
+    if (left) r0 = __byte_perm(r0, r1, 0x3543);      // [x x x S0] [S1 S2 S3 S4] -> [S0 S1 S2 S0]
+    if (right) r2 = __byte_perm(r1, r2, 0x4324);     // [T7 T8 T9 T10] [T11 x x x] -> [T11 T9 T10 T11]
 }
 // Horizontal pass of a quad: m[j] holds channel values 2j (low lane) and 2j+1 (high lane) of the
 // 12 output values (pixel k/3, channel k%3); near = the source pixel of weight 3/4.
@@ -428,8 +424,8 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                     const int j = yy >> 1;                               // source row of weight 3/4
                     const int ja = (yy & 1) ? min(j + 1, h - 1) : max(j - 1, 0);   // source row of weight 1/4
                     uint32_t a0, a1, a2, b0, b1, b2;
-                    x2_load_row(inp_t + ja * w * 3, xq, W0, w, a0, a1, a2);
-                    x2_load_row(inp_t + j * w * 3, xq, W0, w, b0, b1, b2);
+                    x2_load_row(inp_t + ja * w * 3, xq, W0, a0, a1, a2);
+                    x2_load_row(inp_t + j * w * 3, xq, W0, b0, b1, b2);
                     uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
                     uint32_t o[3] = {sp[0], sp[1], sp[2]};
                     uint32_t ma[6], mb[6], up[6];
@@ -442,22 +438,26 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                         if ((n4 >> i) & 1u) {
                             const float a = lut[(item.y >> (4 * i)) & 15u];      // > 0 by construction of `need`
                             const float na = __fsub_rn(1.f, a);
+                            // one branch per pixel: a == 1 (inside, away from the edge) copies the up-scaled bytes
+                            if (a < 1.f) {
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const int k = 3 * i + c;                          // byte k of the 12-byte quad
-                                const uint32_t upw = up[k >> 1];
-                                const uint32_t ub = (k & 1) * 2;                  // its byte in upw
-                                // nibble (k & 3) of the selector takes the new byte, the rest keep o[]
-                                const uint32_t keep = 0x3210u & ~(0xfu << (4 * (k & 3)));
-                                if (a < 1.f) {
-                                    const float v = __fadd_rn(__fmul_rn(a, u8_to_float(upw, ub)),
+                                for (int c = 0; c < 3; ++c) {
+                                    const int k = 3 * i + c;                      // byte k of the 12-byte quad
+                                    const float v = __fadd_rn(__fmul_rn(a, u8_to_float(up[k >> 1], (k & 1) * 2)),
                                                               __fmul_rn(na, u8_to_float(o[k >> 2], k & 3)));
                                     // round-half-even like np.rint: the sum is in [0, 255], so adding 1.5 * 2^23
                                     // leaves the rounded integer in the low mantissa byte
                                     const uint32_t rb = __float_as_uint(__fadd_rn(v, 12582912.f));
+                                    // nibble (k & 3) of the selector takes the new byte, the rest keep o[]
+                                    const uint32_t keep = 0x3210u & ~(0xfu << (4 * (k & 3)));
                                     o[k >> 2] = __byte_perm(o[k >> 2], rb, keep | (4u << (4 * (k & 3))));
-                                } else {
-                                    o[k >> 2] = __byte_perm(o[k >> 2], upw, keep | ((4u + ub) << (4 * (k & 3))));
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    const int k = 3 * i + c;
+                                    const uint32_t keep = 0x3210u & ~(0xfu << (4 * (k & 3)));
+                                    o[k >> 2] = __byte_perm(o[k >> 2], up[k >> 1], keep | ((4u + (k & 1) * 2) << (4 * (k & 3))));
                                 }
                             }
                         }
