@@ -64,7 +64,10 @@ VV_API void vv_reset_launch_count(void);
  *   "k4_warm"    1 = the persistent scan pre-loads the next step's list entries and prefetches their
  *                flow sectors into L2 while the current step runs.
  *   "k3_x2"      1 = K3 uses the closed-form worker for exact x2 up-scales (W0 == 2w, H0 == 2h, TMA
- *                variant); 0 = the generic tap-table worker for every ratio. */
+ *                variant); 0 = the generic tap-table worker for every ratio.
+ *   "k4_pack_ctas" k4_pack launches about 148 x this many CTAs per call (more, shorter CTAs shrink the tail
+ *                of the last wave; default 128);  "k4_pack_occ" 4, 5 (default) or 6 = CTAs per SM the kernel is
+ *                compiled for. */
 VV_API int vv_set_option(const char *name, int value);
 VV_API int vv_get_option(const char *name, int *value);
 

@@ -193,8 +193,8 @@ __device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, l
 // ---- k4_pack: frames + masks -> packed state, and the per-frame lists of hole pixels -----------
 // One launch for every frame of every window of the batch (blockIdx.y = output frame).  Holes of
 // the last frame of a window are never touched by the backward pass, so they go straight to `l2`.
-template <bool VEC>
-__global__ void __launch_bounds__(256)
+template <bool VEC, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
     k4_pack(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, uint32_t *__restrict__ state,
             const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, HoleLists l1, HoleLists l2, int h,
             int w, long long first_out_frame, const __grid_constant__ SubBatch batch) {
@@ -586,11 +586,19 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
         // pack: all frames of the batch at once (grid.y <= 65535 frames per launch)
         for (long long f0 = 0; f0 < bframes; f0 += 32768) {
             const int ny = (int)min(32768LL, bframes - f0);
-            const int gx = max(1, min(ceil_div((npx + 3) / 4, 256), ceil_div(148 * 16, ny)));
-            if (vec)
-                k4_pack<true><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, l1, l2, h, w, first + f0, b);
+            const int ctas = 148 * max(1, min(1024, get_option(OPT_K4_PACK_CTAS)));
+            const int gx = max(1, min(ceil_div((npx + 3) / 4, 256 * K4_PACK_UNROLL), ceil_div(ctas, ny)));
+            const int occ = get_option(OPT_K4_PACK_OCC);
+#define VV_K4_PACK(V, O) k4_pack<V, O><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, l1, l2, h, w, first + f0, b)
+            if (!vec)
+                VV_K4_PACK(false, 4);
+            else if (occ >= 6)
+                VV_K4_PACK(true, 6);
+            else if (occ == 5)
+                VV_K4_PACK(true, 5);
             else
-                k4_pack<false><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, l1, l2, h, w, first + f0, b);
+                VV_K4_PACK(true, 4);
+#undef VV_K4_PACK
             VV_POST_LAUNCH("k4_pack");
         }
         // The serial scans touch hole pixels only.  The hole counts live on the device: the grid is
