@@ -67,7 +67,13 @@ VV_API void vv_reset_launch_count(void);
  *                variant); 0 = the generic tap-table worker for every ratio.
  *   "k4_pack_ctas" k4_pack launches about 148 x this many CTAs per call (more, shorter CTAs shrink the tail
  *                of the last wave; default 128);  "k4_pack_occ" 4, 5 (default) or 6 = CTAs per SM the kernel is
- *                compiled for. */
+ *                compiled for.
+ *   "k4_lean"    5 (default), 6 or 8 = propagation steps run the kernel whose per-step pointers are resolved
+ *                on the host, compiled for that many CTAs per SM; 0 = the older k4_step kernel.
+ *   "k4_step_ctas" CTAs per SM of the step grid (default 5: a resident grid that strides over the hole lists
+ *                with the next entry pre-loaded); 0 = about one thread per hole at a 25 % hole fraction.
+ *   "k4_taps"    1 = the 8 tap loads of a hole are issued unconditionally from clamped positions,
+ *                0 (default, measured faster) = one predicated region per tap. */
 VV_API int vv_set_option(const char *name, int value);
 VV_API int vv_get_option(const char *name, int *value);
 

@@ -251,8 +251,12 @@ def test_k4_zero_padding_fill(ops):
 
 
 @pytest.mark.parametrize("variant", [dict(k4_persistent=1, k4_warm=1), dict(k4_persistent=1, k4_warm=0),
-                                     dict(k4_persistent=0, k4_pdl=1), dict(k4_persistent=0, k4_pdl=0)],
-                         ids=["persistent-warm", "persistent", "launch-per-step-pdl", "launch-per-step"])
+                                     dict(k4_persistent=0, k4_pdl=1), dict(k4_persistent=0, k4_pdl=0),
+                                     dict(k4_lean=0, k4_pdl=1), dict(k4_lean=0, k4_pdl=0), dict(k4_lean=8, k4_step_ctas=0),
+                                     dict(k4_lean=6, k4_taps=1, k4_step_ctas=1),
+                                     dict(k4_pack_ctas=1, k4_pack_occ=4), dict(k4_pack_ctas=1024, k4_pack_occ=6)],
+                         ids=["persistent-warm", "persistent", "lean-pdl", "lean", "step-pdl", "step", "lean8-wide-grid", "lean6-uncond-taps",
+                              "pack-few-ctas", "pack-many-ctas"])
 def test_k4_kernel_variants(ops, variant):
     """The cooperative persistent scan and the launch-per-step fallback give identical states."""
     from videovanish_b200 import _lib
@@ -263,9 +267,9 @@ def test_k4_kernel_variants(ops, variant):
             _lib.set_option(k, v)
         got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb), subvideo_length=8, pad_len=3)).view(np.uint32)
     finally:
-        _lib.set_option("k4_persistent", 0)
-        _lib.set_option("k4_pdl", 1)
-        _lib.set_option("k4_warm", 0)
+        for k, v in dict(k4_persistent=0, k4_pdl=1, k4_warm=0, k4_lean=5, k4_taps=0, k4_step_ctas=5, k4_pack_ctas=128,
+                         k4_pack_occ=5).items():
+            _lib.set_option(k, v)
     assert np.array_equal(got, want)
 
 

@@ -117,6 +117,15 @@ def main():
     _lib.set_option("k4_persistent", 0)
     _lib.set_option("k4_pdl", 1)
     _lib.set_option("k4_warm", 0)
+    for lean, taps, sc in ((0, 0, 0), (5, 0, 0), (6, 0, 0), (8, 0, 0), (5, 1, 5), (5, 0, 5), (6, 0, 6), (8, 0, 8), (5, 0, 10)):
+        _lib.set_option("k4_lean", lean)
+        _lib.set_option("k4_taps", taps)
+        _lib.set_option("k4_step_ctas", sc)
+        report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb), k4_lean=lean,
+               k4_taps=taps, k4_step_ctas=sc)
+    _lib.set_option("k4_lean", 5)
+    _lib.set_option("k4_taps", 0)
+    _lib.set_option("k4_step_ctas", 5)
     for ctas, occ in ((16, 4), (128, 4), (128, 5), (128, 6)):
         _lib.set_option("k4_pack_ctas", ctas)
         _lib.set_option("k4_pack_occ", occ)

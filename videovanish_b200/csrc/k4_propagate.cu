@@ -48,7 +48,7 @@ __device__ __forceinline__ float unnormalized(float pos, int size) {
 // One hole pixel: returns the new packed state.
 // COHERENT: the previous frame's state was written by other CTAs of the SAME (persistent) kernel, so it
 // is read with ld.global.cg (L2), never from a possibly stale L1 line.
-template <bool COHERENT>
+template <bool COHERENT, bool UNCOND = false>
 __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, uint32_t cur, const float2 f,
                                                     const float2 *__restrict__ flow_check, const uint32_t *prev) {
     const float ix = unnormalized(__fadd_rn((float)x, f.x), w);
@@ -60,17 +60,33 @@ __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, 
     // clamp before the int conversion so absurd flows cannot overflow
     const int x0 = (int)fminf(fmaxf(x0f, -4.f), (float)w + 4.f);
     const int y0 = (int)fminf(fmaxf(y0f, -4.f), (float)h + 4.f);
-    const bool xa = x0 >= 0 && x0 < w, xb = x0 + 1 >= 0 && x0 + 1 < w;
-    const bool ya = y0 >= 0 && y0 < h, yb = y0 + 1 >= 0 && y0 + 1 < h;
-    const long long i00 = (long long)y0 * w + x0;
-
+    const bool xa = (unsigned)x0 < (unsigned)w, xb = (unsigned)(x0 + 1) < (unsigned)w;
+    const bool ya = (unsigned)y0 < (unsigned)h, yb = (unsigned)(y0 + 1) < (unsigned)h;
     float2 c00 = make_float2(0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
-    uint32_t p00 = 0, p01 = 0, p10 = 0, p11 = 0;          // out-of-frame taps: not a hole
-    auto ld_state = [&](long long i) { return COHERENT ? __ldcg(prev + i) : prev[i]; };
-    if (ya && xa) c00 = __ldg(flow_check + i00), p00 = ld_state(i00);
-    if (ya && xb) c01 = __ldg(flow_check + i00 + 1), p01 = ld_state(i00 + 1);
-    if (yb && xa) c10 = __ldg(flow_check + i00 + w), p10 = ld_state(i00 + w);
-    if (yb && xb) c11 = __ldg(flow_check + i00 + w + 1), p11 = ld_state(i00 + w + 1);
+    uint32_t p00 = 0, p01 = 0, p10 = 0, p11 = 0;          // out-of-frame taps: zeros padding, not a hole
+    auto ld_state = [&](uint32_t i) { return COHERENT ? __ldcg(prev + i) : prev[i]; };
+    if (UNCOND) {
+        // All 8 tap loads are issued unconditionally from clamped (always valid) positions and zeroed
+        // afterwards when the tap lies outside the frame: no branches, 32-bit index arithmetic
+        // (h * w < 2^32), all loads in flight together.
+        const uint32_t xa_i = (uint32_t)min(max(x0, 0), w - 1), xb_i = (uint32_t)min(max(x0 + 1, 0), w - 1);
+        const uint32_t ra = (uint32_t)min(max(y0, 0), h - 1) * (uint32_t)w, rb = (uint32_t)min(max(y0 + 1, 0), h - 1) * (uint32_t)w;
+        const uint32_t i00 = ra + xa_i, i01 = ra + xb_i, i10 = rb + xa_i, i11 = rb + xb_i;
+        c00 = __ldg(flow_check + i00), c01 = __ldg(flow_check + i01);
+        c10 = __ldg(flow_check + i10), c11 = __ldg(flow_check + i11);
+        p00 = ld_state(i00), p01 = ld_state(i01), p10 = ld_state(i10), p11 = ld_state(i11);
+        const float2 zero2 = make_float2(0.f, 0.f);
+        if (!(ya && xa)) c00 = zero2, p00 = 0;
+        if (!(ya && xb)) c01 = zero2, p01 = 0;
+        if (!(yb && xa)) c10 = zero2, p10 = 0;
+        if (!(yb && xb)) c11 = zero2, p11 = 0;
+    } else {
+        const uint32_t i00 = (uint32_t)(y0 * w + x0);      // only used when the tap is inside the frame
+        if (ya && xa) c00 = __ldg(flow_check + i00), p00 = ld_state(i00);
+        if (ya && xb) c01 = __ldg(flow_check + (i00 + 1u)), p01 = ld_state(i00 + 1u);
+        if (yb && xa) c10 = __ldg(flow_check + (i00 + (uint32_t)w)), p10 = ld_state(i00 + (uint32_t)w);
+        if (yb && xb) c11 = __ldg(flow_check + (i00 + (uint32_t)w + 1u)), p11 = ld_state(i00 + (uint32_t)w + 1u);
+    }
 
     // bilinear, torch CPU order: r = a*nw; r = fma(b, ne, r); r = fma(c, sw, r); r = fma(d, se, r)
     const float bwx = __fmaf_rn(c11.x, se, __fmaf_rn(c10.x, sw, __fmaf_rn(c01.x, ne, __fmul_rn(c00.x, nw))));
@@ -457,6 +473,114 @@ __global__ void __launch_bounds__(256, 8)
     step_body<PASS2, false>(flows_f, flows_b, state, l1, l2, h, w, step, sd, q);
 }
 
+// ---- k4_step_lean: the default step kernel -----------------------------------------------------
+// Same work as k4_step, but every frame / list pointer of the step is resolved on the HOST and arrives
+// in the kernel-parameter constant bank (one StepWin per window): the device code has no 64-bit
+// frame-offset arithmetic left, which matters because the step is bound by instruction issue as much as
+// by its DRAM gathers (ncu: ~500 warp instructions per 32 hole pixels, issue active 70 %, before this).
+// The re-list queue holds four rounds, so the block-wide flush (2 barriers) runs every fourth trip.
+struct StepWin {
+    const uint32_t *prev;        // state of the frame propagated FROM;  NULL = this window has no such step
+    uint32_t *cur;               // state of the frame propagated INTO (updated in place)
+    const float2 *flow_check;    // flow used by the forward/backward consistency check
+    const float2 *next_flow;     // backward pass: forward-pass flow into this frame; NULL = do not re-list
+    const uint32_t *lxy;         // list walked by this step
+    const float2 *lflow;
+    const uint32_t *count;
+    uint32_t *oxy;               // backward pass: forward list of this frame (append)
+    float2 *oflow;
+    uint32_t *ocount;
+};
+struct StepArgs {
+    StepWin win[K4_MAX_SUB];
+};
+constexpr int K4_LEAN_ROUNDS = 4;
+struct LeanQueue {
+    uint32_t xy[K4_LEAN_ROUNDS * K4_BLOCK];
+    float2 flow[K4_LEAN_ROUNDS * K4_BLOCK];
+    uint32_t count, base;
+};
+// All threads of the block must call.
+__device__ __forceinline__ void lean_flush(LeanQueue &q, const StepWin &sw) {
+    __syncthreads();
+    const uint32_t n = q.count;
+    if (n) {
+        if (threadIdx.x == 0) q.base = atomicAdd(sw.ocount, n);
+        __syncthreads();
+        const uint32_t dst = q.base;
+        for (uint32_t j = threadIdx.x; j < n; j += K4_BLOCK) {
+            sw.oxy[dst + j] = q.xy[j];
+            sw.oflow[dst + j] = q.flow[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) q.count = 0;
+    }
+    __syncthreads();
+}
+
+template <bool PASS2, int MIN_CTAS, bool UNCOND>
+__global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS)
+    k4_step_lean(const __grid_constant__ StepArgs args, int h, int w) {
+    asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
+    const StepWin &sw = args.win[blockIdx.y];
+    if (sw.prev == nullptr) return;                          // block-uniform
+    __shared__ LeanQueue q;
+    const bool relist = !PASS2 && sw.next_flow != nullptr;   // holes that stay holes go to the forward list
+    if (!PASS2) {
+        if (threadIdx.x == 0) q.count = 0;
+        __syncthreads();
+    }
+    const uint32_t stride = gridDim.x * K4_BLOCK;
+    const uint32_t first = blockIdx.x * K4_BLOCK + (threadIdx.x & ~31u);      // warp-uniform loop bounds
+    const uint32_t lane = threadIdx.x & 31u;
+    // The backward pass reads what k4_pack wrote (complete before the first step was launched), so it may
+    // load its first entry before the grid dependency resolves; the forward lists come from the preceding
+    // launches.
+    uint32_t xy = 0, n = 0;
+    float2 f = make_float2(0.f, 0.f);
+    if (!PASS2) {
+        n = *sw.count;
+        if (first + lane < n) xy = sw.lxy[first + lane], f = sw.lflow[first + lane];
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (PASS2) n = *sw.count;
+    // backward pass: block-uniform trip count (the queue flush has barriers)
+    const uint32_t n_loop = PASS2 ? n : min(n + (K4_BLOCK - 1), 0xffffff00u) / K4_BLOCK * K4_BLOCK;
+    int trip = 0;
+    if (PASS2 && first + lane < n) xy = sw.lxy[first + lane], f = sw.lflow[first + lane];
+    for (uint32_t base = first; base < n_loop; base += stride, ++trip) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        // software pipeline: the entry of the NEXT trip is requested before this trip's taps, so a thread's
+        // dependency chain is one round trip per item (plus one) instead of two
+        const uint32_t xy_cur = xy;
+        const float2 f_cur = f;
+        if (i + stride < n) xy = sw.lxy[i + stride], f = sw.lflow[i + stride];
+        const int x = (int)(xy_cur & 0xffffu), y = (int)(xy_cur >> 16);
+        const uint32_t pix = (uint32_t)y * (uint32_t)w + (uint32_t)x;
+        uint32_t nv = ST_HOLE | ST_ZERO;
+        float2 nf = make_float2(0.f, 0.f);
+        if (valid) {
+            // the forward-pass flow is fetched speculatively, in the same round trip as the taps
+            if (relist) nf = __ldg(sw.next_flow + pix);
+            nv = propagate_pixel<false, UNCOND>(x, y, h, w, ST_HOLE | ST_ZERO, f_cur, sw.flow_check, sw.prev);
+            if (nv != (ST_HOLE | ST_ZERO)) sw.cur[pix] = nv;
+        }
+        if (relist) {                   // still a hole: the forward pass gets another chance
+            const bool take = valid && nv == (ST_HOLE | ST_ZERO);
+            const uint32_t m = __ballot_sync(0xffffffffu, take);
+            if (m) {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(&q.count, (uint32_t)__popc(m));
+                at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+                if (take) q.xy[at] = xy_cur, q.flow[at] = nf;
+            }
+            if ((trip & (K4_LEAN_ROUNDS - 1)) == K4_LEAN_ROUNDS - 1) lean_flush(q, sw);
+        }
+    }
+    if (relist) lean_flush(q, sw);
+}
+
 // Barrier among the CTAs of one window (blockIdx.y): monotonic arrival counter in global memory.
 // `target` = arrivals expected so far.  The spin is bounded so that a broken launch cannot hang the GPU.
 __device__ __forceinline__ void window_barrier(unsigned int *ctr, unsigned int target, int *failed) {
@@ -630,6 +754,56 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             }
         }
         const int pdl = get_option(OPT_K4_PDL) != 0;
+        const int lean = get_option(OPT_K4_LEAN);
+        if (lean != 0) {
+            // "k4_step_ctas" > 0: that many CTAs per SM in total (a resident grid that strides over the lists)
+            const int per_sm = get_option(OPT_K4_STEP_CTAS);
+            if (per_sm > 0) grid.x = max(1, min(ceil_div(npx / 4, 256), (148 * per_sm) / b.n));
+            for (int pass = 0; pass < 2; ++pass)
+                for (int step = 1; step < blen; ++step) {
+                    StepArgs sa;
+                    for (int s = 0; s < K4_MAX_SUB; ++s) {
+                        StepWin &sw = sa.win[s];
+                        sw = StepWin();
+                        if (s >= b.n || step >= b.sub[s].len) continue;
+                        const SubDesc &sd = b.sub[s];
+                        const int idx = pass ? step : sd.len - 1 - step;
+                        const long long gframe = sd.start + idx, of = sd.out_frame + idx;
+                        const HoleLists &li = pass ? l2 : l1;
+                        sw.cur = out + of * npx;
+                        sw.prev = out + (pass ? of - 1 : of + 1) * npx;
+                        // check flow: backward pass flows_b[idx] (prop = flows_f[idx]), forward pass flows_f[idx-1]
+                        sw.flow_check = pass ? ff + (gframe - 1) * npx : fb + gframe * npx;
+                        sw.next_flow = (!pass && idx >= 1) ? fb + (gframe - 1) * npx : nullptr;
+                        sw.lxy = li.xy + of * npx, sw.lflow = li.flow + of * npx, sw.count = li.count + of;
+                        sw.oxy = l2.xy + of * npx, sw.oflow = l2.flow + of * npx, sw.ocount = l2.count + of;
+                    }
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = grid;
+                    cfg.blockDim = dim3(K4_BLOCK);
+                    cfg.stream = st;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    attr[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = attr;
+                    // the first step after k4_pack is an ordinary launch (see below)
+                    cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
+                    cudaError_t le;
+                    const bool uncond = get_option(OPT_K4_TAPS) != 0;
+#define VV_K4_LEAN(O, U) \
+    (pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, U>, sa, h, w) : cudaLaunchKernelEx(&cfg, k4_step_lean<true, O, U>, sa, h, w))
+                    if (lean >= 8)
+                        le = uncond ? VV_K4_LEAN(8, true) : VV_K4_LEAN(8, false);
+                    else if (lean >= 6)
+                        le = uncond ? VV_K4_LEAN(6, true) : VV_K4_LEAN(6, false);
+                    else
+                        le = uncond ? VV_K4_LEAN(5, true) : VV_K4_LEAN(5, false);
+#undef VV_K4_LEAN
+                    if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step_lean)");
+                    VV_POST_LAUNCH("k4_step_lean");
+                }
+            continue;
+        }
         for (int pass = 0; pass < 2; ++pass)
             for (int step = 1; step < blen; ++step) {
                 cudaLaunchConfig_t cfg = {};
