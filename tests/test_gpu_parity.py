@@ -469,6 +469,25 @@ def test_n3_painter_matches_reference_golden(ops):
     assert all(np.array_equal(a, b) for a, b in zip(want, have))
 
 
+@pytest.mark.parametrize("k", [3, 10])
+@pytest.mark.parametrize("mh,mw,h0,w0", [(40, 64, 40, 64), (36, 48, 72, 96), (25, 32, 61, 64), (40, 64, 80, 96)])
+def test_n3_painter_row_fast_paths(ops, k, mh, mw, h0, w0):
+    """Same-width and exact-x2 canvases take the row-vectorised kernel (the last shape the generic one):
+    bytes equal the reference painter's, for float logits and for u8 masks."""
+    from oracle import painter
+    rng = np.random.default_rng(mh * 7 + k)
+    t = 3
+    logits = (rng.standard_normal((t, k, mh, mw)) - 0.8).astype(np.float32)
+    logits[1, k - 1] = 1.0                                   # the last object covers a whole frame
+    ids = list(range(1, k + 1))
+    colors = [painter.color_for_obj(o) for o in ids]
+    segs = {i: {o: logits[i, j] > 0 for j, o in enumerate(ids)} for i in range(t)}
+    want = np.stack(painter.ref_paint(segs, t, h0, w0))
+    assert np.array_equal(host(ops.paint_masks(dev(logits), colors, out_size=(h0, w0))), want)
+    as_u8 = (logits > 0).astype(np.uint8) * 255
+    assert np.array_equal(host(ops.paint_masks(dev(as_u8), colors, out_size=(h0, w0))), want)
+
+
 def test_n2_state_to_float(ops):
     fr, m, ff, fb = prop_clip(5, 36, 52, seed=61)
     packed = ops.propagate(dev(fr), dev(m), dev(ff), dev(fb))

@@ -54,6 +54,14 @@ __device__ __forceinline__ void stg128_stream(void *p, const uint4 &v) {
 
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 
+// u8 <-> f32 without the conversion pipe (I2F / F2I issue at a quarter of the FP32 rate):
+// byte `sel_byte` (PRMT index 0..3 of `v`) as an exact float = bits(2^23 + b) - 2^23 ...
+__device__ __forceinline__ float u8_to_float(uint32_t v, uint32_t sel_byte) {
+    return __fsub_rn(__uint_as_float(__byte_perm(v, 0x4b000000u, 0x7540u | sel_byte)), 8388608.f);
+}
+// ... and for v in [0, 255]: the low byte of bits(v + 1.5 * 2^23) is rint(v), ties to even (np.rint).
+__device__ __forceinline__ uint32_t rint_u8_bits(float v) { return __float_as_uint(__fadd_rn(v, 12582912.f)); }
+
 // 4 mask bits (bit i <-> pixel i) -> 4 bytes of 0x00 / 0xFF.
 __device__ __forceinline__ uint32_t expand4(uint32_t nib) {
     return (((nib & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;

@@ -64,7 +64,7 @@ __device__ __forceinline__ float alpha_from(float d_in, float d_out, float div) 
 __device__ __forceinline__ uint32_t blend_u8(float a, float one_minus_a, uint32_t up, uint32_t orig) {
     const float v = __fadd_rn(__fmul_rn(a, (float)up), __fmul_rn(one_minus_a, (float)orig));
     // a in (0,1), both inputs in [0,255]: the sum is within half an ulp of [0,255], so np.clip is a no-op
-    return (uint32_t)__float2int_rn(v);            // round-half-even, like np.rint
+    return rint_u8_bits(v) & 0xffu;                // round-half-even, like np.rint
 }
 
 __device__ __forceinline__ int vlin3(int b0, int b1, int h0, int h1) {
@@ -159,17 +159,13 @@ __device__ __forceinline__ void x2_hpass(uint32_t r0, uint32_t r1, uint32_t r2, 
 __device__ __forceinline__ uint32_t x2_vpass(uint32_t m_a, uint32_t m_b) {
     return ((m_a >> 2) + (((m_b * 3u) >> 2) & 0x3fff3fffu) + 0x00020002u) >> 2;
 }
-// byte `sel_byte` (PRMT index 0..3 of `v`) as an exact float: 2^23 + b, minus 2^23
-__device__ __forceinline__ float u8_to_float(uint32_t v, uint32_t sel_byte) {
-    return __fsub_rn(__uint_as_float(__byte_perm(v, 0x4b000000u, 0x7540u | sel_byte)), 8388608.f);
-}
 
 constexpr int K3_THREADS = 256;    // register pass-through kernel
 constexpr int K3_THREADS_TMA = 512;   // TMA-staged kernel (maximum; chosen at launch): the strip occupies shared memory, 2 CTAs per SM
 constexpr int K3_QUEUE1 = 128;    // work items (4-pixel quads) per warp iteration and group: 32 lanes x 4 quads
 
 // Work item = one 4-pixel quad (x aligned to 4) that contains at least one pixel with alpha > 0:
-//   .x = x | row-in-strip << 16 | need(4) << 20 | inside(4) << 24
+//   .x = x | row-in-strip << 16 | need(4) << 20 | inside(4) << 24 | deep-inside(4) << 28 (generic radius)
 //   .y = one LUT index nibble per pixel (SMALL_R): class | inside << 3 for pixel i at bits 4i..4i+3
 
 // K3_NT = 16-pixel groups per thread and iteration.
@@ -355,14 +351,19 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
             } else {
                 // generic radius: decided per pixel by the workers; here only "inside, or some masked
                 // pixel within the window" (a superset of alpha > 0)
-                uint32_t anyM = 0;
+                // Inside pixels with no zero anywhere in their window are "deep": alpha = 1 without a search
+                // (they would otherwise walk the whole cost table).  Deep bits travel in L0.
+                uint32_t anyM = 0, anyZ = 0;
                 for (int d = -R; d <= R; ++d) {
+                    const int yy = y + d;
                     const uint32_t m = bit_window(brow + d * row_words, c0);
-                    uint32_t acc = m;
-                    for (int j = 1; j <= R; ++j) acc |= (m << j) | (m >> j);
-                    anyM |= acc;
+                    const uint32_t z = (yy >= 0 && yy < H0) ? (~m & colvalid) : 0u;
+                    uint32_t acc = m, accz = z;
+                    for (int j = 1; j <= R; ++j) acc |= (m << j) | (m >> j), accz |= (z << j) | (z >> j);
+                    anyM |= acc, anyZ |= accz;
                 }
                 need[k] = (hard ? (M2[k] >> 8) : (anyM >> 8)) & pxmask;
+                L0[k] = M2[k] & ~anyZ;
             }
         }
 
@@ -392,6 +393,7 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                     const int b = 8 + 4 * q;
                     uint2 e;
                     e.x = (uint32_t)(x0[k] + 4 * q) | ((uint32_t)row[k] << 16) | (n4 << 20) | (((M2[k] >> b) & 15u) << 24);
+                    if (!SMALL_R) e.x |= ((L0[k] >> b) & 15u) << 28;      // generic radius: "deep inside" bits
                     // 4x4 bit transpose: planes (l0, l1, l2, inside) x pixels -> one LUT index nibble per pixel
                     uint32_t x4 = ((L0[k] >> b) & 15u) | (((L1[k] >> b) & 15u) << 4) | (((L2[k] >> b) & 15u) << 8) |
                                   (((M2[k] >> b) & 15u) << 12);
@@ -532,6 +534,8 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                             const bool inside = (in4 >> i) & 1u;
                             if (hard) {
                                 a = inside ? 1.f : 0.f;
+                            } else if ((item.x >> (28 + i)) & 1u) {
+                                a = 1.f;                  // deep inside: no zero within the window
                             } else {
                                 float d = 8192.f;   // first (cheapest) window offset whose opposite-class bit is set
                                 for (int e = 0; e < ft.n; ++e) {

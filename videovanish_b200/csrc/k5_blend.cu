@@ -15,8 +15,8 @@ __device__ __forceinline__ uint32_t blend4(uint32_t a, uint32_t b, float w, floa
     uint32_t r[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float v = __fadd_rn(__fmul_rn(nw, (float)byte_of(a, i)), __fmul_rn(w, (float)byte_of(b, i)));
-        r[i] = (uint32_t)__float2int_rn(v);
+        const float v = __fadd_rn(__fmul_rn(nw, u8_to_float(a, i)), __fmul_rn(w, u8_to_float(b, i)));
+        r[i] = rint_u8_bits(v);            // only the low byte is used below
     }
     return __byte_perm(__byte_perm(r[0], r[1], 0x0040), __byte_perm(r[2], r[3], 0x0040), 0x5410);
 }

@@ -69,6 +69,83 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Fast path for the two horizontal ratios the GUI produces (SAM2 returns masks at the video resolution:
+// W0 == mw; half-resolution predictors: W0 == 2 * mw, where OpenCV's NEAREST index is x >> 1): one thread
+// = 16 consecutive canvas pixels of a row, the object planes are read with 16-byte (8-byte) loads and the
+// 48 output bytes leave as three 16-byte stores.  Any vertical ratio (row table `yo`).
+template <typename MaskT, bool X2>
+__device__ __forceinline__ uint32_t k6_hits16(const MaskT *__restrict__ p) {   // bit i = canvas pixel i is set
+    uint32_t bits = 0;
+    if (sizeof(MaskT) == 4) {
+        const float4 *q = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+        for (int j = 0; j < (X2 ? 2 : 4); ++j) {
+            const float4 v = __ldg(q + j);
+            bits |= ((uint32_t)(v.x > 0.f) | ((uint32_t)(v.y > 0.f) << 1) | ((uint32_t)(v.z > 0.f) << 2) |
+                     ((uint32_t)(v.w > 0.f) << 3))
+                    << (4 * j);
+        }
+    } else if (X2) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        bits = nonzero_bits16(make_uint4(v.x, v.y, 0u, 0u));
+    } else {
+        bits = nonzero_bits16(ldg128(p));
+    }
+    if (X2) {             // 8 source bits -> every bit doubled
+        bits = (bits | (bits << 4)) & 0x0f0fu;
+        bits = (bits | (bits << 2)) & 0x3333u;
+        bits = (bits | (bits << 1)) & 0x5555u;
+        bits |= bits << 1;
+    }
+    return bits;
+}
+
+template <typename MaskT, bool X2>
+__global__ void __launch_bounds__(256)
+    k6_paint_masks_rows(const MaskT *__restrict__ masks, int K, int mh, int mw, uint8_t *__restrict__ out, int H0, int W0,
+                        long long T, const int *__restrict__ yo, const __grid_constant__ PaintColors colors) {
+    const int groups = W0 >> 4;
+    const long long total = T * H0 * (long long)groups;
+    const long long plane = (long long)mh * mw;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % groups);
+        const long long q = idx / groups;
+        const int y = (int)(q % H0);
+        const long long t = q / H0;
+        const MaskT *src = masks + t * K * plane + (long long)yo[y] * mw + (X2 ? g * 8 : g * 16);
+        // ascending object order, later objects overwrite (sam2_masker.py:159-173); up to 8 planes in flight
+        uint32_t px[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) px[i] = 0;
+        for (int k0 = 0; k0 < K; k0 += 8) {
+            uint32_t hits[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hits[k] = (k0 + k < K) ? k6_hits16<MaskT, X2>(src + (k0 + k) * plane) : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k0 + k < K && hits[k]) {
+                    const uint8_t *c = colors.rgb + 3 * (k0 + k);
+                    const uint32_t col = c[0] | (c[1] << 8) | (c[2] << 16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if ((hits[k] >> i) & 1u) px[i] = col;
+                }
+            }
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(out + ((t * H0 + y) * (long long)W0 + g * 16) * 3);
+        uint32_t ow[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {          // 4 pixels -> 3 words
+            const uint32_t a = px[4 * j], b = px[4 * j + 1], c = px[4 * j + 2], d = px[4 * j + 3];
+            ow[3 * j] = a | (b << 24), ow[3 * j + 1] = (b >> 8) | (c << 16), ow[3 * j + 2] = (c >> 16) | (d << 8);
+        }
+        stg128_stream(o, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+        stg128_stream(o + 1, make_uint4(ow[4], ow[5], ow[6], ow[7]));
+        stg128_stream(o + 2, make_uint4(ow[8], ow[9], ow[10], ow[11]));
+    }
+}
+
 __global__ void k6_make_nearest_taps(int *__restrict__ ofs, int dst, int src) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= dst) return;
@@ -153,6 +230,30 @@ extern "C" int vv_paint_masks(const void *masks, int mask_is_f32, int T, int K, 
     const int words_ok = ((W0 * 3) % 4 == 0) && ((uintptr_t)out % 4 == 0);
     const long long total = (long long)T * H0 * ((W0 + 3) / 4);
     const int grid = (int)min((long long)ceil_div(total, 256), (long long)148 * 32);
+    // row-vectorised fast paths: identical width or exact x2, 16-byte aligned rows on both sides
+    const size_t esz = mask_is_f32 ? 4 : 1;
+    const bool same_w = W0 == mw, twice_w = W0 == 2 * mw;
+    const int src_per_16 = same_w ? 16 : 8;
+    const bool rows_ok = (same_w || twice_w) && (W0 % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                         ((uintptr_t)masks % (mask_is_f32 ? 16 : src_per_16) == 0) &&
+                         (((size_t)mw * esz) % (mask_is_f32 ? 16 : src_per_16) == 0);
+    if (rows_ok) {
+        const long long tot16 = (long long)T * H0 * (W0 / 16);
+        const int g16 = (int)min((long long)ceil_div(tot16, 256), (long long)148 * 32);
+#define VV_K6_ROWS(MT, X2) \
+    k6_paint_masks_rows<MT, X2><<<g16, 256, 0, st>>>((const MT *)masks, K, mh, mw, out, H0, W0, T, yo, pc)
+        if (mask_is_f32 && twice_w)
+            VV_K6_ROWS(float, true);
+        else if (mask_is_f32)
+            VV_K6_ROWS(float, false);
+        else if (twice_w)
+            VV_K6_ROWS(uint8_t, true);
+        else
+            VV_K6_ROWS(uint8_t, false);
+#undef VV_K6_ROWS
+        VV_POST_LAUNCH("k6_paint_masks_rows");
+        return VV_OK;
+    }
     if (mask_is_f32)
         k6_paint_masks<float><<<grid, 256, 0, st>>>((const float *)masks, K, mh, mw, out, H0, W0, T, xo, yo, words_ok, pc);
     else
