@@ -174,6 +174,18 @@ VV_API int vv_paint_masks(const void *masks, int mask_is_f32, int T, int K, int 
                           size_t workspace_bytes, void *stream);
 VV_API int vv_propagate_to_float(const uint32_t *packed, int n_frames, int h, int w, float *rgb_chw,
                                  float *hole_mask, void *stream);
+/* N4  DiffuEraser wrapper pixel steps either side of the diffusion call made at diffuerase.py:62-67
+ *   [recalled-upstream diffueraser/diffueraser.py; parity unpinned by the reference, the OpenCV
+ *   primitives are pinned against cv2: oracle/wrapper.py].
+ *   vv_wrapper_mask: read_mask = (mask > 0) -> cv2.erode(3x3 rect, 1) -> cv2.dilate(3x3 rect,
+ *     dilation_iter) -> {0,255}; mask, out: u8 [T,h,w] (the reference passes dilation_iter 0).
+ *   vv_wrapper_compose: blended != 0: alpha = u8((1 - (1 - m/255.)(1 - cv2.GaussianBlur(m,(21,21),0)/255.))
+ *     * 255) for the {0, non-zero} mask m, else alpha = m;  out = u8(img * a + frame * (1 - a)) with
+ *     a = f32(alpha)/255 in fp32, truncated.  img, frames, out: u8 [T,h,w,3]; mask255: u8 [T,h,w].
+ *     Blending needs h, w >= 11 (single REFLECT_101 bounce) and w <= ~4000 (shared-memory strip). */
+VV_API int vv_wrapper_mask(const uint8_t *mask, int T, int h, int w, int dilation_iter, uint8_t *out, void *stream);
+VV_API int vv_wrapper_compose(const uint8_t *img, const uint8_t *frames, const uint8_t *mask255, int T, int h,
+                              int w, int blended, uint8_t *out, void *stream);
 
 /* ---------------------------------------------------------------------------------
  * Host-buffer pipeline (the path the Python drop-in takes for lists of numpy frames, i.e. the

@@ -488,6 +488,39 @@ def test_n3_painter_row_fast_paths(ops, k, mh, mw, h0, w0):
     assert np.array_equal(host(ops.paint_masks(dev(as_u8), colors, out_size=(h0, w0))), want)
 
 
+@pytest.mark.parametrize("h,w", [(540, 960), (54, 96), (33, 47), (40, 64), (11, 11), (70, 1100)])
+@pytest.mark.parametrize("n_dilate", [0, 4])
+def test_n4_wrapper_mask_and_compose(ops, h, w, n_dilate):
+    """N4: read_mask (erode + dilate) and the blurred compose equal the cv2 / numpy restatement byte for byte,
+    including masks that touch the borders, empty and full frames."""
+    from oracle import wrapper as ow
+    t = 4
+    rng = np.random.default_rng(h + 3 * w + n_dilate)
+    mk = np.stack(op.model_binarize_dilate(list(synth.masks(t, h, w, seed=h + n_dilate, salt=0.004)), 2))
+    mk[1] = 0
+    mk[2] = 255
+    mk[3, :3] = 200                                  # non-{0,255} values, touching all four borders
+    mk[3, -2:] = 7
+    mk[3, :, :4] = 255
+    mk[3, :, -1:] = 1
+    got_mask = host(ops.wrapper_mask(dev(mk), n_dilate))
+    want_mask = np.stack([ow.ref_wrapper_mask(m, n_dilate) for m in mk])
+    assert np.array_equal(got_mask, want_mask)
+    img = rng.integers(0, 256, (t, h, w, 3), dtype=np.uint8)
+    fr = rng.integers(0, 256, (t, h, w, 3), dtype=np.uint8)
+    for blended in (True, False):
+        got = host(ops.wrapper_compose(dev(img), dev(fr), dev(want_mask), blended))
+        want = np.stack([ow.ref_wrapper_compose(img[i], fr[i], want_mask[i], blended) for i in range(t)])
+        assert np.array_equal(got, want), (blended, int(np.abs(got.astype(int) - want.astype(int)).max()))
+
+
+def test_n4_argument_checks(ops):
+    small = torch.zeros((1, 8, 8, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError, match="not supported"):
+        ops.wrapper_compose(small, small, small[..., 0].contiguous(), True)
+    assert ops.wrapper_compose(small, small, small[..., 0].contiguous(), False).shape == small.shape
+
+
 def test_n2_state_to_float(ops):
     fr, m, ff, fb = prop_clip(5, 36, 52, seed=61)
     packed = ops.propagate(dev(fr), dev(m), dev(ff), dev(fb))

@@ -212,3 +212,40 @@ def test_painter_oracle_matches_golden():
     assert up.any() and np.all(z["out"][0][up & ~cv2.resize(segs[0][ids[2]].squeeze().astype(np.uint8), (w0, h0),
                                                           interpolation=cv2.INTER_NEAREST).astype(bool)] ==
                                np.array(painter.color_for_obj(ids[1])))
+
+
+# ------------------------------------------------------------------ N4 (DiffuEraser wrapper glue): cv2 pins
+@pytest.mark.parametrize("h,w", [(40, 64), (33, 47), (54, 96), (11, 11)])
+@pytest.mark.parametrize("n_dilate", [0, 1, 4])
+def test_N4_wrapper_models_match_cv2(h, w, n_dilate):
+    """The closed forms the K7 kernels implement equal the cv2 / numpy restatement of the upstream wrapper:
+    3x3 erode + dilate with cv2's default borders, the bit-exact u8 GaussianBlur((21, 21), 0) and the
+    float64 -> u8 alpha truncation."""
+    import cv2
+    from oracle import wrapper as ow
+    rng = np.random.default_rng(h * w + n_dilate)
+    for dens in (0.01, 0.2, 0.6):
+        m = (rng.random((h, w)) < dens).astype(np.uint8) * rng.integers(1, 256, (h, w)).astype(np.uint8)
+        m = cv2.dilate(m, np.ones((3, 3), np.uint8), iterations=2)
+        a = ow.ref_wrapper_mask(m, n_dilate)
+        assert np.array_equal(a, ow.model_wrapper_mask(m, n_dilate))
+        assert set(np.unique(a)) <= {0, 255}
+        assert np.array_equal(ow.ref_soft_alpha(a), ow.model_soft_alpha(a))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        fr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for blended in (True, False):
+            assert np.array_equal(ow.ref_wrapper_compose(img, fr, a, blended), ow.model_wrapper_compose(img, fr, a, blended))
+
+
+def test_N4_gaussian_taps_are_cv2s():
+    """GAUSS21_Q8 is OpenCV's bit-exact Q0.8 kernel for ksize 21, sigma 0: impulse responses of the 1-D blur."""
+    import cv2
+    from oracle import wrapper as ow
+    assert int(ow.GAUSS21_Q8.sum()) == 256
+    for amp in (255, 128, 37):
+        img = np.zeros((1, 64), np.uint8)
+        img[0, 32] = amp
+        got = cv2.GaussianBlur(img, (21, 1), 0)[0, 22:43].astype(np.int64)
+        assert np.array_equal(got, (amp * ow.GAUSS21_Q8 + 128) >> 8)
+    lut = ow.alpha_lut()
+    assert lut[0] == 0 and lut[255] == 255 and int((lut != np.arange(256)).sum()) == 42

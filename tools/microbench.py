@@ -141,6 +141,13 @@ def main():
         logits = torch.randn((tn, 3, HS, WS), device=dev, generator=g) - 1.0
         report("N3 paint 3 objects 540p -> 1080p", tn * (3 * 4 * spx + 3 * px),
                lambda: ops.paint_masks(logits, [(55, 255, 208), (148, 255, 55), (182, 255, 55)], out_size=(H0, W0)), frames_n=tn)
+        # N4 at inference resolution: read_mask (erode + 0 / 4 dilations) and the blurred compose
+        for nd in (0, 4):
+            report("N4 wrapper mask (erode + %d dilate) 540p" % nd, t * 2 * spx, lambda: ops.wrapper_mask(low, nd))
+        wm = ops.wrapper_mask(low, 0)
+        comp_out = torch.empty_like(small)
+        report("N4 wrapper compose (blurred) 540p", t * 10 * spx, lambda: ops.wrapper_compose(inp, small, wm, True, out=comp_out))
+        report("N4 wrapper compose (hard) 540p", t * 10 * spx, lambda: ops.wrapper_compose(inp, small, wm, False, out=comp_out))
         packed = ops.propagate(small[:tn], low[:tn], ff[:tn - 1], fb[:tn - 1])
         report("N2 state -> float CHW", tn * (4 + 16) * spx, lambda: ops.propagate_to_float(packed), frames_n=tn)
 

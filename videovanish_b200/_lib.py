@@ -50,6 +50,8 @@ _SIGNATURES = {
     "vv_paint_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, _u8p, c_int, c_int, c_void_p,
                                c_size_t, c_void_p]),
     "vv_propagate_to_float": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vv_wrapper_mask": (c_int, [_u8p, c_int, c_int, c_int, c_int, _u8p, c_void_p]),
+    "vv_wrapper_compose": (c_int, [_u8p, _u8p, _u8p, c_int, c_int, c_int, c_int, _u8p, c_void_p]),
     "vv_chunk_blend": (c_int, [_u8p, _u8p, c_int, c_size_t, c_int, c_int, _u8p, c_void_p]),
     "vv_pipeline_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int]),
     "vv_pipeline_destroy": (None, [c_void_p]),

@@ -204,6 +204,38 @@ def paint_masks(masks, colors, out_size=None):
     return out
 
 
+def wrapper_mask(mask, dilation_iter=0):
+    """N4.  The DiffuEraser wrapper's read_mask on u8 [T,h,w]: (mask > 0), 3x3 erode once, 3x3 dilate
+    ``dilation_iter`` times, {0,255} (the step inside the model call at diffuerase.py:62-67)."""
+    _require_cuda(mask)
+    if mask.dim() != 3 or mask.dtype != torch.uint8:
+        raise ValueError("wrapper_mask: mask must be uint8 [T,h,w]")
+    mask = mask.contiguous()
+    t, h, w = mask.shape
+    with torch.cuda.device(mask.device):
+        out = torch.empty_like(mask)
+        _lib.check(lib.vv_wrapper_mask(_ptr(mask), t, h, w, int(dilation_iter), _ptr(out), _stream()), "vv_wrapper_mask")
+    return out
+
+
+def wrapper_compose(img, frames, mask255, blended=True, out=None):
+    """N4.  The wrapper's compose: model output ``img`` over the resized originals ``frames`` (u8 [T,h,w,3])
+    through the (optionally 21x21-Gaussian-softened) mask u8 [T,h,w]."""
+    _require_cuda(img)
+    if img.shape != frames.shape or img.dim() != 4 or img.shape[3] != 3 or mask255.shape != img.shape[:3]:
+        raise ValueError("wrapper_compose: img / frames must be [T,h,w,3] and mask255 [T,h,w]")
+    if img.dtype != torch.uint8 or frames.dtype != torch.uint8 or mask255.dtype != torch.uint8:
+        raise ValueError("wrapper_compose: uint8 tensors required")
+    img, frames, mask255 = img.contiguous(), frames.contiguous(), mask255.contiguous()
+    t, h, w, _ = img.shape
+    with torch.cuda.device(img.device):
+        if out is None:
+            out = torch.empty_like(img)
+        _lib.check(lib.vv_wrapper_compose(_ptr(img), _ptr(frames), _ptr(mask255), t, h, w, 1 if blended else 0, _ptr(out),
+                                          _stream()), "vv_wrapper_compose")
+    return out
+
+
 def propagate_to_float(packed, want_mask=True):
     """N2.  K4's packed state [N,h,w] -> (f32 [N,3,h,w] in [-1,1], f32 hole mask [N,h,w])."""
     _require_cuda(packed)
