@@ -16,6 +16,9 @@ Layout
 ``propagation.py``  row A10 (ProPainter flow-guided prior; un-vendored
                     upstream, PARITY UNPINNED by the reference).
 ``chunk_blend.py``  row A11 (builder-defined spec; PARITY UNPINNED).
+``painter.py``      next row N3 (SAM2 colour painter; pinned by tests/golden/paint.npz).
+``wrapper.py``      next row N4 (DiffuEraser wrapper read_mask + blurred compose; recalled
+                    upstream, PARITY UNPINNED; its OpenCV primitives are pinned against cv2).
 ``reference_harness.py``  imports the UNMODIFIED reference module from
                     ``/root/reference`` with stub model packages; exists only
                     in the build container and is used to pin this oracle and

@@ -168,7 +168,10 @@ __global__ void __launch_bounds__(K7_THREADS)
             const int p0 = x0 + 32 - K7_R;
             const uint32_t win = __funnelshift_r(row[p0 >> 5], row[(p0 >> 5) + 1], p0 & 31);
             uint32_t hv[4] = {0, 0, 0, 0};
-            if (win) {
+            if ((win & 0x0fffffffu) == 0x0fffffffu) {          // all 28 bits the group looks at are set: 256 each
+                hv[0] = hv[1] = hv[2] = hv[3] = 0x01000100u;
+                colflag[g] = 1u;
+            } else if (win) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const uint32_t wv = win >> i;
@@ -201,15 +204,21 @@ __global__ void __launch_bounds__(K7_THREADS)
         if (!BLENDED) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) alpha[i] = byte_of(m4, i);
-        } else if (colflag[x0 >> 3]) {
-            constexpr int K[21] = {0, 2, 2, 4, 6, 11, 15, 20, 25, 28, 30, 28, 25, 20, 15, 11, 6, 4, 2, 2, 0};
-            uint32_t s[4] = {0, 0, 0, 0};
+        } else if (colflag[x0 >> 3] && !(byte_of(m4, 0) && byte_of(m4, 1) && byte_of(m4, 2) && byte_of(m4, 3))) {
+            // taps 0 and 20 are zero and the kernel is symmetric: rows d and 20-d are added first, two u16
+            // lanes per word.  sum_{d=1..9} K[d] * 512 = 57 856 < 2^16, so the lanes cannot carry into each
+            // other; the centre tap is added after unpacking.
+            constexpr uint32_t K[11] = {0, 2, 2, 4, 6, 11, 15, 20, 25, 28, 30};
+            uint2 acc = make_uint2(0u, 0u);
 #pragma unroll
-            for (int d = 1; d < 20; ++d) {          // taps 0 and 20 are zero
-                const uint2 v = *reinterpret_cast<const uint2 *>(hs + (r + d) * hs_stride + x0);
-                s[0] += K[d] * (v.x & 0xffffu), s[1] += K[d] * (v.x >> 16);
-                s[2] += K[d] * (v.y & 0xffffu), s[3] += K[d] * (v.y >> 16);
+            for (int d = 1; d < 10; ++d) {
+                const uint2 u = *reinterpret_cast<const uint2 *>(hs + (r + d) * hs_stride + x0);
+                const uint2 v = *reinterpret_cast<const uint2 *>(hs + (r + 20 - d) * hs_stride + x0);
+                acc.x += K[d] * (u.x + v.x), acc.y += K[d] * (u.y + v.y);
             }
+            const uint2 c = *reinterpret_cast<const uint2 *>(hs + (r + 10) * hs_stride + x0);
+            const uint32_t s[4] = {(acc.x & 0xffffu) + K[10] * (c.x & 0xffffu), (acc.x >> 16) + K[10] * (c.x >> 16),
+                                   (acc.y & 0xffffu) + K[10] * (c.y & 0xffffu), (acc.y >> 16) + K[10] * (c.y >> 16)};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint32_t blur = (255u * s[i] + 32768u) >> 16;
