@@ -126,6 +126,9 @@ def main():
     _lib.set_option("k4_lean", 5)
     _lib.set_option("k4_taps", 0)
     _lib.set_option("k4_step_ctas", 5)
+    for spec in (0, 1):
+        _lib.set_option("k4_speculate", spec)
+        report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb), k4_speculate=spec)
     for ctas, occ in ((16, 4), (128, 4), (128, 5), (128, 6)):
         _lib.set_option("k4_pack_ctas", ctas)
         _lib.set_option("k4_pack_occ", occ)

@@ -520,7 +520,7 @@ __device__ __forceinline__ void lean_flush(LeanQueue &q, const StepWin &sw) {
 
 template <bool PASS2, int MIN_CTAS, bool UNCOND>
 __global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS)
-    k4_step_lean(const __grid_constant__ StepArgs args, int h, int w) {
+    k4_step_lean(const __grid_constant__ StepArgs args, int h, int w, int speculate) {
     asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
     const StepWin &sw = args.win[blockIdx.y];
     if (sw.prev == nullptr) return;                          // block-uniform
@@ -562,9 +562,10 @@ __global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS)
         float2 nf = make_float2(0.f, 0.f);
         if (valid) {
             // the forward-pass flow is fetched speculatively, in the same round trip as the taps
-            if (relist) nf = __ldg(sw.next_flow + pix);
+            if (relist && speculate) nf = __ldg(sw.next_flow + pix);
             nv = propagate_pixel<false, UNCOND>(x, y, h, w, ST_HOLE | ST_ZERO, f_cur, sw.flow_check, sw.prev);
             if (nv != (ST_HOLE | ST_ZERO)) sw.cur[pix] = nv;
+            else if (relist && !speculate) nf = __ldg(sw.next_flow + pix);
         }
         if (relist) {                   // still a hole: the forward pass gets another chance
             const bool take = valid && nv == (ST_HOLE | ST_ZERO);
@@ -790,8 +791,9 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
                     cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
                     cudaError_t le;
                     const bool uncond = get_option(OPT_K4_TAPS) != 0;
+                    const int spec = get_option(OPT_K4_SPECULATE);
 #define VV_K4_LEAN(O, U) \
-    (pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, U>, sa, h, w) : cudaLaunchKernelEx(&cfg, k4_step_lean<true, O, U>, sa, h, w))
+    (pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, U>, sa, h, w, spec) : cudaLaunchKernelEx(&cfg, k4_step_lean<true, O, U>, sa, h, w, spec))
                     if (lean >= 8)
                         le = uncond ? VV_K4_LEAN(8, true) : VV_K4_LEAN(8, false);
                     else if (lean >= 6)
