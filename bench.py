@@ -88,10 +88,10 @@ class ClockSampler:
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.handle = None
+        self.sample()          # the first query of each kind is slow (lazy NVML set-up): pay for it here; start() clears it
 
     def sample(self):
-        """One sample now (also called from the timed loop right after a step has been enqueued, i.e.
-        while the GPU is executing it, so short timed regions still get one sample per step)."""
+        """One sample now."""
         if self.handle is None:
             return
         nv = self.nv
@@ -107,7 +107,7 @@ class ClockSampler:
     def _loop(self):
         while not self._stop:
             self.sample()
-            time.sleep(0.002)
+            time.sleep(0.003)
 
     def start(self):
         if self.handle is None:
@@ -326,10 +326,10 @@ def run_ours(args, rank, world, local_rank):
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main_stream)
+    # Clocks are sampled by the sampler's own thread only: an NVML query from THIS thread can take
+    # milliseconds on some hosts and would stall the enqueue of the next step (measured: +1.1 ms/step).
     for k in range(args.steps):
         step(evs[k])
-        if rank == 0:
-            sampler.sample()
     e1.record(main_stream)
     sync_all()
     launches = _lib.launch_count()

@@ -31,7 +31,7 @@ if [[ $what == *ncu* ]]; then
       -k 'regex:^k[1-5]' --launch-skip 441 --launch-count 147 --csv --log-file gpurun_out/step_metrics.csv \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu2.log 2>&1
   # ... and full captures of the hot kernels
-  for k in k3_upscale k1a_binarize k1b_dilate k2_resize_linear_half k4_step k4_pack; do
+  for k in k3_upscale k1a_binarize k1b_dilate k2_resize_linear_half k4_step_lean k4_pack; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 2 -f \
         -o gpurun_out/prof_$k python tools/microbench.py --frames 300 --ops "k1 dilate8 + half,k2 resize 1080p->540p,k3 composite (synthetic,k4" > gpurun_out/ncu_$k.log 2>&1
   done
