@@ -45,6 +45,7 @@ struct Tap {
 int build_linear_taps(void *workspace, int H, int W, int h, int w, const Tap **xt, const Tap **yt, cudaStream_t st);
 
 constexpr int K3_TH = 16;          // maximum output rows per CTA strip
+constexpr int K3_MAX_CLASSES = 31;    // distinct chamfer costs < feather_px (30 at the maximum feather of 8): 5 bit planes
 constexpr int K3_MAX_ENTRIES = 224;   // window offsets with cost < feather_px, radius <= 7
 
 struct FeatherTable {      // passed by value as a kernel parameter (constant bank, uniform reads)
@@ -54,6 +55,9 @@ struct FeatherTable {      // passed by value as a kernel parameter (constant ba
     float cost[K3_MAX_ENTRIES];
     int8_t dx[K3_MAX_ENTRIES];
     int8_t dy[K3_MAX_ENTRIES];
+    uint8_t cls[K3_MAX_ENTRIES];    // cost class of the entry, 1 .. n_cls in ascending cost (entries are sorted by cost)
+    float ccost[K3_MAX_CLASSES + 1];   // cost of class c (index 0 unused)
+    int n_cls;
 };
 
 __device__ __forceinline__ float alpha_from(float d_in, float d_out, float div) {
@@ -165,8 +169,9 @@ constexpr int K3_THREADS_TMA = 512;   // TMA-staged kernel (maximum; chosen at l
 constexpr int K3_QUEUE1 = 128;    // work items (4-pixel quads) per warp iteration and group: 32 lanes x 4 quads
 
 // Work item = one 4-pixel quad (x aligned to 4) that contains at least one pixel with alpha > 0:
-//   .x = x | row-in-strip << 16 | need(4) << 20 | inside(4) << 24 | deep-inside(4) << 28 (generic radius)
-//   .y = one LUT index nibble per pixel (SMALL_R): class | inside << 3 for pixel i at bits 4i..4i+3
+//   .x = x | row-in-strip << 16 | need(4) << 20 | inside(4) << 24
+//   .y = one LUT index nibble per pixel (SMALL_R): class | inside << 3 for pixel i at bits 4i..4i+3;
+//        generic radius: one cost-class byte per pixel (0 = no opposite pixel within the window)
 
 // K3_NT = 16-pixel groups per thread and iteration.
 // TMA: the strip of original pixels is brought into shared memory by bulk async copies (one
@@ -282,9 +287,11 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
             }
         }
         uint32_t need[K3_NT], L0[K3_NT], L1[K3_NT], L2[K3_NT], M2[K3_NT];
+        uint32_t L3[SMALL_R ? 1 : K3_NT], L4[SMALL_R ? 1 : K3_NT];     // generic radius: cost-class planes 3 and 4
 #pragma unroll
         for (int k = 0; k < K3_NT; ++k) {
             need[k] = L0[k] = L1[k] = L2[k] = M2[k] = 0;
+            if (!SMALL_R) L3[k] = L4[k] = 0;
             if (!active[k]) continue;
             const int y = y0 + row[k];
             const int npx = VEC ? 16 : min(16, W0 - x0[k]);
@@ -349,10 +356,11 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                     need[k] = (pos >> 8) & pxmask;
                 }
             } else {
-                // generic radius: decided per pixel by the workers; here only "inside, or some masked
-                // pixel within the window" (a superset of alpha > 0)
-                // Inside pixels with no zero anywhere in their window are "deep": alpha = 1 without a search
-                // (they would otherwise walk the whole cost table).  Deep bits travel in L0.
+                // Generic radius: the same first-hit search as above, bit-parallel over the 16 pixels of the
+                // group, driven by the sorted chamfer table: every table entry (dx, dy) shifts the bit row
+                // dy by dx; hits accumulate per cost class, and at the end of a class the still undecided
+                // pixels that were hit get that class (5 bit planes L0..L4).  Pixels whose window holds no
+                // opposite pixel at all are pruned first (class 0: alpha 1 inside, 0 outside).
                 uint32_t anyM = 0, anyZ = 0;
                 for (int d = -R; d <= R; ++d) {
                     const int yy = y + d;
@@ -362,8 +370,36 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                     for (int j = 1; j <= R; ++j) acc |= (m << j) | (m >> j), accz |= (z << j) | (z >> j);
                     anyM |= acc, anyZ |= accz;
                 }
-                need[k] = (hard ? (M2[k] >> 8) : (anyM >> 8)) & pxmask;
-                L0[k] = M2[k] & ~anyZ;
+                const uint32_t inside = M2[k];
+                uint32_t und = hard ? 0u : (((inside & anyZ) | (~inside & anyM)) & (pxmask << 8));
+                uint32_t hcls = 0;
+                int cur = 0;
+                auto close_class = [&]() {
+                    const uint32_t newly = hcls & und;
+                    if (cur & 1) L0[k] |= newly;
+                    if (cur & 2) L1[k] |= newly;
+                    if (cur & 4) L2[k] |= newly;
+                    if (cur & 8) L3[k] |= newly;
+                    if (cur & 16) L4[k] |= newly;
+                    und &= ~hcls;
+                    hcls = 0;
+                };
+                for (int e = 0; e < ft.n && und; ++e) {
+                    const int c = ft.cls[e];
+                    if (c != cur) {
+                        close_class();
+                        cur = c;
+                    }
+                    const int dy = ft.dy[e], dx = ft.dx[e], yy = y + dy;
+                    const uint32_t m = bit_window(brow + dy * row_words, c0);
+                    const uint32_t z = (yy >= 0 && yy < H0) ? (~m & colvalid) : 0u;
+                    const uint32_t sm = dx >= 0 ? (m >> dx) : (m << -dx);      // pixel bit b looks at bit b + dx
+                    const uint32_t sz = dx >= 0 ? (z >> dx) : (z << -dx);
+                    hcls |= (sz & inside) | (sm & ~inside);
+                }
+                close_class();
+                // alpha > 0: every inside pixel, and outside pixels that found a masked pixel closer than feather_px
+                need[k] = ((inside | L0[k] | L1[k] | L2[k] | L3[k] | L4[k]) >> 8) & pxmask;
             }
         }
 
@@ -393,7 +429,6 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                     const int b = 8 + 4 * q;
                     uint2 e;
                     e.x = (uint32_t)(x0[k] + 4 * q) | ((uint32_t)row[k] << 16) | (n4 << 20) | (((M2[k] >> b) & 15u) << 24);
-                    if (!SMALL_R) e.x |= ((L0[k] >> b) & 15u) << 28;      // generic radius: "deep inside" bits
                     // 4x4 bit transpose: planes (l0, l1, l2, inside) x pixels -> one LUT index nibble per pixel
                     uint32_t x4 = ((L0[k] >> b) & 15u) | (((L1[k] >> b) & 15u) << 4) | (((L2[k] >> b) & 15u) << 8) |
                                   (((M2[k] >> b) & 15u) << 12);
@@ -402,6 +437,17 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                     tt = (x4 ^ (x4 >> 6)) & 0x00ccu;
                     x4 ^= tt ^ (tt << 6);
                     e.y = x4;
+                    if (!SMALL_R) {                 // generic radius: one cost-class byte per pixel
+                        uint32_t cb = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int bb = b + i;
+                            cb |= (((L0[k] >> bb) & 1u) | (((L1[k] >> bb) & 1u) << 1) | (((L2[k] >> bb) & 1u) << 2) |
+                                   (((L3[k] >> bb) & 1u) << 3) | (((L4[k] >> bb) & 1u) << 4))
+                                  << (8 * i);
+                        }
+                        e.y = cb;
+                    }
                     queue[pos++] = e;
                 }
             }
@@ -534,20 +580,12 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
                             const bool inside = (in4 >> i) & 1u;
                             if (hard) {
                                 a = inside ? 1.f : 0.f;
-                            } else if ((item.x >> (28 + i)) & 1u) {
-                                a = 1.f;                  // deep inside: no zero within the window
                             } else {
-                                float d = 8192.f;   // first (cheapest) window offset whose opposite-class bit is set
-                                for (int e = 0; e < ft.n; ++e) {
-                                    const int ey = yy + ft.dy[e], ex = xq + i + ft.dx[e];
-                                    if (ey < 0 || ey >= H0 || ex < 0 || ex >= W0) continue;
-                                    const uint32_t wv = bits[(r + R + ft.dy[e]) * row_words + 1 + (ex >> 5)];
-                                    if ((((wv >> (ex & 31)) & 1u) != 0) != inside) {
-                                        d = ft.cost[e];
-                                        break;
-                                    }
-                                }
-                                a = inside ? alpha_from(d, 0.f, ft.div) : alpha_from(0.f, d, ft.div);
+                                const uint32_t c = (item.y >> (8 * i)) & 255u;      // cost class of the first hit, 0 = none
+                                if (c == 0)
+                                    a = inside ? 1.f : 0.f;
+                                else
+                                    a = inside ? alpha_from(ft.ccost[c], 0.f, ft.div) : alpha_from(0.f, ft.ccost[c], ft.div);
                             }
                         }
                         if (SMALL_R || a > 0.f) {
@@ -606,6 +644,7 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
 static void build_feather_table(float feather_px, FeatherTable *ft) {
     ft->div = (float)(2.0 * (double)feather_px);
     ft->n = 0;
+    ft->n_cls = 0;
     ft->radius = 0;
     if (!(feather_px > 0.f)) return;
     const int R = (int)ceilf(feather_px) - 1;
@@ -644,10 +683,16 @@ static void build_feather_table(float feather_px, FeatherTable *ft) {
             if (c < feather_px) ent.push_back(std::make_tuple(c, dy, dx));
         }
     std::sort(ent.begin(), ent.end());
+    ft->n_cls = 0;
     for (size_t i = 0; i < ent.size() && i < (size_t)K3_MAX_ENTRIES; ++i) {
         ft->cost[i] = std::get<0>(ent[i]);
         ft->dy[i] = (int8_t)std::get<1>(ent[i]);
         ft->dx[i] = (int8_t)std::get<2>(ent[i]);
+        if (i == 0 || ft->cost[i] != ft->cost[i - 1]) {
+            if (ft->n_cls == K3_MAX_CLASSES) break;          // cannot happen for feather_px <= VV_MAX_FEATHER
+            ft->ccost[++ft->n_cls] = ft->cost[i];
+        }
+        ft->cls[i] = (uint8_t)ft->n_cls;
         ft->n = (int)i + 1;
     }
 }
