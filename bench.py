@@ -270,8 +270,9 @@ def run_ours(args, rank, world, local_rank):
     # Two streams: the propagation prior (K2 -> K4) is a chain of ~140 short dependent launches that
     # leaves most of the machine idle, while the post stage (K3, + halo blend) is throughput bound and
     # only depends on K1 - so K3 can run on a second stream next to K4 (VV_BENCH_OVERLAP=1).
-    # Measured on B200: the overlap buys < 10 % (both stages compete for issue slots, and K3's CTAs
-    # fill the SMs' shared memory) and blurs the per-stage timings, so it is opt-in.
+    # Measured on B200: with the first step kernel the overlap bought < 10 %; with the resident-grid step
+    # kernel (5 CTAs per SM parked on memory latency) K3 only gets the left-over thread slots and the step
+    # becomes SLOWER (4.99 vs 4.24 ms).  It also blurs the per-stage timings, so it stays opt-in.
     overlap = os.environ.get("VV_BENCH_OVERLAP", "0") != "0"
     for kv in filter(None, os.environ.get("VV_OPTS", "").split(",")):      # e.g. VV_OPTS=k3_tma_rows=8,k3_tma_threads=256
         k, v = kv.split("=")
