@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
     // Work items are carried over between iterations so that the worker rounds below always run
     // with all 32 lanes busy; one extra iteration (no new tasks) drains the remainder.
     int qcount = 0;
+    const int step_row = nthreads / G, step_g = nthreads - step_row * G;
+    int next_row = (int)threadIdx.x / G, next_g = (int)threadIdx.x - next_row * G;
     for (int it = 0; it <= n_iters; ++it) {
         const bool drain = it == n_iters;
         int row[K3_NT], x0[K3_NT];
@@ -277,10 +279,14 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
         uint4 pa[K3_NT], pb[K3_NT], pc[K3_NT];
 #pragma unroll
         for (int k = 0; k < K3_NT; ++k) {
-            const int id = (it * K3_NT + k) * nthreads + threadIdx.x;
-            row[k] = id / G;
-            x0[k] = (id - row[k] * G) * 16;
-            active[k] = id < n_tasks && y0 + row[k] < H0;
+            // task (row, group) = (id / G, id % G) for id = (it * K3_NT + k) * nthreads + tid, advanced
+            // incrementally: one integer division per thread instead of one per task
+            row[k] = next_row;
+            x0[k] = next_g * 16;
+            active[k] = next_row < th && y0 + next_row < H0;
+            next_row += step_row;
+            next_g += step_g;
+            if (next_g >= G) next_g -= G, ++next_row;
             if (VEC && !TMA && active[k]) {
                 const int pix_off = ((y0 + row[k]) * W0 + x0[k]) * 3;
                 pa[k] = ldg128(orig_t + pix_off), pb[k] = ldg128(orig_t + pix_off + 16), pc[k] = ldg128(orig_t + pix_off + 32);
