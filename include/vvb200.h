@@ -66,7 +66,7 @@ VV_API void vv_reset_launch_count(void);
  *   "k3_x2"      1 = K3 uses the closed-form worker for exact x2 up-scales (W0 == 2w, H0 == 2h, TMA
  *                variant); 0 = the generic tap-table worker for every ratio.
  *   "k4_pack_ctas" k4_pack launches about 148 x this many CTAs per call (more, shorter CTAs shrink the tail
- *                of the last wave; default 128);  "k4_pack_occ" 4, 5 (default) or 6 = CTAs per SM the kernel is
+ *                of the last wave; default 128);  "k4_pack_occ" 4 (default), 5 or 6 = CTAs per SM the kernel is
  *                compiled for.
  *   "k4_lean"    5 (default), 6 or 8 = propagation steps run the kernel whose per-step pointers are resolved
  *                on the host, compiled for that many CTAs per SM; 0 = the older k4_step kernel.

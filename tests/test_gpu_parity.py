@@ -264,7 +264,7 @@ def test_k4_kernel_variants(ops, variant):
         got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb), subvideo_length=8, pad_len=3)).view(np.uint32)
     finally:
         for k, v in dict(k4_persistent=0, k4_pdl=1, k4_warm=0, k4_lean=5, k4_taps=0, k4_step_ctas=5, k4_pack_ctas=128,
-                         k4_pack_occ=5).items():
+                         k4_pack_occ=4).items():
             _lib.set_option(k, v)
     assert np.array_equal(got, want)
 

@@ -135,7 +135,7 @@ def main():
         report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb), k4_pack_ctas=ctas,
                k4_pack_occ=occ)
     _lib.set_option("k4_pack_ctas", 128)
-    _lib.set_option("k4_pack_occ", 5)
+    _lib.set_option("k4_pack_occ", 4)
     report("K5 chunk blend 16 frames", 16 * 9 * px, lambda: ops.chunk_blend(fr[:16], fr[16:32], out=out[:16]))
     report("copy (torch) 1080p frames", t * 6 * px, lambda: out.copy_(fr))
     # next rows: N3 painter (3 objects at inference resolution painted onto the 1080p canvas), N2 state -> float

@@ -235,16 +235,28 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long iters = (ngroups + stride * K4_PACK_UNROLL - 1) / (stride * K4_PACK_UNROLL);
     const int lane = threadIdx.x & 31;
+    // VEC (w % 4 == 0): a group never straddles a row end; its (row, first column) is advanced incrementally
+    // from one group to the next (stride groups further) - one division per thread instead of one per group.
+    const uint32_t w4 = VEC ? (uint32_t)w >> 2 : 1u;
+    const uint32_t step_y = (uint32_t)(stride / w4), step_x = (uint32_t)(stride - (long long)step_y * w4);
+    const uint32_t g_first = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t gy = g_first / w4, gx = g_first - gy * w4;
     for (long long itn = 0; itn < iters; ++itn) {
         // K4_PACK_UNROLL groups per thread: all loads first (memory-level parallelism), one flush check per round
         uint32_t c[K4_PACK_UNROLL][4];
         uint32_t m4[K4_PACK_UNROLL], fa[K4_PACK_UNROLL], fb2[K4_PACK_UNROLL], fd[K4_PACK_UNROLL];
         long long p0[K4_PACK_UNROLL];
+        uint32_t xy0[K4_PACK_UNROLL];
         int n[K4_PACK_UNROLL];
 #pragma unroll
         for (int u = 0; u < K4_PACK_UNROLL; ++u) {
             const long long g = (itn * K4_PACK_UNROLL + u) * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
             p0[u] = g * 4;
+            if (VEC) {
+                xy0[u] = (gx << 2) | (gy << 16);
+                gy += step_y, gx += step_x;
+                if (gx >= w4) gx -= w4, ++gy;
+            }
             n[u] = g < ngroups ? (VEC ? 4 : (int)min(4LL, npx - p0[u])) : 0;
             if (VEC && n[u]) {
                 m4[u] = __ldg(reinterpret_cast<const uint32_t *>(mk + p0[u]));
@@ -297,14 +309,20 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
 #pragma unroll
             for (int u = 0; u < K4_PACK_UNROLL; ++u) {
                 if (holes[u]) {
-                    const uint32_t p32 = (uint32_t)p0[u];      // h*w < 2^32 (both <= 65535)
-                    const uint32_t y0 = p32 / (uint32_t)w, x0 = p32 - y0 * (uint32_t)w;
+                    if (VEC) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if ((holes[u] >> i) & 1u) {
-                            uint32_t x = x0 + i, y = y0;
-                            while (x >= (uint32_t)w) x -= w, ++y;   // a group may straddle a row end when w % 4 != 0
-                            q.xy[base++] = x | (y << 16);
+                        for (int i = 0; i < 4; ++i)
+                            if ((holes[u] >> i) & 1u) q.xy[base++] = xy0[u] + i;
+                    } else {
+                        const uint32_t p32 = (uint32_t)p0[u];      // h*w < 2^32 (both <= 65535)
+                        const uint32_t y0 = p32 / (uint32_t)w, x0 = p32 - y0 * (uint32_t)w;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if ((holes[u] >> i) & 1u) {
+                                uint32_t x = x0 + i, y = y0;
+                                while (x >= (uint32_t)w) x -= w, ++y;   // a group may straddle a row end when w % 4 != 0
+                                q.xy[base++] = x | (y << 16);
+                            }
                         }
                     }
                 }
@@ -679,7 +697,7 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
     VV_CHECK_ARG(workspace_bytes >= vv_propagate_workspace_bytes((int)total, h, w), "vv_propagate: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const long long npx = (long long)h * w;
-    const bool vec = (npx % 4 == 0) && ((uintptr_t)frames % 4 == 0) && ((uintptr_t)masks % 4 == 0) &&
+    const bool vec = (w % 4 == 0) && ((uintptr_t)frames % 4 == 0) && ((uintptr_t)masks % 4 == 0) &&
                      ((uintptr_t)out % 16 == 0);
     const size_t l4 = align_up((size_t)total * npx * 4, 256), l8 = align_up((size_t)total * npx * 8, 256);
     uint8_t *wsp = (uint8_t *)workspace;
