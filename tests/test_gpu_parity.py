@@ -616,3 +616,21 @@ def test_chunked_driver_blends_overlaps(ops):
         per_chunk.append(np.stack(op.ref_run_infill_on_frames(list(fr[s:e]), list(mk[s:e]), lambda *a, **k: inp,
                                                               mask_dilation_iter=2, propainer_frames=list(fr[s:e]))))
     assert np.array_equal(np.stack(got), ocb.stitch_chunks(per_chunk, plan, ov))
+
+
+def test_tools_writer_fits_frames_on_the_gpu(ops, tmp_path):
+    """tools.write_video_frames_to_path brings frames of another size to (H0, W0) with NEAREST (tools.py:41-42):
+    same bytes as the reference's cv2.resize, read back from the lossless file."""
+    cv2 = pytest.importorskip("cv2")
+    from videovanish_b200 import tools
+    rng = np.random.default_rng(3)
+    frames = [rng.integers(0, 256, (30, 44, 3), dtype=np.uint8), rng.integers(0, 256, (48, 64, 3), dtype=np.uint8),
+              rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)]
+    path = str(tmp_path / "fit.mkv")
+    try:
+        tools.write_video_frames_to_path(path, frames, 25.0, 48, 64)
+    except AssertionError:
+        pytest.skip("FFV1 writer unavailable in this OpenCV build")
+    got, _ = tools.load_video_frames_from_path(path)
+    want = [f if f.shape[:2] == (48, 64) else cv2.resize(f, (64, 48), interpolation=cv2.INTER_NEAREST) for f in frames]
+    assert len(got) == 3 and all(np.array_equal(g, w) for g, w in zip(got, want))

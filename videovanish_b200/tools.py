@@ -72,6 +72,19 @@ def load_video_frames_from_path(video_path, start_frame=0, max_frames=-1):
     return frames, fps
 
 
+def _fit_nearest(rgb, H0, W0):
+    """A frame of another size is brought to (H0, W0) with NEAREST, like the reference's writer (:41-42) - on
+    the GPU (K2 nearest kernel, bit-exact against cv2.INTER_NEAREST); like every pixel stage of this package it
+    has no CPU fallback."""
+    import torch
+
+    from . import ops
+    if not torch.cuda.is_available():
+        raise RuntimeError("write_video_frames_to_path: resizing a frame needs a CUDA device (no CPU fallback)")
+    src = torch.from_numpy(np.ascontiguousarray(rgb)[None]).cuda()
+    return ops.resize(src, H0, W0, ops.INTER_NEAREST)[0].cpu().numpy()
+
+
 def write_video_frames_to_path(out_video, mask_frames, fps, H0, W0):
     """Encode RGB frames as lossless FFV1 (tools.py:30-45); frames of another size are brought to
     (W0, H0) with NEAREST first, exactly like the reference's writer (:41-42)."""
@@ -79,9 +92,9 @@ def write_video_frames_to_path(out_video, mask_frames, fps, H0, W0):
     assert sink.isOpened(), "Failed to open VideoWriter (FFV1/MKV). Try MJPG or mp4v if needed."
     count = 0
     for rgb in mask_frames:
+        if rgb.shape[:2] != (H0, W0):
+            rgb = _fit_nearest(rgb, H0, W0)         # NEAREST commutes with the channel swap below
         bgr = cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR)
-        if bgr.shape[:2] != (H0, W0):
-            bgr = cv2.resize(bgr, (W0, H0), interpolation=cv2.INTER_NEAREST)
         sink.write(bgr)
         count += 1
     sink.release()
