@@ -150,6 +150,10 @@ def main():
         wm = ops.wrapper_mask(low, 0)
         comp_out = torch.empty_like(small)
         report("N4 wrapper compose (blurred) 540p", t * 10 * spx, lambda: ops.wrapper_compose(inp, small, wm, True, out=comp_out))
+        box = torch.zeros_like(wm)
+        box[:, 180:360, 300:620] = 255                    # one object, 11 % of the frame: the realistic case
+        report("N4 wrapper compose (blurred, one object) 540p", t * 10 * spx,
+               lambda: ops.wrapper_compose(inp, small, box, True, out=comp_out))
         report("N4 wrapper compose (hard) 540p", t * 10 * spx, lambda: ops.wrapper_compose(inp, small, wm, False, out=comp_out))
         packed = ops.propagate(small[:tn], low[:tn], ff[:tn - 1], fb[:tn - 1])
         report("N2 state -> float CHW", tn * (4 + 16) * spx, lambda: ops.propagate_to_float(packed), frames_n=tn)

@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(K7_THREADS)
     // layout (host: smem_for): hs first so that its rows are 16-byte aligned
     uint16_t *hs = reinterpret_cast<uint16_t *>(k7_smem);                  // [R][hs_stride] (BLENDED only)
     uint32_t *bits = k7_smem + (BLENDED ? (R * hs_stride) / 2 : 0);        // [R][roww], bit p = x + 32
-    uint32_t *colflag = bits + R * roww;                                   // [G8] any mask bit in the window of the group
-    float *fa = reinterpret_cast<float *>(colflag + G8);                   // [256] a = alpha / 255
+    uint32_t *colflag = bits + R * roww;                                   // [G8][2] bit r: row r of the buffer has a mask bit in the group's window
+    float *fa = reinterpret_cast<float *>(colflag + 2 * G8);               // [256] a = alpha / 255
     uint16_t *part = reinterpret_cast<uint16_t *>(fa + 256);               // [3][128]
     uint8_t *alut = reinterpret_cast<uint8_t *>(part + 3 * 128);           // [256]
     const long long t = blockIdx.y;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(K7_THREADS)
     for (int i = threadIdx.x; i < 256; i += K7_THREADS) fa[i] = __fdiv_rn((float)i, 255.f);
     for (int i = threadIdx.x; i < 3 * 128; i += K7_THREADS) part[i] = tab.part[i >> 7][i & 127];
     for (int i = threadIdx.x; i < 256; i += K7_THREADS) alut[i] = tab.alpha[i];
-    for (int i = threadIdx.x; i < G8; i += K7_THREADS) colflag[i] = 0;
+    for (int i = threadIdx.x; i < 2 * G8; i += K7_THREADS) colflag[i] = 0;
     if (BLENDED) {
         for (int id = threadIdx.x; id < R * roww; id += K7_THREADS) {
             const int r = id / roww, j = id - r * roww - 1;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(K7_THREADS)
             uint32_t hv[4] = {0, 0, 0, 0};
             if ((win & 0x0fffffffu) == 0x0fffffffu) {          // all 28 bits the group looks at are set: 256 each
                 hv[0] = hv[1] = hv[2] = hv[3] = 0x01000100u;
-                colflag[g] = 1u;
+                atomicOr(colflag + 2 * g + (r >> 5), 1u << (r & 31));
             } else if (win) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(K7_THREADS)
                     const uint32_t s = part[wv & 127u] + part[128 + ((wv >> 7) & 127u)] + part[256 + ((wv >> 14) & 127u)];
                     hv[i >> 1] |= s << (16 * (i & 1));
                 }
-                colflag[g] = 1u;                         // benign race: every writer stores the same value
+                atomicOr(colflag + 2 * g + (r >> 5), 1u << (r & 31));
             }
             *reinterpret_cast<uint4 *>(hs + r * hs_stride + x0) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
         }
@@ -204,7 +204,9 @@ __global__ void __launch_bounds__(K7_THREADS)
         if (!BLENDED) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) alpha[i] = byte_of(m4, i);
-        } else if (colflag[x0 >> 3] && !(byte_of(m4, 0) && byte_of(m4, 1) && byte_of(m4, 2) && byte_of(m4, 3))) {
+        } else if ((((((unsigned long long)colflag[2 * (x0 >> 3) + 1] << 32) | colflag[2 * (x0 >> 3)]) >> r) & 0x1fffffull) &&
+                   !(byte_of(m4, 0) && byte_of(m4, 1) && byte_of(m4, 2) && byte_of(m4, 3))) {
+            // some buffer row r .. r+20 (the 21 taps of output row r) sees a mask bit, and not every pixel is masked
             // taps 0 and 20 are zero and the kernel is symmetric: rows d and 20-d are added first, two u16
             // lanes per word.  sum_{d=1..9} K[d] * 512 = 57 856 < 2^16, so the lanes cannot carry into each
             // other; the centre tap is added after unpacking.
@@ -323,9 +325,9 @@ extern "C" int vv_wrapper_compose(const uint8_t *img, const uint8_t *frames, con
     const int hs_stride = G8 * 8;                       // u16 elements per row, 16-byte aligned rows
     auto smem_for = [&](int th) {
         const size_t R = (size_t)th + 2 * K7_R;
-        return (blended ? R * hs_stride * 2 : 0) + R * (Wp + 2) * 4 + (size_t)G8 * 4 + 256 * 4 + 3 * 128 * 2 + 256;
+        return (blended ? R * hs_stride * 2 : 0) + R * (Wp + 2) * 4 + (size_t)G8 * 8 + 256 * 4 + 3 * 128 * 2 + 256;
     };
-    int th = min(32, h);
+    int th = min(32, h);                                // th + 20 buffer rows must fit the 64-bit row flags
     while (th > 1 && smem_for(th) > 100 * 1024) --th;   // two CTAs per SM when possible ...
     if (smem_for(th) > 100 * 1024) {
         th = min(8, h);
