@@ -370,6 +370,34 @@ def run_ours(args, rank, world, local_rank):
                                 "GBps": alg_k3 / (ms * 1e-3) / 1e9, "frac": alg_k3 / (ms * 1e-3) / 1e9 / peaks()[0]}
         del masks_k3
 
+    # ---- the same step with the moving-box mask only (BASELINE config 0's mask: one object, ~5 % of the
+    # frame after dilation), outside the timed region and for information: the headline above uses the much
+    # denser box + salt mask, which is the worst case for K3 (issue bound) and K4 (30 % of all pixels are holes)
+    box_step = None
+    if rank == 0 and world == 1:
+        from videovanish_b200 import synth as _synth
+        bench_masks = dev["masks"]
+        dev["masks"] = torch.from_numpy(_synth.masks(t, H0, W0, seed=10 + rank + 1, salt=0.0)).to(device)
+        for _ in range(2):
+            step()
+        bev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in stages] for _ in range(3)]
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        b0.record(main_stream)
+        for k in range(3):
+            step(bev[k])
+        b1.record(main_stream)
+        torch.cuda.synchronize()
+        alg_b = algorithmic_bytes(t)
+        bms = b0.elapsed_time(b1) / 3
+        box_step = {"mask": "moving box only, no salt", "value": t / (bms * 1e-3), "unit": "frames/s", "ms_per_step": bms,
+                    "stages": {s: {"ms": float(np.mean([bev[k][i][0].elapsed_time(bev[k][i][1]) for k in range(3)]))}
+                               for i, s in enumerate(stages)}}
+        for s, v in box_step["stages"].items():
+            if s in alg_b:
+                v["frac"] = alg_b[s] / (v["ms"] * 1e-3) / 1e9 / peaks()[0]
+        dev["masks"] = bench_masks
+
     # ---- end to end through the reference-facing call, host buffers in, host buffers out
     class _StubModel:                       # stands in for DiffuEraser / ProPainter (out of scope)
         def forward(self, frames, masks, priors, **kw):
@@ -427,6 +455,7 @@ def run_ours(args, rank, world, local_rank):
                     "path": "diffuerase.run_infill_on_frames(list of pinned host frames), stub models, K1 + K3 via "
                             "the host pipeline; result %dx%d" % (fh, fw)},
             "k3_vs_mask_density": k3_density,
+            "box_mask_step": box_step,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
