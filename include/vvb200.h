@@ -73,7 +73,9 @@ VV_API void vv_reset_launch_count(void);
  *   "k4_step_ctas" CTAs per SM of the step grid (default 5: a resident grid that strides over the hole lists
  *                with the next entry pre-loaded); 0 = about one thread per hole at a 25 % hole fraction.
  *   "k4_taps"    1 = the 8 tap loads of a hole are issued unconditionally from clamped positions,
- *                0 (default, measured faster) = one predicated region per tap. */
+ *                0 (default, measured faster) = one predicated region per tap.
+ *   "k4_speculate" 1 (default, measured faster) = the backward pass fetches the forward-pass flow of a hole
+ *                together with its taps; 0 = only after the hole turned out to stay a hole. */
 VV_API int vv_set_option(const char *name, int value);
 VV_API int vv_get_option(const char *name, int *value);
 
