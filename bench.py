@@ -6,14 +6,17 @@
 
 Workload (BASELINE.json configs[1]): synthetic 1080p 300-frame clip, inference resolution
 960x540.  One step = one pass of the hot path over the whole clip:
-    K1 mask binarise + dilate(8) (+ fused NEAREST low-res mask)      diffuerase.py:28-31
-    K2 bilinear down-size of the frames to 960x540                    row A9
-    K4 flow-guided propagation prior at 960x540, 50+10-frame windows  row A10
-    K3 resize-back + feather(3) + composite                           diffuerase.py:70-112
+    K1 mask binarise + dilate(8) (+ fused NEAREST low-res mask, + 1-bit plane)   diffuerase.py:28-31
+    K2 bilinear down-size of the frames to 960x540                               row A9
+    K4 flow-guided propagation prior at 960x540, 50+10-frame windows             row A10
+    K3 resize-back + feather(3) + composite                                      diffuerase.py:70-112
     (N > 1 only) K5 halo blend of the `overlap` frames shared with the neighbour ranks
-`value` times that with inputs resident in HBM; `e2e` times the reference-facing
-`run_infill_on_frames(list of host frames)` call (pre + post through the host pipeline, stub
-models, H2D/D2H inside the timed region).  Prints ONE JSON line on rank 0.
+`value` times that with inputs resident in HBM.  `e2e` times the reference-facing call
+`diffuerase.run_infill_on_frames(list of host frames, list of host masks)` with the wrapper adapters
+installed: frames + masks cross PCIe once, K1 -> K2 -> K4 -> N2 -> N4 -> K3 run in HBM (networks stubbed),
+finished frames come back - the SAME stage set the reference arm's `e2e` runs on the host cores.
+`e2e_prepost` is the K1 + K3-only pair (host-list models: what a real DiffuEraser install exercises).
+Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -30,11 +33,21 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "c2_1080p: 300x1080x1920 clip, infer 960x540, dilate 8, feather 3, K1+K2+K4+K3"
 T_FRAMES, H0, W0, HS, WS = 300, 1080, 1920, 540, 960
 DILATE, FEATHER, OVERLAP = 8, 3, 16
+METRIC = "1080p frames/sec (pre/post+propagation)"
+E2E_STAGES = "K1+K2+K4+N2+N4+K3"
 
 
-def algorithmic_bytes(t):
+def bench_config(world, frames=T_FRAMES):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "frames_per_gpu": frames, "l2": "inputs (>4 GB/step) larger than L2",
+            "streams": "1", "halo_overlap": OVERLAP if world > 1 else 0,
+            "halo_mode": (os.environ.get("VV_HALO_MODE", "peer") if world > 1 else None),
+            "e2e_stages": E2E_STAGES}
+
+
+def algorithmic_bytes(t, h0=H0, w0=W0, hs=HS, ws=WS):
     """SURVEY section 8d per-frame figures x frames."""
-    px, spx = H0 * W0, HS * WS
+    px, spx = h0 * w0, hs * ws
     return {
         "K1_binarize_dilate": t * (4 * px + spx),                # 3-ch mask in, 1-ch out (+ low-res mask out)
         "K2_resize_down": t * (3 * px + 3 * spx),
@@ -44,8 +57,8 @@ def algorithmic_bytes(t):
 
 
 def measured_traffic(stage, frames):
-    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of a stage's kernels from the committed
-    ncu capture of this same command (profiles/ncu_traffic.json, written by tools/ncu_traffic.py)."""
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of a stage's kernels.  NOT measured in this run:
+    read from the committed ncu capture of this same command (profiles/ncu_traffic.json, tools/ncu_traffic.py)."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(p))
@@ -137,12 +150,10 @@ def cpu_sample_inputs(n):
     return fr, mk, inp, ff, fb
 
 
-def cpu_reference_step(fr, mk, inp, ff, fb, threads):
-    """The reference's CPU implementation of the path on a sample of frames: its own cv2 / scipy /
-    numpy calls per frame (oracle.prepost.ref_*, restating diffuerase.py:28-31, :70-112) spread over
-    `threads` host threads (frames are independent and the library calls release the GIL), plus the
-    torch-CPU restatement of the propagation prior (oracle.propagation)."""
-    from concurrent.futures import ThreadPoolExecutor
+def cpu_core_step(fr, mk, inp, ff, fb, pool):
+    """`value`'s stage set (K1 + K2 + K4 + K3) on a sample of frames: the reference's own cv2 / scipy / numpy calls
+    per frame (oracle.prepost.ref_*, restating diffuerase.py:28-31, :70-112) spread over the host threads (frames
+    are independent and the library calls release the GIL), plus the torch-CPU restatement of the propagation."""
     from oracle import prepost as op
     from oracle import propagation as opp
     n = len(fr)
@@ -151,40 +162,97 @@ def cpu_reference_step(fr, mk, inp, ff, fb, threads):
         d = op.ref_binarize_dilate([mk[i]], DILATE)[0]
         return d, op.ref_resize_nearest(d, HS, WS), op.ref_resize_linear(fr[i], HS, WS)
 
-    with ThreadPoolExecutor(threads) as ex:
-        res = list(ex.map(pre, range(n)))
-        dil = [r[0] for r in res]
-        low = np.stack([r[1] for r in res])
-        small = np.stack([r[2] for r in res])
-        opp.img_propagation_torch(small, low, ff, fb)
-        out = list(ex.map(lambda i: op.ref_post_frame(inp[i], fr[i], dil[i], True, FEATHER), range(n)))
+    res = list(pool.map(pre, range(n)))
+    dil = [r[0] for r in res]
+    low = np.stack([r[1] for r in res])
+    small = np.stack([r[2] for r in res])
+    opp.img_propagation_torch(small, low, ff, fb)
+    return list(pool.map(lambda i: op.ref_post_frame(inp[i], fr[i], dil[i], True, FEATHER), range(n)))
+
+
+def cpu_full_step(fr, mk, ff, fb, pool):
+    """`e2e`'s stage set (K1 + K2 + K4 + N2 + N4 + K3, networks stubbed) on the host: oracle.full_path.run."""
+    from oracle import full_path
+    return full_path.run(list(fr), list(mk), lambda small, low: (ff, fb), mask_dilation_iter=DILATE, max_img_size=960,
+                         feather_px=FEATHER, pool=pool, infer_size=(HS, WS))
+
+
+def cpu_prepost_step(fr, mk, inp, pool):
+    """K1 + K3 only (the stages in the reference's own file), threaded over frames or - pool=None - in the
+    reference's single loop, as shipped."""
+    from oracle import prepost as op
+    n = len(fr)
+    if pool is None:
+        dil = op.ref_binarize_dilate(list(mk), DILATE)
+        return [op.ref_post_frame(inp[i], fr[i], dil[i], True, FEATHER) for i in range(n)]
+    dil = list(pool.map(lambda i: op.ref_binarize_dilate([mk[i]], DILATE)[0], range(n)))
+    return list(pool.map(lambda i: op.ref_post_frame(inp[i], fr[i], dil[i], True, FEATHER), range(n)))
+
+
+def time_cpu(fn, reps):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def cpu_numbers(n, reps, threads, which=("core", "full", "prepost", "as_shipped")):
+    """frames/s of the CPU arm for each stage set on an n-frame sample."""
+    from concurrent.futures import ThreadPoolExecutor
+    import torch
+    torch.set_num_threads(threads)
+    fr, mk, inp, ff, fb = cpu_sample_inputs(n)
+    out = {}
+    with ThreadPoolExecutor(threads) as pool:
+        if "core" in which:
+            out["core"] = n / time_cpu(lambda: cpu_core_step(fr, mk, inp, ff, fb, pool), reps)
+        if "full" in which:
+            out["full"] = n / time_cpu(lambda: cpu_full_step(fr, mk, ff, fb, pool), reps)
+        if "prepost" in which:
+            out["prepost"] = n / time_cpu(lambda: cpu_prepost_step(fr, mk, inp, pool), reps)
+    if "as_shipped" in which:
+        m = min(n, 4)
+        out["as_shipped"] = m / time_cpu(lambda: cpu_prepost_step(fr[:m], mk[:m], inp[:m], None), 1)
     return out
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    from concurrent.futures import ThreadPoolExecutor
     import torch
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     n = args.cpu_sample
-    data = cpu_sample_inputs(n)
-    for _ in range(args.warmup):
-        cpu_reference_step(*data, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_reference_step(*data, threads)
-    dt = (time.perf_counter() - t0) / args.steps
+    fr, mk, inp, ff, fb = cpu_sample_inputs(n)
+    with ThreadPoolExecutor(threads) as pool:
+        for _ in range(args.warmup):
+            cpu_core_step(fr, mk, inp, ff, fb, pool)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_core_step(fr, mk, inp, ff, fb, pool)
+        dt = (time.perf_counter() - t0) / args.steps
+        full_dt = time_cpu(lambda: cpu_full_step(fr, mk, ff, fb, pool), max(1, min(args.steps, 3)))
+        pp_dt = time_cpu(lambda: cpu_prepost_step(fr, mk, inp, pool), max(1, min(args.steps, 3)))
+    m = min(n, 4)
+    shipped_dt = time_cpu(lambda: cpu_prepost_step(fr[:m], mk[:m], inp[:m], None), 1)
     fps = n / dt
-    sample = "%d of the %d frames per step (oracle port: cv2/scipy/numpy per frame over %d threads + torch-CPU propagation)" % (
-        n, T_FRAMES, threads)
+    sample = ("%d of the %d frames per step; oracle port = the reference's cv2/scipy/numpy calls per frame fanned over a "
+              "%d-thread pool (NOT how the reference ships: its single loop is `as_shipped_prepost`) + torch-CPU "
+              "propagation" % (n, T_FRAMES, threads))
     line = {
-        "impl": "reference", "metric": "1080p frames/sec (pre/post+propagation)", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": n},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": bench_config(world, args.frames),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
+                         "frames_per_step": n},
+        "e2e": {"value": n / full_dt, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "stages": E2E_STAGES + " on the host (oracle.full_path.run, networks stubbed), %d-frame sample" % n},
+        "e2e_prepost": {"value": n / pp_dt, "unit": "frames/s", "stages": "K1+K3 (diffuerase.py:28-31, :70-112), thread pool"},
+        "as_shipped_prepost": {"value": m / shipped_dt, "unit": "frames/s", "cores": 1,
+                               "stages": "K1+K3 in the reference's single Python loop (cv2's own threads only), %d frames" % m},
     }
     print(json.dumps(line), flush=True)
 
@@ -192,6 +260,20 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def device_flows(n, h, w, device, seed):
+    """Synthetic bidirectional flows on the device: (3.0, -1.5) + N(0, 0.05^2), 2 % outliers."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n = max(n, 1)
+    base = torch.tensor([3.0, -1.5], device=device)
+    ff = base + 0.05 * torch.randn((n, h, w, 2), device=device, generator=g)
+    fb = -ff + 0.05 * torch.randn((n, h, w, 2), device=device, generator=g)
+    bad = torch.rand((n, h, w), device=device, generator=g) < 0.02
+    ff[bad] += (torch.rand((int(bad.sum()), 2), device=device, generator=g) - 0.5) * 40.0
+    return ff.contiguous(), fb.contiguous()
+
+
 def make_workload(t, device, seed):
     """Host (pinned) and device copies of the synthetic clip.  Frames / inpainted frames repeat a
     32-frame seeded set (generation cost), masks move every frame, flows are drawn on the device."""
@@ -208,15 +290,7 @@ def make_workload(t, device, seed):
         p.numpy()[...] = a
         host[k] = p
     dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
-    g = torch.Generator(device=device)
-    g.manual_seed(seed + 3)
-    n = max(t - 1, 1)
-    basef = torch.tensor([3.0, -1.5], device=device)
-    ff = basef + 0.05 * torch.randn((n, HS, WS, 2), device=device, generator=g)
-    fb = -ff + 0.05 * torch.randn((n, HS, WS, 2), device=device, generator=g)
-    bad = torch.rand((n, HS, WS), device=device, generator=g) < 0.02
-    ff[bad] += (torch.rand((int(bad.sum()), 2), device=device, generator=g) - 0.5) * 40.0
-    dev["flows_f"], dev["flows_b"] = ff.contiguous(), fb.contiguous()
+    dev["flows_f"], dev["flows_b"] = device_flows(t - 1, HS, WS, device, seed + 3)
     torch.cuda.synchronize()
     return host, dev
 
@@ -243,6 +317,235 @@ def bind_to_gpu_numa_node(torch_index):
     return None
 
 
+def timed_ms(fn, reps=3, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def halo_parity_check(device, rank, world, modes=("peer", "nccl")):
+    """N > 1, before the timed loop: the rank-boundary halo blend of a seeded 16-frame-overlap slab in both modes
+    against oracle.chunk_blend for THIS rank's boundaries (uneven frame counts per rank), verdict all-reduced."""
+    import torch
+    import torch.distributed as dist
+    from oracle import chunk_blend as ocb
+    from videovanish_b200 import chunking
+    h, w = 135, 240
+    frames_of = [32 + 4 * ((3 * r) % 5) for r in range(world)]
+    clips = [np.random.default_rng(700 + r).integers(0, 256, (frames_of[r], h, w, 3), dtype=np.uint8) for r in range(world)]
+    t, half = frames_of[rank], OVERLAP // 2
+    expect = clips[rank].copy()
+    if rank < world - 1:
+        expect[t - OVERLAP:t - OVERLAP + half] = ocb.blend_overlap(clips[rank][t - OVERLAP:], clips[rank + 1][:OVERLAP])[:half]
+    if rank > 0:
+        tp = frames_of[rank - 1]
+        expect[half:OVERLAP] = ocb.blend_overlap(clips[rank - 1][tp - OVERLAP:], clips[rank][:OVERLAP])[half:]
+    ok = True
+    for mode in modes:
+        mine = torch.from_numpy(clips[rank]).to(device)
+        window = chunking.PeerWindow(mine) if mode == "peer" else None
+        for _ in range(2):                                       # two epochs without a host sync in between
+            mine.copy_(torch.from_numpy(clips[rank]).to(device))
+            chunking.blend_rank_boundaries(mine, OVERLAP, mode=mode, window=window)
+        torch.cuda.synchronize()
+        ok = ok and np.array_equal(mine.cpu().numpy(), expect) and not (window is not None and window.error())
+        dist.barrier()
+        if window is not None:
+            window.close()
+    v = torch.tensor([1 if ok else 0], device=device)
+    dist.all_reduce(v, op=dist.ReduceOp.MIN)
+    return "bit-exact" if int(v.item()) else "MISMATCH"
+
+
+def c4_sharded_check(device, rank, world, n_frames, halo_mode):
+    """BASELINE config 4 as a system at 4K (2160x3840 -> 536x960, chunk 80 / overlap 16): chunk_plan -> shard_chunks
+    -> every rank runs K1 -> K2 -> [stub model] -> K3 on its chunks -> local K5 stitch -> rank-boundary halo blend.
+    Every rank also computes the single-GPU stitch of the whole clip and compares its owned frames byte for byte."""
+    import torch
+    import torch.distributed as dist
+    from videovanish_b200 import chunking, ops
+    h0, w0 = 2160, 3840
+    h, w = ops.inference_size(h0, w0, 960)
+    chunk, ov = 80, 16
+
+    def frame_inputs(f):
+        g = torch.Generator(device=device)
+        g.manual_seed(9000 + f)
+        fr = torch.randint(0, 256, (h0, w0, 3), dtype=torch.uint8, device=device, generator=g)
+        mk = torch.zeros((h0, w0, 3), dtype=torch.uint8, device=device)
+        y, x = (h0 // 3 + 4 * f) % (h0 - h0 // 4), (w0 // 4 + 12 * f) % (w0 - w0 // 5)
+        mk[y:y + h0 // 4, x:x + w0 // 5, 2] = 255
+        return fr, mk
+
+    def process_chunk(ci, s, e):
+        frs, mks = zip(*[frame_inputs(f) for f in range(s, e)])
+        fr, mk = torch.stack(frs), torch.stack(mks)
+        dil, low, bits = ops.binarize_dilate(mk, DILATE, lowres_size=(h, w), return_bits=True)
+        small = ops.resize(fr, h, w)
+        inpainted = small + (17 * ci + 1)                       # stub model: chunk-dependent, so the cross-fade matters
+        return ops.upscale_feather_composite(inpainted, fr, dil, FEATHER, mask_bits=bits)
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    block, first, owned = chunking.run_sharded(n_frames, chunk, ov, process_chunk, mode=halo_mode)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = time.perf_counter() - t0
+    plan = chunking.chunk_plan(n_frames, chunk, ov)
+    lo, hi = first + owned.start, first + owned.stop
+    # single-GPU stitch of the chunks that cover this rank's owned frames (+ their neighbours): same bytes as the
+    # stitch of the whole clip, without holding 600 4K frames on every rank
+    need = [ci for ci, (s, e) in enumerate(plan) if s < hi and e > lo]
+    need = list(range(max(need[0] - 1, 0), min(need[-1] + 2, len(plan))))
+    base = plan[need[0]][0]
+    whole = chunking.stitch_chunks([process_chunk(ci, *plan[ci]) for ci in need], [(plan[ci][0] - base, plan[ci][1] - base) for ci in need])
+    same = torch.equal(block[owned], whole[lo - base:hi - base])
+    checksum = int(block[owned].sum(dtype=torch.int64).item())
+    ref_checksum = int(whole[lo - base:hi - base].sum(dtype=torch.int64).item())
+    spans = [None] * world
+    dist.all_gather_object(spans, (lo, hi, checksum, ref_checksum, bool(same)))
+    contiguous = spans[0][0] == 0 and spans[-1][1] == n_frames and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    return {"frames": n_frames, "geometry": "2160x3840 -> %dx%d" % (h, w), "chunk": chunk, "overlap": ov, "chunks": len(plan),
+            "chunks_per_rank": [len(c) for c in chunking.shard_chunks(plan, world)], "halo_mode": halo_mode,
+            "stitched_checksum": sum(s[2] for s in spans), "single_gpu_checksum": sum(s[3] for s in spans),
+            "byte_exact": bool(contiguous and all(s[4] for s in spans)),
+            "wall_s_incl_synthesis": dt, "frames_per_s_incl_synthesis": n_frames / dt}
+
+
+def extra_blocks(dev, device, t, out_buf, step, stages, args):
+    """Informational blocks outside the timed region (rank 0, N = 1): other masks and the other BASELINE configs."""
+    import torch
+    from videovanish_b200 import ops, synth
+    peak = peaks()[0]
+    res = {}
+    alg_k3 = algorithmic_bytes(t)["K3_upscale_feather_composite"]
+
+    # ---- K3 against mask density: HBM bound on sparse masks, issue bound on the dense synthetic one
+    box_only = torch.from_numpy(synth.masks(t, H0, W0, seed=11, salt=0.0)).to(device)
+    masks_k3 = {"empty": torch.zeros((t, H0, W0), dtype=torch.uint8, device=device),
+                "box_only_dilated": ops.binarize_dilate(box_only, DILATE),
+                "bench_mask": ops.binarize_dilate(dev["masks"], DILATE)}
+    k3_density = {}
+    for name, mk in masks_k3.items():
+        ms = timed_ms(lambda: ops.upscale_feather_composite(dev["inpainted"], dev["frames"], mk, FEATHER, out=out_buf))
+        k3_density[name] = {"masked_fraction": float((mk > 0).float().mean()), "ms": ms,
+                            "frac": alg_k3 / (ms * 1e-3) / 1e9 / peak}
+    del masks_k3
+    res["k3_vs_mask_density"] = k3_density
+
+    # ---- the same step with the moving-box mask only (BASELINE config 0's mask: one object)
+    bench_masks = dev["masks"]
+    dev["masks"] = box_only
+    for _ in range(2):
+        step()
+    bev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in stages] for _ in range(3)]
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    b0.record()
+    for k in range(3):
+        step(bev[k])
+    b1.record()
+    torch.cuda.synchronize()
+    alg_b = algorithmic_bytes(t)
+    bms = b0.elapsed_time(b1) / 3
+    box_step = {"mask": "moving box only, no salt", "value": t / (bms * 1e-3), "unit": "frames/s", "ms_per_step": bms,
+                "stages": {s: {"ms": float(np.mean([bev[k][i][0].elapsed_time(bev[k][i][1]) for k in range(3)]))}
+                           for i, s in enumerate(stages)}}
+    for s, v in box_step["stages"].items():
+        if s in alg_b:
+            v["frac"] = alg_b[s] / (v["ms"] * 1e-3) / 1e9 / peak
+    res["box_mask_step"] = box_step
+    dev["masks"] = bench_masks
+    del box_only
+
+    # ---- production geometry 960x536 (the wrapper's multiple-of-8 rule): K1 fused low-res mask, K2, K3
+    h2, w2 = ops.inference_size(H0, W0, 960)
+    inp536 = dev["inpainted"][:, :h2].contiguous()
+    dil, low, bits = ops.binarize_dilate(dev["masks"], DILATE, lowres_size=(h2, w2), return_bits=True)
+    a536 = algorithmic_bytes(t, hs=h2, ws=w2)
+    g536 = {"K1_binarize_dilate": timed_ms(lambda: ops.binarize_dilate(dev["masks"], DILATE, lowres_size=(h2, w2), return_bits=True)),
+            "K2_resize_down": timed_ms(lambda: ops.resize(dev["frames"], h2, w2)),
+            "K3_upscale_feather_composite": timed_ms(lambda: ops.upscale_feather_composite(inp536, dev["frames"], dil, FEATHER, out=out_buf,
+                                                                                           mask_bits=bits))}
+    res["c2_production_960x536"] = {"geometry": "1080x1920 -> %dx%d" % (h2, w2),
+                                    "stages": {s: {"ms": ms, "frac": a536[s] / (ms * 1e-3) / 1e9 / peak} for s, ms in g536.items()}}
+    del inp536, dil, low, bits
+
+    # ---- BASELINE config 3: 720p clip with synthetic bidirectional flow, K4 at 720p (sub-videos 50 + 10 + 10)
+    t3, h3, w3 = min(args.c3_frames, 500), 720, 1280
+    fr3 = torch.from_numpy(np.tile(synth.frames(8, h3, w3, seed=31), ((t3 + 7) // 8, 1, 1, 1))[:t3]).to(device)
+    mk3 = ops.binarize_dilate(torch.from_numpy(synth.masks(t3, h3, w3, seed=32)).to(device), DILATE)
+    ff3, fb3 = device_flows(t3 - 1, h3, w3, device, 33)
+    ms3 = timed_ms(lambda: ops.propagate(fr3, mk3, ff3, fb3))
+    ms3_box = None
+    mk3b = ops.binarize_dilate(torch.from_numpy(synth.masks(t3, h3, w3, seed=32, salt=0.0)).to(device), DILATE)
+    ms3_box = timed_ms(lambda: ops.propagate(fr3, mk3b, ff3, fb3))
+    alg3 = t3 * 56 * h3 * w3
+    res["c3_720p_flow"] = {"frames": t3, "geometry": "720x1280, flows f32 both ways, windows 50+10+10",
+                           "K4_propagate": {"ms": ms3, "frames_per_s": t3 / (ms3 * 1e-3), "frac": alg3 / (ms3 * 1e-3) / 1e9 / peak,
+                                            "hole_fraction": float((mk3 > 0).float().mean())},
+                           "K4_propagate_box_mask": {"ms": ms3_box, "frames_per_s": t3 / (ms3_box * 1e-3),
+                                                     "frac_dense_formula": alg3 / (ms3_box * 1e-3) / 1e9 / peak,
+                                                     "hole_fraction": float((mk3b > 0).float().mean())}}
+    del fr3, mk3, mk3b, ff3, fb3
+
+    # ---- BASELINE config 4 geometry on one GPU: 2160x3840 -> 536x960, per-stage roofline fractions
+    t4, h4, w4 = 24, 2160, 3840
+    hs4, ws4 = ops.inference_size(h4, w4, 960)
+    fr4 = torch.from_numpy(np.tile(synth.frames(2, h4, w4, seed=41), (t4 // 2, 1, 1, 1))).to(device)
+    mk4 = torch.from_numpy(synth.masks(t4, h4, w4, seed=42, salt=0.0005)).to(device)
+    inp4 = torch.from_numpy(np.tile(synth.noise_frames(4, hs4, ws4, seed=43), (t4 // 4, 1, 1, 1))).to(device)
+    dil4, low4, bits4 = ops.binarize_dilate(mk4, DILATE, lowres_size=(hs4, ws4), return_bits=True)
+    out4 = torch.empty_like(fr4)
+    a4 = algorithmic_bytes(t4, h4, w4, hs4, ws4)
+    g4 = {"K1_binarize_dilate": timed_ms(lambda: ops.binarize_dilate(mk4, DILATE, lowres_size=(hs4, ws4), return_bits=True)),
+          "K2_resize_down": timed_ms(lambda: ops.resize(fr4, hs4, ws4)),
+          "K3_upscale_feather_composite": timed_ms(lambda: ops.upscale_feather_composite(inp4, fr4, dil4, FEATHER, out=out4, mask_bits=bits4))}
+    ms5 = timed_ms(lambda: ops.chunk_blend(fr4[:8], out4[8:16], out=out4[16:24]))
+    st4 = {s: {"ms": ms, "frac": a4[s] / (ms * 1e-3) / 1e9 / peak} for s, ms in g4.items()}
+    st4["K5_chunk_blend"] = {"ms": ms5, "frac": 8 * 9 * h4 * w4 / (ms5 * 1e-3) / 1e9 / peak, "overlap_frames": 8}
+    res["c4_4k"] = {"frames": t4, "geometry": "2160x3840 -> %dx%d" % (hs4, ws4), "stages": st4,
+                    "frames_per_s_K1_K2_K3": t4 / (sum(g4.values()) * 1e-3)}
+    del fr4, mk4, inp4, dil4, low4, bits4, out4
+    torch.cuda.empty_cache()
+    return res
+
+
+def k2_in_step_probe(dev, out_buf):
+    """Why K2 ran slower inside the step than alone (round-1 verdict): the same launch after different predecessors."""
+    import torch
+    from videovanish_b200 import ops
+    res = {}
+    dil = ops.binarize_dilate(dev["masks"], DILATE)
+
+    def after(pre):
+        ts = []
+        for _ in range(5):
+            pre()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.resize(dev["frames"], HS, WS)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts[1:]))
+
+    res["alone_after_sync"] = after(lambda: torch.cuda.synchronize())
+    res["after_K1"] = after(lambda: ops.binarize_dilate(dev["masks"], DILATE, lowres_size=(HS, WS)))
+    res["after_K3"] = after(lambda: ops.upscale_feather_composite(dev["inpainted"], dev["frames"], dil, FEATHER, out=out_buf))
+    res["after_K2"] = after(lambda: ops.resize(dev["frames"], HS, WS))
+    return res
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -253,8 +556,17 @@ def run_ours(args, rank, world, local_rank):
     bind_to_gpu_numa_node(local_rank)        # before any pinned allocation: first touch places it locally
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    from videovanish_b200 import _lib, chunking, ops
+    from videovanish_b200 import _lib, chunking, hostpipe, ops, wrappers
     from videovanish_b200 import diffuerase as vvd
+
+    for kv in filter(None, os.environ.get("VV_OPTS", "").split(",")):      # e.g. VV_OPTS=k3_x2=1,k4_npt=2
+        k, v = kv.split("=")
+        _lib.set_option(k.strip(), int(v))
+    halo_mode = os.environ.get("VV_HALO_MODE", "peer")
+    multi = {}
+    if world > 1:
+        multi["halo_parity"] = halo_parity_check(device, rank, world)
+        multi["c4_sharded"] = c4_sharded_check(device, rank, world, args.c4_frames, halo_mode)
 
     t = args.frames
     host, dev = make_workload(t, device, seed=10 + rank)
@@ -262,51 +574,29 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         stages.append("K5_halo_blend")
     out_buf = torch.empty((t, H0, W0, 3), dtype=torch.uint8, device=device)
-    # N > 1: the neighbours' overlap frames are read in place over NVLink by the blend kernel (CUDA-IPC
-    # mapping of every rank's output buffer); VV_HALO_MODE=nccl switches to explicit send/recv + blend
-    halo_mode = os.environ.get("VV_HALO_MODE", "peer")
+    packed_buf = torch.empty((t, HS, WS), dtype=torch.int32, device=device)
+    # N > 1: the neighbours' overlap frames are read in place over NVLink by the halo kernel (CUDA-IPC mapping of
+    # every rank's output buffer + device-side ready / consumed flags); VV_HALO_MODE=nccl = send/recv + blend
     window = chunking.PeerWindow(out_buf) if (world > 1 and halo_mode == "peer") else None
-
-    # Two streams: the propagation prior (K2 -> K4) is a chain of ~140 short dependent launches that
-    # leaves most of the machine idle, while the post stage (K3, + halo blend) is throughput bound and
-    # only depends on K1 - so K3 can run on a second stream next to K4 (VV_BENCH_OVERLAP=1).
-    # Measured on B200: with the first step kernel the overlap bought < 10 %; with the resident-grid step
-    # kernel (5 CTAs per SM parked on memory latency) K3 only gets the left-over thread slots and the step
-    # becomes SLOWER (4.99 vs 4.24 ms).  It also blurs the per-stage timings, so it stays opt-in.
-    overlap = os.environ.get("VV_BENCH_OVERLAP", "0") != "0"
-    for kv in filter(None, os.environ.get("VV_OPTS", "").split(",")):      # e.g. VV_OPTS=k3_tma_rows=8,k3_tma_threads=256
-        k, v = kv.split("=")
-        _lib.set_option(k.strip(), int(v))
-    if overlap:
-        # the latency-bound chain gets the high-priority stream so that its short kernels are scheduled
-        # ahead of the post stage's CTAs as soon as resources free up
-        main_stream = torch.cuda.Stream(device=device, priority=-1)
-        post_stream = torch.cuda.Stream(device=device, priority=0)
-    else:
-        main_stream = post_stream = torch.cuda.current_stream()
+    use_bits = os.environ.get("VV_BENCH_BITS", "1") != "0"
 
     def step(ev=None):
-        # ev[i] = (start, end) events of stage i, recorded on the stream that stage runs on
-        def timed(i, fn, stream):
-            with torch.cuda.stream(stream):
-                if ev is not None:
-                    ev[i][0].record()
-                r = fn()
-                if ev is not None:
-                    ev[i][1].record()
+        # ev[i] = (start, end) events of stage i, recorded on the stream the stages run on
+        def timed(i, fn):
+            if ev is not None:
+                ev[i][0].record()
+            r = fn()
+            if ev is not None:
+                ev[i][1].record()
             return r
-        dil, low = timed(0, lambda: ops.binarize_dilate(dev["masks"], DILATE, lowres_size=(HS, WS)), main_stream)
-        if overlap:
-            post_stream.wait_stream(main_stream)              # K3 needs the dilated masks (and the previous step's K4 is done)
-            dil.record_stream(post_stream)
-        small = timed(1, lambda: ops.resize(dev["frames"], HS, WS), main_stream)
-        packed = timed(2, lambda: ops.propagate(small, low, dev["flows_f"], dev["flows_b"]), main_stream)
-        out = timed(3, lambda: ops.upscale_feather_composite(dev["inpainted"], dev["frames"], dil, FEATHER, out=out_buf),
-                    post_stream)
+        dil, low, bits = timed(0, lambda: ops.binarize_dilate(dev["masks"], DILATE, lowres_size=(HS, WS), return_bits=use_bits)
+                               if use_bits else ops.binarize_dilate(dev["masks"], DILATE, lowres_size=(HS, WS)) + (None,))
+        small = timed(1, lambda: ops.resize(dev["frames"], HS, WS))
+        packed = timed(2, lambda: ops.propagate(small, low, dev["flows_f"], dev["flows_b"], out=packed_buf))
+        out = timed(3, lambda: ops.upscale_feather_composite(dev["inpainted"], dev["frames"], dil, FEATHER, out=out_buf,
+                                                             mask_bits=bits))
         if world > 1:
-            timed(4, lambda: chunking.blend_rank_boundaries(out, OVERLAP, mode=halo_mode, window=window), post_stream)
-        if overlap:
-            main_stream.wait_stream(post_stream)              # the step ends when both streams are done
+            timed(4, lambda: chunking.blend_rank_boundaries(out, OVERLAP, mode=halo_mode, window=window))
         return out, packed
 
     def sync_all():
@@ -326,12 +616,12 @@ def run_ours(args, rank, world, local_rank):
     _lib.reset_launch_count()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main_stream)
+    e0.record()
     # Clocks are sampled by the sampler's own thread only: an NVML query from THIS thread can take
     # milliseconds on some hosts and would stall the enqueue of the next step (measured: +1.1 ms/step).
     for k in range(args.steps):
         step(evs[k])
-    e1.record(main_stream)
+    e1.record()
     sync_all()
     launches = _lib.launch_count()
     clocks = sampler.stop() if rank == 0 else None
@@ -342,138 +632,178 @@ def run_ours(args, rank, world, local_rank):
     ms_step = float(tm.item()) / args.steps
     stage_ms = {s: float(np.mean([evs[k][i][0].elapsed_time(evs[k][i][1]) for k in range(args.steps)]))
                 for i, s in enumerate(stages)}
+    halo_error = bool(window.error()) if window is not None else False
 
-    # ---- K3 against mask density (outside the timed region): the post kernel is HBM bound on sparse
-    # masks and issue bound on the dense synthetic one, so its roofline fraction is reported for three
-    # masks: none, the moving box only (5 % of the frame), and the bench mask (box + dilated salt, 18 %)
-    k3_density = None
-    if rank == 0:
-        from videovanish_b200 import synth as _synth
-        box_only = torch.from_numpy(_synth.masks(t, H0, W0, seed=10 + rank + 1, salt=0.0)).to(device)
-        masks_k3 = {"empty": torch.zeros((t, H0, W0), dtype=torch.uint8, device=device),
-                    "box_only_dilated": ops.binarize_dilate(box_only, DILATE),
-                    "bench_mask": ops.binarize_dilate(dev["masks"], DILATE)}
-        del box_only
-        k3_density = {}
-        alg_k3 = algorithmic_bytes(t)["K3_upscale_feather_composite"]
-        for name, mk in masks_k3.items():
-            for _ in range(2):
-                ops.upscale_feather_composite(dev["inpainted"], dev["frames"], mk, FEATHER, out=out_buf)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(3):
-                ops.upscale_feather_composite(dev["inpainted"], dev["frames"], mk, FEATHER, out=out_buf)
-            b.record()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / 3
-            k3_density[name] = {"masked_fraction": float((mk > 0).float().mean()), "ms": ms,
-                                "GBps": alg_k3 / (ms * 1e-3) / 1e9, "frac": alg_k3 / (ms * 1e-3) / 1e9 / peaks()[0]}
-        del masks_k3
-
-    # ---- the same step with the moving-box mask only (BASELINE config 0's mask: one object, ~5 % of the
-    # frame after dilation), outside the timed region and for information: the headline above uses the much
-    # denser box + salt mask, which is the worst case for K3 (issue bound) and K4 (30 % of all pixels are holes)
-    box_step = None
+    # ---- the same loop again for >= 1 s (longer than the K-step region: more clock samples, steadier number)
+    sustained = None
     if rank == 0 and world == 1:
-        from videovanish_b200 import synth as _synth
-        bench_masks = dev["masks"]
-        dev["masks"] = torch.from_numpy(_synth.masks(t, H0, W0, seed=10 + rank + 1, salt=0.0)).to(device)
-        for _ in range(2):
+        n_rep = max(args.steps, int(1000.0 / max(ms_step, 1e-3)) + 1)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        torch.cuda.synchronize()
+        s0.record()
+        for _ in range(n_rep):
             step()
-        bev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in stages] for _ in range(3)]
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s1.record()
         torch.cuda.synchronize()
-        b0.record(main_stream)
-        for k in range(3):
-            step(bev[k])
-        b1.record(main_stream)
-        torch.cuda.synchronize()
-        alg_b = algorithmic_bytes(t)
-        bms = b0.elapsed_time(b1) / 3
-        box_step = {"mask": "moving box only, no salt", "value": t / (bms * 1e-3), "unit": "frames/s", "ms_per_step": bms,
-                    "stages": {s: {"ms": float(np.mean([bev[k][i][0].elapsed_time(bev[k][i][1]) for k in range(3)]))}
-                               for i, s in enumerate(stages)}}
-        for s, v in box_step["stages"].items():
-            if s in alg_b:
-                v["frac"] = alg_b[s] / (v["ms"] * 1e-3) / 1e9 / peaks()[0]
-        dev["masks"] = bench_masks
+        sustained = {"steps": n_rep, "ms_per_step": s0.elapsed_time(s1) / n_rep, "clocks": s2.stop()}
+        sustained["value"] = t / (sustained["ms_per_step"] * 1e-3)
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = extra_blocks(dev, device, t, out_buf, step, stages, args)
+        extras["k2_in_step_probe_ms"] = k2_in_step_probe(dev, out_buf)
 
     # ---- end to end through the reference-facing call, host buffers in, host buffers out
-    class _StubModel:                       # stands in for DiffuEraser / ProPainter (out of scope)
-        def forward(self, frames, masks, priors, **kw):
-            return list(inpainted_host)
-
     frames_host = list(host["frames"].numpy())
     masks_host = list(host["masks"].numpy())
     inpainted_host = list(host["inpainted"].numpy())
-    vvd.set_models(diffueraser=_StubModel())
+    flows = (dev["flows_f"], dev["flows_b"])
+    del dev, out_buf, packed_buf
+    torch.cuda.empty_cache()
+
+    # (1) the full stage set, device resident: the wrapper adapters with stub networks
+    prior = wrappers.ProPainterPrior(flow_fn=lambda small, low: flows,                       # RAFT + flow completion: out of scope
+                                     network_fn=lambda upd, um, low, ids, refs: upd[ids[0]:ids[-1] + 1], max_img_size=960)
+    eraser = wrappers.DiffuEraserWrapper(network_fn=lambda masked, m, priors: priors)         # diffusion: out of scope
+    orig_inference_size = ops.inference_size
+    if (HS, WS) != ops.inference_size(H0, W0, 960):
+        # the named configuration infers at 960x540 (BASELINE configs[1]); the wrapper's multiple-of-8 rule would give 960x536
+        ops.inference_size = lambda h0, w0, m=960: (HS, WS) if (h0, w0) == (H0, W0) else orig_inference_size(h0, w0, m)
+    vvd.set_models(diffueraser=eraser, propainter_model=prior)
     e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(2):          # warm-up: also lets torch's pinned-memory cache hold the result blocks
-        res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host, max_img_size=960)
-        del res
+    sync_all()
+    c0 = time.perf_counter()
+    res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, max_img_size=960)          # cold: first call, nothing cached
+    torch.cuda.synchronize()
+    cold_dt = time.perf_counter() - c0
+    del res
+    res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, max_img_size=960)
+    del res
     sync_all()
     marks = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         res = None              # the caller drops the previous result before asking for the next one
-        res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host,
-                                       max_img_size=960, prog=lambda p, s: marks.append((p, time.perf_counter())))
+        res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, max_img_size=960,
+                                       prog=lambda p, s: marks.append((p, time.perf_counter())))
         marks.append((100, time.perf_counter()))
     torch.cuda.synchronize()
     e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=device)
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_fps = world * t / float(e2e_dt.item())
-    # phases of the last call, from the progress milestones: 5 -> 10 = pre (K1), 90 -> end = post (K3)
-    last = dict(marks[-5:]) if len(marks) >= 5 else {}
-    e2e_phases = {"pre_ms": (last[10] - last[5]) * 1e3, "post_ms": (last[100] - last[90]) * 1e3} if 90 in last else None
+    last = dict(marks[-6:]) if len(marks) >= 6 else {}
+    e2e_phases = ({"upload_K1_ms": (last[10] - last[5]) * 1e3, "prior_ms": (last[50] - last[20]) * 1e3,
+                   "wrapper_ms": (last[90] - last[50]) * 1e3, "K3_download_ms": (last[100] - last[90]) * 1e3}
+                  if 90 in last and 20 in last else None)
     fh, fw = res[0].shape[:2]
-    px, spx = H0 * W0, inpainted_host[0].shape[0] * inpainted_host[0].shape[1]
-    h2d = t * (3 * px + 3 * spx + 3 * px)           # masks (pre) + inpainted + originals (post)
-    d2h = t * (px + 3 * px)                         # dilated masks (model hand-off) + composited frames
+    del res
+    px = H0 * W0
+    h2d_full, d2h_full = t * (3 * px + 3 * px), t * 3 * px       # masks + frames up, composited frames down
+
+    # (2) K1 + K3 only: host-list models (what a real DiffuEraser / ProPainter install exercises)
+    class _StubModel:
+        def forward(self, frames, masks, priors, **kw):
+            return list(inpainted_host)
+    vvd.set_models(diffueraser=_StubModel())
+    vvd.propainter = None
+    for _ in range(2):
+        res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host, max_img_size=960)
+        del res
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = None
+        res = vvd.run_infill_on_frames(frames_host, masks_host, DILATE, propainer_frames=frames_host, max_img_size=960)
+    torch.cuda.synchronize()
+    pp_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=device)
+    if world > 1:
+        dist.all_reduce(pp_dt, op=dist.ReduceOp.MAX)
+    del res
+    spx = inpainted_host[0].shape[0] * inpainted_host[0].shape[1]
+    e2e_prepost = {"value": world * t / float(pp_dt.item()), "unit": "frames/s",
+                   "h2d_bytes_per_step": t * (3 * px + 3 * spx + 3 * px), "d2h_bytes_per_step": t * (px + 3 * px),
+                   "stages": "K1+K3 via the host pipeline, stub models that take and return host lists"}
+
+    # (3) BASELINE config 5 idea: a long clip (pageable host arrays, results beyond the pinned budget) through the ring
+    c5 = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        n5 = args.c5_frames
+        fr5 = [frames_host[i % t] for i in range(n5)]
+        mk5 = [np.array(masks_host[i % t]) if i < 8 else masks_host[i % t] for i in range(n5)]     # a few pageable copies
+        fr5 = [np.array(f) if i < 8 else f for i, f in enumerate(fr5)]
+        inpainted5 = [inpainted_host[i % t] for i in range(n5)]
+
+        class _Stub5:
+            def forward(self, frames, masks, priors, **kw):
+                return list(inpainted5)
+        vvd.set_models(diffueraser=_Stub5())
+        old_limit = hostpipe.PINNED_RESULT_LIMIT
+        hostpipe.PINNED_RESULT_LIMIT = 2 << 30                   # results (6.2 GB) exceed it: pageable, through the pinned ring
+        try:
+            r5 = vvd.run_infill_on_frames(fr5, mk5, DILATE, propainer_frames=fr5, max_img_size=960)
+            del r5
+            t0 = time.perf_counter()
+            r5 = vvd.run_infill_on_frames(fr5, mk5, DILATE, propainer_frames=fr5, max_img_size=960)
+            c5_dt = time.perf_counter() - t0
+            del r5
+        finally:
+            hostpipe.PINNED_RESULT_LIMIT = old_limit
+        c5 = {"frames": n5, "frames_per_s": n5 / c5_dt, "stages": "K1+K3, host lists, results in pageable memory via the pinned ring",
+              "note": "config 5 names 5000 frames; %d streamed here (the path is per-batch, so the rate is length independent)" % n5}
+    ops.inference_size = orig_inference_size
 
     if rank == 0:
         peak, peak_src = peaks()
         alg = algorithmic_bytes(t)
         dom = max((s for s in stages if s in alg), key=lambda s: stage_ms[s])
         achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        st = {}
+        for s in stages:
+            st[s] = {"ms": stage_ms[s], "GBps": (alg[s] / (stage_ms[s] * 1e-3) / 1e9) if s in alg else None,
+                     "frac": (alg[s] / (stage_ms[s] * 1e-3) / 1e9 / peak) if s in alg else None}
+            tr = measured_traffic(s, t)
+            if tr is not None:
+                st[s]["frac_of_dram_traffic"] = tr / (stage_ms[s] * 1e-3) / 1e9 / peak
         line = {
-            "metric": "1080p frames/sec (pre/post+propagation)", "value": world * t / (ms_step * 1e-3),
+            "metric": METRIC, "value": world * t / (ms_step * 1e-3),
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": t, "l2": "inputs (>4 GB/step) larger than L2",
-                       "streams": ("2: K1,K2,K4 | K3" + (",K5" if world > 1 else "")) if overlap else "1",
-                       "halo_overlap": OVERLAP if world > 1 else 0,
-                       "halo_mode": (halo_mode if world > 1 else None)},
+            "config": bench_config(world, t),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(dom, t), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg[dom]},
-            "stages": {s: {"ms": stage_ms[s], "GBps": (alg[s] / (stage_ms[s] * 1e-3) / 1e9) if s in alg else None,
-                           "frac": (alg[s] / (stage_ms[s] * 1e-3) / 1e9 / peak) if s in alg else None} for s in stages},
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "phases": e2e_phases,
-                    "path": "diffuerase.run_infill_on_frames(list of pinned host frames), stub models, K1 + K3 via "
-                            "the host pipeline; result %dx%d" % (fh, fw)},
-            "k3_vs_mask_density": k3_density,
-            "box_mask_step": box_step,
+                         "frac": achieved / peak, "traffic": measured_traffic(dom, t),
+                         "traffic_source": "profiles/ncu_traffic.json (ncu capture of this command; not measured in this run)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom]},
+            "stages": st,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d_full, "d2h_bytes_per_step": d2h_full,
+                    "phases": e2e_phases, "cold_first_call_frames_per_s": t / cold_dt,
+                    "path": "diffuerase.run_infill_on_frames(pinned host lists) with the wrapper adapters (stub networks): "
+                            + E2E_STAGES + " device resident between one upload and one download; result %dx%d" % (fh, fw)},
+            "e2e_prepost": e2e_prepost,
+            "sustained_1s": sustained,
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        line.update(extras)
+        if c5 is not None:
+            line["c5_long"] = c5
+        if world > 1:
+            line.update(multi)
+            line["halo_handshake_error"] = halo_error
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n = args.cpu_sample
-            data = cpu_sample_inputs(n)
-            cpu_reference_step(*data, threads)
-            c0 = time.perf_counter()
-            reps = 2
-            for _ in range(reps):
-                cpu_reference_step(*data, threads)
-            cdt = (time.perf_counter() - c0) / reps
+            cpu = cpu_numbers(n, 1, threads, which=("core",))
             line["cpu_baseline"] = {
-                "value": n / cdt, "unit": "frames/s", "cores": threads, "kind": "port",
-                "sample": "%d frames of the workload x %d passes: reference cv2/scipy/numpy stages per frame over %d "
-                          "host threads + torch-CPU propagation restatement" % (n, reps, threads)}
+                "value": cpu["core"], "unit": "frames/s", "cores": threads, "kind": "port",
+                "sample": "%d frames of the workload (value's stage set K1+K2+K4+K3): reference cv2/scipy/numpy stages per frame "
+                          "over %d host threads + torch-CPU propagation restatement" % (n, threads)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        if window is not None:
+            dist.barrier()
+            window.close()
         dist.barrier()
         dist.destroy_process_group()
 
@@ -487,6 +817,10 @@ def main():
     ap.add_argument("--frames", type=int, default=T_FRAMES, help="frames per GPU per step (default: the named config)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="frames in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational blocks (other masks / configs)")
+    ap.add_argument("--c3-frames", type=int, default=200)
+    ap.add_argument("--c4-frames", type=int, default=600)
+    ap.add_argument("--c5-frames", type=int, default=1000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

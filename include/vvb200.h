@@ -58,18 +58,17 @@ VV_API void vv_reset_launch_count(void);
  *                (TMA) when the frame is 16-byte aligned, 0 = register pass-through kernel.
  *   "k3_tma_rows" maximum rows per staged strip (2..16);  "k3_tma_threads" 256, 384 or 512.
  *   "k4_pdl"     1 = propagation steps use programmatic dependent launch (multi-launch mode).
- *   "k4_persistent" 1 = the whole propagation scan runs in one cooperative launch with per-window
- *                barriers, 0 (default; measured equal on B200: the steps are bound by their DRAM
- *                gathers, not by launch latency) = one launch per time step.
- *   "k4_warm"    1 = the persistent scan pre-loads the next step's list entries and prefetches their
- *                flow sectors into L2 while the current step runs.
- *   "k3_x2"      1 = K3 uses the closed-form worker for exact x2 up-scales (W0 == 2w, H0 == 2h, TMA
- *                variant); 0 = the generic tap-table worker for every ratio.
+ *   "k4_npt"     hole pixels per thread and trip of a propagation step: 1 (default) or 2 (twice the loads in
+ *                flight per thread, fewer resident CTAs).
+ *   "k3_bits"    1 (default) = K3 reads the dilated 1-bit mask plane K1 left in its workspace when the caller
+ *                passes it (vv_upscale_feather_composite_bits); 0 = always rebuild the bit rows from the u8 mask.
+ *   "k3_x2"      2 (default) = the k3_fast kernel whenever W0 == 2w (closed-form horizontal pass, closed-form or
+ *                table-driven vertical pass, rolling classification, packed-fp32 blend); 1 = the older closed-form
+ *                worker (needs H0 == 2h as well); 0 = the generic tap-table worker for every ratio.
  *   "k4_pack_ctas" k4_pack launches about 148 x this many CTAs per call (more, shorter CTAs shrink the tail
  *                of the last wave; default 128);  "k4_pack_occ" 4 (default), 5 or 6 = CTAs per SM the kernel is
  *                compiled for.
- *   "k4_lean"    5 (default), 6 or 8 = propagation steps run the kernel whose per-step pointers are resolved
- *                on the host, compiled for that many CTAs per SM; 0 = the older k4_step kernel.
+ *   "k4_lean"    5 (default), 6 or 8 = CTAs per SM the propagation step kernel is compiled for.
  *   "k4_step_ctas" CTAs per SM of the step grid (default 5: a resident grid that strides over the hole lists
  *                with the next entry pre-loaded); 0 = about one thread per hole at a 25 % hole fraction.
  *   "k4_taps"    1 = the 8 tap loads of a hole are issued unconditionally from clamped positions,
@@ -93,6 +92,13 @@ VV_API size_t vv_binarize_dilate_workspace_bytes(int T, int H, int W);
 VV_API int vv_binarize_dilate(const uint8_t *mask, int T, int H, int W, int C, int iterations,
                        uint8_t *out, uint8_t *lowres_out, int lh, int lw,
                        void *workspace, size_t workspace_bytes, void *stream);
+/* Same, and additionally (bits_out != NULL) the dilated mask as a 1-bit plane: u32 [T,H,ceil(W/32)], pixel x of a
+ * row = bit (x & 31) of word (x >> 5), bits at x >= W zero.  The pass computes it anyway; handing it to
+ * vv_upscale_feather_composite_bits saves K3 the re-read and re-packing of the u8 mask (stage fusion across
+ * diffuerase.py:28-31 and :77-90). */
+VV_API int vv_binarize_dilate_ex(const uint8_t *mask, int T, int H, int W, int C, int iterations,
+                          uint8_t *out, uint8_t *lowres_out, int lh, int lw, uint32_t *bits_out,
+                          void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------
  * K2  resize.            Replaces cv2.resize at diffuerase.py:73 / :86, tools.py:42 and the
@@ -124,6 +130,13 @@ VV_API int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, int w,
                                  const uint8_t *orig, const uint8_t *mask, int H0, int W0,
                                  float feather_px, int keep_unmasked, uint8_t *out,
                                  void *workspace, size_t workspace_bytes, void *stream);
+/* Same with the mask ALSO given as the 1-bit plane of vv_binarize_dilate_ex (mask_bits may be NULL): kernels
+ * that can use it read 1/8 byte per pixel instead of 1; `mask` is still required (other kernels use it) and must
+ * describe the same set. */
+VV_API int vv_upscale_feather_composite_bits(const uint8_t *inp, int T, int h, int w,
+                                 const uint8_t *orig, const uint8_t *mask, const uint32_t *mask_bits,
+                                 int H0, int W0, float feather_px, int keep_unmasked, uint8_t *out,
+                                 void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------
  * K4  ProPainter-style flow-guided propagation prior (image propagation, 'nearest').
@@ -134,17 +147,21 @@ VV_API int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, int w,
  *   independent scans and are advanced in lock step.
  *   frames:   u8  [N,h,w,3]        masks: u8 [N,h,w] (>0 = hole)
  *   flows_f:  f32 [N-1,h,w,2]      flow t -> t+1 (x,y in pixels);  flows_b: t+1 -> t
- *   out:      u32 [sum(sub_len),h,w], windows concatenated in the given order; each word is
+ *   sub_keep_start / sub_keep_len (HOST int arrays, both NULL = keep every frame of every window):
+ *             frames [keep_start, keep_start+keep_len) of window s are kept, the others are the pad
+ *             frames upstream computes and throws away; their state only lives in the workspace.
+ *   out:      u32 [sum(keep_len),h,w], the kept frames of the windows concatenated in the given order
+ *             (for the upstream window plan that is exactly [N,h,w]); each word is
  *             R | G<<8 | B<<16 | state<<24 of the forward pass; state bit0 = still a hole,
  *             bit1 = value is the float 0.0 of the masked frame (hole or zero-padded warp)
  *             rather than a u8 level.
- *   workspace: vv_propagate_workspace_bytes(sum(sub_len), h, w) bytes.
+ *   workspace: vv_propagate_workspace_bytes(sum(sub_len), sum(sub_len) - sum(keep_len), h, w) bytes.
  * --------------------------------------------------------------------------------- */
-VV_API size_t vv_propagate_workspace_bytes(int n_out_frames, int h, int w);
+VV_API size_t vv_propagate_workspace_bytes(int n_window_frames, int n_pad_frames, int h, int w);
 VV_API int vv_propagate(const uint8_t *frames, const uint8_t *masks, const float *flows_f,
                  const float *flows_b, int n_frames, int h, int w, const int *sub_start,
-                 const int *sub_len, int n_sub, uint32_t *out, void *workspace,
-                 size_t workspace_bytes, void *stream);
+                 const int *sub_len, const int *sub_keep_start, const int *sub_keep_len, int n_sub,
+                 uint32_t *out, void *workspace, size_t workspace_bytes, void *stream);
 /* Unpack K4's output: rgb u8 [N,3] (zero-valued pixels get `zero_level`), hole mask u8 [N]
  * in {0,255}.  Either output may be NULL. */
 VV_API int vv_propagate_unpack(const uint32_t *packed, size_t n_pixels, uint8_t zero_level,
@@ -159,6 +176,20 @@ VV_API int vv_propagate_unpack(const uint32_t *packed, size_t n_pixels, uint8_t 
  * --------------------------------------------------------------------------------- */
 VV_API int vv_chunk_blend(const uint8_t *A, const uint8_t *B, int O, size_t frame_bytes, int k0,
                    int O_total, uint8_t *out, void *stream);
+
+/* Rank-boundary halo blend (one process per GPU, consecutive ranks share `overlap` frames), with a
+ * device-side handshake instead of host barriers.  `out`: this rank's u8 frames [T, frame_bytes], blended in
+ * place: overlap indices [0, overlap/2) of the boundary with the next rank (frames T-overlap+k) against
+ * `next_head` = the next rank's frame 0 (peer memory, CUDA-IPC mapped), and [overlap/2, overlap) of the boundary
+ * with the previous rank (frames k) against `prev_tail` = the previous rank's frame T_prev-overlap+overlap/2.
+ * Either neighbour may be absent (NULL frames and NULL flags).  `*_flags`: 8 x u32 per rank in IPC-mapped,
+ * zero-initialised device memory: [0] ready epoch, [1] consumed by the previous rank, [2] consumed by the next
+ * rank, [3] block counter, [4] error (a peer did not show up within ~2 s).  `epoch` must increase by one on
+ * every call, identically on all ranks.  The kernel polls the peers' ready flags before reading their frames and
+ * only completes once the neighbours have read this rank's frames, so the stream may overwrite `out` next. */
+VV_API int vv_halo_blend(uint8_t *out, int T, size_t frame_bytes, int overlap, const uint8_t *next_head,
+                         const uint8_t *prev_tail, uint32_t *my_flags, uint32_t *next_flags, uint32_t *prev_flags,
+                         uint32_t epoch, void *stream);
 
 /* ---------------------------------------------------------------------------------
  * "Next" rows: the pixel glue immediately either side of the hot path.
@@ -189,6 +220,21 @@ VV_API int vv_wrapper_mask(const uint8_t *mask, int T, int h, int w, int dilatio
 VV_API int vv_wrapper_compose(const uint8_t *img, const uint8_t *frames, const uint8_t *mask255, int T, int h,
                               int w, int blended, uint8_t *out, void *stream);
 
+/* N2  neighbour-window merge of the ProPainter network's output (call site diffuerase.py:52-57;
+ *   [recalled-upstream propainter/inference.py], oracle/propagation.py ref_neighbor_merge):
+ *     img  = mask ? u8(((pred + 1) / 2) * 255) : ori          (float32, truncation)
+ *     comp = first ? img : (comp + img) >> 1                   (== u8(f32(comp)*0.5 + f32(img)*0.5))
+ *   pred_chw: f32 [L,3,h,w] in [-1,1]; mask: u8 [L,h,w] (> 0 = masked); ori, comp: u8 [L,h,w,3]; comp is
+ *   updated in place.  Bit l of first_mask = frame l of the window has not been composed before.  L <= 64. */
+VV_API int vv_neighbor_merge(const float *pred_chw, const uint8_t *mask, const uint8_t *ori, uint8_t *comp, int L,
+                             int h, int w, unsigned long long first_mask, void *stream);
+/* N4  masked frames of the DiffuEraser wrapper: out = mask > 0 ? 0 : frame  (frame * (1 - m)).
+ *   frames, out: u8 [T,h,w,3]; mask: u8 [T,h,w]. */
+VV_API int vv_apply_mask(const uint8_t *frames, const uint8_t *mask, int T, int h, int w, uint8_t *out, void *stream);
+/* N1  channel swap BGR <-> RGB of packed 3-byte pixels (tools.py:21 cv2.cvtColor(..., COLOR_BGR2RGB), and
+ *   the swap back before VideoWriter.write at tools.py:43); src == dst is allowed. */
+VV_API int vv_swap_rb(const uint8_t *src, uint8_t *dst, size_t n_pixels, void *stream);
+
 /* ---------------------------------------------------------------------------------
  * Host-buffer pipeline (the path the Python drop-in takes for lists of numpy frames, i.e. the
  * whole of diffuerase.py:26-31 and :69-114 with per-frame HOST pointers in and out).
@@ -215,6 +261,17 @@ VV_API int vv_pipeline_downsize(vv_pipeline *p, const uint8_t *const *frames, in
 VV_API int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted, int h, int w,
                             const uint8_t *const *orig, const uint8_t *const *dilated, int T,
                             float feather_px, int keep_unmasked, uint8_t *const *out);
+
+/* Device-resident clips (the adapter around the two networks, videovanish_b200/wrappers.py): T per-frame host
+ * buffers of `frame_bytes` each -> one contiguous device array, and back.  `stream` is the stream that consumes
+ * (upload) / produced (download) the device data: the upload makes it wait on the copies, the download waits
+ * for the work enqueued on it so far.  The upload is asynchronous for page-locked sources (they must stay
+ * alive and unmodified until `stream` has passed the wait; pageable ones are staged before it returns); the
+ * download returns when the data is in the caller's host buffers. */
+VV_API int vv_pipeline_upload(vv_pipeline *p, const uint8_t *const *src, int T, size_t frame_bytes, uint8_t *dev_dst,
+                              void *stream);
+VV_API int vv_pipeline_download(vv_pipeline *p, const uint8_t *dev_src, int T, size_t frame_bytes,
+                                uint8_t *const *dst, void *stream);
 
 /* Peer-memory helpers for the multi-GPU halo blend (one process per GPU). */
 /* handle of the allocation that contains dev_ptr + the offset of dev_ptr inside it */

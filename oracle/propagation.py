@@ -266,3 +266,57 @@ def model_propagate_clip(frames_u8, masks_u8, flows_f, flows_b, subvideo_length=
         p = model_propagate(frames_u8[s_f:e_f], masks_u8[s_f:e_f], flows_f[s_f:e_f - 1], flows_b[s_f:e_f - 1])
         outs.append(p[ps:e_f - s_f - pe])
     return np.concatenate(outs)
+
+
+# ======================================================================================
+# N2: the pixel glue after the ProPainter network (neighbour windows, 0.5 / 0.5 merge)
+# ======================================================================================
+
+def get_ref_index(mid_neighbor_id, neighbor_ids, length, ref_stride=10, ref_num=-1):
+    """propainter/inference.py get_ref_index: the non-local reference frames of one window."""
+    ref_index = []
+    if ref_num == -1:
+        for i in range(0, length, ref_stride):
+            if i not in neighbor_ids:
+                ref_index.append(i)
+    else:
+        start_idx = max(0, mid_neighbor_id - ref_stride * (ref_num // 2))
+        end_idx = min(length, mid_neighbor_id + ref_stride * (ref_num // 2))
+        for i in range(start_idx, end_idx, ref_stride):
+            if i not in neighbor_ids:
+                if len(ref_index) > ref_num:
+                    break
+                ref_index.append(i)
+    return ref_index
+
+
+def neighbor_plan(video_length, neighbor_length=10, ref_stride=10, subvideo_length=50):
+    """The sliding windows of the feature-propagation + transformer loop of propainter/inference.py:
+    [(neighbor_ids, ref_ids)] for f in range(0, video_length, neighbor_length // 2)
+    (diffuerase.py:54 passes ref_stride=10, neighbor_length=10, subvideo_length=50)."""
+    neighbor_stride = neighbor_length // 2
+    ref_num = subvideo_length // ref_stride if video_length > subvideo_length else -1
+    plan = []
+    for f in range(0, video_length, neighbor_stride):
+        ids = list(range(max(0, f - neighbor_stride), min(video_length, f + neighbor_stride + 1)))
+        plan.append((ids, get_ref_index(f, ids, video_length, ref_stride, ref_num)))
+    return plan
+
+
+def ref_neighbor_merge(pred_windows, plan, masks01, ori_frames):
+    """The compose loop of propainter/inference.py restated with numpy.  pred_windows[k] = network output
+    f32 [len(neighbor_ids_k), 3, h, w] in [-1, 1]; masks01 u8 [T,h,w] in {0,1}; ori_frames u8 [T,h,w,3].
+    Returns the list of composed u8 frames."""
+    comp = [None] * len(ori_frames)
+    for (ids, _), pred in zip(plan, pred_windows):
+        pred_img = ((pred.astype(f32) + f32(1)) / f32(2)).astype(f32)
+        pred_img = np.transpose(pred_img, (0, 2, 3, 1)) * 255          # float32 * python int stays float32
+        for i, idx in enumerate(ids):
+            m = masks01[idx][..., None]
+            img = np.array(pred_img[i]).astype(np.uint8) * m + ori_frames[idx] * (1 - m)
+            if comp[idx] is None:
+                comp[idx] = img
+            else:
+                comp[idx] = comp[idx].astype(np.float32) * 0.5 + img.astype(np.float32) * 0.5
+            comp[idx] = comp[idx].astype(np.uint8)
+    return comp

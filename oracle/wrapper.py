@@ -109,3 +109,9 @@ def model_wrapper_compose(img, frame, mask255, blended=True):
     one_minus = (f32(1.0) - a).astype(f32)
     v = (img.astype(f32) * a).astype(f32) + (frame.astype(f32) * one_minus).astype(f32)
     return v.astype(np.uint8)
+
+
+def ref_masked_frame(frame, mask255):
+    """read_mask's masked image: frame * (1 - m) with m = mask > 0 (broadcast over RGB)."""
+    m = (np.asarray(mask255) > 0).astype(np.uint8)[..., None]
+    return (np.asarray(frame) * (1 - m)).astype(np.uint8)

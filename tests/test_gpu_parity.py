@@ -246,15 +246,15 @@ def test_k4_zero_padding_fill(ops):
     assert np.array_equal(gf, rf) and np.array_equal(gm, rm)
 
 
-@pytest.mark.parametrize("variant", [dict(k4_persistent=1, k4_warm=1), dict(k4_persistent=1, k4_warm=0),
-                                     dict(k4_persistent=0, k4_pdl=1), dict(k4_persistent=0, k4_pdl=0),
-                                     dict(k4_lean=0, k4_pdl=1), dict(k4_lean=0, k4_pdl=0), dict(k4_lean=8, k4_step_ctas=0),
-                                     dict(k4_lean=6, k4_taps=1, k4_step_ctas=1),
+@pytest.mark.parametrize("variant", [dict(k4_pdl=1), dict(k4_pdl=0), dict(k4_lean=8, k4_step_ctas=0),
+                                     dict(k4_lean=6, k4_taps=1, k4_step_ctas=1), dict(k4_npt=2, k4_lean=3, k4_step_ctas=3),
+                                     dict(k4_npt=2, k4_lean=4, k4_step_ctas=4, k4_speculate=0),
                                      dict(k4_pack_ctas=1, k4_pack_occ=4), dict(k4_pack_ctas=1024, k4_pack_occ=6)],
-                         ids=["persistent-warm", "persistent", "lean-pdl", "lean", "step-pdl", "step", "lean8-wide-grid", "lean6-uncond-taps",
+                         ids=["lean-pdl", "lean", "lean8-wide-grid", "lean6-uncond-taps", "two-per-trip-3", "two-per-trip-4",
                               "pack-few-ctas", "pack-many-ctas"])
 def test_k4_kernel_variants(ops, variant):
-    """The cooperative persistent scan and the launch-per-step fallback give identical states."""
+    """Every step-kernel / pack-kernel variant gives the same state (and the pad frames kept in scratch
+    never leak into the [N,h,w] result)."""
     from videovanish_b200 import _lib
     fr, m, ff, fb = prop_clip(26, 96, 160, seed=91)
     want = opp.model_propagate_clip(fr, m, ff, fb, subvideo_length=8, pad_len=3)
@@ -263,10 +263,30 @@ def test_k4_kernel_variants(ops, variant):
             _lib.set_option(k, v)
         got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb), subvideo_length=8, pad_len=3)).view(np.uint32)
     finally:
-        for k, v in dict(k4_persistent=0, k4_pdl=1, k4_warm=0, k4_lean=5, k4_taps=0, k4_step_ctas=5, k4_pack_ctas=128,
-                         k4_pack_occ=4).items():
+        for k, v in dict(k4_pdl=1, k4_npt=1, k4_lean=5, k4_taps=0, k4_step_ctas=5, k4_pack_ctas=128, k4_pack_occ=4,
+                         k4_speculate=1).items():
             _lib.set_option(k, v)
     assert np.array_equal(got, want)
+
+
+def test_k4_keep_pads_returns_raw_windows(ops):
+    """keep_pads=True: the windows, pad frames included, concatenated; the kept frames of each window are
+    the same bytes the default (pads discarded, written in place) call returns."""
+    from videovanish_b200 import ops as vops
+    fr, m, ff, fb = prop_clip(23, 32, 48, seed=78)
+    args = (dev(fr), dev(m), dev(ff), dev(fb))
+    raw = host(ops.propagate(*args, subvideo_length=6, pad_len=2, keep_pads=True)).view(np.uint32)
+    got = host(ops.propagate(*args, subvideo_length=6, pad_len=2)).view(np.uint32)
+    plan = vops.subvideo_plan(23, 6, 2)
+    assert raw.shape[0] == sum(e - s for s, e, _, _ in plan) and got.shape[0] == 23
+    off, kept = 0, []
+    for s, e, ps, pe in plan:
+        kept.append(raw[off + ps: off + (e - s) - pe])
+        off += e - s
+    assert np.array_equal(np.concatenate(kept), got)
+    buf = torch.empty((23, 32, 48), dtype=torch.int32, device="cuda")
+    assert ops.propagate(*args, subvideo_length=6, pad_len=2, out=buf) is buf
+    assert np.array_equal(host(buf).view(np.uint32), got)
 
 
 def test_k4_subvideo_windows(ops):

@@ -1,0 +1,83 @@
+"""CPU tests added in round 2: the N2 / full-path oracles, the window planners mirrored on the product side,
+and the C-ABI surface (symbols only: no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.ndimage
+
+from oracle import full_path as ofp
+from oracle import propagation as opp
+from oracle import wrapper as ow
+from videovanish_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_neighbor_plan_matches_between_oracle_and_product():
+    pytest.importorskip("torch")
+    from videovanish_b200 import wrappers
+    for n in (1, 4, 10, 11, 23, 50, 51, 120):
+        for nl, rs, sv in ((10, 10, 50), (6, 4, 20)):
+            assert wrappers.neighbor_plan(n, nl, rs, sv) == opp.neighbor_plan(n, nl, rs, sv)
+    plan = opp.neighbor_plan(23)
+    assert plan[0][0] == list(range(0, 6)) and plan[1][0] == list(range(0, 11)) and plan[-1][0] == list(range(15, 23))
+    covered = sorted({i for ids, _ in plan for i in ids})
+    assert covered == list(range(23)), "every frame is composed at least once"
+
+
+def test_neighbor_merge_is_integer_average_and_select():
+    """The compose loop of propainter/inference.py in closed form: masked pixels take u8(((p+1)/2)*255)
+    (truncation), the others the original; a frame seen twice is (a + b) >> 1."""
+    rng = np.random.default_rng(5)
+    t, h, w = 12, 5, 7
+    plan = opp.neighbor_plan(t, 4, 10, 50)
+    preds = [rng.uniform(-1, 1, (len(ids), 3, h, w)).astype(np.float32) for ids, _ in plan]
+    m = (rng.random((t, h, w)) < 0.5).astype(np.uint8)
+    ori = rng.integers(0, 256, (t, h, w, 3), dtype=np.uint8)
+    got = opp.ref_neighbor_merge(preds, plan, m, ori)
+    comp = [None] * t
+    for (ids, _), p in zip(plan, preds):
+        for i, idx in enumerate(ids):
+            v = ((p[i] + np.float32(1)) * np.float32(0.5) * np.float32(255)).astype(np.float32)
+            img = np.where(m[idx][..., None] > 0, np.transpose(v, (1, 2, 0)).astype(np.int32) & 255, ori[idx]).astype(np.uint8)
+            comp[idx] = img if comp[idx] is None else ((comp[idx].astype(np.int32) + img) >> 1).astype(np.uint8)
+    assert all(np.array_equal(a, b) for a, b in zip(got, comp))
+
+
+def test_masked_frame_and_full_path_smoke():
+    """oracle.full_path.run composes the stage oracles; with an empty mask the clip comes back unchanged,
+    with a mask only the dilated region (+ feather band) may change."""
+    t, h0, w0 = 7, 72, 128
+    fr, mk = synth.frames(t, h0, w0, seed=1), synth.masks(t, h0, w0, seed=2, salt=0.0005)
+    flow_fn = lambda small, low: synth.flows(len(small), small.shape[1], small.shape[2], seed=3)
+    st = {}
+    out = ofp.run(list(fr), list(mk), flow_fn, mask_dilation_iter=3, max_img_size=64, stages=st)
+    assert len(out) == t and out[0].shape == (h0, w0, 3) and out[0].dtype == np.uint8
+    dil = np.stack(st["dil"])
+    untouched = np.stack([ow.model_wrapper_mask(d, 0) for d in dil]) == 0          # not even eroded-in
+    far = np.stack([scipy.ndimage.binary_dilation(d > 0, iterations=4) for d in dil])        # mask + feather band
+    assert np.array_equal(np.stack(out)[~far], fr[~far]), "pixels away from the mask keep the original bytes"
+    assert np.array_equal(st["masked"][0][st["wrapper_mask"][0] > 0], np.zeros_like(st["masked"][0][st["wrapper_mask"][0] > 0]))
+    empty = ofp.run(list(fr), [np.zeros_like(m) for m in mk], flow_fn, max_img_size=64)
+    assert np.array_equal(np.stack(empty), fr)
+    assert untouched.any()
+
+
+def test_header_symbols_are_exported_and_bound():
+    """Every VV_API declaration of include/vvb200.h is exported by the built library and bound in _lib."""
+    hdr = open(os.path.join(ROOT, "include", "vvb200.h")).read()
+    names = set(re.findall(r"VV_API\s+[\w\s\*]+?\b(vv_\w+)\s*\(", hdr))
+    assert {"vv_neighbor_merge", "vv_apply_mask", "vv_swap_rb", "vv_binarize_dilate_ex", "vv_upscale_feather_composite_bits",
+            "vv_pipeline_upload", "vv_pipeline_download"} <= names
+    path = os.path.join(ROOT, "videovanish_b200", "csrc", "libvvb200.so")
+    if not os.path.isfile(path):
+        pytest.skip("library not built")
+    lib = ctypes.CDLL(path)
+    for n in names:
+        assert hasattr(lib, n), n
+    pytest.importorskip("torch")
+    from videovanish_b200 import _lib
+    assert names == set(_lib.EXPORTED), names ^ set(_lib.EXPORTED)

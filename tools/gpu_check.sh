@@ -6,15 +6,15 @@ what=${1:-"tests bench micro ncu"}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit --format=csv > gpurun_out/gpu.csv 2>&1
 if [[ $what == *tests* ]]; then
-  timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
+  timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -x > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-  tail -25 gpurun_out/pytest_gpu.log
+  tail -40 gpurun_out/pytest_gpu.log
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
   echo "smoke exit $?" >> gpurun_out/smoke.log
-  tail -3 gpurun_out/smoke.log
+  tail -5 gpurun_out/smoke.log
 fi
 if [[ $what == *micro* ]]; then
-  timeout 600 python tools/microbench.py > gpurun_out/micro.log 2>&1
+  timeout 900 python tools/microbench.py > gpurun_out/micro.log 2>&1
   cat gpurun_out/micro.log
 fi
 if [[ $what == *bench* ]]; then
@@ -22,18 +22,19 @@ if [[ $what == *bench* ]]; then
   echo "bench exit $?" >> gpurun_out/bench.log
   tail -5 gpurun_out/bench.log
 fi
+if [[ $what == *refarm* ]]; then
+  timeout 900 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/bench_reference.log 2>&1
+  tail -2 gpurun_out/bench_reference.log
+fi
 if [[ $what == *ncu* ]]; then
   # launch list of the bench command (cold-cache, serialised: compare shares) ...
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^k[1-5]' -c 600 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-  # ... DRAM traffic of exactly one step (147 launches per step; skip the 3 warm-up steps)
   timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-      -k 'regex:^k[1-5]' --launch-skip 441 --launch-count 147 --csv --log-file gpurun_out/step_metrics.csv \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu2.log 2>&1
+      -k 'regex:^k[1-5]' -c 700 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_under_ncu.log 2>&1
   # ... and full captures of the hot kernels
-  for k in k3_upscale k1a_binarize k1b_dilate k2_resize_linear_half k4_step_lean k4_pack; do
+  for k in k3_fast k1a_binarize k1b_dilate k2_resize_linear_half k4_step_lean k4_pack; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 2 -f \
-        -o gpurun_out/prof_$k python tools/microbench.py --frames 300 --ops "k1 dilate8 + half,k2 resize 1080p->540p,k3 composite (synthetic,k4" > gpurun_out/ncu_$k.log 2>&1
+        -o gpurun_out/prof_$k python tools/microbench.py --frames 300 --ops "k1 dilate8 + half,k2 resize 1080p->540p,k3 composite (synthetic,k4 propagate 50+10 windows (fresh" > gpurun_out/ncu_$k.log 2>&1
   done
   ls -la gpurun_out
 fi

@@ -84,58 +84,50 @@ def main():
     report("K2 resize 1080p->540p", t * (3 * px + 3 * spx), lambda: ops.resize(fr, HS, WS))
     report("K2 resize 1080p->536p", t * (3 * px + 3 * 536 * 960), lambda: ops.resize(fr, 536, 960))
     report("K2 nearest mask 1080p->540p", t * (px + spx), lambda: ops.resize(dil, HS, WS, ops.INTER_NEAREST))
-    for tma, nt, rows, thr in ((1, 1, 16, 512), (1, 1, 16, 384), (1, 1, 8, 512), (1, 1, 8, 256), (0, 2, 16, 512)):
-        _lib.set_option("k3_tma", tma)
-        _lib.set_option("k3_nt", nt)
-        _lib.set_option("k3_tma_rows", rows)
-        _lib.set_option("k3_tma_threads", thr)
-        kw = dict(k3_tma=tma, k3_nt=nt, rows=rows, threads=thr)
-        report("K3 composite (synthetic mask)", t * (7 * px + 3 * spx),
-               lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out), **kw)
-        report("K3 composite (empty mask)", t * (7 * px + 3 * spx),
-               lambda: ops.upscale_feather_composite(inp, fr, empty_mask, 3, out=out), **kw)
-        report("K3 composite (full mask)", t * (7 * px + 3 * spx),
-               lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out), **kw)
-    _lib.set_option("k3_tma", 1)
+    # ---- K3: the k3_fast kernel (default) with / without K1's bit plane and per rows-per-task, against the
+    # round-1 kernels, on four masks; and the production 960x536 geometry
+    dil_b, _, bits = ops.binarize_dilate(mk, 8, return_bits=True)
+    full_bits = torch.full_like(bits, -1)
+    box_dil, _, box_bits = ops.binarize_dilate(torch.from_numpy(synth.masks(t, H0, W0, seed=3, salt=0.0)).to(dev), 8, return_bits=True)
+    k3b = t * (7 * px + 3 * spx)
+    for x2 in (2, 1, 0):
+        _lib.set_option("k3_x2", x2)
+        report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out), k3_x2=x2, bits=0)
+        report("K3 composite (full mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out), k3_x2=x2, bits=0)
+    _lib.set_option("k3_x2", 2)
+    report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1)
+    report("K3 composite (full mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out, mask_bits=full_bits), k3_x2=2, bits=1)
+    report("K3 composite (empty mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, empty_mask, 3, out=out, mask_bits=torch.zeros_like(bits)), k3_x2=2, bits=1)
+    report("K3 composite (box mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, box_dil, 3, out=out, mask_bits=box_bits), k3_x2=2, bits=1)
+    for rpt in (3, 4, 8, 16):
+        _lib.set_option("k3_nt", rpt)
+        report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1, rpt=rpt)
     _lib.set_option("k3_nt", 2)
+    for rows in (8, 12):
+        _lib.set_option("k3_tma_rows", rows)
+        report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1, rows=rows)
     _lib.set_option("k3_tma_rows", 16)
-    _lib.set_option("k3_tma_threads", 512)
+    inp536 = inp[:, :536].contiguous()
+    report("K3 composite 960x536 (synthetic mask)", t * (7 * px + 3 * 536 * 960),
+           lambda: ops.upscale_feather_composite(inp536, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1)
     _lib.set_option("k3_x2", 0)
-    report("K3 composite (synthetic mask)", t * (7 * px + 3 * spx),
-           lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out), k3_x2=0)
-    report("K3 composite (full mask)", t * (7 * px + 3 * spx),
-           lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out), k3_x2=0)
-    _lib.set_option("k3_x2", 1)
-    report("K3 composite feather 5 (generic path)", t * (7 * px + 3 * spx),
-           lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
-    for pers, pdl, warm in ((1, 1, 1), (1, 1, 0), (0, 1, 0), (0, 0, 0)):
-        _lib.set_option("k4_persistent", pers)
-        _lib.set_option("k4_pdl", pdl)
-        _lib.set_option("k4_warm", warm)
-        report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb), k4_persistent=pers,
-               k4_pdl=pdl, k4_warm=warm)
-    _lib.set_option("k4_persistent", 0)
-    _lib.set_option("k4_pdl", 1)
-    _lib.set_option("k4_warm", 0)
-    for lean, taps, sc in ((0, 0, 0), (5, 0, 0), (6, 0, 0), (8, 0, 0), (5, 1, 5), (5, 0, 5), (6, 0, 6), (8, 0, 8), (5, 0, 10)):
-        _lib.set_option("k4_lean", lean)
-        _lib.set_option("k4_taps", taps)
-        _lib.set_option("k4_step_ctas", sc)
-        report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb), k4_lean=lean,
-               k4_taps=taps, k4_step_ctas=sc)
-    _lib.set_option("k4_lean", 5)
-    _lib.set_option("k4_taps", 0)
-    _lib.set_option("k4_step_ctas", 5)
-    for spec in (0, 1):
-        _lib.set_option("k4_speculate", spec)
-        report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb), k4_speculate=spec)
-    for ctas, occ in ((16, 4), (128, 4), (128, 5), (128, 6)):
-        _lib.set_option("k4_pack_ctas", ctas)
-        _lib.set_option("k4_pack_occ", occ)
-        report("K4 propagate 50+10 windows", t * 56 * spx, lambda: ops.propagate(small, low, ff, fb), k4_pack_ctas=ctas,
-               k4_pack_occ=occ)
-    _lib.set_option("k4_pack_ctas", 128)
-    _lib.set_option("k4_pack_occ", 4)
+    report("K3 composite 960x536 (synthetic mask)", t * (7 * px + 3 * 536 * 960),
+           lambda: ops.upscale_feather_composite(inp536, fr, dil, 3, out=out), k3_x2=0, bits=0)
+    _lib.set_option("k3_x2", 2)
+    report("K3 composite feather 5 (generic path)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
+    del dil_b, full_bits, box_dil, box_bits, inp536
+    # ---- K4: step-kernel variants
+    pbuf = torch.empty((t, HS, WS), dtype=torch.int32, device=dev)
+    k4b = t * 56 * spx
+    for lean, npt, sc, spec in ((5, 1, 5, 1), (5, 1, 5, 0), (6, 1, 6, 1), (8, 1, 8, 1), (3, 2, 3, 1), (4, 2, 4, 1), (3, 2, 4, 1), (4, 2, 5, 1)):
+        for k, v in dict(k4_lean=lean, k4_npt=npt, k4_step_ctas=sc, k4_speculate=spec).items():
+            _lib.set_option(k, v)
+        report("K4 propagate 50+10 windows", k4b, lambda: ops.propagate(small, low, ff, fb, out=pbuf), k4_lean=lean, k4_npt=npt,
+               k4_step_ctas=sc, k4_speculate=spec)
+    for k, v in dict(k4_lean=5, k4_npt=1, k4_step_ctas=5, k4_speculate=1).items():
+        _lib.set_option(k, v)
+    report("K4 propagate 50+10 windows (fresh output tensor)", k4b, lambda: ops.propagate(small, low, ff, fb))
+    del pbuf
     report("K5 chunk blend 16 frames", 16 * 9 * px, lambda: ops.chunk_blend(fr[:16], fr[16:32], out=out[:16]))
     report("copy (torch) 1080p frames", t * 6 * px, lambda: out.copy_(fr))
     # next rows: N3 painter (3 objects at inference resolution painted onto the 1080p canvas), N2 state -> float
@@ -157,6 +149,12 @@ def main():
         report("N4 wrapper compose (hard) 540p", t * 10 * spx, lambda: ops.wrapper_compose(inp, small, wm, False, out=comp_out))
         packed = ops.propagate(small[:tn], low[:tn], ff[:tn - 1], fb[:tn - 1])
         report("N2 state -> float CHW", tn * (4 + 16) * spx, lambda: ops.propagate_to_float(packed), frames_n=tn)
+        upd, _ = ops.propagate_to_float(packed)
+        comp = torch.empty_like(small[:11])
+        report("N2 neighbour merge (11-frame window)", 11 * (12 + 1 + 3 + 3 + 3) * spx,
+               lambda: ops.neighbor_merge(upd[:11], low[:11], small[:11], comp, [False] * 11), frames_n=11)
+        report("N4 masked frames 540p", t * 7 * spx, lambda: ops.apply_mask(small, wm, out=comp_out))
+        report("N1 channel swap 1080p", t * 6 * px, lambda: ops.swap_rb(fr, out=out))
 
     # BASELINE config 4 shape: 4K frames, inference 960x536 (x ratio exactly 4, y ratio 4.03)
     if wanted is None or any("4k" in w_ for w_ in wanted):
@@ -167,12 +165,12 @@ def main():
         mk4 = torch.from_numpy(synth.masks(t4, H4, W4, seed=6)).to(dev)
         inp4 = torch.from_numpy(np.tile(synth.noise_frames(4, h4, w4, seed=7), (12, 1, 1, 1))).to(dev)
         px4, spx4 = H4 * W4, h4 * w4
-        dil4 = ops.binarize_dilate(mk4, 8)
+        dil4, _, bits4 = ops.binarize_dilate(mk4, 8, return_bits=True)
         out4 = torch.empty_like(fr4)
         report("4K K1 dilate8 + low-res 960x536", t4 * (4 * px4 + spx4), lambda: ops.binarize_dilate(mk4, 8, lowres_size=(h4, w4)), frames_4k=t4)
         report("4K K2 resize ->960x536", t4 * (3 * px4 + 3 * spx4), lambda: ops.resize(fr4, h4, w4), frames_4k=t4)
         report("4K K3 composite (synthetic mask)", t4 * (7 * px4 + 3 * spx4),
-               lambda: ops.upscale_feather_composite(inp4, fr4, dil4, 3, out=out4), frames_4k=t4)
+               lambda: ops.upscale_feather_composite(inp4, fr4, dil4, 3, out=out4, mask_bits=bits4), frames_4k=t4)
         report("4K K5 chunk blend 16 frames", 16 * 9 * px4, lambda: ops.chunk_blend(fr4[:16], fr4[16:32], out=out4[:16]), frames_4k=t4)
 
 

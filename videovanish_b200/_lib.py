@@ -36,15 +36,19 @@ _SIGNATURES = {
     "vv_binarize_dilate_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vv_binarize_dilate": (c_int, [_u8p, c_int, c_int, c_int, c_int, c_int, _u8p, _u8p, c_int, c_int, c_void_p,
                                    c_size_t, c_void_p]),
+    "vv_binarize_dilate_ex": (c_int, [_u8p, c_int, c_int, c_int, c_int, c_int, _u8p, _u8p, c_int, c_int, c_void_p, c_void_p,
+                                      c_size_t, c_void_p]),
     "vv_resize_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vv_resize": (c_int, [_u8p, c_int, c_int, c_int, c_int, _u8p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vv_inference_size": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "vv_composite_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vv_upscale_feather_composite": (c_int, [_u8p, c_int, c_int, c_int, _u8p, _u8p, c_int, c_int, c_float, c_int, _u8p,
                                              c_void_p, c_size_t, c_void_p]),
-    "vv_propagate_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "vv_propagate": (c_int, [_u8p, _u8p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int,
-                             c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vv_upscale_feather_composite_bits": (c_int, [_u8p, c_int, c_int, c_int, _u8p, _u8p, c_void_p, c_int, c_int, c_float,
+                                                  c_int, _u8p, c_void_p, c_size_t, c_void_p]),
+    "vv_propagate_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "vv_propagate": (c_int, [_u8p, _u8p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int),
+                             POINTER(c_int), POINTER(c_int), c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vv_propagate_unpack": (c_int, [c_void_p, c_size_t, c_ubyte, _u8p, _u8p, c_void_p]),
     "vv_paint_masks_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vv_paint_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, _u8p, c_int, c_int, c_void_p,
@@ -52,12 +56,18 @@ _SIGNATURES = {
     "vv_propagate_to_float": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vv_wrapper_mask": (c_int, [_u8p, c_int, c_int, c_int, c_int, _u8p, c_void_p]),
     "vv_wrapper_compose": (c_int, [_u8p, _u8p, _u8p, c_int, c_int, c_int, c_int, _u8p, c_void_p]),
+    "vv_neighbor_merge": (c_int, [c_void_p, _u8p, _u8p, _u8p, c_int, c_int, c_int, c_ulonglong, c_void_p]),
+    "vv_apply_mask": (c_int, [_u8p, _u8p, c_int, c_int, c_int, _u8p, c_void_p]),
+    "vv_swap_rb": (c_int, [_u8p, _u8p, c_size_t, c_void_p]),
     "vv_chunk_blend": (c_int, [_u8p, _u8p, c_int, c_size_t, c_int, c_int, _u8p, c_void_p]),
+    "vv_halo_blend": (c_int, [_u8p, c_int, c_size_t, c_int, _u8p, _u8p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
     "vv_pipeline_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int]),
     "vv_pipeline_destroy": (None, [c_void_p]),
     "vv_pipeline_pre": (c_int, [c_void_p, _pp, c_int, c_int, c_int, _pp, _pp, c_int, c_int]),
     "vv_pipeline_downsize": (c_int, [c_void_p, _pp, c_int, c_int, c_int, _pp]),
     "vv_pipeline_post": (c_int, [c_void_p, _pp, c_int, c_int, _pp, _pp, c_int, c_float, c_int, _pp]),
+    "vv_pipeline_upload": (c_int, [c_void_p, _pp, c_int, c_size_t, _u8p, c_void_p]),
+    "vv_pipeline_download": (c_int, [c_void_p, _u8p, c_int, c_size_t, _pp, c_void_p]),
     "vv_ipc_get_handle": (c_int, [c_void_p, c_void_p, POINTER(c_size_t)]),
     "vv_ipc_open_handle": (c_int, [c_void_p, POINTER(c_void_p)]),
     "vv_ipc_close_handle": (c_int, [c_void_p]),

@@ -37,12 +37,14 @@ def chunk_plan(n_frames, chunk=80, overlap=16):
 
 
 def shard_chunks(plan, world_size):
-    """Contiguous blocks of chunks per rank, sizes differing by at most one: [[chunk indices]]."""
+    """Contiguous blocks of chunks per rank, sizes differing by at most one: [[chunk indices]].  The ranks at the
+    END get the extra chunks: the last chunk of a clip is usually clipped short, and a rank's block must hold at
+    least 2 x overlap frames for the halo blend."""
     n = len(plan)
     base, extra = divmod(n, world_size)
     out, i = [], 0
     for r in range(world_size):
-        k = base + (1 if r < extra else 0)
+        k = base + (1 if r >= world_size - extra else 0)
         out.append(list(range(i, i + k)))
         i += k
     return out
@@ -69,70 +71,120 @@ def stitch_chunks(chunk_outputs, plan, blend_fn=_default_blend):
     return out
 
 
+_ipc_cache = {}          # 64-byte handle -> [mapped base pointer, reference count]: a handle may only be opened once per process
+
+
+def _ipc_open(raw):
+    ent = _ipc_cache.get(raw)
+    if ent is None:
+        ptr = ctypes.c_void_p()
+        _lib.check(_lib.lib.vv_ipc_open_handle(ctypes.create_string_buffer(raw, 64), ctypes.byref(ptr)), "vv_ipc_open_handle")
+        ent = _ipc_cache[raw] = [ptr.value, 0]
+    ent[1] += 1
+    return ent[0]
+
+
+def _ipc_close(raw):
+    ent = _ipc_cache.get(raw)
+    if ent is None:
+        return
+    ent[1] -= 1
+    if ent[1] <= 0:
+        _lib.lib.vv_ipc_close_handle(ctypes.c_void_p(ent[0]))
+        del _ipc_cache[raw]
+
+
+def _ipc_export(tensor):
+    handle = (ctypes.c_ubyte * 64)()
+    offset = ctypes.c_size_t()
+    _lib.check(_lib.lib.vv_ipc_get_handle(ctypes.c_void_p(tensor.data_ptr()), handle, ctypes.byref(offset)), "vv_ipc_get_handle")
+    return bytes(handle), int(offset.value)
+
+
 class PeerWindow:
-    """CUDA-IPC mapping of every rank's halo source buffer (mode="peer")."""
+    """CUDA-IPC mapping of the neighbour ranks' halo source buffers and handshake flags (mode="peer").
+
+    Every rank contributes its frame buffer ``tensor`` [T,H,W,C] (T may differ between ranks: the last chunk of a
+    clip is clipped and ``shard_chunks`` sizes differ by one), its frame count and a small zero-initialised flag
+    block; the neighbours' buffers and flags are mapped into this process."""
+
+    FLAG_WORDS = 8
 
     def __init__(self, tensor, group=None):
         self.group = group
         self.tensor = tensor
-        handle = (ctypes.c_ubyte * 64)()
-        offset = ctypes.c_size_t()
-        _lib.check(_lib.lib.vv_ipc_get_handle(ctypes.c_void_p(tensor.data_ptr()), handle, ctypes.byref(offset)),
-                   "vv_ipc_get_handle")
-        mine = (bytes(handle), int(offset.value))
+        self.flags = torch.zeros(self.FLAG_WORDS, dtype=torch.int32, device=tensor.device)
+        self.epoch = 0
+        torch.cuda.current_stream().synchronize()              # the zeros are in memory before anybody maps them
+        mine = (_ipc_export(tensor), _ipc_export(self.flags), int(tensor.shape[0]))
         everyone = [None] * dist.get_world_size(group)
         dist.all_gather_object(everyone, mine, group=group)
         self.rank = dist.get_rank(group)
-        self.mapped = {}
+        self.frames = [e[2] for e in everyone]                 # T of every rank
+        self.mapped, self._raw = {}, []
         for r in (self.rank - 1, self.rank + 1):
             if 0 <= r < len(everyone):
-                raw, off = everyone[r]
-                ptr = ctypes.c_void_p()
-                _lib.check(_lib.lib.vv_ipc_open_handle(ctypes.create_string_buffer(raw, 64), ctypes.byref(ptr)),
-                           "vv_ipc_open_handle")
-                self.mapped[r] = (ptr.value, off)
+                (raw_t, off_t), (raw_f, off_f), _ = everyone[r]
+                self.mapped[r] = (_ipc_open(raw_t) + off_t, _ipc_open(raw_f) + off_f)
+                self._raw += [raw_t, raw_f]
 
     def ptr(self, rank, byte_offset=0):
-        base, off = self.mapped[rank]
-        return base + off + byte_offset
+        return self.mapped[rank][0] + byte_offset
+
+    def flags_ptr(self, rank):
+        return self.mapped[rank][1]
+
+    def error(self):
+        """True when a halo kernel of this rank gave up waiting for a neighbour."""
+        return bool(int(self.flags[4].item()))
 
     def close(self):
-        for base, _ in self.mapped.values():
-            _lib.lib.vv_ipc_close_handle(ctypes.c_void_p(base))
-        self.mapped = {}
+        for raw in self._raw:
+            _ipc_close(raw)
+        self.mapped, self._raw = {}, []
 
 
 def blend_rank_boundaries(out, overlap, group=None, mode="nccl", blend_fn=_default_blend, window=None):
-    """``out`` u8 [T,H,W,C] is this rank's chunk; its last ``overlap`` frames coincide with the
-    first ``overlap`` frames of the next rank's chunk.  Blends, in place, the half of each boundary
+    """``out`` u8 [T,H,W,C] is this rank's block of frames; its last ``overlap`` frames coincide with the
+    first ``overlap`` frames of the next rank's block.  Blends, in place, the half of each boundary
     this rank owns: overlap indices [0, overlap/2) of the boundary with the next rank (stored in
     ``out[T-overlap+k]``) and [overlap/2, overlap) of the boundary with the previous rank (stored
-    in ``out[k]``).  Returns the number of bytes received from / read on peers."""
+    in ``out[k]``).  Returns the number of bytes received from / read on peers.
+
+    ``mode="peer"``: one kernel per rank and step reads the neighbours' frames in place over NVLink and
+    synchronises with their kernels through flags in IPC-mapped memory (``vv_halo_blend``) - no host barrier,
+    no stream synchronisation.  ``mode="nccl"`` (gloo in the CPU tests): explicit halo send/recv, then K5."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     t = out.shape[0]
     half = overlap // 2
     if world == 1 or overlap == 0:
         return 0
+    if t < 2 * overlap:
+        raise ValueError("blend_rank_boundaries: a rank needs at least 2 x overlap frames (%d < %d): the halves it "
+                         "overwrites would overlap the frames a neighbour still reads" % (t, 2 * overlap))
     frame_bytes = out[0].numel() * out.element_size()
     has_prev, has_next = rank > 0, rank < world - 1
     moved = 0
     if mode == "peer":
         if window is None:
             raise ValueError("mode='peer' needs a PeerWindow over `out`")
-        dist.barrier(group)                       # neighbours' chunks are complete
-        # read the ORIGINAL neighbour frames: each side only overwrites the half it owns, and the
-        # halves read remotely are the ones the neighbour does not write
-        if has_next and half > 0:
-            blend_fn(out[t - overlap:t - overlap + half], window.ptr(rank + 1, 0), 0, overlap,
-                     out[t - overlap:t - overlap + half])
-            moved += half * frame_bytes
-        if has_prev and overlap - half > 0:
-            src = window.ptr(rank - 1, (t - overlap + half) * frame_bytes)
-            blend_fn(src, out[half:overlap], half, overlap, out[half:overlap])
-            moved += (overlap - half) * frame_bytes
-        torch.cuda.current_stream().synchronize()
-        dist.barrier(group)                       # nobody reuses `out` while a peer still reads it
-        return moved
+        if window.tensor.data_ptr() != out.data_ptr() or window.frames[rank] != t:
+            raise ValueError("the PeerWindow was built over another buffer")
+        if overlap < 2:
+            raise ValueError("mode='peer' needs overlap >= 2")
+        window.epoch += 1
+        # the previous rank's tail starts at ITS frame T_prev - overlap + half
+        prev_tail = window.ptr(rank - 1, (window.frames[rank - 1] - overlap + half) * frame_bytes) if has_prev else None
+        next_head = window.ptr(rank + 1, 0) if has_next else None
+        vp = ctypes.c_void_p
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.lib.vv_halo_blend(vp(out.data_ptr()), t, frame_bytes, overlap, vp(next_head), vp(prev_tail),
+                                              vp(window.flags.data_ptr()),
+                                              vp(window.flags_ptr(rank + 1)) if has_next else None,
+                                              vp(window.flags_ptr(rank - 1)) if has_prev else None,
+                                              window.epoch & 0xffffffff, vp(torch.cuda.current_stream().cuda_stream)),
+                       "vv_halo_blend")
+        return (half if has_next else 0) * frame_bytes + ((overlap - half) if has_prev else 0) * frame_bytes
     # mode == "nccl" (or gloo in the CPU tests): explicit halo send/recv, then blend locally
     reqs, recv_next, recv_prev = [], None, None
     if has_next and half > 0:
@@ -155,3 +207,38 @@ def blend_rank_boundaries(out, overlap, group=None, mode="nccl", blend_fn=_defau
         blend_fn(recv_prev, out[half:overlap], half, overlap, out[half:overlap])
         moved += recv_prev.numel()
     return moved
+
+
+def run_sharded(n_frames, chunk, overlap, process_chunk, group=None, mode="peer"):
+    """BASELINE config 4 as a system: ``chunk_plan`` -> ``shard_chunks`` -> every rank runs ``process_chunk(ci, s, e)
+    -> u8 [e-s,H,W,C]`` (device tensor) on its own chunks, stitches them locally with K5 and blends the boundaries it
+    shares with the neighbour ranks (halo only, no other exchange).
+
+    Returns ``(block, first_frame, owned)``: this rank's frames [first_frame, first_frame + len(block)) of the clip
+    and the slice of ``block`` this rank is authoritative for (each rank owns half of each shared overlap), so that
+    concatenating ``block[owned]`` over the ranks gives the stitched clip."""
+    plan = chunk_plan(n_frames, chunk, overlap)
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if len(plan) < world:
+        raise ValueError("run_sharded: %d chunks cannot be spread over %d ranks" % (len(plan), world))
+    mine = shard_chunks(plan, world)[rank]
+    first = plan[mine[0]][0]
+    outs = [process_chunk(ci, *plan[ci]) for ci in mine]
+    block = stitch_chunks(outs, [(plan[ci][0] - first, plan[ci][1] - first) for ci in mine])
+    del outs
+    t = block.shape[0]
+    half = overlap // 2
+    has_prev, has_next = rank > 0, rank < world - 1
+    if world > 1:
+        window = PeerWindow(block, group) if mode == "peer" else None
+        blend_rank_boundaries(block, overlap, group, mode=mode, window=window)
+        if window is not None:
+            torch.cuda.current_stream().synchronize()
+            failed = window.error()
+            dist.barrier(group)                   # nobody unmaps while a neighbour's kernel may still poll
+            window.close()
+            if failed:
+                raise RuntimeError("halo blend: a neighbour rank did not show up")
+    owned = slice(half if has_prev else 0, t - (overlap - half) if has_next else t)
+    return block, first, owned

@@ -222,6 +222,18 @@ __global__ void __launch_bounds__(256) k1c_fill(const uint32_t *__restrict__ fla
         o[i] = v;
 }
 
+// bit plane of a flooded frame: every in-frame bit set (bits at x >= W stay zero)
+__global__ void __launch_bounds__(256) k1c_fill_bits(const uint32_t *__restrict__ flags, uint32_t *__restrict__ bits, int H,
+                                                     int W, int Wp) {
+    const long long t = blockIdx.y;
+    const uint32_t on = flags[t] ? 0xffffffffu : 0u;
+    const long long n = (long long)H * Wp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Wp), valid = W - k * 32;
+        bits[t * n + i] = on & (valid >= 32 ? 0xffffffffu : ((1u << valid) - 1u));
+    }
+}
+
 // ------------------------------------------------------------------ fused low-res mask
 // INTER_NEAREST down-size of the dilated mask (SURVEY row A9 mask path), sampled from the
 // dilated bit plane so the full-resolution u8 mask is not re-read.
@@ -305,6 +317,13 @@ extern "C" size_t vv_binarize_dilate_workspace_bytes(int T, int H, int W) {
 extern "C" int vv_binarize_dilate(const uint8_t *mask, int T, int H, int W, int C, int iterations, uint8_t *out,
                                   uint8_t *lowres_out, int lh, int lw, void *workspace, size_t workspace_bytes,
                                   void *stream) {
+    return vv_binarize_dilate_ex(mask, T, H, W, C, iterations, out, lowres_out, lh, lw, nullptr, workspace,
+                                 workspace_bytes, stream);
+}
+
+extern "C" int vv_binarize_dilate_ex(const uint8_t *mask, int T, int H, int W, int C, int iterations, uint8_t *out,
+                                     uint8_t *lowres_out, int lh, int lw, uint32_t *bits_out, void *workspace,
+                                     size_t workspace_bytes, void *stream) {
     VV_CHECK_ARG(mask && out && workspace, "vv_binarize_dilate: NULL pointer");
     VV_CHECK_ARG(T > 0 && H > 0 && W > 0, "vv_binarize_dilate: bad shape T=%d H=%d W=%d", T, H, W);
     VV_CHECK_ARG(C == 1 || C == 3 || C == 4, "vv_binarize_dilate: C must be 1, 3 or 4 (got %d)", C);
@@ -342,6 +361,11 @@ extern "C" int vv_binarize_dilate(const uint8_t *mask, int T, int H, int W, int 
             k1c_fill<<<g3, 256, 0, st>>>(flags, lowres_out, (long long)lh * lw);
             VV_POST_LAUNCH("k1c_fill");
         }
+        if (bits_out) {
+            dim3 g4((unsigned)min((long long)ceil_div(wpf, 256), 64LL), (unsigned)T);
+            k1c_fill_bits<<<g4, 256, 0, st>>>(flags, bits_out, H, W, Wp);
+            VV_POST_LAUNCH("k1c_fill_bits");
+        }
         return VV_OK;
     }
 
@@ -361,14 +385,15 @@ extern "C" int vv_binarize_dilate(const uint8_t *mask, int T, int H, int W, int 
     // exact x2 down-size: the low-res mask is written by the dilation pass itself
     const bool half = lowres_out && H == 2 * lh && W == 2 * lw;
     const bool vec_half = vec_out && (lw % 16 == 0) && ((uintptr_t)lowres_out % 16 == 0);
-    rc = dilate_pass(cur, (lowres_out && !half) ? nxt : nullptr, out, half ? lowres_out : nullptr, T, H, W, Wp, left,
-                     half ? vec_half : vec_out, st);
+    // the dilated bit plane goes to the caller (K3 consumes it instead of the u8 mask) and / or feeds the low-res mask
+    uint32_t *dil_plane = bits_out ? bits_out : ((lowres_out && !half) ? nxt : nullptr);
+    rc = dilate_pass(cur, dil_plane, out, half ? lowres_out : nullptr, T, H, W, Wp, left, half ? vec_half : vec_out, st);
     if (rc) return rc;
     if (lowres_out && !half) {
         const long long total = (long long)T * lh * ((lw + 15) / 16);
         const int vec_low = (lw % 16 == 0) && ((uintptr_t)lowres_out % 16 == 0);
         k1d_lowres_from_bits<<<(int)min((long long)ceil_div(total, 256), (long long)148 * 32), 256, 0, st>>>(
-            nxt, H, W, Wp, lowres_out, lh, lw, T, vec_low);
+            dil_plane, H, W, Wp, lowres_out, lh, lw, T, vec_low);
         VV_POST_LAUNCH("k1d_lowres_from_bits");
     }
     return VV_OK;

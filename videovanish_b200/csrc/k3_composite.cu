@@ -645,6 +645,315 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
     }
 }
 
+// =====================================================================================================
+// k3_fast: the kernel for the production geometry - exact x2 horizontal up-scale (W0 == 2w: 1080p <- 960x540
+// or 960x536), feather radius <= 2 (the GUI's feather_px = 3), 16-byte aligned frames.  Same structure as the
+// kernel above (TMA-staged strip, bit rows, quad work queue), rebuilt around the instruction counts ncu's
+// source view showed for it (profiles/r02_k3_source_breakdown.txt):
+//   phase 1  BITS: the dilated mask arrives as the 1-bit plane K1 already produced (32x fewer bytes, no
+//            byte -> bit packing); otherwise packed from the u8 mask with one row per warp (no division)
+//   phase 2  ROLLING window: a thread owns one 16-pixel column group for RPT consecutive rows, so each bit row
+//            is fetched and masked once instead of five times and the column masks are per-task constants
+//   phase 3  work items carry position + LUT nibbles only; the blend is BRANCH-FREE over all 12 bytes of a quad in
+//            packed fp32 (FMUL2 / FFMA2 / FADD2): alpha 0 and 1 reproduce orig / up exactly, so no per-pixel
+//            branches.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (which would change the rounding),
+//            so the sum is written as fma(p1, one, p2) with `one` = 1.0f from a kernel parameter: two rounded
+//            products, one rounded sum - exactly np.float32 arithmetic.
+//   VX2      vertical axis also exact x2 (closed form); otherwise table-driven vertical taps on the closed-form
+//            horizontal pass (h >> 4 == 32 * (far + 3 * near), so (b * (h >> 4)) >> 16 == (b * m) >> 11).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2u(f32x2 v, uint32_t &lo, uint32_t &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+constexpr int K3F_THREADS = 512;
+constexpr int K3F_QCAP = 128 + 32;      // one classified row of the warp (32 lanes x 4 quads) + carried-over items
+
+template <bool VX2, bool BITS>
+__global__ void __launch_bounds__(K3F_THREADS, 2)
+    k3_fast(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ mask,
+            const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ yt, int h, int w,
+            int H0, int W0, int strips_per_frame, int th, int rpt, float div, float one) {
+    extern __shared__ __align__(128) uint32_t smem_base[];
+    const int strip_words = (th * W0 * 3) / 4;
+    uint8_t *strip = reinterpret_cast<uint8_t *>(smem_base);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_base + strip_words);
+    const int Wp = W0 >> 5;                     // W0 % 16 == 0; a trailing half word is covered by row_words
+    const int Wpc = (W0 + 31) >> 5;
+    const int row_words = Wpc + 2;
+    const int rows_s = th + 4;
+    uint32_t *bits = smem_base + strip_words + 4;                                   // [rows_s][row_words]
+    float4 *lut = reinterpret_cast<float4 *>(smem_base + ((strip_words + 4 + rows_s * row_words + 3) & ~3));   // {a, a, 1-a, 1-a}
+    uint2 *queue = reinterpret_cast<uint2 *>(lut + 16) + (threadIdx.x >> 5) * K3F_QCAP;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    (void)Wp;
+
+    const long long t = blockIdx.x / strips_per_frame;
+    const int y0 = (blockIdx.x % strips_per_frame) * th;
+    const uint8_t *orig_t = orig + t * H0 * (long long)W0 * 3;
+    uint8_t *out_t = out + t * H0 * (long long)W0 * 3;
+    const uint32_t strip_bytes = (uint32_t)(min(th, H0 - y0) * W0 * 3);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, strip_bytes);
+        const uint8_t *src = orig_t + (long long)y0 * W0 * 3;
+        for (uint32_t off = 0; off < strip_bytes; off += 32768u)
+            bulk_g2s(strip + off, src + off, min(32768u, strip_bytes - off), bar);
+    }
+
+    // ---------------- phase 1: bit rows [y0 - 2, y0 + th + 2), one zero pad word on each side
+    for (int i = warp; i < rows_s; i += K3F_THREADS / 32) {
+        const int y = y0 - 2 + i;
+        const bool row_ok = y >= 0 && y < H0;
+        if (BITS) {
+            const uint32_t *src = mask_bits + (t * H0 + y) * (long long)Wpc;
+            for (int k = lane; k < row_words; k += 32)
+                bits[i * row_words + k] = (row_ok && k >= 1 && k <= Wpc) ? __ldg(src + (k - 1)) : 0u;
+        } else {
+            uint16_t *b16 = reinterpret_cast<uint16_t *>(bits + i * row_words);
+            const uint8_t *src = mask + (t * H0 + y) * (long long)W0;
+            for (int k = lane; k < 2 * row_words; k += 32) {
+                const int x0 = (k - 2) * 16;
+                b16[k] = (row_ok && x0 >= 0 && x0 < W0) ? (uint16_t)nonzero_bits16(ldg128(src + x0)) : (uint16_t)0;
+            }
+        }
+    }
+    if (threadIdx.x < 16) {
+        // alpha levels: index = class (0 = no hit within the window, 1..5 = cost classes 1, 1.4, 2, 2.1969, 2.8) | inside << 3
+        const float cost[6] = {8192.f, 1.0f, 1.4f, 2.0f, 2.1969f, __fadd_rn(1.4f, 1.4f)};
+        const int cls = threadIdx.x & 7, inside = threadIdx.x >> 3;
+        float a = inside ? 1.f : 0.f;
+        if (cls <= 5) a = inside ? alpha_from(cost[cls], 0.f, div) : alpha_from(0.f, cost[cls], div);
+        const float na = __fsub_rn(1.f, a);
+        lut[threadIdx.x] = make_float4(a, a, na, na);
+    }
+    __syncthreads();
+
+    uint32_t lut_pos = 0;          // which LUT levels have alpha > 0
+#pragma unroll
+    for (int k = 0; k < 16; ++k) lut_pos |= (uint32_t)(lut[k].x > 0.f) << k;
+    // outside classes 1..5 that still blend (alpha > 0), as masks applied to p1..p5
+    const uint32_t e1 = (lut_pos >> 1) & 1u ? ~0u : 0u, e2 = (lut_pos >> 2) & 1u ? ~0u : 0u, e3 = (lut_pos >> 3) & 1u ? ~0u : 0u,
+                   e4 = (lut_pos >> 4) & 1u ? ~0u : 0u, e5 = (lut_pos >> 5) & 1u ? ~0u : 0u;
+
+    const uint8_t *inp_t = inp + t * h * (long long)w * 3;
+    const f32x2 one2 = pack2(one, one), magic2 = pack2(12582912.f, 12582912.f), unbias2 = pack2(-8388608.f, -8388608.f);
+
+    // ---- phase 3 worker: one 4-pixel quad per lane
+    auto work = [&](const uint2 item) {
+        const int xq = item.x & 0xffff, r = (int)(item.x >> 16);
+        const int yy = y0 + r;
+        uint32_t a0, a1, a2, b0, b1, b2, wa = 0, wb = 0;
+        if (VX2) {
+            const int j = yy >> 1;                                           // source row of weight 3/4
+            const int ja = (yy & 1) ? min(j + 1, h - 1) : max(j - 1, 0);     // source row of weight 1/4
+            x2_load_row(inp_t + ja * w * 3, xq, W0, a0, a1, a2);
+            x2_load_row(inp_t + j * w * 3, xq, W0, b0, b1, b2);
+        } else {
+            const Tap ty = yt[yy];
+            wa = (uint32_t)(ty.w & 0xffff) << 20, wb = ((uint32_t)ty.w >> 16) << 20;
+            const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
+            x2_load_row(inp_t + ya * w * 3, xq, W0, a0, a1, a2);
+            x2_load_row(inp_t + yb * w * 3, xq, W0, b0, b1, b2);
+        }
+        uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
+        const uint32_t o0 = sp[0], o1 = sp[1], o2 = sp[2];
+        const float4 l0 = lut[item.y & 15u], l1 = lut[(item.y >> 4) & 15u], l2 = lut[(item.y >> 8) & 15u],
+                     l3 = lut[(item.y >> 12) & 15u];
+        uint32_t ma[6], mb[6], up[6];
+        x2_hpass(a0, a1, a2, ma);
+        x2_hpass(b0, b1, b2, mb);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (VX2) {
+                up[k] = x2_vpass(ma[k], mb[k]);
+            } else {
+                const uint32_t am = ma[k] << 1, bm = mb[k] << 1;        // lanes <= 2040: no carry into the high lane
+                const uint32_t lo = (__umulhi(wa, am & 0xffffu) + __umulhi(wb, bm & 0xffffu) + 2u) >> 2;
+                const uint32_t hi = (__umulhi(wa, am >> 16) + __umulhi(wb, bm >> 16) + 2u) >> 2;
+                up[k] = lo | (hi << 16);
+            }
+        }
+        // byte pair p = bytes (2p, 2p+1) of the 12-byte quad; byte k belongs to pixel k / 3
+        const f32x2 al[6] = {pack2(l0.x, l0.y), pack2(l0.x, l1.x), pack2(l1.x, l1.y),
+                             pack2(l2.x, l2.y), pack2(l2.x, l3.x), pack2(l3.x, l3.y)};
+        const f32x2 nl[6] = {pack2(l0.z, l0.w), pack2(l0.z, l1.z), pack2(l1.z, l1.w),
+                             pack2(l2.z, l2.w), pack2(l2.z, l3.z), pack2(l3.z, l3.w)};
+        const uint32_t ow[3] = {o0, o1, o2};
+        uint32_t rb[12];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+            // u8 -> f32 through the mantissa: bits(2^23 + b) - 2^23 (both lanes at once)
+            const f32x2 uf = fadd2(pack2u(__byte_perm(up[p], 0x4b000000u, 0x7540u), __byte_perm(up[p], 0x4b000000u, 0x7542u)),
+                                   unbias2);
+            const uint32_t wsrc = ow[p >> 1];
+            const uint32_t s0 = 0x7540u | (uint32_t)((2 * p) & 3), s1 = 0x7540u | (uint32_t)((2 * p + 1) & 3);
+            const f32x2 of = fadd2(pack2u(__byte_perm(wsrc, 0x4b000000u, s0), __byte_perm(wsrc, 0x4b000000u, s1)), unbias2);
+            // f32(a * up) + f32((1 - a) * orig), then round half to even through the mantissa
+            const f32x2 v = fadd2(ffma2(fmul2(al[p], uf), one2, fmul2(nl[p], of)), magic2);
+            unpack2u(v, rb[2 * p], rb[2 * p + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            sp[j] = __byte_perm(__byte_perm(rb[4 * j], rb[4 * j + 1], 0x0040), __byte_perm(rb[4 * j + 2], rb[4 * j + 3], 0x0040),
+                                0x5410);
+    };
+
+    // ---------------- phase 2: classification, rolling over `rpt` rows per thread
+    // One flat, rolled loop (a step = one row of every thread's task) so that the classification and the worker
+    // exist once in the instruction stream; the last step only drains the queue.
+    const int G = W0 >> 4;
+    const int RB = (th + rpt - 1) / rpt;
+    const int n_tasks = G * RB;
+    const int n_steps = ((n_tasks + K3F_THREADS - 1) / K3F_THREADS) * rpt;
+    int qcount = 0, it = 0, j = 0;
+    bool landed = false, task_ok = false;
+    int c0 = 0, r0 = 0;
+    uint32_t colvalid = 0, xbase = 0;
+    uint32_t Mw[5] = {0, 0, 0, 0, 0}, Zw[5] = {0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int step = 0; step <= n_steps; ++step) {
+        const bool drain = step == n_steps;
+        uint32_t need = 0, L0 = 0, L1 = 0, L2 = 0, M2 = 0;
+        const int r = r0 + j;
+        if (!drain) {
+            if (j == 0) {                                                    // new task: (column group, row block)
+                const int id = it * K3F_THREADS + (int)threadIdx.x;
+                task_ok = id < n_tasks;
+                const int rbk = task_ok ? id / G : 0, g = task_ok ? id - rbk * G : 0;
+                r0 = rbk * rpt, c0 = g * 16 - 8, xbase = (uint32_t)(g * 16);
+                const int lo = max(0, -c0), hi = min(32, W0 - c0);
+                colvalid = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                // window rows: strip row r - 2 .. r + 2  <->  bit row index r .. r + 4
+#pragma unroll
+                for (int d = 1; d < 5; ++d) {
+                    const int bi = min(r0 + d - 1, rows_s - 1), yy = y0 + r0 + d - 3;
+                    Mw[d] = bit_window(bits + bi * row_words, c0);
+                    Zw[d] = (yy >= 0 && yy < H0) ? (~Mw[d] & colvalid) : 0u;
+                }
+            }
+            const int rr = r0 + j;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) Mw[d] = Mw[d + 1], Zw[d] = Zw[d + 1];
+            {
+                const int bi = min(rr + 4, rows_s - 1), yy = y0 + rr + 2;
+                Mw[4] = bit_window(bits + bi * row_words, c0);
+                Zw[4] = (yy >= 0 && yy < H0) ? (~Mw[4] & colvalid) : 0u;
+            }
+            M2 = Mw[2];
+            if (task_ok && rr < th && y0 + rr < H0) {
+                const uint32_t anyM = Mw[0] | Mw[1] | Mw[2] | Mw[3] | Mw[4];
+                // the 5x5 window of pixel i covers bits i+6 .. i+10, i.e. bits 6..25 for the whole group
+                if (anyM & 0x03ffffc0u) {
+                    auto classes = [](const uint32_t *S, uint32_t *hc) {
+                        const uint32_t A1 = S[1] | S[3], A0 = S[0] | S[4];
+                        hc[0] = (S[2] << 1) | (S[2] >> 1) | A1;                                  // cost 1
+                        hc[1] = (A1 << 1) | (A1 >> 1);                                           // 1.4
+                        hc[2] = (S[2] << 2) | (S[2] >> 2) | A0;                                  // 2
+                        hc[3] = (A0 << 1) | (A0 >> 1) | (A1 << 2) | (A1 >> 2);                   // 2.1969
+                        hc[4] = (A0 << 2) | (A0 >> 2);                                           // 2.8
+                    };
+                    uint32_t hm[5], hz[5], hsel[5];
+                    classes(Mw, hm);
+                    classes(Zw, hz);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) hsel[k] = (hz[k] & M2) | (hm[k] & ~M2);   // inside pixels look for zeros
+                    const uint32_t p1 = hsel[0];
+                    const uint32_t p2 = hsel[1] & ~p1;
+                    const uint32_t s12 = p1 | hsel[1];
+                    const uint32_t p3 = hsel[2] & ~s12;
+                    const uint32_t s123 = s12 | hsel[2];
+                    const uint32_t p4 = hsel[3] & ~s123;
+                    const uint32_t p5 = hsel[4] & ~(s123 | hsel[3]);
+                    L0 = p1 | p3 | p5, L1 = p2 | p3, L2 = p4 | p5;
+                    // alpha > 0: every inside pixel, and outside pixels whose first hit has alpha > 0
+                    const uint32_t pos = M2 | (p1 & e1) | (p2 & e2) | (p3 & e3) | (p4 & e4) | (p5 & e5);
+                    need = (pos >> 8) & 0xffffu;
+                }
+            }
+        }
+        // ---- warp-level compaction: every quad with a pixel to blend becomes one work item
+        if (__ballot_sync(0xffffffffu, need != 0)) {                         // warp-uniform
+            const uint32_t nzq = (need | (need >> 1) | (need >> 2) | (need >> 3)) & 0x1111u;   // bit 4q = quad q has work
+            const int qn = __popc(nzq);
+            int pre = qn;                                                    // inclusive scan over lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += v;
+            }
+            int pos = qcount + pre - qn;
+            qcount += __shfl_sync(0xffffffffu, pre, 31);
+            if (need) {
+                const uint32_t xr = xbase | ((uint32_t)r << 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if ((nzq >> (4 * q)) & 1u) {
+                        const int b = 8 + 4 * q;
+                        // 4x4 bit transpose: planes (l0, l1, l2, inside) x pixels -> one LUT index nibble per pixel
+                        uint32_t x4 = ((L0 >> b) & 15u) | (((L1 >> b) & 15u) << 4) | (((L2 >> b) & 15u) << 8) |
+                                      (((M2 >> b) & 15u) << 12);
+                        uint32_t tt = (x4 ^ (x4 >> 3)) & 0x0a0au;
+                        x4 ^= tt ^ (tt << 3);
+                        tt = (x4 ^ (x4 >> 6)) & 0x00ccu;
+                        x4 ^= tt ^ (tt << 6);
+                        queue[pos++] = make_uint2(xr + 4u * q, x4);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (qcount >= 32 || (drain && qcount > 0)) {                         // warp-uniform
+            if (!landed) {
+                mbar_wait(bar, 0);
+                landed = true;
+            }
+            do {
+                const int take = min(qcount, 32);
+                qcount -= take;
+                if (lane < take) work(queue[qcount + lane]);
+            } while (qcount >= 32);
+            __syncwarp();              // the queue tail is overwritten by the next pushes
+        }
+        if (++j == rpt) j = 0, ++it;
+    }
+    if (!landed) mbar_wait(bar, 0);
+    fence_proxy_async();                 // the patched quads must be visible to the bulk store
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint8_t *dst = out_t + (long long)y0 * W0 * 3;
+        for (uint32_t off = 0; off < strip_bytes; off += 32768u)
+            bulk_s2g(dst + off, strip + off, min(32768u, strip_bytes - off));
+        bulk_commit_and_wait_read();     // shared memory must outlive the reads of the store
+    }
+}
+
 // Host: float32 Dijkstra over the 5x5-chamfer step set (same construction as
 // oracle/prepost.py chamfer_cost_table, verified bit-exact against cv2.distanceTransform).
 static void build_feather_table(float feather_px, FeatherTable *ft) {
@@ -709,9 +1018,9 @@ using namespace vv;
 
 extern "C" size_t vv_composite_workspace_bytes(int H0, int W0) { return vv_resize_workspace_bytes(H0, W0); }
 
-extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, int w, const uint8_t *orig,
-                                            const uint8_t *mask, int H0, int W0, float feather_px, int keep_unmasked,
-                                            uint8_t *out, void *workspace, size_t workspace_bytes, void *stream) {
+static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t *orig, const uint8_t *mask,
+                          const uint32_t *mask_bits, int H0, int W0, float feather_px, int keep_unmasked, uint8_t *out,
+                          void *workspace, size_t workspace_bytes, void *stream) {
     VV_CHECK_ARG(inp && out && workspace, "vv_upscale_feather_composite: NULL pointer");
     VV_CHECK_ARG(T > 0 && h > 0 && w > 0 && H0 > 0 && W0 > 0, "vv_upscale_feather_composite: bad shape");
     VV_CHECK_ARG(workspace_bytes >= vv_composite_workspace_bytes(H0, W0),
@@ -775,15 +1084,64 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
     const long long grid = (long long)T * strips;
     VV_CHECK_ARG(grid < 2147483647LL, "vv_upscale_feather_composite: too many strips");
 
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    dev_id = min(max(dev_id, 0), 63);
+    // cudaFuncSetAttribute is per device: remember the opt-in shared-memory size per (kernel, device)
+#define VV_K3_SMEM(kfn)                                                                                         \
+    do {                                                                                                        \
+        static std::atomic<size_t> smem_set[64];                                                                \
+        if (smem > 48 * 1024 && smem > smem_set[dev_id].load()) {                                               \
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(k3)");                              \
+            smem_set[dev_id].store(smem);                                                                       \
+        }                                                                                                       \
+    } while (0)
+
+    // ---- k3_fast: exact x2 horizontal up-scale, feather radius <= 2, TMA-able frames (the production geometry)
+    const int x2opt = get_option(OPT_K3_X2);
+    if (vec && small_r && x2opt >= 2 && get_option(OPT_K3_TMA) != 0 && W0 == 2 * w && W0 >= 8 && ((uintptr_t)inp % 4 == 0)) {
+        int fth = 0;
+        size_t fsm = 0;
+        for (fth = min(16, max(2, get_option(OPT_K3_TMA_ROWS))); fth >= 2; --fth) {
+            fsm = (size_t)fth * W0 * 3 + 16 + ((size_t)(fth + 4) * (Wp + 2) + 3) * 4 + 256 + (K3F_THREADS / 32) * K3F_QCAP * 8;
+            if (fsm <= 113 * 1024) break;
+        }
+        if (fth >= 2) {
+            const int fstrips = ceil_div(H0, fth);
+            const long long fgrid = (long long)T * fstrips;
+            VV_CHECK_ARG(fgrid < 2147483647LL, "vv_upscale_feather_composite: too many strips");
+            const bool vx2 = H0 == 2 * h;
+            const bool bits = mask_bits != nullptr && get_option(OPT_K3_BITS) != 0;
+            // rows per classification task: 4 when that still gives most threads a task, else 2
+            int rpt = ((W0 / 16) * ceil_div(fth, 4) >= (K3F_THREADS * 7) / 10) ? 4 : 2;
+            if (get_option(OPT_K3_NT) > 2) rpt = min(16, get_option(OPT_K3_NT));      // A/B switch
+            smem = fsm;
+#define VV_K3_FAST(V, B)                                                                                        \
+    do {                                                                                                        \
+        auto kfn = k3_fast<V, B>;                                                                               \
+        VV_K3_SMEM(kfn);                                                                                        \
+        kfn<<<(unsigned)fgrid, K3F_THREADS, smem, st>>>(inp, orig, mask, mask_bits, out, yt, h, w, H0, W0, fstrips, fth,  \
+                                                        rpt, ft.div, 1.0f);                                     \
+    } while (0)
+            if (vx2 && bits)
+                VV_K3_FAST(true, true);
+            else if (vx2)
+                VV_K3_FAST(true, false);
+            else if (bits)
+                VV_K3_FAST(false, true);
+            else
+                VV_K3_FAST(false, false);
+#undef VV_K3_FAST
+            VV_POST_LAUNCH("k3_fast");
+            return VV_OK;
+        }
+    }
+
 #define VV_K3_LAUNCH(V, S, N, M, ...)                                                                                \
     do {                                                                                                        \
         auto kfn = k3_upscale_feather_composite<V, S, N, M, ##__VA_ARGS__>;                                                    \
-        static std::atomic<size_t> smem_set{48 * 1024};                                                        \
-        if (smem > smem_set.load()) {                                                                           \
-            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-            if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(k3)");                              \
-            smem_set.store(smem);                                                                               \
-        }                                                                                                       \
+        VV_K3_SMEM(kfn);                                                                                        \
         kfn<<<(unsigned)grid, (M) ? tma_threads : K3_THREADS, smem, st>>>(inp, orig, mask, out, xt, yt, h, w, H0,   \
                                                                             W0, strips, th, ft);                \
     } while (0)
@@ -794,8 +1152,7 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
         else                            \
             VV_K3_LAUNCH(V, S, 2, false); \
     } while (0)
-    const bool x2 = tma && small_r && W0 == 2 * w && H0 == 2 * h && ((uintptr_t)inp % 4 == 0) &&
-                    get_option(OPT_K3_X2) != 0;
+    const bool x2 = tma && small_r && W0 == 2 * w && H0 == 2 * h && ((uintptr_t)inp % 4 == 0) && x2opt != 0;
     if (x2)
         VV_K3_LAUNCH(true, true, 1, true, true);
     else if (tma && small_r)
@@ -812,6 +1169,22 @@ extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, in
         VV_K3_DISPATCH(false, false);
 #undef VV_K3_DISPATCH
 #undef VV_K3_LAUNCH
+#undef VV_K3_SMEM
     VV_POST_LAUNCH("k3_upscale_feather_composite");
     return VV_OK;
+}
+
+extern "C" int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, int w, const uint8_t *orig,
+                                            const uint8_t *mask, int H0, int W0, float feather_px, int keep_unmasked,
+                                            uint8_t *out, void *workspace, size_t workspace_bytes, void *stream) {
+    return composite_impl(inp, T, h, w, orig, mask, nullptr, H0, W0, feather_px, keep_unmasked, out, workspace,
+                          workspace_bytes, stream);
+}
+
+extern "C" int vv_upscale_feather_composite_bits(const uint8_t *inp, int T, int h, int w, const uint8_t *orig,
+                                                 const uint8_t *mask, const uint32_t *mask_bits, int H0, int W0,
+                                                 float feather_px, int keep_unmasked, uint8_t *out, void *workspace,
+                                                 size_t workspace_bytes, void *stream) {
+    return composite_impl(inp, T, h, w, orig, mask, mask_bits, H0, W0, feather_px, keep_unmasked, out, workspace,
+                          workspace_bytes, stream);
 }

@@ -21,6 +21,10 @@
 // sub-video, in place on the state buffer (backward pass, then forward pass over the same buffer).
 // Up to 32 independent sub-videos (propainter/inference.py windows: 50 frames + 10 pad each side)
 // advance in lock step, so the chain is 2*(window length - 1) short launches whatever the clip length.
+//
+// Frame placement: the frames a window KEEPS live directly in the caller's output array, its pad
+// frames (which upstream computes and discards) in workspace scratch, so the result needs no
+// compaction copy afterwards (`frame_ptr`).
 #include "common.cuh"
 
 namespace vv {
@@ -32,12 +36,24 @@ constexpr int K4_MAX_SUB = 32;
 struct SubDesc {
     int start;            // first frame of the window in the clip arrays
     int len;              // frames in the window
-    long long out_frame;  // first frame of the window in the packed output / workspace
+    int pad_s;            // leading pad frames (state kept in scratch)
+    int keep;             // frames [pad_s, pad_s + keep) of the window are written to the output array
+    long long out_frame;  // first frame of the window in the hole-list arrays (windows concatenated)
+    long long keep_out;   // output-array frame index of the first kept frame
+    long long pad_out;    // scratch frame index of the window's first pad frame
 };
 struct SubBatch {
     SubDesc sub[K4_MAX_SUB];
     int n;
 };
+
+// State of frame `idx` of a window: kept frames sit in `out`, pad frames in `pads`.
+__host__ __device__ __forceinline__ uint32_t *frame_ptr(const SubDesc &sd, int idx, uint32_t *out, uint32_t *pads,
+                                                        long long npx) {
+    if (idx < sd.pad_s) return pads + (sd.pad_out + idx) * npx;
+    if (idx < sd.pad_s + sd.keep) return out + (sd.keep_out + (idx - sd.pad_s)) * npx;
+    return pads + (sd.pad_out + (idx - sd.keep)) * npx;
+}
 
 __device__ __forceinline__ float unnormalized(float pos, int size) {
     // flow_warp: 2*g/max(size-1,1) - 1 ; grid_sample(align_corners=True): (c+1) * ((size-1)/2)
@@ -46,9 +62,7 @@ __device__ __forceinline__ float unnormalized(float pos, int size) {
 }
 
 // One hole pixel: returns the new packed state.
-// COHERENT: the previous frame's state was written by other CTAs of the SAME (persistent) kernel, so it
-// is read with ld.global.cg (L2), never from a possibly stale L1 line.
-template <bool COHERENT, bool UNCOND = false>
+template <bool UNCOND = false>
 __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, uint32_t cur, const float2 f,
                                                     const float2 *__restrict__ flow_check, const uint32_t *prev) {
     const float ix = unnormalized(__fadd_rn((float)x, f.x), w);
@@ -64,7 +78,7 @@ __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, 
     const bool ya = (unsigned)y0 < (unsigned)h, yb = (unsigned)(y0 + 1) < (unsigned)h;
     float2 c00 = make_float2(0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
     uint32_t p00 = 0, p01 = 0, p10 = 0, p11 = 0;          // out-of-frame taps: zeros padding, not a hole
-    auto ld_state = [&](uint32_t i) { return COHERENT ? __ldcg(prev + i) : prev[i]; };
+    auto ld_state = [&](uint32_t i) { return prev[i]; };
     if (UNCOND) {
         // All 8 tap loads are issued unconditionally from clamped (always valid) positions and zeroed
         // afterwards when the tap lies outside the frame: no branches, 32-bit index arithmetic
@@ -132,45 +146,6 @@ struct BlockQueue {
     uint32_t xy[K4_QCAP];
     uint32_t count, base;
 };
-struct FlowQueue {                            // k4_step: entries carry their flow (loaded speculatively)
-    uint32_t xy[2 * K4_BLOCK];
-    float2 flow[2 * K4_BLOCK];
-    uint32_t count, base;
-};
-
-__device__ __forceinline__ void queue_push(FlowQueue &q, bool take, uint32_t xy, float2 flow) {   // all 32 lanes must call
-    const uint32_t m = __ballot_sync(0xffffffffu, take);
-    if (m == 0) return;
-    const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&q.count, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (take) {
-        const uint32_t j = base + __popc(m & ((1u << lane) - 1u));
-        q.xy[j] = xy;
-        q.flow[j] = flow;
-    }
-}
-
-// k4_step flavour: entries already carry their flow.  All threads of the block must call.
-__device__ __forceinline__ void queue_flush(FlowQueue &q, const HoleLists &l, long long of, long long npx, bool force) {
-    __syncthreads();
-    const uint32_t n = q.count;
-    __syncthreads();                                            // everyone has read the count before it can change
-    if (!force && n + K4_BLOCK <= 2 * K4_BLOCK) return;         // block-uniform
-    if (n) {
-        if (threadIdx.x == 0) q.base = atomicAdd(l.count + of, n);
-        __syncthreads();
-        const long long dst = of * npx + q.base;
-        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-            l.xy[dst + j] = q.xy[j];
-            l.flow[dst + j] = q.flow[j];
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) q.count = 0;
-    __syncthreads();
-}
 
 // All threads of the block must call (contains barriers).  `flow_frame` is gathered for each entry.
 // With `force == false` the queue is only written out when another push round might overflow it.
@@ -212,7 +187,7 @@ __device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, l
 template <bool VEC, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
     k4_pack(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, uint32_t *__restrict__ state,
-            const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, HoleLists l1, HoleLists l2, int h,
+            uint32_t *__restrict__ pads, const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, HoleLists l1, HoleLists l2, int h,
             int w, long long first_out_frame, const __grid_constant__ SubBatch batch) {
     const long long of = first_out_frame + blockIdx.y;          // output frame handled by this CTA row
     int s = 0;
@@ -222,7 +197,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
     const long long npx = (long long)h * w;
     const uint8_t *fr = frames + gframe * npx * 3;
     const uint8_t *mk = masks + gframe * npx;
-    uint32_t *dst = state + of * npx;
+    uint32_t *dst = frame_ptr(batch.sub[s], idx, state, pads, npx);
     const bool last = idx == len - 1;
     const bool listed = len > 1;                                // a single-frame window has no steps at all
     // flow that propagates INTO this frame: backward pass flows_f[gframe], forward pass flows_b[gframe-1]
@@ -333,9 +308,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
     if (listed) queue_flush(q, dl, of, npx, w, pflow, true);
 }
 
-// ---- k4_step: one time step of one direction, in place, over the hole lists -------------------
-// blockIdx.y = sub-video.  The state buffer holds the input frames after k4_pack, the backward
-// result after pass 1 and the forward result after pass 2:
+// ---- k4_step_lean: one time step of one direction, in place, over the hole lists ----------------
+// blockIdx.y = sub-video.  The state frames hold the input after k4_pack, the backward result after
+// pass 1 and the forward result after pass 2:
 //   PASS2 == false (backward, t = len-2 .. 0):  frame idx is updated from frame idx+1; holes that
 //                                               stay holes are appended to the frame's forward list
 //   PASS2 == true  (forward,  t = 1 .. len-1):  frame idx (backward result) is updated from frame
@@ -343,160 +318,13 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
 // Frame len-1 / frame 0 are the first step of their pass and stay as they are.
 //
 // The chain of 2*(len-1) dependent launches is latency bound, so the per-item dependency chain is
-// kept at two memory round trips and the forward pass only visits what the backward pass left.
-// With programmatic dependent launch the next step's CTAs are resident before this one retires.
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Frame / list / flow pointers of one step of one window.
-struct StepView {
-    long long of;                 // frame index in the state / list buffers
-    const float2 *flow_check;
-    const uint32_t *lxy;
-    const float2 *lflow;
-    const uint32_t *count;
-    bool valid;
-};
-template <bool PASS2>
-__device__ __forceinline__ StepView step_view(const SubDesc &sd, int step, const float2 *flows_f, const float2 *flows_b,
-                                              const HoleLists &l1, const HoleLists &l2, long long npx) {
-    StepView v;
-    v.valid = step >= 1 && step < sd.len;
-    const int idx = PASS2 ? step : sd.len - 1 - step;
-    const long long gframe = sd.start + idx;
-    v.flow_check = (PASS2 ? flows_f + (gframe - 1) * npx : flows_b + gframe * npx);
-    v.of = sd.out_frame + idx;
-    const HoleLists &li = PASS2 ? l2 : l1;
-    v.lxy = li.xy + v.of * npx;
-    v.lflow = li.flow + v.of * npx;
-    v.count = li.count + v.of;
-    return v;
-}
-
-// Persistent mode, software pipelining across steps: while a step runs, each thread already loads the
-// list entries it will own in the NEXT step and prefetches the flow_check sectors their taps will touch
-// into L2, so that the next step's dependency chain runs out of L2 instead of DRAM.
-constexpr int K4_WARM = 4;        // entries per thread warmed ahead
-struct WarmSet {
-    uint32_t xy[K4_WARM];
-    float2 f[K4_WARM];
-    int n;
-};
-__device__ __forceinline__ void warm_load(WarmSet &ws, const StepView &nv, uint32_t first, uint32_t lane, uint32_t stride) {
-    ws.n = 0;
-    if (!nv.valid) return;
-    const uint32_t n = __ldcg(nv.count);
-#pragma unroll
-    for (int k = 0; k < K4_WARM; ++k) {
-        const uint32_t i = first + lane + (uint32_t)k * stride;
-        if (i < n) {
-            ws.xy[k] = __ldcg(nv.lxy + i);
-            ws.f[k] = __ldcg(nv.lflow + i);
-            ws.n = k + 1;
-        }
-    }
-}
-__device__ __forceinline__ void warm_taps(const WarmSet &ws, const StepView &nv, int h, int w) {
-#pragma unroll
-    for (int k = 0; k < K4_WARM; ++k) {
-        if (k < ws.n) {
-            const int x = (int)(ws.xy[k] & 0xffffu), y = (int)(ws.xy[k] >> 16);
-            const float ix = unnormalized(__fadd_rn((float)x, ws.f[k].x), w);
-            const float iy = unnormalized(__fadd_rn((float)y, ws.f[k].y), h);
-            const int x0 = (int)fminf(fmaxf(floorf(ix), 0.f), (float)(w - 1));
-            const int y0 = (int)fminf(fmaxf(floorf(iy), 0.f), (float)(h - 1));
-            const float2 *r0 = nv.flow_check + (long long)y0 * w + x0;
-            const float2 *r1 = nv.flow_check + (long long)min(y0 + 1, h - 1) * w + x0;
-            prefetch_l2(r0);
-            prefetch_l2(r0 + 1);
-            prefetch_l2(r1);
-            prefetch_l2(r1 + 1);
-        }
-    }
-}
-
-template <bool PASS2, bool PERSIST>
-__device__ __forceinline__ void step_body(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b,
-                                          uint32_t *state, const HoleLists &l1, const HoleLists &l2, int h, int w, int step,
-                                          const SubDesc &sd, FlowQueue &q) {
-    const long long npx = (long long)h * w;
-    const int idx = PASS2 ? step : sd.len - 1 - step;
-    const long long gframe = sd.start + idx;
-    // check flow: backward pass flows_b[idx] (prop = flows_f[idx]), forward pass flows_f[idx-1] (prop = flows_b[idx-1])
-    const float2 *flow_check = (PASS2 ? flows_f + (gframe - 1) * npx : flows_b + gframe * npx);
-    const float2 *next_flow = flows_b + (gframe - 1) * npx;       // forward-pass flow into this frame (idx >= 1)
-    const long long of = sd.out_frame + idx;
-    uint32_t *cur = state + of * npx;
-    const uint32_t *prev = state + (PASS2 ? of - 1 : of + 1) * npx;
-    const HoleLists &li = PASS2 ? l2 : l1;
-    const uint32_t *lxy = li.xy + of * npx;
-    const float2 *lflow = li.flow + of * npx;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);    // warp-uniform loop bounds
-    const uint32_t lane = threadIdx.x & 31u;
-    const bool relist = !PASS2 && idx >= 1;      // holes that stay holes go to the forward list
-    // Multi-launch mode: the backward pass reads what k4_pack wrote (complete before the first step was
-    // launched) and may load its first entry before the grid dependency resolves; the forward lists are
-    // produced by the preceding launches.  Persistent mode: forward lists come from other CTAs of this
-    // kernel -> L2-coherent loads.
-    uint32_t xy = 0;
-    float2 f = make_float2(0.f, 0.f);
-    uint32_t n = 0;
-    if (!PERSIST) {
-        if (!PASS2) {
-            n = li.count[of];
-            if (first + lane < n) xy = lxy[first + lane], f = lflow[first + lane];
-        }
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (PASS2) n = li.count[of];
-    } else {
-        n = __ldcg(li.count + of);
-    }
-    // backward pass: block-uniform trip count (the queue flush has barriers)
-    const uint32_t n_loop = PASS2 ? n : min(n + (K4_BLOCK - 1), 0xffffff00u) / K4_BLOCK * K4_BLOCK;
-    for (uint32_t base = first; base < n_loop; base += stride) {
-        const uint32_t i = base + lane;
-        const bool valid = i < n;
-        if (valid && (PERSIST || PASS2 || base != first)) {
-            xy = PERSIST ? __ldcg(lxy + i) : lxy[i];
-            f = PERSIST ? __ldcg(lflow + i) : lflow[i];
-        }
-        const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
-        uint32_t nv = ST_HOLE | ST_ZERO;
-        float2 nf = make_float2(0.f, 0.f);
-        if (valid) {
-            // the forward-pass flow is fetched speculatively, in the same round trip as the taps
-            if (relist) nf = __ldg(next_flow + (long long)y * w + x);
-            nv = propagate_pixel<PERSIST>(x, y, h, w, ST_HOLE | ST_ZERO, f, flow_check, prev);
-            if (nv != (ST_HOLE | ST_ZERO)) cur[(long long)y * w + x] = nv;
-        }
-        if (relist) {                   // still a hole: the forward pass gets another chance
-            queue_push(q, valid && nv == (ST_HOLE | ST_ZERO), xy, nf);
-            queue_flush(q, l2, of, npx, false);
-        }
-    }
-    if (relist) queue_flush(q, l2, of, npx, true);
-}
-
-// One launch per step (fallback, and the variant the ncu launch lists show step by step).
-template <bool PASS2>
-__global__ void __launch_bounds__(256, 8)
-    k4_step(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state, HoleLists l1,
-            HoleLists l2, int h, int w, int step, const __grid_constant__ SubBatch batch) {
-    asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
-    const SubDesc sd = batch.sub[blockIdx.y];
-    if (step >= sd.len) return;
-    __shared__ FlowQueue q;
-    if (threadIdx.x == 0) q.count = 0;
-    __syncthreads();
-    step_body<PASS2, false>(flows_f, flows_b, state, l1, l2, h, w, step, sd, q);
-}
-
-// ---- k4_step_lean: the default step kernel -----------------------------------------------------
-// Same work as k4_step, but every frame / list pointer of the step is resolved on the HOST and arrives
-// in the kernel-parameter constant bank (one StepWin per window): the device code has no 64-bit
-// frame-offset arithmetic left, which matters because the step is bound by instruction issue as much as
-// by its DRAM gathers (ncu: ~500 warp instructions per 32 hole pixels, issue active 70 %, before this).
-// The re-list queue holds four rounds, so the block-wide flush (2 barriers) runs every fourth trip.
+// kept short and the forward pass only visits what the backward pass left.  With programmatic
+// dependent launch the next step's CTAs are resident before this one retires.
+// Every frame / list pointer of the step is resolved on the HOST and arrives in the kernel-parameter
+// constant bank (one StepWin per window): the device code has no 64-bit frame-offset arithmetic left,
+// which matters because the step is bound by instruction issue as much as by its DRAM gathers (ncu:
+// ~500 warp instructions per 32 hole pixels, issue active 70 %, before this).
+// The re-list queue holds four rounds, so the block-wide flush (2 barriers) runs every fourth round.
 struct StepWin {
     const uint32_t *prev;        // state of the frame propagated FROM;  NULL = this window has no such step
     uint32_t *cur;               // state of the frame propagated INTO (updated in place)
@@ -536,7 +364,9 @@ __device__ __forceinline__ void lean_flush(LeanQueue &q, const StepWin &sw) {
     __syncthreads();
 }
 
-template <bool PASS2, int MIN_CTAS, bool UNCOND>
+// NPT = hole pixels per thread and trip: their list entries and taps are independent, so NPT = 2 doubles
+// the loads a thread keeps in flight at the price of registers (fewer resident CTAs).
+template <bool PASS2, int MIN_CTAS, bool UNCOND, int NPT>
 __global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS)
     k4_step_lean(const __grid_constant__ StepArgs args, int h, int w, int speculate) {
     asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
@@ -548,109 +378,83 @@ __global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS)
         if (threadIdx.x == 0) q.count = 0;
         __syncthreads();
     }
-    const uint32_t stride = gridDim.x * K4_BLOCK;
+    const uint32_t stride = gridDim.x * K4_BLOCK;            // entries per round; a trip is NPT rounds
     const uint32_t first = blockIdx.x * K4_BLOCK + (threadIdx.x & ~31u);      // warp-uniform loop bounds
     const uint32_t lane = threadIdx.x & 31u;
     // The backward pass reads what k4_pack wrote (complete before the first step was launched), so it may
-    // load its first entry before the grid dependency resolves; the forward lists come from the preceding
+    // load its first entries before the grid dependency resolves; the forward lists come from the preceding
     // launches.
-    uint32_t xy = 0, n = 0;
-    float2 f = make_float2(0.f, 0.f);
+    uint32_t xy[NPT], n = 0;
+    float2 f[NPT];
+#pragma unroll
+    for (int u = 0; u < NPT; ++u) xy[u] = 0, f[u] = make_float2(0.f, 0.f);
     if (!PASS2) {
         n = *sw.count;
-        if (first + lane < n) xy = sw.lxy[first + lane], f = sw.lflow[first + lane];
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) {
+            const uint32_t i = first + lane + u * stride;
+            if (i < n) xy[u] = sw.lxy[i], f[u] = sw.lflow[i];
+        }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (PASS2) n = *sw.count;
+    if (PASS2) {
+        n = *sw.count;
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) {
+            const uint32_t i = first + lane + u * stride;
+            if (i < n) xy[u] = sw.lxy[i], f[u] = sw.lflow[i];
+        }
+    }
     // backward pass: block-uniform trip count (the queue flush has barriers)
     const uint32_t n_loop = PASS2 ? n : min(n + (K4_BLOCK - 1), 0xffffff00u) / K4_BLOCK * K4_BLOCK;
     int trip = 0;
-    if (PASS2 && first + lane < n) xy = sw.lxy[first + lane], f = sw.lflow[first + lane];
-    for (uint32_t base = first; base < n_loop; base += stride, ++trip) {
-        const uint32_t i = base + lane;
-        const bool valid = i < n;
-        // software pipeline: the entry of the NEXT trip is requested before this trip's taps, so a thread's
+    for (uint32_t base = first; base < n_loop; base += NPT * stride, ++trip) {
+        uint32_t xy_cur[NPT], nv[NPT], pix[NPT];
+        float2 f_cur[NPT], nf[NPT];
+        bool valid[NPT];
+        // software pipeline: the entries of the NEXT trip are requested before this trip's taps, so a thread's
         // dependency chain is one round trip per item (plus one) instead of two
-        const uint32_t xy_cur = xy;
-        const float2 f_cur = f;
-        if (i + stride < n) xy = sw.lxy[i + stride], f = sw.lflow[i + stride];
-        const int x = (int)(xy_cur & 0xffffu), y = (int)(xy_cur >> 16);
-        const uint32_t pix = (uint32_t)y * (uint32_t)w + (uint32_t)x;
-        uint32_t nv = ST_HOLE | ST_ZERO;
-        float2 nf = make_float2(0.f, 0.f);
-        if (valid) {
-            // the forward-pass flow is fetched speculatively, in the same round trip as the taps
-            if (relist && speculate) nf = __ldg(sw.next_flow + pix);
-            nv = propagate_pixel<false, UNCOND>(x, y, h, w, ST_HOLE | ST_ZERO, f_cur, sw.flow_check, sw.prev);
-            if (nv != (ST_HOLE | ST_ZERO)) sw.cur[pix] = nv;
-            else if (relist && !speculate) nf = __ldg(sw.next_flow + pix);
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) {
+            const uint32_t i = base + lane + u * stride;
+            valid[u] = i < n;
+            xy_cur[u] = xy[u], f_cur[u] = f[u];
+            const uint32_t inext = i + NPT * stride;
+            if (inext < n) xy[u] = sw.lxy[inext], f[u] = sw.lflow[inext];
         }
-        if (relist) {                   // still a hole: the forward pass gets another chance
-            const bool take = valid && nv == (ST_HOLE | ST_ZERO);
-            const uint32_t m = __ballot_sync(0xffffffffu, take);
-            if (m) {
-                uint32_t at = 0;
-                if (lane == 0) at = atomicAdd(&q.count, (uint32_t)__popc(m));
-                at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
-                if (take) q.xy[at] = xy_cur, q.flow[at] = nf;
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) {
+            const int x = (int)(xy_cur[u] & 0xffffu), y = (int)(xy_cur[u] >> 16);
+            pix[u] = (uint32_t)y * (uint32_t)w + (uint32_t)x;
+            nv[u] = ST_HOLE | ST_ZERO;
+            nf[u] = make_float2(0.f, 0.f);
+            if (valid[u]) {
+                // the forward-pass flow is fetched speculatively, in the same round trip as the taps
+                if (relist && speculate) nf[u] = __ldg(sw.next_flow + pix[u]);
+                nv[u] = propagate_pixel<UNCOND>(x, y, h, w, ST_HOLE | ST_ZERO, f_cur[u], sw.flow_check, sw.prev);
             }
-            if ((trip & (K4_LEAN_ROUNDS - 1)) == K4_LEAN_ROUNDS - 1) lean_flush(q, sw);
         }
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) {
+            if (valid[u]) {
+                if (nv[u] != (ST_HOLE | ST_ZERO)) sw.cur[pix[u]] = nv[u];
+                else if (relist && !speculate) nf[u] = __ldg(sw.next_flow + pix[u]);
+            }
+            if (relist) {                   // still a hole: the forward pass gets another chance
+                const bool take = valid[u] && nv[u] == (ST_HOLE | ST_ZERO);
+                const uint32_t m = __ballot_sync(0xffffffffu, take);
+                if (m) {
+                    uint32_t at = 0;
+                    if (lane == 0) at = atomicAdd(&q.count, (uint32_t)__popc(m));
+                    at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+                    if (take) q.xy[at] = xy_cur[u], q.flow[at] = nf[u];
+                }
+            }
+        }
+        constexpr int FLUSH_EVERY = K4_LEAN_ROUNDS / NPT;
+        if (relist && (trip % FLUSH_EVERY) == FLUSH_EVERY - 1) lean_flush(q, sw);
     }
     if (relist) lean_flush(q, sw);
-}
-
-// Barrier among the CTAs of one window (blockIdx.y): monotonic arrival counter in global memory.
-// `target` = arrivals expected so far.  The spin is bounded so that a broken launch cannot hang the GPU.
-__device__ __forceinline__ void window_barrier(unsigned int *ctr, unsigned int target, int *failed) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();                                   // this CTA's state / list writes are visible device-wide
-        atomicAdd(ctr, 1u);
-        unsigned int seen, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-        } while (seen < target && ++spins < (1u << 22));
-        if (seen < target) *failed = 1;
-    }
-    __syncthreads();
-}
-
-// The whole scan of a batch of windows in ONE cooperative launch: every CTA stays resident, walks its
-// share of the hole list of each step and meets the other CTAs of its window at a barrier.  A step then
-// costs two memory round trips + one barrier (~5 us) instead of a kernel launch + ramp-up (~11-16 us).
-__global__ void __launch_bounds__(256)
-    k4_scan_persistent(const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, uint32_t *state,
-                       HoleLists l1, HoleLists l2, int h, int w, unsigned int *barriers, int *failed, int warm,
-                       const __grid_constant__ SubBatch batch) {
-    const SubDesc sd = batch.sub[blockIdx.y];
-    __shared__ FlowQueue q;
-    if (threadIdx.x == 0) q.count = 0;
-    __syncthreads();
-    const long long npx = (long long)h * w;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u), lane = threadIdx.x & 31u;
-    unsigned int arrivals = 0;
-    WarmSet ws;
-    for (int step = 1; step < sd.len; ++step) {
-        // next step: step+1 of the backward pass, or step 1 of the forward pass after the last one (its
-        // list is complete by then only for frames the backward pass has already left: frame 1 is
-        // written in this very step, so the forward pass's first step is not warmed)
-        const StepView nv = step_view<false>(sd, step + 1, flows_f, flows_b, l1, l2, npx);
-        if (warm) warm_load(ws, nv, first, lane, stride);
-        step_body<false, true>(flows_f, flows_b, state, l1, l2, h, w, step, sd, q);
-        if (warm) warm_taps(ws, nv, h, w);
-        arrivals += gridDim.x;
-        window_barrier(barriers + blockIdx.y, arrivals, failed);
-    }
-    for (int step = 1; step < sd.len; ++step) {
-        const StepView nv = step_view<true>(sd, step + 1, flows_f, flows_b, l1, l2, npx);
-        if (warm) warm_load(ws, nv, first, lane, stride);
-        step_body<true, true>(flows_f, flows_b, state, l1, l2, h, w, step, sd, q);
-        if (warm) warm_taps(ws, nv, h, w);
-        arrivals += gridDim.x;
-        if (step + 1 < sd.len) window_barrier(barriers + blockIdx.y, arrivals, failed);
-    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -672,29 +476,41 @@ __global__ void __launch_bounds__(256)
 
 using namespace vv;
 
-extern "C" size_t vv_propagate_workspace_bytes(int n_out_frames, int h, int w) {
-    if (n_out_frames <= 0 || h <= 0 || w <= 0) return 0;
-    // two hole-list sets, worst case one entry per pixel: u32 position + float2 flow; counters per frame
-    const size_t n = (size_t)n_out_frames * h * w;
-    return 2 * (align_up(n * 4, 256) + align_up(n * 8, 256)) + align_up((size_t)n_out_frames * 8, 256) + 256;
+extern "C" size_t vv_propagate_workspace_bytes(int n_window_frames, int n_pad_frames, int h, int w) {
+    if (n_window_frames <= 0 || h <= 0 || w <= 0) return 0;
+    if (n_pad_frames < 0) n_pad_frames = 0;
+    // two hole-list sets, worst case one entry per pixel: u32 position + float2 flow; counters per frame;
+    // packed state of the pad frames
+    const size_t n = (size_t)n_window_frames * h * w;
+    return 2 * (align_up(n * 4, 256) + align_up(n * 8, 256)) + align_up((size_t)n_window_frames * 8, 256) +
+           align_up((size_t)n_pad_frames * h * w * 4, 256) + 256;
 }
 
 extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const float *flows_f, const float *flows_b,
-                            int n_frames, int h, int w, const int *sub_start, const int *sub_len, int n_sub,
-                            uint32_t *out, void *workspace, size_t workspace_bytes, void *stream) {
+                            int n_frames, int h, int w, const int *sub_start, const int *sub_len,
+                            const int *sub_keep_start, const int *sub_keep_len, int n_sub, uint32_t *out,
+                            void *workspace, size_t workspace_bytes, void *stream) {
     VV_CHECK_ARG(frames && masks && out && workspace && sub_start && sub_len, "vv_propagate: NULL pointer");
+    VV_CHECK_ARG((sub_keep_start == nullptr) == (sub_keep_len == nullptr),
+                 "vv_propagate: sub_keep_start and sub_keep_len must be given together");
     VV_CHECK_ARG(n_frames > 0 && h > 0 && w > 0 && n_sub > 0, "vv_propagate: bad shape");
     VV_CHECK_ARG(h <= 65535 && w <= 65535, "vv_propagate: frame too large");
     VV_CHECK_ARG(n_frames == 1 || (flows_f && flows_b), "vv_propagate: flows required when there is more than one frame");
-    long long total = 0;
+    long long total = 0, kept = 0;
     for (int s = 0; s < n_sub; ++s) {
         VV_CHECK_ARG(sub_len[s] > 0 && sub_start[s] >= 0 && sub_start[s] + sub_len[s] <= n_frames,
                      "vv_propagate: sub-video %d [%d,+%d) outside the clip of %d frames", s, sub_start[s], sub_len[s],
                      n_frames);
+        if (sub_keep_start)
+            VV_CHECK_ARG(sub_keep_start[s] >= 0 && sub_keep_len[s] >= 0 && sub_keep_start[s] + sub_keep_len[s] <= sub_len[s],
+                         "vv_propagate: kept range [%d,+%d) outside sub-video %d of %d frames", sub_keep_start[s],
+                         sub_keep_len[s], s, sub_len[s]);
         total += sub_len[s];
+        kept += sub_keep_start ? sub_keep_len[s] : sub_len[s];
     }
     VV_CHECK_ARG(total < (1LL << 31), "vv_propagate: too many frames");
-    VV_CHECK_ARG(workspace_bytes >= vv_propagate_workspace_bytes((int)total, h, w), "vv_propagate: workspace too small");
+    VV_CHECK_ARG(workspace_bytes >= vv_propagate_workspace_bytes((int)total, (int)(total - kept), h, w),
+                 "vv_propagate: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const long long npx = (long long)h * w;
     const bool vec = (w % 4 == 0) && ((uintptr_t)frames % 4 == 0) && ((uintptr_t)masks % 4 == 0) &&
@@ -706,24 +522,26 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
     l2.xy = (uint32_t *)(wsp + l4 + l8), l2.flow = (float2 *)(wsp + 2 * l4 + l8);
     l1.count = (uint32_t *)(wsp + 2 * (l4 + l8));
     l2.count = l1.count + total;
-    unsigned int *barriers = (unsigned int *)(wsp + 2 * (l4 + l8) + align_up((size_t)total * 8, 256));   // 32 + failure flag
-    int *failed = (int *)(barriers + K4_MAX_SUB);
+    uint32_t *pads = (uint32_t *)(wsp + 2 * (l4 + l8) + align_up((size_t)total * 8, 256));
     const float2 *ff = (const float2 *)flows_f, *fb = (const float2 *)flows_b;
     cudaError_t e = cudaMemsetAsync(l1.count, 0, (size_t)total * 8, st);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
 
-    long long out_frame = 0;
+    long long out_frame = 0, keep_out = 0, pad_out = 0;
     for (int base = 0; base < n_sub; base += K4_MAX_SUB) {
         SubBatch b;
         b.n = min(K4_MAX_SUB, n_sub - base);
         int blen = 0;
         const long long first = out_frame;
         for (int s = 0; s < b.n; ++s) {
-            b.sub[s].start = sub_start[base + s];
-            b.sub[s].len = sub_len[base + s];
-            b.sub[s].out_frame = out_frame;
-            out_frame += sub_len[base + s];
-            blen = max(blen, sub_len[base + s]);
+            SubDesc &sd = b.sub[s];
+            sd.start = sub_start[base + s];
+            sd.len = sub_len[base + s];
+            sd.pad_s = sub_keep_start ? sub_keep_start[base + s] : 0;
+            sd.keep = sub_keep_start ? sub_keep_len[base + s] : sd.len;
+            sd.out_frame = out_frame, sd.keep_out = keep_out, sd.pad_out = pad_out;
+            out_frame += sd.len, keep_out += sd.keep, pad_out += sd.len - sd.keep;
+            blen = max(blen, sd.len);
         }
         const long long bframes = out_frame - first;
         // pack: all frames of the batch at once (grid.y <= 65535 frames per launch)
@@ -732,7 +550,8 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             const int ctas = 148 * max(1, min(1024, get_option(OPT_K4_PACK_CTAS)));
             const int gx = max(1, min(ceil_div((npx + 3) / 4, 256 * K4_PACK_UNROLL), ceil_div(ctas, ny)));
             const int occ = get_option(OPT_K4_PACK_OCC);
-#define VV_K4_PACK(V, O) k4_pack<V, O><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, ff, fb, l1, l2, h, w, first + f0, b)
+#define VV_K4_PACK(V, O) \
+    k4_pack<V, O><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, pads, ff, fb, l1, l2, h, w, first + f0, b)
             if (!vec)
                 VV_K4_PACK(false, 4);
             else if (occ >= 6)
@@ -744,91 +563,39 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
 #undef VV_K4_PACK
             VV_POST_LAUNCH("k4_pack");
         }
-        // The serial scans touch hole pixels only.  The hole counts live on the device: the grid is
-        // sized for ~1 item per thread at a 25 % hole fraction and strides over the list otherwise.
+        // The serial scans touch hole pixels only.  The hole counts live on the device: "k4_step_ctas" > 0 =
+        // that many CTAs per SM in total (a resident grid that strides over the lists), 0 = about one thread
+        // per hole at a 25 % hole fraction.
         dim3 grid(max(1, min(ceil_div(npx / 4, 256), ceil_div(148 * 16, b.n))), b.n);
-        if (get_option(OPT_K4_PERSISTENT) != 0 && blen > 1) {
-            // persistent scan: as many co-resident CTAs per window as the device can hold
-            static int max_blocks_per_sm = 0, sm_count = 0, coop = -1;
-            if (coop < 0) {
-                int dev = 0;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-                cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, k4_scan_persistent, 256, 0);
-            }
-            const int resident = max_blocks_per_sm * sm_count;
-            const int gpw = min(resident / b.n, ceil_div(npx / 4, 256));     // CTAs per window
-            if (coop > 0 && gpw >= 1) {
-                cudaError_t me = cudaMemsetAsync(barriers, 0, (K4_MAX_SUB + 1) * sizeof(unsigned int), st);
-                if (me != cudaSuccess) return fail_cuda(me, "cudaMemsetAsync");
-                int warm = get_option(OPT_K4_WARM) != 0;
-                void *args[] = {(void *)&ff, (void *)&fb, (void *)&out, (void *)&l1, (void *)&l2, (void *)&h, (void *)&w,
-                                (void *)&barriers, (void *)&failed, (void *)&warm, (void *)&b};
-                cudaError_t le = cudaLaunchCooperativeKernel((const void *)k4_scan_persistent, dim3(gpw, b.n), dim3(256),
-                                                             args, 0, st);
-                if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchCooperativeKernel(k4_scan_persistent)");
-                VV_POST_LAUNCH("k4_scan_persistent");
-                continue;
-            }
-        }
+        const int per_sm = get_option(OPT_K4_STEP_CTAS);
+        if (per_sm > 0) grid.x = max(1, min(ceil_div(npx / 4, 256), (148 * per_sm) / b.n));
         const int pdl = get_option(OPT_K4_PDL) != 0;
         const int lean = get_option(OPT_K4_LEAN);
-        if (lean != 0) {
-            // "k4_step_ctas" > 0: that many CTAs per SM in total (a resident grid that strides over the lists)
-            const int per_sm = get_option(OPT_K4_STEP_CTAS);
-            if (per_sm > 0) grid.x = max(1, min(ceil_div(npx / 4, 256), (148 * per_sm) / b.n));
-            for (int pass = 0; pass < 2; ++pass)
-                for (int step = 1; step < blen; ++step) {
-                    StepArgs sa;
-                    for (int s = 0; s < K4_MAX_SUB; ++s) {
-                        StepWin &sw = sa.win[s];
-                        sw = StepWin();
-                        if (s >= b.n || step >= b.sub[s].len) continue;
-                        const SubDesc &sd = b.sub[s];
-                        const int idx = pass ? step : sd.len - 1 - step;
-                        const long long gframe = sd.start + idx, of = sd.out_frame + idx;
-                        const HoleLists &li = pass ? l2 : l1;
-                        sw.cur = out + of * npx;
-                        sw.prev = out + (pass ? of - 1 : of + 1) * npx;
-                        // check flow: backward pass flows_b[idx] (prop = flows_f[idx]), forward pass flows_f[idx-1]
-                        sw.flow_check = pass ? ff + (gframe - 1) * npx : fb + gframe * npx;
-                        sw.next_flow = (!pass && idx >= 1) ? fb + (gframe - 1) * npx : nullptr;
-                        sw.lxy = li.xy + of * npx, sw.lflow = li.flow + of * npx, sw.count = li.count + of;
-                        sw.oxy = l2.xy + of * npx, sw.oflow = l2.flow + of * npx, sw.ocount = l2.count + of;
-                    }
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = grid;
-                    cfg.blockDim = dim3(K4_BLOCK);
-                    cfg.stream = st;
-                    cudaLaunchAttribute attr[1];
-                    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                    attr[0].val.programmaticStreamSerializationAllowed = 1;
-                    cfg.attrs = attr;
-                    // the first step after k4_pack is an ordinary launch (see below)
-                    cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
-                    cudaError_t le;
-                    const bool uncond = get_option(OPT_K4_TAPS) != 0;
-                    const int spec = get_option(OPT_K4_SPECULATE);
-#define VV_K4_LEAN(O, U) \
-    (pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, U>, sa, h, w, spec) : cudaLaunchKernelEx(&cfg, k4_step_lean<true, O, U>, sa, h, w, spec))
-                    if (lean >= 8)
-                        le = uncond ? VV_K4_LEAN(8, true) : VV_K4_LEAN(8, false);
-                    else if (lean >= 6)
-                        le = uncond ? VV_K4_LEAN(6, true) : VV_K4_LEAN(6, false);
-                    else
-                        le = uncond ? VV_K4_LEAN(5, true) : VV_K4_LEAN(5, false);
-#undef VV_K4_LEAN
-                    if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step_lean)");
-                    VV_POST_LAUNCH("k4_step_lean");
-                }
-            continue;
-        }
+        const bool uncond = get_option(OPT_K4_TAPS) != 0;
+        const int spec = get_option(OPT_K4_SPECULATE);
+        const int npt = get_option(OPT_K4_NPT) >= 2 ? 2 : 1;
         for (int pass = 0; pass < 2; ++pass)
             for (int step = 1; step < blen; ++step) {
+                StepArgs sa;
+                for (int s = 0; s < K4_MAX_SUB; ++s) {
+                    StepWin &sw = sa.win[s];
+                    sw = StepWin();
+                    if (s >= b.n || step >= b.sub[s].len) continue;
+                    const SubDesc &sd = b.sub[s];
+                    const int idx = pass ? step : sd.len - 1 - step;
+                    const long long gframe = sd.start + idx, of = sd.out_frame + idx;
+                    const HoleLists &li = pass ? l2 : l1;
+                    sw.cur = frame_ptr(sd, idx, out, pads, npx);
+                    sw.prev = frame_ptr(sd, pass ? idx - 1 : idx + 1, out, pads, npx);
+                    // check flow: backward pass flows_b[idx] (prop = flows_f[idx]), forward pass flows_f[idx-1]
+                    sw.flow_check = pass ? ff + (gframe - 1) * npx : fb + gframe * npx;
+                    sw.next_flow = (!pass && idx >= 1) ? fb + (gframe - 1) * npx : nullptr;
+                    sw.lxy = li.xy + of * npx, sw.lflow = li.flow + of * npx, sw.count = li.count + of;
+                    sw.oxy = l2.xy + of * npx, sw.oflow = l2.flow + of * npx, sw.ocount = l2.count + of;
+                }
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = grid;
-                cfg.blockDim = dim3(256);
+                cfg.blockDim = dim3(K4_BLOCK);
                 cfg.stream = st;
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -837,10 +604,21 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
                 // the first step after k4_pack is an ordinary launch: backward steps read the lists k4_pack
                 // wrote BEFORE their griddepcontrol.wait, and only a full stream dependency makes those visible
                 cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
-                cudaError_t le = pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step<false>, ff, fb, out, l1, l2, h, w, step, b)
-                                           : cudaLaunchKernelEx(&cfg, k4_step<true>, ff, fb, out, l1, l2, h, w, step, b);
-                if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step)");
-                VV_POST_LAUNCH("k4_step");
+                cudaError_t le;
+#define VV_K4_LEAN(O, U, N)                                                                    \
+    (pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, U, N>, sa, h, w, spec)        \
+               : cudaLaunchKernelEx(&cfg, k4_step_lean<true, O, U, N>, sa, h, w, spec))
+                if (npt == 2)
+                    le = lean >= 4 && lean < 5 ? VV_K4_LEAN(4, false, 2) : VV_K4_LEAN(3, false, 2);
+                else if (lean >= 8)
+                    le = uncond ? VV_K4_LEAN(8, true, 1) : VV_K4_LEAN(8, false, 1);
+                else if (lean >= 6)
+                    le = uncond ? VV_K4_LEAN(6, true, 1) : VV_K4_LEAN(6, false, 1);
+                else
+                    le = uncond ? VV_K4_LEAN(5, true, 1) : VV_K4_LEAN(5, false, 1);
+#undef VV_K4_LEAN
+                if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step_lean)");
+                VV_POST_LAUNCH("k4_step_lean");
             }
     }
     return VV_OK;

@@ -153,6 +153,28 @@ static int drain(vv_pipeline *p) {
     return rc;
 }
 
+// Error exit of a batch loop: copies may have been enqueued on a slot stream without its `done` event
+// (the batch failed half way), so every stream is synchronised before the call returns and the caller's
+// host buffers can go away; staged results of failed jobs are dropped.
+static void quiesce(vv_pipeline *p) {
+    for (Slot &s : p->slots) {
+        if (s.st) cudaStreamSynchronize(s.st);
+        s.copyout.clear();
+        s.pending = false;
+    }
+    cudaGetLastError();
+}
+
+static int finish(vv_pipeline *p, int rc) {
+    if (rc) {
+        quiesce(p);
+        return rc;
+    }
+    rc = drain(p);
+    if (rc) quiesce(p);
+    return rc;
+}
+
 // Copies n per-frame host buffers into consecutive device frames.
 static int upload(vv_pipeline *p, Slot &s, const uint8_t *const *src, int n, size_t bytes, uint8_t *dev,
                   size_t pin_off) {
@@ -278,8 +300,7 @@ extern "C" int vv_pipeline_pre(vv_pipeline *p, const uint8_t *const *masks, int 
         VV_CUDA(cudaEventRecord(s.done, s.st));
         s.pending = true;
     }
-    const int rd = drain(p);
-    return rc ? rc : rd;
+    return finish(p, rc);
 }
 
 extern "C" int vv_pipeline_downsize(vv_pipeline *p, const uint8_t *const *frames, int T, int h, int w,
@@ -302,8 +323,7 @@ extern "C" int vv_pipeline_downsize(vv_pipeline *p, const uint8_t *const *frames
         VV_CUDA(cudaEventRecord(s.done, s.st));
         s.pending = true;
     }
-    const int rd = drain(p);
-    return rc ? rc : rd;
+    return finish(p, rc);
 }
 
 extern "C" int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted, int h, int w,
@@ -316,9 +336,9 @@ extern "C" int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted,
         return VV_ERR_UNSUPPORTED;
     }
     VV_CHECK_ARG(!keep_unmasked || orig, "vv_pipeline_post: original frames required when keep_unmasked != 0");
+    std::lock_guard<std::mutex> g(p->mu);
     VV_CHECK_ARG(!keep_unmasked || dilated || p->res_frames >= T,
                  "vv_pipeline_post: no dilated masks supplied and none resident from vv_pipeline_pre");
-    std::lock_guard<std::mutex> g(p->mu);
     VV_CUDA(cudaSetDevice(p->device));
     const size_t px = (size_t)p->H0 * p->W0, spx = (size_t)h * w;
     int rc = VV_OK;
@@ -344,6 +364,63 @@ extern "C" int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted,
         VV_CUDA(cudaEventRecord(s.done, s.st));
         s.pending = true;
     }
-    const int rd = drain(p);
-    return rc ? rc : rd;
+    return finish(p, rc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Device-resident clips (videovanish_b200/wrappers.py): per-frame host buffers <-> one contiguous device
+// array, through the same slots (direct DMA for page-locked buffers, pinned ring + memcpy pool otherwise).
+extern "C" int vv_pipeline_upload(vv_pipeline *p, const uint8_t *const *src, int T, size_t frame_bytes, uint8_t *dev_dst,
+                                  void *stream) {
+    VV_CHECK_ARG(p && src && dev_dst && T > 0 && frame_bytes > 0, "vv_pipeline_upload: bad argument");
+    VV_CHECK_ARG(frame_bytes <= (size_t)p->H0 * p->W0 * 4, "vv_pipeline_upload: frame larger than the context geometry");
+    std::lock_guard<std::mutex> g(p->mu);
+    VV_CUDA(cudaSetDevice(p->device));
+    int rc = VV_OK;
+    for (int b = 0, t0 = 0; t0 < T && !rc; ++b, t0 += p->fpb) {
+        Slot &s = p->slots[b % p->n_slots];
+        const int n = std::min(p->fpb, T - t0);
+        if ((rc = slot_wait(p, s))) break;
+        if ((rc = upload(p, s, src + t0, n, frame_bytes, dev_dst + (size_t)t0 * frame_bytes, 0))) break;
+        VV_CUDA(cudaEventRecord(s.done, s.st));
+        s.pending = true;
+    }
+    if (rc) return finish(p, rc);
+    // The consumer stream waits for every slot ON THE DEVICE; the host does not wait: pageable sources have
+    // already been copied into the pinned ring, page-locked ones are read by DMA until `stream` gets there.
+    for (Slot &s : p->slots)
+        if (s.pending) VV_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, s.done, 0));
+    return VV_OK;
+}
+
+extern "C" int vv_pipeline_download(vv_pipeline *p, const uint8_t *dev_src, int T, size_t frame_bytes, uint8_t *const *dst,
+                                    void *stream) {
+    VV_CHECK_ARG(p && dev_src && dst && T > 0 && frame_bytes > 0, "vv_pipeline_download: bad argument");
+    VV_CHECK_ARG(frame_bytes <= (size_t)p->H0 * p->W0 * 3, "vv_pipeline_download: frame larger than the context geometry");
+    std::lock_guard<std::mutex> g(p->mu);
+    VV_CUDA(cudaSetDevice(p->device));
+    // the producer stream's work so far must be complete before any slot copies
+    cudaEvent_t ready;
+    VV_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ready, (cudaStream_t)stream);
+    int rc = e == cudaSuccess ? VV_OK : fail_cuda(e, "cudaEventRecord");
+    for (int b = 0, t0 = 0; t0 < T && !rc; ++b, t0 += p->fpb) {
+        Slot &s = p->slots[b % p->n_slots];
+        const int n = std::min(p->fpb, T - t0);
+        if ((rc = slot_wait(p, s))) break;
+        if (b < p->n_slots && (e = cudaStreamWaitEvent(s.st, ready, 0)) != cudaSuccess) {
+            rc = fail_cuda(e, "cudaStreamWaitEvent");
+            break;
+        }
+        if ((rc = download(p, s, dev_src + (size_t)t0 * frame_bytes, dst + t0, n, frame_bytes, 0))) break;
+        e = cudaEventRecord(s.done, s.st);
+        if (e != cudaSuccess) {
+            rc = fail_cuda(e, "cudaEventRecord");
+            break;
+        }
+        s.pending = true;
+    }
+    rc = finish(p, rc);
+    cudaEventDestroy(ready);
+    return rc;
 }

@@ -12,6 +12,10 @@ Differences, all deliberate and documented in DESIGN.md:
   Here every frame is processed (the evident intent); ``BUG_COMPAT = True`` restores the literal
   behaviour.
 * There is no CPU fallback: without a CUDA device the call raises.
+
+When every model in play offers ``forward_device`` (the adapters of ``wrappers.py`` around the networks),
+the call is device-resident: frames and masks are uploaded once, K1 -> [prior stages] -> [DiffuEraser
+wrapper stages] -> K3 run back to back in HBM, and only the finished frames come back.
 """
 import numpy as np
 
@@ -54,11 +58,15 @@ def run_infill_on_frames(frames_rgb, mask_frames, mask_dilation_iter=8, ckpt="2-
     H0, W0 = frames_rgb[0].shape[:2]
     pipe = _get_pipeline(H0, W0)
 
+    if _device_route(propainer_frames):
+        return _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_frames, max_img_size,
+                              keep_unmasked_original, feather_px, prog)
+
     if prog is not None: prog(5, "dilating frames")
     dilated_mask_frames = pipe.pre(mask_frames, mask_dilation_iter)                      # :27-31 (K1)
 
     if prog is not None: prog(10, "loading weights")
-    if last_ckpt != ckpt and video_inpainting_sd is None:                                # :35-45
+    if last_ckpt != ckpt:                                                                # :35-45
         from diffueraser.diffueraser import DiffuEraser
         from propainter.inference import get_device
         device = get_device()
@@ -95,6 +103,56 @@ def run_infill_on_frames(frames_rgb, mask_frames, mask_dilation_iter=8, ckpt="2-
     for i in range(n):
         inpainted_frames[i] = out[i]
     return inpainted_frames
+
+
+def _device_route(propainer_frames):
+    """True when the models that this call will use are the device-resident adapters."""
+    if video_inpainting_sd is None or last_ckpt != "2-Step" or not hasattr(video_inpainting_sd, "forward_device"):
+        return False
+    return propainer_frames is not None or (propainter is not None and hasattr(propainter, "forward_device"))
+
+
+def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_frames, max_img_size,
+                   keep_unmasked_original, feather_px, prog):
+    """Same stages, milestones and results as the host-list route of ``run_infill_on_frames``, with the clip
+    resident in HBM from the first upload to the last download."""
+    import torch
+
+    from . import ops, wrappers
+    H0, W0 = frames_rgb[0].shape[:2]
+    t = len(frames_rgb)
+    with torch.cuda.device(pipe.device):
+        if prog is not None: prog(5, "dilating frames")
+        c = 1 if mask_frames[0].ndim == 2 else mask_frames[0].shape[2]
+        masks = pipe.upload(mask_frames, (H0, W0) if mask_frames[0].ndim == 2 else (H0, W0, c), is_mask=True)
+        h, w = ops.inference_size(H0, W0, max_img_size)
+        dil, low, bits = ops.binarize_dilate(masks, mask_dilation_iter, lowres_size=(h, w), return_bits=True)   # K1
+        del masks
+        frames = pipe.upload(frames_rgb, (H0, W0, 3))
+        clip = wrappers.DeviceClip(frames, dil, lowres=low)
+        clip.mask_bits = bits
+        if prog is not None: prog(10, "loading weights")
+        if propainer_frames is None:
+            if prog is not None: prog(20, "running propainter prior")
+            priors = propainter.forward_device(clip, ref_stride=10, neighbor_length=10, subvideo_length=50,
+                                               mask_dilation=0, progress=prog)
+        else:
+            priors = pipe.upload(propainer_frames, tuple(propainer_frames[0].shape))
+        if prog is not None: prog(50, "running DiffuEraser")
+        inpainted = video_inpainting_sd.forward_device(clip, priors, max_img_size=max_img_size, mask_dilation_iter=0,
+                                                       guidance_scale=None, progress=prog)
+        del priors
+        if prog is not None: prog(90, "resizing and merging finished frames")
+        n = min(1, t) if BUG_COMPAT else t
+        fh, fw = inpainted.shape[1:3]
+        if (fh, fw) == (H0, W0) and not keep_unmasked_original:
+            return pipe.download(inpainted)
+        out = ops.upscale_feather_composite(inpainted[:n], frames[:n], dil[:n], feather_px, keep_unmasked_original,
+                                            mask_bits=None if bits is None else bits[:n])            # K3
+        result = pipe.download(out)
+        if n < t:
+            result += pipe.download(inpainted[n:])
+        return result
 
 
 def run_infill_on_frames_chunked(frames_rgb, mask_frames, chunk=80, overlap=16, **kwargs):

@@ -17,13 +17,19 @@ from ._lib import lib
 PINNED_RESULT_LIMIT = 8 << 30
 
 
-def _ptr_array(frames, shape=None):
-    """Per-frame host pointers.  Returns (ctypes array, keep-alive list)."""
+def _ptr_array(frames, shape=None, is_mask=False):
+    """Per-frame host pointers.  Returns (ctypes array, keep-alive list).  Masks that are not uint8 are
+    binarised on their own dtype first (the reference tests ``m > 0`` before any cast, diffuerase.py:29:
+    a float mask in (0,1) or an int16 value of 256 must stay "set")."""
     keep = []
     arr = (ctypes.c_void_p * len(frames))()
     for i, f in enumerate(frames):
-        a = f if (isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.flags.c_contiguous) else \
-            np.ascontiguousarray(f, dtype=np.uint8)
+        if isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.flags.c_contiguous:
+            a = f
+        elif is_mask and np.asarray(f).dtype != np.uint8:
+            a = np.ascontiguousarray(np.asarray(f) > 0, dtype=np.uint8)
+        else:
+            a = np.ascontiguousarray(f, dtype=np.uint8)
         if shape is not None and tuple(a.shape) != tuple(shape):
             raise ValueError("frame %d has shape %s, expected %s" % (i, a.shape, tuple(shape)))
         keep.append(a)
@@ -75,7 +81,7 @@ class HostPipeline:
         h0, w0 = self.geometry
         c = 1 if mask_frames[0].ndim == 2 else mask_frames[0].shape[2]
         shape = (h0, w0) if mask_frames[0].ndim == 2 else (h0, w0, c)
-        src, keep = _ptr_array(mask_frames, shape)
+        src, keep = _ptr_array(mask_frames, shape, is_mask=True)
         t = len(mask_frames)
         dil = pinned_frames(t, (h0, w0))
         dptr, _ = _ptr_array(dil)
@@ -106,9 +112,40 @@ class HostPipeline:
         h, w = inpainted[0].shape[:2]
         iptr, k1 = _ptr_array(inpainted, (h, w, 3))
         optr, k2 = _ptr_array(orig, (h0, w0, 3)) if keep_unmasked_original else (None, None)
-        mptr, k3 = _ptr_array(dilated, (h0, w0)) if (dilated is not None and keep_unmasked_original) else (None, None)
+        mptr, k3 = _ptr_array(dilated, (h0, w0), is_mask=True) if (dilated is not None and keep_unmasked_original) \
+            else (None, None)
         out = pinned_frames(t, (h0, w0, 3))
         _lib.check(lib.vv_pipeline_post(self._h, iptr, int(h), int(w), optr, mptr, t, float(feather_px),
                                         1 if keep_unmasked_original else 0, _ptr_array(out)[0]), "vv_pipeline_post")
         del k1, k2, k3
+        return out
+
+    # ---- device-resident clips (wrappers.py): lists of host frames <-> one contiguous device tensor
+    def upload(self, frames, shape, out=None, is_mask=False):
+        """List of host arrays of ``shape`` -> u8 device tensor [T, *shape].  The copies are ordered before
+        whatever is enqueued on the current torch stream afterwards; page-locked sources are read by DMA
+        asynchronously, so the list must stay alive until that stream has been synchronised."""
+        t = len(frames)
+        src, keep = _ptr_array(frames, shape, is_mask=is_mask)
+        nbytes = int(np.prod(shape))
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((t,) + tuple(shape), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.vv_pipeline_upload(self._h, src, t, nbytes, ctypes.c_void_p(out.data_ptr()),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                       "vv_pipeline_upload")
+        self._inflight = keep        # keep converted copies alive until the next call
+        return out
+
+    def download(self, tensor):
+        """u8 device tensor [T, ...] -> list of T host arrays (page-locked when the budget allows); waits for
+        the work enqueued on the current torch stream."""
+        t = tensor.shape[0]
+        shape = tuple(tensor.shape[1:])
+        out = pinned_frames(t, shape)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.vv_pipeline_download(self._h, ctypes.c_void_p(tensor.data_ptr()), t, int(np.prod(shape)),
+                                                _ptr_array(out)[0],
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                       "vv_pipeline_download")
         return out

@@ -45,9 +45,11 @@ def inference_size(h0, w0, max_img_size=960):
     return h.value, w.value
 
 
-def binarize_dilate(mask, iterations=8, lowres_size=None):
+def binarize_dilate(mask, iterations=8, lowres_size=None, return_bits=False):
     """K1.  mask u8 [T,H,W,C] (or [T,H,W]) -> u8 [T,H,W] in {0,255}   (diffuerase.py:28-31).
-    With ``lowres_size=(h, w)`` also returns the INTER_NEAREST down-sized mask [T,h,w]."""
+    With ``lowres_size=(h, w)`` also returns the INTER_NEAREST down-sized mask [T,h,w].
+    ``return_bits=True`` returns ``(out, low_or_None, bits)`` where ``bits`` is the dilated mask as the 1-bit
+    plane i32 [T,H,ceil(W/32)] the pass computes anyway (``upscale_feather_composite(mask_bits=...)``)."""
     if mask.dim() == 3:
         mask = mask.unsqueeze(-1)
     _require_cuda(mask)
@@ -61,10 +63,13 @@ def binarize_dilate(mask, iterations=8, lowres_size=None):
         if lowres_size is not None:
             lh, lw = int(lowres_size[0]), int(lowres_size[1])
             low = torch.empty((t, lh, lw), dtype=torch.uint8, device=mask.device)
+        bits = torch.empty((t, h, (w + 31) // 32), dtype=torch.int32, device=mask.device) if return_bits else None
         nbytes = lib.vv_binarize_dilate_workspace_bytes(t, h, w)
         ws = _ws(nbytes, mask.device)
-        _lib.check(lib.vv_binarize_dilate(_ptr(mask), t, h, w, c, int(iterations), _ptr(out), _ptr(low), lh, lw,
-                                          _ptr(ws), nbytes, _stream()), "vv_binarize_dilate")
+        _lib.check(lib.vv_binarize_dilate_ex(_ptr(mask), t, h, w, c, int(iterations), _ptr(out), _ptr(low), lh, lw,
+                                             _ptr(bits), _ptr(ws), nbytes, _stream()), "vv_binarize_dilate")
+    if return_bits:
+        return out, low, bits
     return out if low is None else (out, low)
 
 
@@ -86,10 +91,11 @@ def resize(src, h, w, interpolation=INTER_LINEAR):
     return dst.squeeze(-1) if squeeze else dst
 
 
-def upscale_feather_composite(inpainted, orig, mask, feather_px=3, keep_unmasked_original=True, out=None):
+def upscale_feather_composite(inpainted, orig, mask, feather_px=3, keep_unmasked_original=True, out=None, mask_bits=None):
     """K3.  inpainted u8 [T,h,w,3], orig u8 [T,H0,W0,3], mask u8 [T,H0,W0] -> u8 [T,H0,W0,3]
-    (diffuerase.py:70-112 applied to every frame)."""
-    _require_cuda(inpainted, orig, mask)
+    (diffuerase.py:70-112 applied to every frame).  ``mask_bits``: the same mask as K1's 1-bit plane
+    (``binarize_dilate(return_bits=True)``); kernels that can use it skip the u8 mask."""
+    _require_cuda(inpainted, orig, mask, mask_bits)
     t, h, w, _ = inpainted.shape
     if keep_unmasked_original:
         if orig is None or mask is None:
@@ -97,6 +103,8 @@ def upscale_feather_composite(inpainted, orig, mask, feather_px=3, keep_unmasked
         h0, w0 = orig.shape[1:3]
         if tuple(mask.shape) != (t, h0, w0) or orig.shape[0] != t:
             raise ValueError("upscale_feather_composite: shape mismatch")
+        if mask_bits is not None and (tuple(mask_bits.shape) != (t, h0, (w0 + 31) // 32) or mask_bits.dtype != torch.int32):
+            raise ValueError("upscale_feather_composite: mask_bits must be int32 [T,H0,ceil(W0/32)]")
     else:
         h0, w0 = (orig.shape[1:3] if orig is not None else mask.shape[1:3])
     with torch.cuda.device(inpainted.device):
@@ -104,10 +112,11 @@ def upscale_feather_composite(inpainted, orig, mask, feather_px=3, keep_unmasked
             out = torch.empty((t, h0, w0, 3), dtype=torch.uint8, device=inpainted.device)
         nbytes = lib.vv_composite_workspace_bytes(h0, w0)
         ws = _ws(nbytes, inpainted.device)
-        _lib.check(lib.vv_upscale_feather_composite(
+        _lib.check(lib.vv_upscale_feather_composite_bits(
             _ptr(inpainted), t, h, w, _ptr(orig) if keep_unmasked_original else None,
-            _ptr(mask) if keep_unmasked_original else None, h0, w0, float(feather_px),
-            1 if keep_unmasked_original else 0, _ptr(out), _ptr(ws), nbytes, _stream()), "vv_upscale_feather_composite")
+            _ptr(mask) if keep_unmasked_original else None, _ptr(mask_bits) if keep_unmasked_original else None,
+            h0, w0, float(feather_px), 1 if keep_unmasked_original else 0, _ptr(out), _ptr(ws), nbytes, _stream()),
+            "vv_upscale_feather_composite")
     return out
 
 
@@ -124,30 +133,35 @@ def subvideo_plan(video_length, subvideo_length=50, pad_len=10):
     return plan
 
 
-def propagate(frames, masks, flows_f, flows_b, subvideo_length=50, pad_len=10, keep_pads=False):
+def propagate(frames, masks, flows_f, flows_b, subvideo_length=50, pad_len=10, keep_pads=False, out=None):
     """K4.  frames u8 [N,h,w,3], masks u8 [N,h,w] (>0 = hole), flows f32 [N-1,h,w,2] ->
-    packed u32 [N,h,w] (R | G<<8 | B<<16 | state<<24) of the forward propagation pass, pad
-    frames of every sub-video window discarded (``keep_pads=True`` returns the raw windows)."""
-    _require_cuda(frames, masks, flows_f, flows_b)
+    packed u32 [N,h,w] (R | G<<8 | B<<16 | state<<24) of the forward propagation pass.  The pad
+    frames of every sub-video window are discarded like upstream does: the kernels keep their state
+    in the workspace and write the kept frames straight into the [N,h,w] result
+    (``keep_pads=True`` returns the raw windows, pads included, concatenated)."""
+    _require_cuda(frames, masks, flows_f, flows_b, out)
     n, h, w, _ = frames.shape
     plan = subvideo_plan(n, subvideo_length, pad_len)
-    starts = (ctypes.c_int * len(plan))(*[p[0] for p in plan])
-    lens = (ctypes.c_int * len(plan))(*[p[1] - p[0] for p in plan])
+    ints = lambda v: (ctypes.c_int * len(plan))(*v)
+    starts, lens = ints([p[0] for p in plan]), ints([p[1] - p[0] for p in plan])
     total = sum(p[1] - p[0] for p in plan)
+    if keep_pads:
+        kstart = klen = None
+        n_out = total
+    else:
+        kstart, klen = ints([p[2] for p in plan]), ints([p[1] - p[0] - p[2] - p[3] for p in plan])
+        n_out = n
     with torch.cuda.device(frames.device):
-        out = torch.empty((total, h, w), dtype=torch.int32, device=frames.device)
-        nbytes = lib.vv_propagate_workspace_bytes(total, h, w)
+        if out is None:
+            out = torch.empty((n_out, h, w), dtype=torch.int32, device=frames.device)
+        elif tuple(out.shape) != (n_out, h, w) or out.dtype != torch.int32:
+            raise ValueError("propagate: out must be int32 [%d,%d,%d]" % (n_out, h, w))
+        nbytes = lib.vv_propagate_workspace_bytes(total, total - n_out, h, w)
         ws = _ws(nbytes, frames.device)
         _lib.check(lib.vv_propagate(_ptr(frames), _ptr(masks), _ptr(flows_f) if n > 1 else None,
-                                    _ptr(flows_b) if n > 1 else None, n, h, w, starts, lens, len(plan), _ptr(out),
-                                    _ptr(ws), nbytes, _stream()), "vv_propagate")
-        if keep_pads or len(plan) == 1:
-            return out
-        keep, off = [], 0
-        for s_f, e_f, ps, pe in plan:
-            keep.append(out[off + ps: off + (e_f - s_f) - pe])
-            off += e_f - s_f
-        return torch.cat(keep)
+                                    _ptr(flows_b) if n > 1 else None, n, h, w, starts, lens, kstart, klen, len(plan),
+                                    _ptr(out), _ptr(ws), nbytes, _stream()), "vv_propagate")
+    return out
 
 
 def propagate_unpack(packed, zero_level=127):
@@ -246,3 +260,46 @@ def propagate_to_float(packed, want_mask=True):
         _lib.check(lib.vv_propagate_to_float(_ptr(packed), n, h, w, _ptr(rgb), _ptr(hole), _stream()),
                    "vv_propagate_to_float")
     return (rgb, hole) if want_mask else rgb
+
+
+def neighbor_merge(pred, mask, ori, comp, first):
+    """N2.  One sliding window of the ProPainter network output merged into the running result, in place:
+    pred f32 [L,3,h,w] in [-1,1], mask u8 [L,h,w] (>0 = masked), ori / comp u8 [L,h,w,3];
+    ``first[l]`` = frame l has not been composed before (then comp = img, else the 0.5 / 0.5 average)."""
+    _require_cuda(pred, mask, ori, comp)
+    l, c, h, w = pred.shape
+    if c != 3 or pred.dtype != torch.float32 or tuple(mask.shape) != (l, h, w) or tuple(ori.shape) != (l, h, w, 3) \
+            or tuple(comp.shape) != (l, h, w, 3) or len(first) != l:
+        raise ValueError("neighbor_merge: pred f32 [L,3,h,w], mask u8 [L,h,w], ori / comp u8 [L,h,w,3], first [L]")
+    if mask.dtype != torch.uint8 or ori.dtype != torch.uint8 or comp.dtype != torch.uint8:
+        raise ValueError("neighbor_merge: uint8 tensors required")
+    bits = sum(1 << i for i, f in enumerate(first) if f)
+    with torch.cuda.device(pred.device):
+        _lib.check(lib.vv_neighbor_merge(_ptr(pred), _ptr(mask), _ptr(ori), _ptr(comp), l, h, w, bits, _stream()),
+                   "vv_neighbor_merge")
+    return comp
+
+
+def apply_mask(frames, mask, out=None):
+    """N4.  frames u8 [T,h,w,3] with the pixels of mask u8 [T,h,w] > 0 set to zero (frame * (1 - m))."""
+    _require_cuda(frames, mask, out)
+    t, h, w, c = frames.shape
+    if c != 3 or tuple(mask.shape) != (t, h, w) or frames.dtype != torch.uint8 or mask.dtype != torch.uint8:
+        raise ValueError("apply_mask: frames u8 [T,h,w,3], mask u8 [T,h,w]")
+    with torch.cuda.device(frames.device):
+        if out is None:
+            out = torch.empty_like(frames)
+        _lib.check(lib.vv_apply_mask(_ptr(frames), _ptr(mask), t, h, w, _ptr(out), _stream()), "vv_apply_mask")
+    return out
+
+
+def swap_rb(frames, out=None):
+    """N1.  BGR <-> RGB on u8 [...,3] (tools.py:21 / :43); ``out`` may be ``frames`` itself."""
+    _require_cuda(frames, out)
+    if frames.dtype != torch.uint8 or frames.shape[-1] != 3:
+        raise ValueError("swap_rb: uint8 [...,3] required")
+    with torch.cuda.device(frames.device):
+        if out is None:
+            out = torch.empty_like(frames)
+        _lib.check(lib.vv_swap_rb(_ptr(frames), _ptr(out), frames.numel() // 3, _stream()), "vv_swap_rb")
+    return out
