@@ -698,7 +698,7 @@ template <bool VX2, bool BITS>
 __global__ void __launch_bounds__(K3F_THREADS, 2)
     k3_fast(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ mask,
             const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ yt, int h, int w,
-            int H0, int W0, int strips_per_frame, int th, int rpt, float div, float one) {
+            int H0, int W0, int th, int rpt, float div, float one) {
     extern __shared__ __align__(128) uint32_t smem_base[];
     const int strip_words = (th * W0 * 3) / 4;
     uint8_t *strip = reinterpret_cast<uint8_t *>(smem_base);
@@ -713,8 +713,8 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     (void)Wp;
 
-    const long long t = blockIdx.x / strips_per_frame;
-    const int y0 = (blockIdx.x % strips_per_frame) * th;
+    const long long t = blockIdx.y;                  // grid = (strips, frames): no division
+    const int y0 = (int)blockIdx.x * th;
     const uint8_t *orig_t = orig + t * H0 * (long long)W0 * 3;
     uint8_t *out_t = out + t * H0 * (long long)W0 * 3;
     const uint32_t strip_bytes = (uint32_t)(min(th, H0 - y0) * W0 * 3);
@@ -728,20 +728,24 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
     }
 
     // ---------------- phase 1: bit rows [y0 - 2, y0 + th + 2), one zero pad word on each side
-    for (int i = warp; i < rows_s; i += K3F_THREADS / 32) {
-        const int y = y0 - 2 + i;
-        const bool row_ok = y >= 0 && y < H0;
-        if (BITS) {
+    if (BITS) {
+        for (int i = warp; i < rows_s; i += K3F_THREADS / 32) {
+            const int y = y0 - 2 + i;
+            const bool row_ok = y >= 0 && y < H0;
             const uint32_t *src = mask_bits + (t * H0 + y) * (long long)Wpc;
             for (int k = lane; k < row_words; k += 32)
                 bits[i * row_words + k] = (row_ok && k >= 1 && k <= Wpc) ? __ldg(src + (k - 1)) : 0u;
-        } else {
-            uint16_t *b16 = reinterpret_cast<uint16_t *>(bits + i * row_words);
-            const uint8_t *src = mask + (t * H0 + y) * (long long)W0;
-            for (int k = lane; k < 2 * row_words; k += 32) {
-                const int x0 = (k - 2) * 16;
-                b16[k] = (row_ok && x0 >= 0 && x0 < W0) ? (uint16_t)nonzero_bits16(ldg128(src + x0)) : (uint16_t)0;
-            }
+        }
+    } else {
+        uint16_t *b16 = reinterpret_cast<uint16_t *>(bits);
+        const int halves = 2 * row_words;
+        const uint8_t *mask_t = mask + t * H0 * (long long)W0;
+        for (int id = threadIdx.x; id < rows_s * halves; id += K3F_THREADS) {
+            const int i = id / halves, hw = id - i * halves;
+            const int y = y0 - 2 + i, x0 = (hw - 2) * 16;
+            uint32_t v = 0;
+            if (y >= 0 && y < H0 && x0 >= 0 && x0 < W0) v = nonzero_bits16(ldg128(mask_t + (long long)y * W0 + x0));
+            b16[id] = (uint16_t)v;
         }
     }
     if (threadIdx.x < 16) {
@@ -784,8 +788,16 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
         }
         uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
         const uint32_t o0 = sp[0], o1 = sp[1], o2 = sp[2];
-        const float4 l0 = lut[item.y & 15u], l1 = lut[(item.y >> 4) & 15u], l2 = lut[(item.y >> 8) & 15u],
-                     l3 = lut[(item.y >> 12) & 15u];
+        // item.y = plane nibbles of the quad: L0 @ bits 0-3, L2 @ 4-7, L1 @ 16-19, inside @ 20-23 (bit i = pixel i).
+        // LUT byte offset of pixel i = 16 * (L0 | L1 << 1 | L2 << 2 | inside << 3): one multiply gathers the four
+        // bits (0x140028 = 2^20 + 2^18 + 2^5 + 2^3 sends bits 0, 16, 4, 20 to bits 20..23; no two partial products
+        // share a bit position, so there are no carries).
+        const uint8_t *lutb = reinterpret_cast<const uint8_t *>(lut);
+        auto lut_at = [&](int i) {
+            const uint32_t tsel = (item.y >> i) & 0x00110011u;
+            return *reinterpret_cast<const float4 *>(lutb + (((tsel * 0x140028u) >> 16) & 0xf0u));
+        };
+        const float4 l0 = lut_at(0), l1 = lut_at(1), l2 = lut_at(2), l3 = lut_at(3);
         uint32_t ma[6], mb[6], up[6];
         x2_hpass(a0, a1, a2, ma);
         x2_hpass(b0, b1, b2, mb);
@@ -841,10 +853,13 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
     for (int step = 0; step <= n_steps; ++step) {
         const bool drain = step == n_steps;
         uint32_t need = 0, L0 = 0, L1 = 0, L2 = 0, M2 = 0;
-        const int r = r0 + j;
+        int r = 0;
         if (!drain) {
             if (j == 0) {                                                    // new task: (column group, row block)
-                const int id = it * K3F_THREADS + (int)threadIdx.x;
+                // Each warp's 32 lanes sample the strip evenly (8 runs of 4 consecutive tasks, 64 tasks apart), so that
+                // the warps of a CTA get the same amount of blend work whatever the mask looks like: they all meet
+                // at the final barrier, and ncu showed barrier stalls on top when a warp owned 512 contiguous pixels.
+                const int id = it * K3F_THREADS + ((lane >> 2) << 6) + (warp << 2) + (lane & 3);
                 task_ok = id < n_tasks;
                 const int rbk = task_ok ? id / G : 0, g = task_ok ? id - rbk * G : 0;
                 r0 = rbk * rpt, c0 = g * 16 - 8, xbase = (uint32_t)(g * 16);
@@ -859,6 +874,7 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
                 }
             }
             const int rr = r0 + j;
+            r = rr;
 #pragma unroll
             for (int d = 0; d < 4; ++d) Mw[d] = Mw[d + 1], Zw[d] = Zw[d + 1];
             {
@@ -912,20 +928,17 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
             qcount += __shfl_sync(0xffffffffu, pre, 31);
             if (need) {
                 const uint32_t xr = xbase | ((uint32_t)r << 16);
+                // plane nibbles of the four quads (the pixels of the group are bits 8..23 = bytes 1, 2 of each plane):
+                //   W = [L0 px 0..15 | L1 px 0..15], V = [L2 | inside];  E / O interleave the nibbles of the even / odd
+                //   quads as bytes [L0q L2q] ... [L1q Mq], and one byte permute per quad isolates its two bytes
+                const uint32_t W = __byte_perm(L0, L1, 0x6521), V = __byte_perm(L2, M2, 0x6521);
+                const uint32_t E = (W & 0x0f0f0f0fu) | ((V << 4) & 0xf0f0f0f0u);
+                const uint32_t O = ((W >> 4) & 0x0f0f0f0fu) | (V & 0xf0f0f0f0u);
+                const uint32_t yq[4] = {__byte_perm(E, 0u, 0x4240), __byte_perm(O, 0u, 0x4240), __byte_perm(E, 0u, 0x4341),
+                                        __byte_perm(O, 0u, 0x4341)};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if ((nzq >> (4 * q)) & 1u) {
-                        const int b = 8 + 4 * q;
-                        // 4x4 bit transpose: planes (l0, l1, l2, inside) x pixels -> one LUT index nibble per pixel
-                        uint32_t x4 = ((L0 >> b) & 15u) | (((L1 >> b) & 15u) << 4) | (((L2 >> b) & 15u) << 8) |
-                                      (((M2 >> b) & 15u) << 12);
-                        uint32_t tt = (x4 ^ (x4 >> 3)) & 0x0a0au;
-                        x4 ^= tt ^ (tt << 3);
-                        tt = (x4 ^ (x4 >> 6)) & 0x00ccu;
-                        x4 ^= tt ^ (tt << 6);
-                        queue[pos++] = make_uint2(xr + 4u * q, x4);
-                    }
-                }
+                for (int q = 0; q < 4; ++q)
+                    if ((nzq >> (4 * q)) & 1u) queue[pos++] = make_uint2(xr + 4u * q, yq[q]);
             }
             __syncwarp();
         }
@@ -1109,8 +1122,6 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         }
         if (fth >= 2) {
             const int fstrips = ceil_div(H0, fth);
-            const long long fgrid = (long long)T * fstrips;
-            VV_CHECK_ARG(fgrid < 2147483647LL, "vv_upscale_feather_composite: too many strips");
             const bool vx2 = H0 == 2 * h;
             const bool bits = mask_bits != nullptr && get_option(OPT_K3_BITS) != 0;
             // rows per classification task: 4 when that still gives most threads a task, else 2
@@ -1121,8 +1132,15 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
     do {                                                                                                        \
         auto kfn = k3_fast<V, B>;                                                                               \
         VV_K3_SMEM(kfn);                                                                                        \
-        kfn<<<(unsigned)fgrid, K3F_THREADS, smem, st>>>(inp, orig, mask, mask_bits, out, yt, h, w, H0, W0, fstrips, fth,  \
-                                                        rpt, ft.div, 1.0f);                                     \
+        for (int t0 = 0; t0 < T; t0 += 32768) {        /* grid.y <= 65535 frames per launch */                  \
+            const int tn = min(32768, T - t0);                                                                  \
+            const size_t fo = (size_t)t0 * H0 * W0;                                                             \
+            kfn<<<dim3((unsigned)fstrips, (unsigned)tn), K3F_THREADS, smem, st>>>(                              \
+                inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo,                                         \
+                mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : nullptr, out + fo * 3, yt, h, w, H0, W0, fth, rpt, \
+                ft.div, 1.0f);                                                                                  \
+            VV_POST_LAUNCH("k3_fast");                                                                          \
+        }                                                                                                       \
     } while (0)
             if (vx2 && bits)
                 VV_K3_FAST(true, true);
@@ -1133,7 +1151,6 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
             else
                 VV_K3_FAST(false, false);
 #undef VV_K3_FAST
-            VV_POST_LAUNCH("k3_fast");
             return VV_OK;
         }
     }
