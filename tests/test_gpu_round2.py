@@ -88,6 +88,12 @@ def test_k3_fast_kernel(ops, h0, w0, h, w, f):
             _lib.set_option("k3_nt", rpt)
             variants["rpt%d" % rpt] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
         _lib.set_option("k3_nt", 2)
+        for thr, rows in ((256, 16), (256, 6), (512, 5)):
+            _lib.set_option("k3_tma_threads", thr)
+            _lib.set_option("k3_tma_rows", rows)
+            variants["threads%d-rows%d" % (thr, rows)] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
+        _lib.set_option("k3_tma_threads", 512)
+        _lib.set_option("k3_tma_rows", 16)
         _lib.set_option("k3_bits", 0)
         variants["bits-ignored"] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
         _lib.set_option("k3_bits", 1)
@@ -99,6 +105,8 @@ def test_k3_fast_kernel(ops, h0, w0, h, w, f):
         _lib.set_option("k3_nt", 2)
         _lib.set_option("k3_bits", 1)
         _lib.set_option("k3_x2", 2)
+        _lib.set_option("k3_tma_threads", 512)
+        _lib.set_option("k3_tma_rows", 16)
     assert np.array_equal(got, ref)
     assert np.array_equal(got_bits, ref)
     for name, v in variants.items():

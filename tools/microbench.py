@@ -107,6 +107,15 @@ def main():
         _lib.set_option("k3_tma_rows", rows)
         report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1, rows=rows)
     _lib.set_option("k3_tma_rows", 16)
+    _lib.set_option("k3_tma_threads", 256)
+    for rows in (16, 6, 7, 8):
+        _lib.set_option("k3_tma_rows", rows)
+        report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1, rows=rows, threads=256)
+    _lib.set_option("k3_tma_rows", 6)
+    report("K3 composite (full mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out, mask_bits=full_bits), k3_x2=2, bits=1, rows=6, threads=256)
+    report("K3 composite (box mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, box_dil, 3, out=out, mask_bits=box_bits), k3_x2=2, bits=1, rows=6, threads=256)
+    _lib.set_option("k3_tma_rows", 16)
+    _lib.set_option("k3_tma_threads", 512)
     inp536 = inp[:, :536].contiguous()
     report("K3 composite 960x536 (synthetic mask)", t * (7 * px + 3 * 536 * 960),
            lambda: ops.upscale_feather_composite(inp536, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1)

@@ -694,29 +694,36 @@ __device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
 constexpr int K3F_THREADS = 512;
 constexpr int K3F_QCAP = 128 + 32;      // one classified row of the warp (32 lanes x 4 quads) + carried-over items
 
-template <bool VX2, bool BITS>
-__global__ void __launch_bounds__(K3F_THREADS, 2)
+// Geometry the host resolves once per call (kernel-parameter constant bank: no per-CTA index arithmetic).
+struct FastGeom {
+    int h, w, H0, W0, th, rpt;
+    int Wpc, row_words, rows_s;          // mask words per frame row; per shared-memory bit row (+2 pad words); bit rows
+    int bits_off, lut_off, queue_off;    // word offsets inside dynamic shared memory (after the strip)
+    int G, n_tasks, n_steps;
+    long long frame_bytes, mask_frame_bytes, inp_frame_bytes, bits_frame_words;
+    float div, one;
+};
+
+template <bool VX2, bool BITS, int NTH>
+__global__ void __launch_bounds__(NTH, 1024 / NTH)
     k3_fast(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ mask,
-            const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ yt, int h, int w,
-            int H0, int W0, int th, int rpt, float div, float one) {
+            const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ yt,
+            const __grid_constant__ FastGeom gm) {
     extern __shared__ __align__(128) uint32_t smem_base[];
-    const int strip_words = (th * W0 * 3) / 4;
+    const int h = gm.h, w = gm.w, H0 = gm.H0, W0 = gm.W0, th = gm.th, rpt = gm.rpt;
+    const int Wpc = gm.Wpc, row_words = gm.row_words, rows_s = gm.rows_s;
+    const float div = gm.div, one = gm.one;
     uint8_t *strip = reinterpret_cast<uint8_t *>(smem_base);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_base + strip_words);
-    const int Wp = W0 >> 5;                     // W0 % 16 == 0; a trailing half word is covered by row_words
-    const int Wpc = (W0 + 31) >> 5;
-    const int row_words = Wpc + 2;
-    const int rows_s = th + 4;
-    uint32_t *bits = smem_base + strip_words + 4;                                   // [rows_s][row_words]
-    float4 *lut = reinterpret_cast<float4 *>(smem_base + ((strip_words + 4 + rows_s * row_words + 3) & ~3));   // {a, a, 1-a, 1-a}
-    uint2 *queue = reinterpret_cast<uint2 *>(lut + 16) + (threadIdx.x >> 5) * K3F_QCAP;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_base + gm.bits_off - 4);
+    uint32_t *bits = smem_base + gm.bits_off;                                       // [rows_s][row_words]
+    float4 *lut = reinterpret_cast<float4 *>(smem_base + gm.lut_off);               // {a, a, 1-a, 1-a} x 16, then lut_pos
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    (void)Wp;
+    uint2 *queue = reinterpret_cast<uint2 *>(smem_base + gm.queue_off) + warp * K3F_QCAP;
 
     const long long t = blockIdx.y;                  // grid = (strips, frames): no division
     const int y0 = (int)blockIdx.x * th;
-    const uint8_t *orig_t = orig + t * H0 * (long long)W0 * 3;
-    uint8_t *out_t = out + t * H0 * (long long)W0 * 3;
+    const uint8_t *orig_t = orig + t * gm.frame_bytes;
+    uint8_t *out_t = out + t * gm.frame_bytes;
     const uint32_t strip_bytes = (uint32_t)(min(th, H0 - y0) * W0 * 3);
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -729,18 +736,18 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
 
     // ---------------- phase 1: bit rows [y0 - 2, y0 + th + 2), one zero pad word on each side
     if (BITS) {
-        for (int i = warp; i < rows_s; i += K3F_THREADS / 32) {
+        for (int i = warp; i < rows_s; i += NTH / 32) {
             const int y = y0 - 2 + i;
             const bool row_ok = y >= 0 && y < H0;
-            const uint32_t *src = mask_bits + (t * H0 + y) * (long long)Wpc;
+            const uint32_t *src = mask_bits + t * gm.bits_frame_words + (long long)y * Wpc;
             for (int k = lane; k < row_words; k += 32)
                 bits[i * row_words + k] = (row_ok && k >= 1 && k <= Wpc) ? __ldg(src + (k - 1)) : 0u;
         }
     } else {
         uint16_t *b16 = reinterpret_cast<uint16_t *>(bits);
         const int halves = 2 * row_words;
-        const uint8_t *mask_t = mask + t * H0 * (long long)W0;
-        for (int id = threadIdx.x; id < rows_s * halves; id += K3F_THREADS) {
+        const uint8_t *mask_t = mask + t * gm.mask_frame_bytes;
+        for (int id = threadIdx.x; id < rows_s * halves; id += NTH) {
             const int i = id / halves, hw = id - i * halves;
             const int y = y0 - 2 + i, x0 = (hw - 2) * 16;
             uint32_t v = 0;
@@ -748,25 +755,25 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
             b16[id] = (uint16_t)v;
         }
     }
-    if (threadIdx.x < 16) {
+    if (warp == 0) {
         // alpha levels: index = class (0 = no hit within the window, 1..5 = cost classes 1, 1.4, 2, 2.1969, 2.8) | inside << 3
-        const float cost[6] = {8192.f, 1.0f, 1.4f, 2.0f, 2.1969f, __fadd_rn(1.4f, 1.4f)};
-        const int cls = threadIdx.x & 7, inside = threadIdx.x >> 3;
+        const int cls = lane & 7, inside = (lane >> 3) & 1;
+        const float cost = cls == 1 ? 1.0f : cls == 2 ? 1.4f : cls == 3 ? 2.0f : cls == 4 ? 2.1969f : __fadd_rn(1.4f, 1.4f);
         float a = inside ? 1.f : 0.f;
-        if (cls <= 5) a = inside ? alpha_from(cost[cls], 0.f, div) : alpha_from(0.f, cost[cls], div);
+        if (cls >= 1 && cls <= 5) a = inside ? alpha_from(cost, 0.f, div) : alpha_from(0.f, cost, div);
         const float na = __fsub_rn(1.f, a);
-        lut[threadIdx.x] = make_float4(a, a, na, na);
+        if (lane < 16) lut[lane] = make_float4(a, a, na, na);
+        const uint32_t posmask = __ballot_sync(0xffffffffu, lane < 16 && a > 0.f);     // which LUT levels have alpha > 0
+        if (lane == 0) reinterpret_cast<uint32_t *>(lut + 16)[0] = posmask;
     }
     __syncthreads();
 
-    uint32_t lut_pos = 0;          // which LUT levels have alpha > 0
-#pragma unroll
-    for (int k = 0; k < 16; ++k) lut_pos |= (uint32_t)(lut[k].x > 0.f) << k;
+    const uint32_t lut_pos = reinterpret_cast<const uint32_t *>(lut + 16)[0];
     // outside classes 1..5 that still blend (alpha > 0), as masks applied to p1..p5
     const uint32_t e1 = (lut_pos >> 1) & 1u ? ~0u : 0u, e2 = (lut_pos >> 2) & 1u ? ~0u : 0u, e3 = (lut_pos >> 3) & 1u ? ~0u : 0u,
                    e4 = (lut_pos >> 4) & 1u ? ~0u : 0u, e5 = (lut_pos >> 5) & 1u ? ~0u : 0u;
 
-    const uint8_t *inp_t = inp + t * h * (long long)w * 3;
+    const uint8_t *inp_t = inp + t * gm.inp_frame_bytes;
     const f32x2 one2 = pack2(one, one), magic2 = pack2(12582912.f, 12582912.f), unbias2 = pack2(-8388608.f, -8388608.f);
 
     // ---- phase 3 worker: one 4-pixel quad per lane
@@ -840,10 +847,7 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
     // ---------------- phase 2: classification, rolling over `rpt` rows per thread
     // One flat, rolled loop (a step = one row of every thread's task) so that the classification and the worker
     // exist once in the instruction stream; the last step only drains the queue.
-    const int G = W0 >> 4;
-    const int RB = (th + rpt - 1) / rpt;
-    const int n_tasks = G * RB;
-    const int n_steps = ((n_tasks + K3F_THREADS - 1) / K3F_THREADS) * rpt;
+    const int G = gm.G, n_tasks = gm.n_tasks, n_steps = gm.n_steps;
     int qcount = 0, it = 0, j = 0;
     bool landed = false, task_ok = false;
     int c0 = 0, r0 = 0;
@@ -856,10 +860,10 @@ __global__ void __launch_bounds__(K3F_THREADS, 2)
         int r = 0;
         if (!drain) {
             if (j == 0) {                                                    // new task: (column group, row block)
-                // Each warp's 32 lanes sample the strip evenly (8 runs of 4 consecutive tasks, 64 tasks apart), so that
+                // Each warp's 32 lanes sample the strip evenly (8 runs of 4 consecutive tasks, NTH / 8 tasks apart), so that
                 // the warps of a CTA get the same amount of blend work whatever the mask looks like: they all meet
                 // at the final barrier, and ncu showed barrier stalls on top when a warp owned 512 contiguous pixels.
-                const int id = it * K3F_THREADS + ((lane >> 2) << 6) + (warp << 2) + (lane & 3);
+                const int id = it * NTH + (lane >> 2) * (NTH / 8) + (warp << 2) + (lane & 3);
                 task_ok = id < n_tasks;
                 const int rbk = task_ok ? id / G : 0, g = task_ok ? id - rbk * G : 0;
                 r0 = rbk * rpt, c0 = g * 16 - 8, xbase = (uint32_t)(g * 16);
@@ -1114,42 +1118,70 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
     // ---- k3_fast: exact x2 horizontal up-scale, feather radius <= 2, TMA-able frames (the production geometry)
     const int x2opt = get_option(OPT_K3_X2);
     if (vec && small_r && x2opt >= 2 && get_option(OPT_K3_TMA) != 0 && W0 == 2 * w && W0 >= 8 && ((uintptr_t)inp % 4 == 0)) {
+        // dynamic shared memory (words): [strip][mbarrier 4][bit rows][pad to 4][lut 16 x float4 + lut_pos 4][queues]
         int fth = 0;
         size_t fsm = 0;
+        FastGeom gm = {};
+        // 512 threads x 2 CTAs per SM (default) or 256 threads x 4 CTAs per SM with shorter strips
+        const int nth = get_option(OPT_K3_TMA_THREADS) <= 256 ? 256 : 512;
+        const size_t smem_cap = nth == 256 ? 56 * 1024 : 113 * 1024;
         for (fth = min(16, max(2, get_option(OPT_K3_TMA_ROWS))); fth >= 2; --fth) {
-            fsm = (size_t)fth * W0 * 3 + 16 + ((size_t)(fth + 4) * (Wp + 2) + 3) * 4 + 256 + (K3F_THREADS / 32) * K3F_QCAP * 8;
-            if (fsm <= 113 * 1024) break;
+            gm.bits_off = fth * W0 * 3 / 4 + 4;
+            gm.lut_off = (gm.bits_off + (fth + 4) * (Wp + 2) + 3) & ~3;
+            gm.queue_off = gm.lut_off + 16 * 4 + 4;
+            fsm = ((size_t)gm.queue_off + (nth / 32) * K3F_QCAP * 2) * 4;
+            if (fsm <= smem_cap) break;
         }
         if (fth >= 2) {
             const int fstrips = ceil_div(H0, fth);
             const bool vx2 = H0 == 2 * h;
             const bool bits = mask_bits != nullptr && get_option(OPT_K3_BITS) != 0;
             // rows per classification task: 4 when that still gives most threads a task, else 2
-            int rpt = ((W0 / 16) * ceil_div(fth, 4) >= (K3F_THREADS * 7) / 10) ? 4 : 2;
+            int rpt = 4;
+            for (int cand : {4, 3, 2})                      // fewest idle threads in the first pass over the tasks
+                if ((W0 / 16) * ceil_div(fth, cand) <= nth && (W0 / 16) * ceil_div(fth, cand) * 10 >= nth * 7) {
+                    rpt = cand;
+                    break;
+                }
+            if ((W0 / 16) * ceil_div(fth, 4) > nth) rpt = 4;
             if (get_option(OPT_K3_NT) > 2) rpt = min(16, get_option(OPT_K3_NT));      // A/B switch
             smem = fsm;
-#define VV_K3_FAST(V, B)                                                                                        \
+            gm.h = h, gm.w = w, gm.H0 = H0, gm.W0 = W0, gm.th = fth, gm.rpt = rpt;
+            gm.Wpc = Wp, gm.row_words = Wp + 2, gm.rows_s = fth + 4;
+            gm.G = W0 / 16, gm.n_tasks = gm.G * ceil_div(fth, rpt);
+            gm.n_steps = ceil_div(gm.n_tasks, nth) * rpt;
+            gm.frame_bytes = (long long)H0 * W0 * 3, gm.mask_frame_bytes = (long long)H0 * W0;
+            gm.inp_frame_bytes = (long long)h * w * 3, gm.bits_frame_words = (long long)H0 * Wp;
+            gm.div = ft.div, gm.one = 1.0f;
+#define VV_K3_FAST(V, B, N)                                                                                     \
     do {                                                                                                        \
-        auto kfn = k3_fast<V, B>;                                                                               \
+        auto kfn = k3_fast<V, B, N>;                                                                            \
         VV_K3_SMEM(kfn);                                                                                        \
         for (int t0 = 0; t0 < T; t0 += 32768) {        /* grid.y <= 65535 frames per launch */                  \
             const int tn = min(32768, T - t0);                                                                  \
             const size_t fo = (size_t)t0 * H0 * W0;                                                             \
-            kfn<<<dim3((unsigned)fstrips, (unsigned)tn), K3F_THREADS, smem, st>>>(                              \
+            kfn<<<dim3((unsigned)fstrips, (unsigned)tn), N, smem, st>>>(                                        \
                 inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo,                                         \
-                mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : nullptr, out + fo * 3, yt, h, w, H0, W0, fth, rpt, \
-                ft.div, 1.0f);                                                                                  \
+                mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : nullptr, out + fo * 3, yt, gm);                  \
             VV_POST_LAUNCH("k3_fast");                                                                          \
         }                                                                                                       \
     } while (0)
+#define VV_K3_FAST_N(V, B)        \
+    do {                          \
+        if (nth == 256)           \
+            VV_K3_FAST(V, B, 256); \
+        else                      \
+            VV_K3_FAST(V, B, 512); \
+    } while (0)
             if (vx2 && bits)
-                VV_K3_FAST(true, true);
+                VV_K3_FAST_N(true, true);
             else if (vx2)
-                VV_K3_FAST(true, false);
+                VV_K3_FAST_N(true, false);
             else if (bits)
-                VV_K3_FAST(false, true);
+                VV_K3_FAST_N(false, true);
             else
-                VV_K3_FAST(false, false);
+                VV_K3_FAST_N(false, false);
+#undef VV_K3_FAST_N
 #undef VV_K3_FAST
             return VV_OK;
         }
