@@ -62,12 +62,13 @@ def test_k1_returns_its_bit_plane(ops, h, w, n):
 
 # ------------------------------------------------------------------------------- k3_fast
 @pytest.mark.parametrize("h0,w0,h,w", [(120, 176, 60, 88), (120, 176, 56, 88), (16, 16, 8, 8), (66, 80, 33, 40),
-                                       (72, 128, 32, 64), (100, 96, 48, 48), (30, 48, 16, 24)])
+                                       (72, 128, 32, 64), (100, 96, 48, 48), (30, 48, 16, 24),
+                                       (72, 128, 20, 32), (40, 64, 10, 16), (135, 240, 33, 60), (64, 16, 16, 4)])
 @pytest.mark.parametrize("f", [3, 2.5, 1.5, 0.5])
 def test_k3_fast_kernel(ops, h0, w0, h, w, f):
-    """W0 == 2w takes k3_fast (closed-form horizontal pass; vertical closed form when H0 == 2h, table driven
-    otherwise - the 1080p <- 960x536 production case): same bytes as the oracle, as the older kernels, with
-    and without the 1-bit mask plane, for every rows-per-task setting."""
+    """W0 == 2w or 4w takes k3_fast (closed-form horizontal pass; vertical closed form when H0 == 2h, table driven
+    otherwise - the 1080p <- 960x536 and 4K <- 960x536 production cases): same bytes as the oracle, as the older
+    kernels, with and without the 1-bit mask plane, for every rows-per-task setting."""
     from videovanish_b200 import _lib
     t = 3
     fr = synth.frames(t, h0, w0, seed=61)

@@ -164,6 +164,54 @@ __device__ __forceinline__ uint32_t x2_vpass(uint32_t m_a, uint32_t m_b) {
     return ((m_a >> 2) + (((m_b * 3u) >> 2) & 0x3fff3fffu) + 0x00020002u) >> 2;
 }
 
+// ---- exact x4 horizontal up-scale (W0 == 4w: 4K <- 960 wide, BASELINE config 4) ---------------------------
+// OpenCV's horizontal taps are then (768,1280), (256,1792), (1792,256), (1280,768) of 2048 for the four pixels of
+// a quad = 256 * (3,5), (1,7), (7,1), (5,3): with A, B, C = source pixels i-1, i, i+1 (i = xq / 4, clamped at the
+// borders, which reproduces OpenCV's coefficient clamp) the horizontal pass is m = {3A+5B, A+7B, 7B+C, 5B+3C}
+// (exact: h >> 4 == 16 * m, m <= 2040).
+//
+// The 9 source bytes A0 A1 A2 B0 B1 B2 C0 C1 C2 of one row as [A0 A1 A2 B0] [B1 B2 C0 C1] [C2 . . .].
+__device__ __forceinline__ void x4_load_row(const uint8_t *__restrict__ rowp, int xq, int W0, uint32_t &r0, uint32_t &r1,
+                                            uint32_t &r2) {
+    const bool left = xq == 0, right = xq == W0 - 4;
+    const int i = xq >> 2;
+    const int bo = left ? 0 : 3 * i - 3;                  // left border: start at pixel 0 and duplicate it below
+    const int last = ((W0 >> 2) * 3 - 1) >> 2;            // last word of the row (row bytes = 3 * w, a multiple of 4)
+    const int wi = bo >> 2;
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(rowp);
+    const uint32_t w0 = __ldg(p + wi), w1 = __ldg(p + min(wi + 1, last)), w2 = __ldg(p + min(wi + 2, last));
+    const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(bo & 3);
+    const uint32_t s0 = __byte_perm(w0, w1, sel), s1 = __byte_perm(w1, w2, sel), s2 = __byte_perm(w2, 0u, sel);
+    r0 = s0, r1 = s1, r2 = s2;
+    if (left) {            // s = [B0 B1 B2 C0] [C1 C2 . .]  ->  A := B
+        r0 = __byte_perm(s0, 0u, 0x0210);
+        r1 = __byte_perm(s0, s1, 0x4321);
+        r2 = s1 >> 8;
+    }
+    if (right) {           // s = [A0 A1 A2 B0] [B1 B2 . .]  ->  C := B
+        r1 = __byte_perm(s0, s1, 0x4354);
+        r2 = s1 >> 8;
+    }
+}
+// m[j] holds channel values 2j (low lane) and 2j+1 (high lane) of the 12 output values (pixel k/3, channel k%3).
+__device__ __forceinline__ void x4_hpass(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t m[6]) {
+    const uint32_t e0 = __byte_perm(r0, 0, 0x4140), e1 = __byte_perm(r0, 0, 0x4342);   // (A0,A1) (A2,B0)
+    const uint32_t e2 = __byte_perm(r1, 0, 0x4140), e3 = __byte_perm(r1, 0, 0x4342);   // (B1,B2) (C0,C1)
+    const uint32_t e4 = __byte_perm(r2, 0, 0x4140);                                    // (C2, .)
+    const uint32_t b01 = __byte_perm(e1, e2, 0x5432);                                  // (B0,B1)
+    const uint32_t a12 = __byte_perm(e0, e1, 0x5432);                                  // (A1,A2)
+    const uint32_t c12 = __byte_perm(e3, e4, 0x5432);                                  // (C1,C2)
+    const uint32_t X = __byte_perm(e1, e0, 0x5410);                                    // (A2,A0)
+    const uint32_t Y = __byte_perm(e2, e1, 0x7632);                                    // (B2,B0)
+    const uint32_t Q = __byte_perm(e4, e3, 0x5410);                                    // (C2,C0)
+    m[0] = e0 * 3u + b01 * 5u;                                               // (3A0+5B0, 3A1+5B1)
+    m[1] = X + ((X & 0xffffu) << 1) + Y * 5u + ((Y & 0xffff0000u) << 1);     // (3A2+5B2,  A0+7B0)
+    m[2] = a12 + e2 * 7u;                                                    // ( A1+7B1,  A2+7B2)
+    m[3] = b01 * 7u + e3;                                                    // (7B0+C0,  7B1+C1)
+    m[4] = Y * 5u + ((Y & 0xffffu) << 1) + Q + ((Q & 0xffff0000u) << 1);     // (7B2+C2,  5B0+3C0)
+    m[5] = e2 * 5u + c12 * 3u;                                               // (5B1+3C1, 5B2+3C2)
+}
+
 constexpr int K3_THREADS = 256;    // register pass-through kernel
 constexpr int K3_THREADS_TMA = 512;   // TMA-staged kernel (maximum; chosen at launch): the strip occupies shared memory, 2 CTAs per SM
 constexpr int K3_QUEUE1 = 128;    // work items (4-pixel quads) per warp iteration and group: 32 lanes x 4 quads
@@ -704,7 +752,7 @@ struct FastGeom {
     float div, one;
 };
 
-template <bool VX2, bool BITS, int NTH>
+template <bool VX2, bool BITS, int NTH, int HR = 2>
 __global__ void __launch_bounds__(NTH, 1024 / NTH)
     k3_fast(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ mask,
             const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ yt,
@@ -790,8 +838,13 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
             const Tap ty = yt[yy];
             wa = (uint32_t)(ty.w & 0xffff) << 20, wb = ((uint32_t)ty.w >> 16) << 20;
             const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
-            x2_load_row(inp_t + ya * w * 3, xq, W0, a0, a1, a2);
-            x2_load_row(inp_t + yb * w * 3, xq, W0, b0, b1, b2);
+            if (HR == 4) {
+                x4_load_row(inp_t + ya * w * 3, xq, W0, a0, a1, a2);
+                x4_load_row(inp_t + yb * w * 3, xq, W0, b0, b1, b2);
+            } else {
+                x2_load_row(inp_t + ya * w * 3, xq, W0, a0, a1, a2);
+                x2_load_row(inp_t + yb * w * 3, xq, W0, b0, b1, b2);
+            }
         }
         uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
         const uint32_t o0 = sp[0], o1 = sp[1], o2 = sp[2];
@@ -806,14 +859,20 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
         };
         const float4 l0 = lut_at(0), l1 = lut_at(1), l2 = lut_at(2), l3 = lut_at(3);
         uint32_t ma[6], mb[6], up[6];
-        x2_hpass(a0, a1, a2, ma);
-        x2_hpass(b0, b1, b2, mb);
+        if (HR == 4) {
+            x4_hpass(a0, a1, a2, ma);
+            x4_hpass(b0, b1, b2, mb);
+        } else {
+            x2_hpass(a0, a1, a2, ma);
+            x2_hpass(b0, b1, b2, mb);
+        }
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             if (VX2) {
                 up[k] = x2_vpass(ma[k], mb[k]);
             } else {
-                const uint32_t am = ma[k] << 1, bm = mb[k] << 1;        // lanes <= 2040: no carry into the high lane
+                // (b * (h >> 4)) >> 16 with h >> 4 == 32 m (x2) or 16 m (x4): umulhi(b << 20, m << 1 or m)
+                const uint32_t am = HR == 4 ? ma[k] : ma[k] << 1, bm = HR == 4 ? mb[k] : mb[k] << 1;   // lanes <= 2040 / 4080: no carry
                 const uint32_t lo = (__umulhi(wa, am & 0xffffu) + __umulhi(wb, bm & 0xffffu) + 2u) >> 2;
                 const uint32_t hi = (__umulhi(wa, am >> 16) + __umulhi(wb, bm >> 16) + 2u) >> 2;
                 up[k] = lo | (hi << 16);
@@ -1117,13 +1176,15 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
 
     // ---- k3_fast: exact x2 horizontal up-scale, feather radius <= 2, TMA-able frames (the production geometry)
     const int x2opt = get_option(OPT_K3_X2);
-    if (vec && small_r && x2opt >= 2 && get_option(OPT_K3_TMA) != 0 && W0 == 2 * w && W0 >= 8 && ((uintptr_t)inp % 4 == 0)) {
+    const int hr = W0 == 2 * w ? 2 : (W0 == 4 * w ? 4 : 0);
+    if (vec && small_r && x2opt >= 2 && get_option(OPT_K3_TMA) != 0 && hr != 0 && w >= 4 && (w * 3) % 4 == 0 &&
+        ((uintptr_t)inp % 4 == 0)) {
         // dynamic shared memory (words): [strip][mbarrier 4][bit rows][pad to 4][lut 16 x float4 + lut_pos 4][queues]
         int fth = 0;
         size_t fsm = 0;
         FastGeom gm = {};
         // 512 threads x 2 CTAs per SM (default) or 256 threads x 4 CTAs per SM with shorter strips
-        const int nth = get_option(OPT_K3_TMA_THREADS) <= 256 ? 256 : 512;
+        const int nth = (hr == 2 && get_option(OPT_K3_TMA_THREADS) <= 256) ? 256 : 512;
         const size_t smem_cap = nth == 256 ? 56 * 1024 : 113 * 1024;
         for (fth = min(16, max(2, get_option(OPT_K3_TMA_ROWS))); fth >= 2; --fth) {
             gm.bits_off = fth * W0 * 3 / 4 + 4;
@@ -1134,7 +1195,7 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         }
         if (fth >= 2) {
             const int fstrips = ceil_div(H0, fth);
-            const bool vx2 = H0 == 2 * h;
+            const bool vx2 = hr == 2 && H0 == 2 * h;
             const bool bits = mask_bits != nullptr && get_option(OPT_K3_BITS) != 0;
             // rows per classification task: 4 when that still gives most threads a task, else 2
             int rpt = 4;
@@ -1173,7 +1234,27 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         else                      \
             VV_K3_FAST(V, B, 512); \
     } while (0)
-            if (vx2 && bits)
+            if (hr == 4) {        // x4: always table-driven vertical taps, 512 threads
+                if (bits) {
+                    auto kfn = k3_fast<false, true, 512, 4>;
+                    VV_K3_SMEM(kfn);
+                } else {
+                    auto kfn = k3_fast<false, false, 512, 4>;
+                    VV_K3_SMEM(kfn);
+                }
+                for (int t0 = 0; t0 < T; t0 += 32768) {
+                    const int tn = min(32768, T - t0);
+                    const size_t fo = (size_t)t0 * H0 * W0;
+                    const uint32_t *mb = mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : nullptr;
+                    if (bits)
+                        k3_fast<false, true, 512, 4><<<dim3((unsigned)fstrips, (unsigned)tn), 512, smem, st>>>(
+                            inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo, mb, out + fo * 3, yt, gm);
+                    else
+                        k3_fast<false, false, 512, 4><<<dim3((unsigned)fstrips, (unsigned)tn), 512, smem, st>>>(
+                            inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo, mb, out + fo * 3, yt, gm);
+                    VV_POST_LAUNCH("k3_fast");
+                }
+            } else if (vx2 && bits)
                 VV_K3_FAST_N(true, true);
             else if (vx2)
                 VV_K3_FAST_N(true, false);
