@@ -285,3 +285,60 @@ def test_non_uint8_masks_are_binarised_before_the_cast(ops):
     dil = pipe.pre([m_f, m_i], 2)
     pipe.close()
     assert np.array_equal(np.stack(dil), np.stack(op.ref_binarize_dilate([m_f, m_i], 2)))
+
+
+# ------------------------------------------------------------------------------- N1: device-resident frame I/O
+def test_n1_device_resident_frame_io(ops, tmp_path):
+    """tools.load_video_frames_from_path(device='cuda') == the host loader (decode -> pinned ring -> H2D -> swap on
+    the device), the writer takes the device clip (NEAREST fix-up + swap on the device, double-buffered download),
+    and run_infill_on_frames takes DeviceFrames in and gives DeviceFrames out without touching the host."""
+    pytest.importorskip("cv2")
+    from videovanish_b200 import tools
+    rng = np.random.default_rng(12)
+    t, h0, w0 = 70, 72, 128                          # more than two ring blocks of 32 frames
+    frames = list(rng.integers(0, 256, (t, h0, w0, 3), dtype=np.uint8))
+    path, path2, path3 = (str(tmp_path / n) for n in ("a.mkv", "b.mkv", "c.mkv"))
+    try:
+        tools.write_video_frames_to_path(path, frames, 25.0, h0, w0)
+    except AssertionError:
+        pytest.skip("FFV1 writer unavailable in this OpenCV build")
+    host_frames, fps = tools.load_video_frames_from_path(path, start_frame=3, max_frames=66)
+    clip, fps2 = tools.load_video_frames_from_path(path, start_frame=3, max_frames=66, device="cuda")
+    assert fps == fps2 and len(clip) == len(host_frames) == 66
+    assert np.array_equal(host(clip.tensor), np.stack(host_frames)) and np.array_equal(np.stack(host_frames), np.stack(frames[3:69]))
+    assert np.array_equal(clip[5], host_frames[5])                              # list behaviour (lazy download)
+    tools.write_video_frames_to_path(path2, clip, fps, h0, w0)
+    back, _ = tools.load_video_frames_from_path(path2)
+    assert np.array_equal(np.stack(back), np.stack(host_frames))
+    tools.write_video_frames_to_path(path3, clip, fps, 36, 64)                   # the writer's NEAREST fix-up (tools.py:41-42)
+    small, _ = tools.load_video_frames_from_path(path3)
+    assert np.array_equal(np.stack(small), np.stack([op.ref_resize_nearest(f, 36, 64) for f in host_frames]))
+
+    # device clip in -> device clip out through the drop-in
+    vvd_max[0] = 64
+    vvd = _install_adapters(seed=4)
+    mk = synth.masks(66, h0, w0, seed=8, salt=0.0008)
+    try:
+        out = vvd.run_infill_on_frames(clip, tools.DeviceFrames(dev(mk)), mask_dilation_iter=3, max_img_size=64)
+    finally:
+        vvd.propainter = None
+    assert isinstance(out, tools.DeviceFrames)
+    want = ofp.run(host_frames, list(mk), _flow_fn_np(4), mask_dilation_iter=3, max_img_size=64)
+    assert np.array_equal(host(out.tensor), np.stack(want))
+
+
+def test_loader_pinned_budget(ops, tmp_path, monkeypatch):
+    """Beyond tools.PINNED_BUDGET the loader hands out ordinary host memory (no unbounded pinning)."""
+    pytest.importorskip("cv2")
+    from videovanish_b200 import tools
+    frames = list(np.random.default_rng(1).integers(0, 256, (40, 32, 48, 3), dtype=np.uint8))
+    path = str(tmp_path / "p.mkv")
+    try:
+        tools.write_video_frames_to_path(path, frames, 25.0, 32, 48)
+    except AssertionError:
+        pytest.skip("FFV1 writer unavailable in this OpenCV build")
+    monkeypatch.setattr(tools, "PINNED_BUDGET", 32 * 32 * 48 * 3)               # exactly one block
+    got, _ = tools.load_video_frames_from_path(path)
+    assert np.array_equal(np.stack(got), np.stack(frames))
+    pinned = [torch.from_numpy(g).is_pinned() for g in got]
+    assert all(pinned[:32]) and not any(pinned[32:])

@@ -55,7 +55,7 @@ def run_infill_on_frames(frames_rgb, mask_frames, mask_dilation_iter=8, ckpt="2-
     """Same contract as reference diffuerase.py:20-114."""
     global device, last_ckpt, video_inpainting_sd, propainter
 
-    H0, W0 = frames_rgb[0].shape[:2]
+    H0, W0 = _frame_size(frames_rgb)
     pipe = _get_pipeline(H0, W0)
 
     if _device_route(propainer_frames):
@@ -105,6 +105,15 @@ def run_infill_on_frames(frames_rgb, mask_frames, mask_dilation_iter=8, ckpt="2-
     return inpainted_frames
 
 
+def _frame_size(frames):
+    """(H0, W0) of a list of host frames or of a tools.DeviceFrames clip (without downloading it)."""
+    return tuple(frames.tensor.shape[1:3]) if hasattr(frames, "tensor") else tuple(frames[0].shape[:2])
+
+
+def _frame_shape(frames):
+    return tuple(frames.tensor.shape[1:]) if hasattr(frames, "tensor") else tuple(frames[0].shape)
+
+
 def _device_route(propainer_frames):
     """True when the models that this call will use are the device-resident adapters."""
     if video_inpainting_sd is None or last_ckpt != "2-Step" or not hasattr(video_inpainting_sd, "forward_device"):
@@ -119,12 +128,12 @@ def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_
     import torch
 
     from . import ops, wrappers
-    H0, W0 = frames_rgb[0].shape[:2]
+    H0, W0 = _frame_size(frames_rgb)
     t = len(frames_rgb)
+    resident = hasattr(frames_rgb, "tensor")            # tools.DeviceFrames in -> tools.DeviceFrames out
     with torch.cuda.device(pipe.device):
         if prog is not None: prog(5, "dilating frames")
-        c = 1 if mask_frames[0].ndim == 2 else mask_frames[0].shape[2]
-        masks = pipe.upload(mask_frames, (H0, W0) if mask_frames[0].ndim == 2 else (H0, W0, c), is_mask=True)
+        masks = pipe.upload(mask_frames, _frame_shape(mask_frames), is_mask=True)
         h, w = ops.inference_size(H0, W0, max_img_size)
         dil, low, bits = ops.binarize_dilate(masks, mask_dilation_iter, lowres_size=(h, w), return_bits=True)   # K1
         del masks
@@ -137,7 +146,7 @@ def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_
             priors = propainter.forward_device(clip, ref_stride=10, neighbor_length=10, subvideo_length=50,
                                                mask_dilation=0, progress=prog)
         else:
-            priors = pipe.upload(propainer_frames, tuple(propainer_frames[0].shape))
+            priors = pipe.upload(propainer_frames, _frame_shape(propainer_frames))
         if prog is not None: prog(50, "running DiffuEraser")
         inpainted = video_inpainting_sd.forward_device(clip, priors, max_img_size=max_img_size, mask_dilation_iter=0,
                                                        guidance_scale=None, progress=prog)
@@ -146,11 +155,15 @@ def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_
         n = min(1, t) if BUG_COMPAT else t
         fh, fw = inpainted.shape[1:3]
         if (fh, fw) == (H0, W0) and not keep_unmasked_original:
-            return pipe.download(inpainted)
-        out = ops.upscale_feather_composite(inpainted[:n], frames[:n], dil[:n], feather_px, keep_unmasked_original,
-                                            mask_bits=None if bits is None else bits[:n])            # K3
+            out = inpainted
+        else:
+            out = ops.upscale_feather_composite(inpainted[:n], frames[:n], dil[:n], feather_px, keep_unmasked_original,
+                                                mask_bits=None if bits is None else bits[:n])        # K3
+        if resident and n == t:
+            from .tools import DeviceFrames
+            return DeviceFrames(out)
         result = pipe.download(out)
-        if n < t:
+        if n < t and out is not inpainted:
             result += pipe.download(inpainted[n:])
         return result
 

@@ -125,6 +125,10 @@ class HostPipeline:
         """List of host arrays of ``shape`` -> u8 device tensor [T, *shape].  The copies are ordered before
         whatever is enqueued on the current torch stream afterwards; page-locked sources are read by DMA
         asynchronously, so the list must stay alive until that stream has been synchronised."""
+        if hasattr(frames, "tensor"):                 # tools.DeviceFrames: already resident
+            if tuple(frames.tensor.shape[1:]) != tuple(shape):
+                raise ValueError("device clip has shape %s, expected [T,%s]" % (tuple(frames.tensor.shape), tuple(shape)))
+            return frames.tensor
         t = len(frames)
         src, keep = _ptr_array(frames, shape, is_mask=is_mask)
         nbytes = int(np.prod(shape))
