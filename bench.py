@@ -703,6 +703,25 @@ def run_ours(args, rank, world, local_rank):
     px = H0 * W0
     h2d_full, d2h_full = t * (3 * px + 3 * px), t * 3 * px       # masks + frames up, composited frames down
 
+    # (1b) a long clip in overlapping chunks, device resident: chunk c+1 uploads / computes while chunk c downloads
+    chunked = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        n_long = args.c5_frames
+        fr_long = [frames_host[i % t] for i in range(n_long)]
+        mk_long = [masks_host[i % t] for i in range(n_long)]
+        flows_c = (flows[0][:199], flows[1][:199])
+        prior.flow_fn = lambda small, low: (flows_c[0][:small.shape[0] - 1], flows_c[1][:small.shape[0] - 1])
+        r = vvd.run_infill_on_frames_chunked(fr_long[:400], mk_long[:400], chunk=200, overlap=OVERLAP, mask_dilation_iter=DILATE,
+                                             max_img_size=960)
+        del r
+        t0 = time.perf_counter()
+        r = vvd.run_infill_on_frames_chunked(fr_long, mk_long, chunk=200, overlap=OVERLAP, mask_dilation_iter=DILATE, max_img_size=960)
+        cdt = time.perf_counter() - t0
+        del r
+        prior.flow_fn = lambda small, low: flows
+        chunked = {"frames": n_long, "chunk": 200, "overlap": OVERLAP, "frames_per_s": n_long / cdt,
+                   "stages": E2E_STAGES + " per chunk + K5 cross-fade in HBM; uploads of chunk c+1 overlap the download of chunk c"}
+
     # (2) K1 + K3 only: host-list models (what a real DiffuEraser / ProPainter install exercises)
     class _StubModel:
         def forward(self, frames, masks, priors, **kw):
@@ -788,6 +807,8 @@ def run_ours(args, rank, world, local_rank):
         line.update(extras)
         if c5 is not None:
             line["c5_long"] = c5
+        if chunked is not None:
+            line["c5_long_chunked_device"] = chunked
         if world > 1:
             line.update(multi)
             line["halo_handshake_error"] = halo_error

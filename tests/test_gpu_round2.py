@@ -342,3 +342,24 @@ def test_loader_pinned_budget(ops, tmp_path, monkeypatch):
     assert np.array_equal(np.stack(got), np.stack(frames))
     pinned = [torch.from_numpy(g).is_pinned() for g in got]
     assert all(pinned[:32]) and not any(pinned[32:])
+
+
+def test_chunked_driver_device_resident(ops):
+    """run_infill_on_frames_chunked with the adapters installed: every chunk runs device resident, the overlaps are
+    cross-faded in HBM, chunk c+1 uploads while chunk c downloads - and the clip equals the per-chunk full-path
+    oracle outputs stitched by the oracle's blend (row A11)."""
+    from oracle import chunk_blend as ocb
+    from videovanish_b200 import chunking
+    t, h0, w0, size, chunk, ov = 47, 72, 128, 64, 20, 6
+    vvd_max[0] = size
+    vvd = _install_adapters(seed=9)
+    fr, mk = synth.frames(t, h0, w0, seed=111), synth.masks(t, h0, w0, seed=112, salt=0.0008)
+    try:
+        got = vvd.run_infill_on_frames_chunked(list(fr), list(mk), chunk=chunk, overlap=ov, mask_dilation_iter=3,
+                                               max_img_size=size)
+    finally:
+        vvd.propainter = None
+    plan = chunking.chunk_plan(t, chunk, ov)
+    per_chunk = [np.stack(ofp.run(list(fr[s:e]), list(mk[s:e]), _flow_fn_np(9), mask_dilation_iter=3, max_img_size=size))
+                 for s, e in plan]
+    assert len(got) == t and np.array_equal(np.stack(got), ocb.stitch_chunks(per_chunk, plan, ov))

@@ -272,6 +272,28 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Same for W == 2 * lw (1080p -> 960x536, the wrapper's real inference size): the NEAREST source column of
+// low-res pixel d is exactly 2d, so 16 low-res pixels are the even bits of ONE word of the source row; only the
+// row mapping needs the table rule.  One thread = one 128-bit store.
+__global__ void __launch_bounds__(256)
+    k1d_lowres_x2_from_bits(const uint32_t *__restrict__ bits, int H, int Wp, uint8_t *__restrict__ low, int lh, int lw,
+                            long long T) {
+    const int groups = lw >> 4;                       // lw % 16 == 0
+    const long long total = T * lh * (long long)groups;
+    const double sy = __ddiv_rn(1.0, __ddiv_rn((double)lh, (double)H));
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % groups);
+        const long long q = idx / groups;
+        const int y = (int)(q % lh);
+        const long long t = q / lh;
+        const int srcy = min((int)floor(__dmul_rn((double)y, sy)), H - 1);
+        const uint32_t e = even_bits(__ldg(bits + (t * H + srcy) * Wp + g));
+        stg128_stream(low + (t * lh + y) * (long long)lw + g * 16,
+                      make_uint4(expand4(e), expand4(e >> 4), expand4(e >> 8), expand4(e >> 12)));
+    }
+}
+
 template <int C>
 static int launch_k1a(const uint8_t *mask, uint16_t *bits, int W, int Wp, long long n_rows, bool vec, int grid,
                       cudaStream_t st) {
@@ -392,9 +414,14 @@ extern "C" int vv_binarize_dilate_ex(const uint8_t *mask, int T, int H, int W, i
     if (lowres_out && !half) {
         const long long total = (long long)T * lh * ((lw + 15) / 16);
         const int vec_low = (lw % 16 == 0) && ((uintptr_t)lowres_out % 16 == 0);
-        k1d_lowres_from_bits<<<(int)min((long long)ceil_div(total, 256), (long long)148 * 32), 256, 0, st>>>(
-            dil_plane, H, W, Wp, lowres_out, lh, lw, T, vec_low);
-        VV_POST_LAUNCH("k1d_lowres_from_bits");
+        const int grid_d = (int)min((long long)ceil_div(total, 256), (long long)148 * 32);
+        if (W == 2 * lw && vec_low) {
+            k1d_lowres_x2_from_bits<<<grid_d, 256, 0, st>>>(dil_plane, H, Wp, lowres_out, lh, lw, T);
+            VV_POST_LAUNCH("k1d_lowres_x2_from_bits");
+        } else {
+            k1d_lowres_from_bits<<<grid_d, 256, 0, st>>>(dil_plane, H, W, Wp, lowres_out, lh, lw, T, vec_low);
+            VV_POST_LAUNCH("k1d_lowres_from_bits");
+        }
     }
     return VV_OK;
 }

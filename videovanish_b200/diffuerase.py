@@ -122,22 +122,25 @@ def _device_route(propainer_frames):
 
 
 def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_frames, max_img_size,
-                   keep_unmasked_original, feather_px, prog):
+                   keep_unmasked_original, feather_px, prog, upload_pipe=None, keep_on_device=False):
     """Same stages, milestones and results as the host-list route of ``run_infill_on_frames``, with the clip
-    resident in HBM from the first upload to the last download."""
+    resident in HBM from the first upload to the last download.  ``upload_pipe``: a second pipeline for the
+    uploads, so that they do not queue behind another chunk's download; ``keep_on_device``: return the u8
+    [T,H0,W0,3] device tensor instead of downloading it (the chunked driver cross-fades overlaps in HBM)."""
     import torch
 
     from . import ops, wrappers
     H0, W0 = _frame_size(frames_rgb)
     t = len(frames_rgb)
     resident = hasattr(frames_rgb, "tensor")            # tools.DeviceFrames in -> tools.DeviceFrames out
+    up = upload_pipe if upload_pipe is not None else pipe
     with torch.cuda.device(pipe.device):
         if prog is not None: prog(5, "dilating frames")
-        masks = pipe.upload(mask_frames, _frame_shape(mask_frames), is_mask=True)
+        masks = up.upload(mask_frames, _frame_shape(mask_frames), is_mask=True)
         h, w = ops.inference_size(H0, W0, max_img_size)
         dil, low, bits = ops.binarize_dilate(masks, mask_dilation_iter, lowres_size=(h, w), return_bits=True)   # K1
         del masks
-        frames = pipe.upload(frames_rgb, (H0, W0, 3))
+        frames = up.upload(frames_rgb, (H0, W0, 3))
         clip = wrappers.DeviceClip(frames, dil, lowres=low)
         clip.mask_bits = bits
         if prog is not None: prog(10, "loading weights")
@@ -146,7 +149,7 @@ def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_
             priors = propainter.forward_device(clip, ref_stride=10, neighbor_length=10, subvideo_length=50,
                                                mask_dilation=0, progress=prog)
         else:
-            priors = pipe.upload(propainer_frames, _frame_shape(propainer_frames))
+            priors = up.upload(propainer_frames, _frame_shape(propainer_frames))
         if prog is not None: prog(50, "running DiffuEraser")
         inpainted = video_inpainting_sd.forward_device(clip, priors, max_img_size=max_img_size, mask_dilation_iter=0,
                                                        guidance_scale=None, progress=prog)
@@ -159,6 +162,8 @@ def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_
         else:
             out = ops.upscale_feather_composite(inpainted[:n], frames[:n], dil[:n], feather_px, keep_unmasked_original,
                                                 mask_bits=None if bits is None else bits[:n])        # K3
+        if keep_on_device and n == t:
+            return out
         if resident and n == t:
             from .tools import DeviceFrames
             return DeviceFrames(out)
@@ -168,28 +173,79 @@ def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_
         return result
 
 
+_upload_pipeline = None
+
+
 def run_infill_on_frames_chunked(frames_rgb, mask_frames, chunk=80, overlap=16, **kwargs):
     """Long clips in overlapping chunks (the feature the reference advertises at README.md:18 and lists as
     a TODO at README.md:76; builder-defined spec): every chunk of ``chunk`` frames goes
     through ``run_infill_on_frames`` on its own (so the models only ever see ``chunk`` frames), and the
     ``overlap`` frames shared by consecutive chunks are cross-faded on the GPU by K5
-    (``w = (k+1)/(overlap+1)``).  ``propainer_frames``, if given, is sliced per chunk."""
+    (``w = (k+1)/(overlap+1)``).  ``propainer_frames``, if given, is sliced per chunk.
+
+    With the device-resident adapters installed the chunks never leave HBM between their stages and the
+    cross-fade: chunk c+1 is uploaded and computed while chunk c's finished frames are downloaded (two pipelines,
+    PCIe both ways at once), and the shared frames are blended in place on the device."""
     import torch
 
-    from . import chunking, ops
+    from . import chunking, hostpipe, ops
+    global _upload_pipeline
     n = len(frames_rgb)
     plan = chunking.chunk_plan(n, chunk, overlap)
     priors = kwargs.pop("propainer_frames", None)
     result = [None] * n
+
+    if _device_route(priors) and not BUG_COMPAT:
+        H0, W0 = _frame_size(frames_rgb)
+        pipe = _get_pipeline(H0, W0)
+        if _upload_pipeline is None or _upload_pipeline.geometry != (H0, W0):
+            _upload_pipeline = hostpipe.HostPipeline(H0, W0)
+        args = dict(mask_dilation_iter=kwargs.get("mask_dilation_iter", 8), max_img_size=kwargs.get("max_img_size", 960),
+                    keep_unmasked_original=kwargs.get("keep_unmasked_original", True), feather_px=kwargs.get("feather_px", 3),
+                    prog=kwargs.get("prog"))
+        dl_stream = torch.cuda.Stream()
+        pending = None                       # (device frames to emit, first clip index, event) of the previous chunk
+
+        def emit(item):
+            tensor, first, ev = item
+            with torch.cuda.stream(dl_stream):
+                dl_stream.wait_event(ev)
+                frames = pipe.download(tensor)
+            result[first:first + len(frames)] = frames
+
+        prev_tail = None
+        for ci, (s, e) in enumerate(plan):
+            out = _run_on_device(pipe, frames_rgb[s:e], mask_frames[s:e], args["mask_dilation_iter"],
+                                 None if priors is None else priors[s:e], args["max_img_size"],
+                                 args["keep_unmasked_original"], args["feather_px"], args["prog"],
+                                 upload_pipe=_upload_pipeline, keep_on_device=True)
+            if ci > 0:
+                ov = plan[ci - 1][1] - s
+                ops.chunk_blend(prev_tail[prev_tail.shape[0] - ov:], out[:ov], out=out[:ov])      # in place, in HBM
+            nxt_ov = (e - plan[ci + 1][0]) if ci + 1 < len(plan) else 0
+            keep = (e - s) - nxt_ov
+            prev_tail = out[keep:] if nxt_ov else None
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:
+                emit(pending)                # blocks on the previous chunk's download while this chunk uploads / computes
+            pending = (out[:keep], s, ev)
+        emit(pending)
+        return result
+
     prev_tail = None                     # device copy of the previous chunk's last `overlap` frames
+    pipe = None
     for ci, (s, e) in enumerate(plan):
         out = run_infill_on_frames(frames_rgb[s:e], mask_frames[s:e],
                                    propainer_frames=None if priors is None else priors[s:e], **kwargs)
+        if pipe is None:
+            pipe = _get_pipeline(*out[0].shape[:2])
+        shape = tuple(out[0].shape)
         lo = 0
         if ci > 0:
             ov = plan[ci - 1][1] - s
-            head = torch.from_numpy(np.stack(out[:ov])).cuda(non_blocking=True)
-            blended = ops.chunk_blend(prev_tail[prev_tail.shape[0] - ov:], head).cpu().numpy()
+            head = pipe.upload(out[:ov], shape)
+            blended = pipe.download(ops.chunk_blend(prev_tail[prev_tail.shape[0] - ov:], head))
             for k in range(ov):
                 result[s + k] = blended[k]
             lo = ov
@@ -197,7 +253,7 @@ def run_infill_on_frames_chunked(frames_rgb, mask_frames, chunk=80, overlap=16, 
             result[s + k] = out[k]
         if ci + 1 < len(plan):
             nxt_ov = e - plan[ci + 1][0]
-            prev_tail = torch.from_numpy(np.stack(out[(e - s) - nxt_ov:])).cuda(non_blocking=True)
+            prev_tail = pipe.upload(out[(e - s) - nxt_ov:], shape)
     return result
 
 
