@@ -71,8 +71,11 @@ VV_API void vv_reset_launch_count(void);
  *   "k4_lean"    5 (default), 6 or 8 = CTAs per SM the propagation step kernel is compiled for.
  *   "k4_step_ctas" CTAs per SM of the step grid (default 5: a resident grid that strides over the hole lists
  *                with the next entry pre-loaded); 0 = about one thread per hole at a 25 % hole fraction.
- *   "k4_taps"    1 = the 8 tap loads of a hole are issued unconditionally from clamped positions,
- *                0 (default, measured faster) = one predicated region per tap.
+ *   "k4_precheck" 1 = k4_pack decides the forward / backward flow-consistency check of the backward pass for every
+ *                hole of every frame at once and stores the un-normalised sample position in the list entry, so that the
+ *                serial backward steps only gather the four state taps; 0 (default, measured faster: in the steps the
+ *                flow taps ride along with the state taps in one latency-bound round trip, in the bandwidth-bound pack
+ *                they cost their full, badly coalesced bytes) = the steps do it all.
  *   "k4_speculate" 1 (default, measured faster) = the backward pass fetches the forward-pass flow of a hole
  *                together with its taps; 0 = only after the hole turned out to stay a hole. */
 VV_API int vv_set_option(const char *name, int value);

@@ -250,10 +250,10 @@ def test_k4_zero_padding_fill(ops):
 
 
 @pytest.mark.parametrize("variant", [dict(k4_pdl=1), dict(k4_pdl=0), dict(k4_lean=8, k4_step_ctas=0),
-                                     dict(k4_lean=6, k4_taps=1, k4_step_ctas=1), dict(k4_npt=2, k4_lean=3, k4_step_ctas=3),
+                                     dict(k4_lean=6, k4_precheck=1, k4_step_ctas=1), dict(k4_precheck=1), dict(k4_precheck=1, k4_npt=2, k4_lean=4), dict(k4_npt=2, k4_lean=3, k4_step_ctas=3),
                                      dict(k4_npt=2, k4_lean=4, k4_step_ctas=4, k4_speculate=0),
                                      dict(k4_pack_ctas=1, k4_pack_occ=4), dict(k4_pack_ctas=1024, k4_pack_occ=6)],
-                         ids=["lean-pdl", "lean", "lean8-wide-grid", "lean6-uncond-taps", "two-per-trip-3", "two-per-trip-4",
+                         ids=["lean-pdl", "lean", "lean8-wide-grid", "lean6-precheck", "precheck", "precheck-npt2", "two-per-trip-3", "two-per-trip-4",
                               "pack-few-ctas", "pack-many-ctas"])
 def test_k4_kernel_variants(ops, variant):
     """Every step-kernel / pack-kernel variant gives the same state (and the pad frames kept in scratch
@@ -266,7 +266,7 @@ def test_k4_kernel_variants(ops, variant):
             _lib.set_option(k, v)
         got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb), subvideo_length=8, pad_len=3)).view(np.uint32)
     finally:
-        for k, v in dict(k4_pdl=1, k4_npt=1, k4_lean=5, k4_taps=0, k4_step_ctas=5, k4_pack_ctas=128, k4_pack_occ=4,
+        for k, v in dict(k4_pdl=1, k4_npt=1, k4_lean=5, k4_precheck=0, k4_step_ctas=5, k4_pack_ctas=128, k4_pack_occ=4,
                          k4_speculate=1).items():
             _lib.set_option(k, v)
     assert np.array_equal(got, want)

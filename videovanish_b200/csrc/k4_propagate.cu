@@ -61,69 +61,96 @@ __device__ __forceinline__ float unnormalized(float pos, int size) {
     return __fmul_rn(__fadd_rn(n, 1.0f), (float)(size - 1) * 0.5f);
 }
 
-// One hole pixel: returns the new packed state.
-template <bool UNCOND = false>
-__device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, uint32_t cur, const float2 f,
-                                                    const float2 *__restrict__ flow_check, const uint32_t *prev) {
-    const float ix = unnormalized(__fadd_rn((float)x, f.x), w);
-    const float iy = unnormalized(__fadd_rn((float)y, f.y), h);
-    const float x0f = floorf(ix), y0f = floorf(iy);
-    const float wx = __fsub_rn(ix, x0f), wy = __fsub_rn(iy, y0f);
+// The arithmetic of one hole pixel, split into the parts that depend on the flows only (sample position, forward /
+// backward consistency - computable for every frame at once) and the part that depends on the serial scan (the
+// previous frame's state).
+struct Taps {
+    float ix, iy, x0f, y0f, nw, ne, sw, se;
+    uint32_t i00;             // linear index of tap (y0, x0): only used when the tap is inside the frame
+    bool xa, xb, ya, yb;      // which taps lie inside the frame (the others are zeros padding)
+};
+__device__ __forceinline__ float2 sample_pos(int x, int y, float2 f, int h, int w) {
+    return make_float2(unnormalized(__fadd_rn((float)x, f.x), w), unnormalized(__fadd_rn((float)y, f.y), h));
+}
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int h, int w) {
+    Taps t;
+    t.ix = ix, t.iy = iy;
+    t.x0f = floorf(ix), t.y0f = floorf(iy);
+    const float wx = __fsub_rn(ix, t.x0f), wy = __fsub_rn(iy, t.y0f);
     const float ex = __fsub_rn(1.f, wx), sy = __fsub_rn(1.f, wy);
-    const float nw = __fmul_rn(sy, ex), ne = __fmul_rn(sy, wx), sw = __fmul_rn(wy, ex), se = __fmul_rn(wy, wx);
+    t.nw = __fmul_rn(sy, ex), t.ne = __fmul_rn(sy, wx), t.sw = __fmul_rn(wy, ex), t.se = __fmul_rn(wy, wx);
     // clamp before the int conversion so absurd flows cannot overflow
-    const int x0 = (int)fminf(fmaxf(x0f, -4.f), (float)w + 4.f);
-    const int y0 = (int)fminf(fmaxf(y0f, -4.f), (float)h + 4.f);
-    const bool xa = (unsigned)x0 < (unsigned)w, xb = (unsigned)(x0 + 1) < (unsigned)w;
-    const bool ya = (unsigned)y0 < (unsigned)h, yb = (unsigned)(y0 + 1) < (unsigned)h;
-    float2 c00 = make_float2(0.f, 0.f), c01 = c00, c10 = c00, c11 = c00;
-    uint32_t p00 = 0, p01 = 0, p10 = 0, p11 = 0;          // out-of-frame taps: zeros padding, not a hole
-    auto ld_state = [&](uint32_t i) { return prev[i]; };
-    if (UNCOND) {
-        // All 8 tap loads are issued unconditionally from clamped (always valid) positions and zeroed
-        // afterwards when the tap lies outside the frame: no branches, 32-bit index arithmetic
-        // (h * w < 2^32), all loads in flight together.
-        const uint32_t xa_i = (uint32_t)min(max(x0, 0), w - 1), xb_i = (uint32_t)min(max(x0 + 1, 0), w - 1);
-        const uint32_t ra = (uint32_t)min(max(y0, 0), h - 1) * (uint32_t)w, rb = (uint32_t)min(max(y0 + 1, 0), h - 1) * (uint32_t)w;
-        const uint32_t i00 = ra + xa_i, i01 = ra + xb_i, i10 = rb + xa_i, i11 = rb + xb_i;
-        c00 = __ldg(flow_check + i00), c01 = __ldg(flow_check + i01);
-        c10 = __ldg(flow_check + i10), c11 = __ldg(flow_check + i11);
-        p00 = ld_state(i00), p01 = ld_state(i01), p10 = ld_state(i10), p11 = ld_state(i11);
-        const float2 zero2 = make_float2(0.f, 0.f);
-        if (!(ya && xa)) c00 = zero2, p00 = 0;
-        if (!(ya && xb)) c01 = zero2, p01 = 0;
-        if (!(yb && xa)) c10 = zero2, p10 = 0;
-        if (!(yb && xb)) c11 = zero2, p11 = 0;
-    } else {
-        const uint32_t i00 = (uint32_t)(y0 * w + x0);      // only used when the tap is inside the frame
-        if (ya && xa) c00 = __ldg(flow_check + i00), p00 = ld_state(i00);
-        if (ya && xb) c01 = __ldg(flow_check + (i00 + 1u)), p01 = ld_state(i00 + 1u);
-        if (yb && xa) c10 = __ldg(flow_check + (i00 + (uint32_t)w)), p10 = ld_state(i00 + (uint32_t)w);
-        if (yb && xb) c11 = __ldg(flow_check + (i00 + (uint32_t)w + 1u)), p11 = ld_state(i00 + (uint32_t)w + 1u);
-    }
-
-    // bilinear, torch CPU order: r = a*nw; r = fma(b, ne, r); r = fma(c, sw, r); r = fma(d, se, r)
-    const float bwx = __fmaf_rn(c11.x, se, __fmaf_rn(c10.x, sw, __fmaf_rn(c01.x, ne, __fmul_rn(c00.x, nw))));
-    const float bwy = __fmaf_rn(c11.y, se, __fmaf_rn(c10.y, sw, __fmaf_rn(c01.y, ne, __fmul_rn(c00.y, nw))));
+    const int x0 = (int)fminf(fmaxf(t.x0f, -4.f), (float)w + 4.f);
+    const int y0 = (int)fminf(fmaxf(t.y0f, -4.f), (float)h + 4.f);
+    t.xa = (unsigned)x0 < (unsigned)w, t.xb = (unsigned)(x0 + 1) < (unsigned)w;
+    t.ya = (unsigned)y0 < (unsigned)h, t.yb = (unsigned)(y0 + 1) < (unsigned)h;
+    t.i00 = (uint32_t)(y0 * w + x0);
+    return t;
+}
+// Tap loads are separate from the arithmetic so that a caller can issue all eight (flow + state) before anything
+// waits on them: one memory round trip per hole.
+struct FlowTaps {
+    float2 c00, c01, c10, c11;
+};
+struct StateTaps {
+    uint32_t p00, p01, p10, p11;
+};
+__device__ __forceinline__ FlowTaps load_flow_taps(const Taps &t, const float2 *__restrict__ flow_check, int w) {
+    FlowTaps c;
+    c.c00 = c.c01 = c.c10 = c.c11 = make_float2(0.f, 0.f);          // out-of-frame taps: zeros padding
+    if (t.ya && t.xa) c.c00 = __ldg(flow_check + t.i00);
+    if (t.ya && t.xb) c.c01 = __ldg(flow_check + (t.i00 + 1u));
+    if (t.yb && t.xa) c.c10 = __ldg(flow_check + (t.i00 + (uint32_t)w));
+    if (t.yb && t.xb) c.c11 = __ldg(flow_check + (t.i00 + (uint32_t)w + 1u));
+    return c;
+}
+__device__ __forceinline__ StateTaps load_state_taps(const Taps &t, const uint32_t *prev, int w) {
+    StateTaps p;
+    p.p00 = p.p01 = p.p10 = p.p11 = 0;                              // out-of-frame taps: zeros padding, not a hole
+    if (t.ya && t.xa) p.p00 = prev[t.i00];
+    if (t.ya && t.xb) p.p01 = prev[t.i00 + 1u];
+    if (t.yb && t.xa) p.p10 = prev[t.i00 + (uint32_t)w];
+    if (t.yb && t.xb) p.p11 = prev[t.i00 + (uint32_t)w + 1u];
+    return p;
+}
+// fbConsistencyCheck for one pixel: bilinear (zeros padding, torch CPU FMA chain) warp of the check flow at the
+// sample position, then |f + bw|^2 < 0.01 (|f|^2 + |bw|^2) + 0.5
+__device__ __forceinline__ bool flow_consistent(const float2 f, const Taps &t, const FlowTaps &c) {
+    // r = a*nw; r = fma(b, ne, r); r = fma(c, sw, r); r = fma(d, se, r)
+    const float bwx = __fmaf_rn(c.c11.x, t.se, __fmaf_rn(c.c10.x, t.sw, __fmaf_rn(c.c01.x, t.ne, __fmul_rn(c.c00.x, t.nw))));
+    const float bwy = __fmaf_rn(c.c11.y, t.se, __fmaf_rn(c.c10.y, t.sw, __fmaf_rn(c.c01.y, t.ne, __fmul_rn(c.c00.y, t.nw))));
     const float dx = __fadd_rn(f.x, bwx), dy = __fadd_rn(f.y, bwy);
     const float diff = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
     const float mag = __fadd_rn(__fadd_rn(__fmul_rn(f.x, f.x), __fmul_rn(f.y, f.y)),
                                 __fadd_rn(__fmul_rn(bwx, bwx), __fmul_rn(bwy, bwy)));
-    const float thr = __fadd_rn(__fmul_rn(0.01f, mag), 0.5f);
-    const bool valid = diff < thr;
-
-    const float h00 = (p00 & ST_HOLE) ? 1.f : 0.f, h01 = (p01 & ST_HOLE) ? 1.f : 0.f;
-    const float h10 = (p10 & ST_HOLE) ? 1.f : 0.f, h11 = (p11 & ST_HOLE) ? 1.f : 0.f;
-    const float mpv = __fmaf_rn(h11, se, __fmaf_rn(h10, sw, __fmaf_rn(h01, ne, __fmul_rn(h00, nw))));
-    if (!valid || mpv > 0.1f) return cur;
-
-    // nearest source: rint (half-to-even) of the same un-normalised position; it is one of the 4 taps
-    const float xr = rintf(ix), yr = rintf(iy);
-    const bool right = xr > x0f, down = yr > y0f;
-    const bool inb = (right ? xb : xa) && (down ? yb : ya);
-    const uint32_t src = down ? (right ? p11 : p10) : (right ? p01 : p00);
-    return inb ? (src & ~ST_HOLE) : ST_ZERO;
+    return diff < __fadd_rn(__fmul_rn(0.01f, mag), 0.5f);
 }
+// The state-dependent part for a pixel whose flow passed the check: bilinear warp of the previous hole mask > 0.1
+// blocks the fill; otherwise the NEAREST previous pixel (one of the four taps) or the zero padding is copied.
+__device__ __forceinline__ uint32_t fill_from_prev(const Taps &t, uint32_t cur, const StateTaps &p) {
+    const float h00 = (p.p00 & ST_HOLE) ? 1.f : 0.f, h01 = (p.p01 & ST_HOLE) ? 1.f : 0.f;
+    const float h10 = (p.p10 & ST_HOLE) ? 1.f : 0.f, h11 = (p.p11 & ST_HOLE) ? 1.f : 0.f;
+    const float mpv = __fmaf_rn(h11, t.se, __fmaf_rn(h10, t.sw, __fmaf_rn(h01, t.ne, __fmul_rn(h00, t.nw))));
+    // nearest source: rint (half-to-even) of the same un-normalised position
+    const float xr = rintf(t.ix), yr = rintf(t.iy);
+    const bool right = xr > t.x0f, down = yr > t.y0f;
+    const bool inb = (right ? t.xb : t.xa) && (down ? t.yb : t.ya);
+    const uint32_t src = down ? (right ? p.p11 : p.p10) : (right ? p.p01 : p.p00);
+    const uint32_t filled = inb ? (src & ~ST_HOLE) : ST_ZERO;
+    return mpv > 0.1f ? cur : filled;
+}
+
+// One hole pixel, everything in one go (forward pass; backward pass when nothing was precomputed).
+__device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, uint32_t cur, const float2 f,
+                                                    const float2 *__restrict__ flow_check, const uint32_t *prev) {
+    const float2 pos = sample_pos(x, y, f, h, w);
+    const Taps t = make_taps(pos.x, pos.y, h, w);
+    const FlowTaps c = load_flow_taps(t, flow_check, w);           // all eight taps requested together
+    const StateTaps p = load_state_taps(t, prev, w);
+    return flow_consistent(f, t, c) ? fill_from_prev(t, cur, p) : cur;
+}
+
+constexpr uint32_t XY_INVALID = 1u << 31;     // backward-list entry whose flow failed the consistency check
 
 // Hole lists.  One entry per hole pixel: position (x | y << 16) and the flow vector that will
 // propagate INTO that pixel, so that a step's dependency chain is two memory round trips (entry,
@@ -149,8 +176,12 @@ struct BlockQueue {
 
 // All threads of the block must call (contains barriers).  `flow_frame` is gathered for each entry.
 // With `force == false` the queue is only written out when another push round might overflow it.
-__device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, long long of, long long npx, int w,
-                                            const float2 *__restrict__ flow_frame, bool force) {
+// `check_frame` != NULL (backward-pass lists with "k4_precheck"): the entry does not carry the flow but what the
+// serial step needs of it - the un-normalised sample position - and the verdict of the forward / backward
+// consistency check in bit 31 of the position word, both computed here, fully parallel over all frames.
+__device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, long long of, long long npx, int h, int w,
+                                            const float2 *__restrict__ flow_frame, const float2 *__restrict__ check_frame,
+                                            bool force) {
     __syncthreads();
     const uint32_t n = q.count;
     __syncthreads();                                            // everyone has read the count before it can change
@@ -168,6 +199,25 @@ __device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, l
                 const uint32_t j = j0 + u * blockDim.x;
                 xy[u] = j < n ? q.xy[j] : 0u;
                 f[u] = __ldg(flow_frame + (long long)(xy[u] >> 16) * w + (xy[u] & 0xffffu));
+            }
+            if (check_frame != nullptr) {                       // block-uniform
+                // two entries at a time: their 8 check-flow taps are in flight together (four would spill)
+#pragma unroll
+                for (int u0 = 0; u0 < 4; u0 += 2) {
+                    Taps tp[2];
+                    FlowTaps ct[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float2 pos = sample_pos((int)(xy[u0 + u] & 0xffffu), (int)(xy[u0 + u] >> 16), f[u0 + u], h, w);
+                        tp[u] = make_taps(pos.x, pos.y, h, w);
+                        ct[u] = load_flow_taps(tp[u], check_frame, w);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (!flow_consistent(f[u0 + u], tp[u], ct[u])) xy[u0 + u] |= XY_INVALID;
+                        f[u0 + u] = make_float2(tp[u].ix, tp[u].iy);
+                    }
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -187,8 +237,9 @@ __device__ __forceinline__ void queue_flush(BlockQueue &q, const HoleLists &l, l
 template <bool VEC, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
     k4_pack(const uint8_t *__restrict__ frames, const uint8_t *__restrict__ masks, uint32_t *__restrict__ state,
-            uint32_t *__restrict__ pads, const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b, HoleLists l1, HoleLists l2, int h,
-            int w, long long first_out_frame, const __grid_constant__ SubBatch batch) {
+            uint32_t *__restrict__ pads, const float2 *__restrict__ flows_f, const float2 *__restrict__ flows_b,
+            HoleLists l1, HoleLists l2, int h, int w, long long first_out_frame, int precheck,
+            const __grid_constant__ SubBatch batch) {
     const long long of = first_out_frame + blockIdx.y;          // output frame handled by this CTA row
     int s = 0;
     while (s + 1 < batch.n && batch.sub[s + 1].out_frame <= of) ++s;
@@ -202,6 +253,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
     const bool listed = len > 1;                                // a single-frame window has no steps at all
     // flow that propagates INTO this frame: backward pass flows_f[gframe], forward pass flows_b[gframe-1]
     const float2 *pflow = last ? flows_b + (gframe - 1) * npx : flows_f + gframe * npx;
+    // backward-pass entries: consistency of flows_f[gframe] against flows_b[gframe], decided here
+    const float2 *pcheck = (precheck && !last && listed) ? flows_b + gframe * npx : nullptr;
     const HoleLists dl = {last ? l2.xy : l1.xy, last ? l2.flow : l1.flow, last ? l2.count : l1.count};   // selected member-wise: stays in registers
     __shared__ BlockQueue q;
     if (threadIdx.x == 0) q.count = 0;
@@ -303,9 +356,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
                 }
             }
         }
-        queue_flush(q, dl, of, npx, w, pflow, false);          // same trip count for every thread of the block
+        queue_flush(q, dl, of, npx, h, w, pflow, pcheck, false);          // same trip count for every thread of the block
     }
-    if (listed) queue_flush(q, dl, of, npx, w, pflow, true);
+    if (listed) queue_flush(q, dl, of, npx, h, w, pflow, pcheck, true);
 }
 
 // ---- k4_step_lean: one time step of one direction, in place, over the hole lists ----------------
@@ -366,7 +419,10 @@ __device__ __forceinline__ void lean_flush(LeanQueue &q, const StepWin &sw) {
 
 // NPT = hole pixels per thread and trip: their list entries and taps are independent, so NPT = 2 doubles
 // the loads a thread keeps in flight at the price of registers (fewer resident CTAs).
-template <bool PASS2, int MIN_CTAS, bool UNCOND, int NPT>
+// PRE (backward pass with "k4_precheck"): the list entry holds the un-normalised sample position and, in bit 31
+// of the position word, the verdict of the consistency check (both from k4_pack); the step only gathers the four
+// state taps.  Entries that failed the check go straight to the forward list.
+template <bool PASS2, int MIN_CTAS, bool PRE, int NPT>
 __global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS)
     k4_step_lean(const __grid_constant__ StepArgs args, int h, int w, int speculate) {
     asm volatile("griddepcontrol.launch_dependents;");      // let the next step's CTAs get scheduled early
@@ -424,14 +480,22 @@ __global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS)
         }
 #pragma unroll
         for (int u = 0; u < NPT; ++u) {
-            const int x = (int)(xy_cur[u] & 0xffffu), y = (int)(xy_cur[u] >> 16);
+            const int x = (int)(xy_cur[u] & 0xffffu), y = (int)((xy_cur[u] >> 16) & 0x7fffu);
             pix[u] = (uint32_t)y * (uint32_t)w + (uint32_t)x;
             nv[u] = ST_HOLE | ST_ZERO;
             nf[u] = make_float2(0.f, 0.f);
             if (valid[u]) {
                 // the forward-pass flow is fetched speculatively, in the same round trip as the taps
                 if (relist && speculate) nf[u] = __ldg(sw.next_flow + pix[u]);
-                nv[u] = propagate_pixel<UNCOND>(x, y, h, w, ST_HOLE | ST_ZERO, f_cur[u], sw.flow_check, sw.prev);
+                if (PRE) {
+                    if (!(xy_cur[u] & XY_INVALID))
+                    {
+                        const Taps tp = make_taps(f_cur[u].x, f_cur[u].y, h, w);
+                        nv[u] = fill_from_prev(tp, ST_HOLE | ST_ZERO, load_state_taps(tp, sw.prev, w));
+                    }
+                } else {
+                    nv[u] = propagate_pixel(x, y, h, w, ST_HOLE | ST_ZERO, f_cur[u], sw.flow_check, sw.prev);
+                }
             }
         }
 #pragma unroll
@@ -447,7 +511,7 @@ __global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS)
                     uint32_t at = 0;
                     if (lane == 0) at = atomicAdd(&q.count, (uint32_t)__popc(m));
                     at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
-                    if (take) q.xy[at] = xy_cur[u], q.flow[at] = nf[u];
+                    if (take) q.xy[at] = xy_cur[u] & ~XY_INVALID, q.flow[at] = nf[u];
                 }
             }
         }
@@ -494,7 +558,7 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
     VV_CHECK_ARG((sub_keep_start == nullptr) == (sub_keep_len == nullptr),
                  "vv_propagate: sub_keep_start and sub_keep_len must be given together");
     VV_CHECK_ARG(n_frames > 0 && h > 0 && w > 0 && n_sub > 0, "vv_propagate: bad shape");
-    VV_CHECK_ARG(h <= 65535 && w <= 65535, "vv_propagate: frame too large");
+    VV_CHECK_ARG(h <= 32767 && w <= 65535, "vv_propagate: frame too large (h <= 32767, w <= 65535)");
     VV_CHECK_ARG(n_frames == 1 || (flows_f && flows_b), "vv_propagate: flows required when there is more than one frame");
     long long total = 0, kept = 0;
     for (int s = 0; s < n_sub; ++s) {
@@ -544,6 +608,7 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             blen = max(blen, sd.len);
         }
         const long long bframes = out_frame - first;
+        const int pre = get_option(OPT_K4_TAPS) != 0;          // "k4_precheck"
         // pack: all frames of the batch at once (grid.y <= 65535 frames per launch)
         for (long long f0 = 0; f0 < bframes; f0 += 32768) {
             const int ny = (int)min(32768LL, bframes - f0);
@@ -551,7 +616,7 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
             const int gx = max(1, min(ceil_div((npx + 3) / 4, 256 * K4_PACK_UNROLL), ceil_div(ctas, ny)));
             const int occ = get_option(OPT_K4_PACK_OCC);
 #define VV_K4_PACK(V, O) \
-    k4_pack<V, O><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, pads, ff, fb, l1, l2, h, w, first + f0, b)
+    k4_pack<V, O><<<dim3(gx, ny), 256, 0, st>>>(frames, masks, out, pads, ff, fb, l1, l2, h, w, first + f0, pre, b)
             if (!vec)
                 VV_K4_PACK(false, 4);
             else if (occ >= 6)
@@ -571,7 +636,6 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
         if (per_sm > 0) grid.x = max(1, min(ceil_div(npx / 4, 256), (148 * per_sm) / b.n));
         const int pdl = get_option(OPT_K4_PDL) != 0;
         const int lean = get_option(OPT_K4_LEAN);
-        const bool uncond = get_option(OPT_K4_TAPS) != 0;
         const int spec = get_option(OPT_K4_SPECULATE);
         const int npt = get_option(OPT_K4_NPT) >= 2 ? 2 : 1;
         for (int pass = 0; pass < 2; ++pass)
@@ -605,17 +669,19 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
                 // wrote BEFORE their griddepcontrol.wait, and only a full stream dependency makes those visible
                 cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
                 cudaError_t le;
-#define VV_K4_LEAN(O, U, N)                                                                    \
-    (pass == 0 ? cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, U, N>, sa, h, w, spec)        \
-               : cudaLaunchKernelEx(&cfg, k4_step_lean<true, O, U, N>, sa, h, w, spec))
+                // backward pass with precheck: PRE kernel; forward pass always carries flows
+#define VV_K4_LEAN(O, N)                                                                              \
+    (pass == 0 ? (pre ? cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, true, N>, sa, h, w, spec)      \
+                      : cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, false, N>, sa, h, w, spec))    \
+               : cudaLaunchKernelEx(&cfg, k4_step_lean<true, O, false, N>, sa, h, w, spec))
                 if (npt == 2)
-                    le = lean >= 4 && lean < 5 ? VV_K4_LEAN(4, false, 2) : VV_K4_LEAN(3, false, 2);
+                    le = lean == 4 ? VV_K4_LEAN(4, 2) : VV_K4_LEAN(3, 2);
                 else if (lean >= 8)
-                    le = uncond ? VV_K4_LEAN(8, true, 1) : VV_K4_LEAN(8, false, 1);
+                    le = VV_K4_LEAN(8, 1);
                 else if (lean >= 6)
-                    le = uncond ? VV_K4_LEAN(6, true, 1) : VV_K4_LEAN(6, false, 1);
+                    le = VV_K4_LEAN(6, 1);
                 else
-                    le = uncond ? VV_K4_LEAN(5, true, 1) : VV_K4_LEAN(5, false, 1);
+                    le = VV_K4_LEAN(5, 1);
 #undef VV_K4_LEAN
                 if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step_lean)");
                 VV_POST_LAUNCH("k4_step_lean");
