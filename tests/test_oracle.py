@@ -104,7 +104,7 @@ def test_T3_binarize_any_channel():
 # ---------------------------------------------------------------- KATs T4/T5/T9: resize
 RESIZE_CASES = [(540, 960, 1080, 1920), (536, 960, 1080, 1920), (176, 320, 360, 640), (1080, 1920, 540, 960),
                 (1080, 1920, 536, 960), (97, 131, 200, 333), (200, 333, 97, 131), (7, 5, 31, 47), (1, 1, 8, 8),
-                (2, 3, 9, 9), (100, 100, 25, 25), (2160, 3840, 536, 952), (64, 64, 64, 200), (300, 400, 150, 100)]
+                (2, 3, 9, 9), (100, 100, 25, 25), (2160, 3840, 536, 960), (536, 960, 2160, 3840), (64, 64, 64, 200), (300, 400, 150, 100)]
 
 
 @pytest.mark.parametrize("sh,sw,dh,dw", RESIZE_CASES)

@@ -81,3 +81,17 @@ def test_header_symbols_are_exported_and_bound():
     pytest.importorskip("torch")
     from videovanish_b200 import _lib
     assert names == set(_lib.EXPORTED), names ^ set(_lib.EXPORTED)
+
+
+def test_synth_config_table_matches_the_inference_size_rule():
+    """synth.CONFIGS names the five BASELINE configurations; their inference sizes follow the wrapper's rule
+    (round 1 carried a wrong 536x952 for 4K), c2 being the one BASELINE names at 960x540 instead of 960x536."""
+    from oracle import prepost as op
+    for name, (t, h0, w0, hw) in synth.CONFIGS.items():
+        rule = op.inference_size(h0, w0, 320 if name == "c1_360p" else 960)
+        if name == "c3_720p_flow":
+            rule = (h0, w0)                       # propagation runs at the clip's own resolution in config 3
+        if name == "c2_1080p":
+            assert hw == (540, 960) and rule == (536, 960)
+        else:
+            assert hw == rule, name

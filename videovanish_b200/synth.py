@@ -6,12 +6,15 @@ the loop: the "inpainted" frames are independent noise at inference resolution.
 """
 import numpy as np
 
-# name -> (T, H0, W0, inference (h, w))            BASELINE.json configs[0..4]
+# name -> (T, H0, W0, inference (h, w))            BASELINE.json configs[0..4]; (h, w) = oracle.prepost.inference_size
+# with max_img_size 320 for c1 and 960 for the others, except c2, which BASELINE names at 960x540 (the wrapper's
+# multiple-of-8 rule gives 960x536: bench.py's `c2_production_960x536` block and the GPU tests cover that too).
+# tests/test_host_logic.py checks the table against vv_inference_size.
 CONFIGS = {
     "c1_360p": (64, 360, 640, (176, 320)),
     "c2_1080p": (300, 1080, 1920, (540, 960)),
     "c3_720p_flow": (500, 720, 1280, (720, 1280)),
-    "c4_4k_chunked": (600, 2160, 3840, (536, 952)),
+    "c4_4k_chunked": (600, 2160, 3840, (536, 960)),
     "c5_1080p_long": (5000, 1080, 1920, (536, 960)),
 }
 
