@@ -761,8 +761,8 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
     const int h = gm.h, w = gm.w, H0 = gm.H0, W0 = gm.W0, th = gm.th, rpt = gm.rpt;
     const int Wpc = gm.Wpc, row_words = gm.row_words, rows_s = gm.rows_s;
     const float div = gm.div, one = gm.one;
-    uint8_t *strip = reinterpret_cast<uint8_t *>(smem_base);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_base + gm.bits_off - 4);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_base);                        // mbarrier first, strip 16 bytes in
+    uint8_t *strip = reinterpret_cast<uint8_t *>(smem_base + 4);
     uint32_t *bits = smem_base + gm.bits_off;                                       // [rows_s][row_words]
     float4 *lut = reinterpret_cast<float4 *>(smem_base + gm.lut_off);               // {a, a, 1-a, 1-a} x 16, then lut_pos
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1019,10 +1019,12 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
         }
         if (++j == rpt) j = 0, ++it;
     }
-    if (!landed) mbar_wait(bar, 0);
+    // Warps that patched the strip have waited for it; the thread that stores it must have, too (the others
+    // never touch the strip and need not look at the mbarrier).
     fence_proxy_async();                 // the patched quads must be visible to the bulk store
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (!landed) mbar_wait(bar, 0);
         uint8_t *dst = out_t + (long long)y0 * W0 * 3;
         for (uint32_t off = 0; off < strip_bytes; off += 32768u)
             bulk_s2g(dst + off, strip + off, min(32768u, strip_bytes - off));
@@ -1179,7 +1181,7 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
     const int hr = W0 == 2 * w ? 2 : (W0 == 4 * w ? 4 : 0);
     if (vec && small_r && x2opt >= 2 && get_option(OPT_K3_TMA) != 0 && hr != 0 && w >= 4 && (w * 3) % 4 == 0 &&
         ((uintptr_t)inp % 4 == 0)) {
-        // dynamic shared memory (words): [strip][mbarrier 4][bit rows][pad to 4][lut 16 x float4 + lut_pos 4][queues]
+        // dynamic shared memory (words): [mbarrier 4][strip][bit rows][pad to 4][lut 16 x float4 + lut_pos 4][queues]
         int fth = 0;
         size_t fsm = 0;
         FastGeom gm = {};
