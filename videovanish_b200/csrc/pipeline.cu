@@ -376,15 +376,30 @@ extern "C" int vv_pipeline_upload(vv_pipeline *p, const uint8_t *const *src, int
     VV_CHECK_ARG(frame_bytes <= (size_t)p->H0 * p->W0 * 4, "vv_pipeline_upload: frame larger than the context geometry");
     std::lock_guard<std::mutex> g(p->mu);
     VV_CUDA(cudaSetDevice(p->device));
-    int rc = VV_OK;
+    // `dev_dst` usually comes from a stream-ordered caching allocator: the block may have been freed by work that is
+    // still PENDING on the consumer stream.  The copies run on the slot streams, so they must not start before the
+    // consumer stream has got to this point (otherwise they overwrite memory that earlier kernels still use).
+    cudaEvent_t fence;
+    VV_CUDA(cudaEventCreateWithFlags(&fence, cudaEventDisableTiming));
+    cudaError_t fe = cudaEventRecord(fence, (cudaStream_t)stream);
+    int rc = fe == cudaSuccess ? VV_OK : fail_cuda(fe, "cudaEventRecord");
     for (int b = 0, t0 = 0; t0 < T && !rc; ++b, t0 += p->fpb) {
         Slot &s = p->slots[b % p->n_slots];
         const int n = std::min(p->fpb, T - t0);
         if ((rc = slot_wait(p, s))) break;
+        if (b < p->n_slots && (fe = cudaStreamWaitEvent(s.st, fence, 0)) != cudaSuccess) {
+            rc = fail_cuda(fe, "cudaStreamWaitEvent");
+            break;
+        }
         if ((rc = upload(p, s, src + t0, n, frame_bytes, dev_dst + (size_t)t0 * frame_bytes, 0))) break;
-        VV_CUDA(cudaEventRecord(s.done, s.st));
+        fe = cudaEventRecord(s.done, s.st);
+        if (fe != cudaSuccess) {
+            rc = fail_cuda(fe, "cudaEventRecord");
+            break;
+        }
         s.pending = true;
     }
+    cudaEventDestroy(fence);
     if (rc) return finish(p, rc);
     // The consumer stream waits for every slot ON THE DEVICE; the host does not wait: pageable sources have
     // already been copied into the pinned ring, page-locked ones are read by DMA until `stream` gets there.
