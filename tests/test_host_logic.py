@@ -96,7 +96,11 @@ def test_dropin_surface_matches_reference():
     if rh.available():
         ref = rh.load_reference()
         assert str(inspect.signature(ref.run_infill_on_frames)) == str(sig)
-    assert list(inspect.signature(tools.load_video_frames_from_path).parameters) == ["video_path", "start_frame", "max_frames"]
+    # the reference's three parameters first, same defaults; `device=None` is an optional extension (N1)
+    load = inspect.signature(tools.load_video_frames_from_path).parameters
+    assert list(load)[:3] == ["video_path", "start_frame", "max_frames"]
+    assert [load[k].default for k in ("start_frame", "max_frames")] == [0, -1]
+    assert all(p.default is None for k, p in load.items() if k not in ("video_path", "start_frame", "max_frames"))
     assert list(inspect.signature(tools.write_video_frames_to_path).parameters) == ["out_video", "mask_frames", "fps", "H0", "W0"]
 
 
