@@ -167,7 +167,7 @@ def test_k3_exact_x2_worker(ops, h, w, f):
     dil[2, :3] = dil[2, -2:] = 255
     dil[2, :, :5] = dil[2, :, -3:] = 255
     ref = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, f) for i in range(t)])
-    assert _lib.get_option("k3_x2") == 2                     # default: the k3_fast kernel
+    assert _lib.get_option("k3_x2") == 3                     # default: the k3_fastw kernel
     fast = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=f))
     try:
         _lib.set_option("k3_x2", 1)                          # round-1 closed-form x2 worker
@@ -175,7 +175,7 @@ def test_k3_exact_x2_worker(ops, h, w, f):
         _lib.set_option("k3_x2", 0)
         generic = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=f))
     finally:
-        _lib.set_option("k3_x2", 2)
+        _lib.set_option("k3_x2", 3)
     assert np.array_equal(fast, ref)
     assert np.array_equal(got, ref)
     assert np.array_equal(generic, ref)

@@ -75,7 +75,7 @@ def test_k3_fast_kernel(ops, h0, w0, h, w, f):
     inp = synth.noise_frames(t, h, w, seed=62)
     dil = border_masks(t, h0, w0, 63)
     ref = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, f) for i in range(t)])
-    assert _lib.get_option("k3_x2") == 2
+    assert _lib.get_option("k3_x2") == 3                     # default: k3_fastw (word tasks)
     d_inp, d_fr, d_dil = dev(inp), dev(fr), dev(dil)
     wp = (w0 + 31) // 32
     padded = np.zeros((t, h0, wp * 32), np.uint8)
@@ -85,6 +85,15 @@ def test_k3_fast_kernel(ops, h0, w0, h, w, f):
     got_bits = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
     variants = {}
     try:
+        for thr, rows in ((256, 16), (256, 6), (512, 5)):
+            _lib.set_option("k3_tma_threads", thr)
+            _lib.set_option("k3_tma_rows", rows)
+            variants["w-threads%d-rows%d" % (thr, rows)] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
+        _lib.set_option("k3_tma_threads", 512)
+        _lib.set_option("k3_tma_rows", 16)
+        _lib.set_option("k3_x2", 2)                          # k3_fast: 16-pixel rolling tasks
+        variants["rolling"] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f))
+        variants["rolling-bits"] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
         for rpt in (3, 4, 8, 16):
             _lib.set_option("k3_nt", rpt)
             variants["rpt%d" % rpt] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
@@ -96,6 +105,8 @@ def test_k3_fast_kernel(ops, h0, w0, h, w, f):
         _lib.set_option("k3_tma_threads", 512)
         _lib.set_option("k3_tma_rows", 16)
         _lib.set_option("k3_bits", 0)
+        variants["rolling-bits-ignored"] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
+        _lib.set_option("k3_x2", 3)
         variants["bits-ignored"] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
         _lib.set_option("k3_bits", 1)
         _lib.set_option("k3_x2", 1)
@@ -105,7 +116,7 @@ def test_k3_fast_kernel(ops, h0, w0, h, w, f):
     finally:
         _lib.set_option("k3_nt", 2)
         _lib.set_option("k3_bits", 1)
-        _lib.set_option("k3_x2", 2)
+        _lib.set_option("k3_x2", 3)
         _lib.set_option("k3_tma_threads", 512)
         _lib.set_option("k3_tma_rows", 16)
     assert np.array_equal(got, ref)

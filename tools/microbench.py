@@ -90,41 +90,33 @@ def main():
     full_bits = torch.full_like(bits, -1)
     box_dil, _, box_bits = ops.binarize_dilate(torch.from_numpy(synth.masks(t, H0, W0, seed=3, salt=0.0)).to(dev), 8, return_bits=True)
     k3b = t * (7 * px + 3 * spx)
-    for x2 in (2, 1, 0):
+    K3 = lambda m, b=None, i=None: (lambda: ops.upscale_feather_composite(inp if i is None else i, fr, m, 3, out=out, mask_bits=b))
+    empty_bits = torch.zeros_like(bits)
+    inp536 = inp[:, :536].contiguous()
+    k3b536 = t * (7 * px + 3 * 536 * 960)
+    for x2 in (3, 2):                                       # 3 = k3_fastw (word tasks, default), 2 = k3_fast (rolling 16-pixel tasks)
         _lib.set_option("k3_x2", x2)
-        report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out), k3_x2=x2, bits=0)
-        report("K3 composite (full mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out), k3_x2=x2, bits=0)
-    _lib.set_option("k3_x2", 2)
-    report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1)
-    report("K3 composite (full mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out, mask_bits=full_bits), k3_x2=2, bits=1)
-    report("K3 composite (empty mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, empty_mask, 3, out=out, mask_bits=torch.zeros_like(bits)), k3_x2=2, bits=1)
-    report("K3 composite (box mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, box_dil, 3, out=out, mask_bits=box_bits), k3_x2=2, bits=1)
-    for rpt in (3, 4, 8, 16):
-        _lib.set_option("k3_nt", rpt)
-        report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1, rpt=rpt)
-    _lib.set_option("k3_nt", 2)
-    for rows in (8, 12):
-        _lib.set_option("k3_tma_rows", rows)
-        report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1, rows=rows)
-    _lib.set_option("k3_tma_rows", 16)
-    _lib.set_option("k3_tma_threads", 256)
-    for rows in (16, 6, 7, 8):
-        _lib.set_option("k3_tma_rows", rows)
-        report("K3 composite (synthetic mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1, rows=rows, threads=256)
-    _lib.set_option("k3_tma_rows", 6)
-    report("K3 composite (full mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, full_mask, 3, out=out, mask_bits=full_bits), k3_x2=2, bits=1, rows=6, threads=256)
-    report("K3 composite (box mask)", k3b, lambda: ops.upscale_feather_composite(inp, fr, box_dil, 3, out=out, mask_bits=box_bits), k3_x2=2, bits=1, rows=6, threads=256)
+        report("K3 composite (synthetic mask)", k3b, K3(dil, bits), k3_x2=x2, bits=1)
+        report("K3 composite (synthetic mask)", k3b, K3(dil), k3_x2=x2, bits=0)
+        report("K3 composite (full mask)", k3b, K3(full_mask, full_bits), k3_x2=x2, bits=1)
+        report("K3 composite (empty mask)", k3b, K3(empty_mask, empty_bits), k3_x2=x2, bits=1)
+        report("K3 composite (box mask)", k3b, K3(box_dil, box_bits), k3_x2=x2, bits=1)
+        report("K3 composite 960x536 (synthetic mask)", k3b536, K3(dil, bits, inp536), k3_x2=x2, bits=1)
+    _lib.set_option("k3_x2", 3)
+    for thr, rows_list in ((512, (8, 12, 14)), (256, (16, 6, 7))):
+        _lib.set_option("k3_tma_threads", thr)
+        for rows in rows_list:
+            _lib.set_option("k3_tma_rows", rows)
+            report("K3 composite (synthetic mask)", k3b, K3(dil, bits), k3_x2=3, bits=1, rows=rows, threads=thr)
     _lib.set_option("k3_tma_rows", 16)
     _lib.set_option("k3_tma_threads", 512)
-    inp536 = inp[:, :536].contiguous()
-    report("K3 composite 960x536 (synthetic mask)", t * (7 * px + 3 * 536 * 960),
-           lambda: ops.upscale_feather_composite(inp536, fr, dil, 3, out=out, mask_bits=bits), k3_x2=2, bits=1)
-    _lib.set_option("k3_x2", 0)
-    report("K3 composite 960x536 (synthetic mask)", t * (7 * px + 3 * 536 * 960),
-           lambda: ops.upscale_feather_composite(inp536, fr, dil, 3, out=out), k3_x2=0, bits=0)
-    _lib.set_option("k3_x2", 2)
+    for x2 in (1, 0):                                       # round-1 kernels
+        _lib.set_option("k3_x2", x2)
+        report("K3 composite (synthetic mask)", k3b, K3(dil), k3_x2=x2, bits=0)
+    report("K3 composite 960x536 (synthetic mask)", k3b536, K3(dil, None, inp536), k3_x2=0, bits=0)
+    _lib.set_option("k3_x2", 3)
     report("K3 composite feather 5 (generic path)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
-    del dil_b, full_bits, box_dil, box_bits, inp536
+    del dil_b, full_bits, box_dil, box_bits, inp536, empty_bits
     # ---- K4: step-kernel variants
     pbuf = torch.empty((t, HS, WS), dtype=torch.int32, device=dev)
     k4b = t * 56 * spx

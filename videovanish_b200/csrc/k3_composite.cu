@@ -746,7 +746,7 @@ constexpr int K3F_QCAP = 128 + 32;      // one classified row of the warp (32 la
 struct FastGeom {
     int h, w, H0, W0, th, rpt;
     int Wpc, row_words, rows_s;          // mask words per frame row; per shared-memory bit row (+2 pad words); bit rows
-    int bits_off, lut_off, queue_off;    // word offsets inside dynamic shared memory (after the strip)
+    int bits_off, zbits_off, lut_off, queue_off;    // word offsets inside dynamic shared memory (after the strip); zbits: k3_fastw only
     int G, n_tasks, n_steps;
     long long frame_bytes, mask_frame_bytes, inp_frame_bytes, bits_frame_words;
     float div, one;
@@ -1032,6 +1032,296 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
     }
 }
 
+// =====================================================================================================
+// k3_fastw: k3_fast with WORD tasks.  ncu's source view of k3_fast (profiles/r02_k3_source_breakdown.txt) put 36 %
+// of the warp instructions into classification + compaction, because a lane classified 16 useful pixels out of the
+// 32 bits it shifted around (8 halo bits on each side) and carried a rolling 5-row window in registers.  Here a
+// task is one whole 32-bit word of one strip row: the +-1 / +-2 column shifts take their carry-in from the
+// neighbour words through funnel shifts (one SHF each, like a plain shift), so all 32 bits are useful; the five
+// window rows of both polarities (mask M and in-frame complement Z, both kept in shared memory) are simply
+// re-loaded per task (LSU pipe, which idles) instead of being rolled through registers (ALU pipe, which is the
+// bound).  A lane-step yields up to 8 quads; work items shrink to ONE word
+//     bits 0..9 quad index in the row (x / 4), 10..15 row in strip, 16..31 plane nibbles [L0 | L1 | L2 | inside]
+// and the worker's LUT index is again one multiply (0x1248 sends bits 0, 4, 8, 12 to bits 12..15 without carries).
+// Requires W0 <= 4096.  Worker arithmetic is k3_fast's.
+constexpr int K3W_QCAP = 256 + 32;      // one classified word per lane (32 lanes x 8 quads) + carried-over items
+
+template <bool VX2, bool BITS, int NTH, int HR = 2>
+__global__ void __launch_bounds__(NTH, 1024 / NTH)
+    k3_fastw(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ mask,
+             const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ yt,
+             const __grid_constant__ FastGeom gm) {
+    extern __shared__ __align__(128) uint32_t smem_base[];
+    const int h = gm.h, w = gm.w, H0 = gm.H0, W0 = gm.W0, th = gm.th;
+    const int Wpc = gm.Wpc, row_words = gm.row_words, rows_s = gm.rows_s;
+    const float div = gm.div, one = gm.one;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_base);                        // mbarrier first, strip 16 bytes in
+    uint8_t *strip = reinterpret_cast<uint8_t *>(smem_base + 4);
+    uint32_t *bitsM = smem_base + gm.bits_off;                                      // [rows_s][row_words] mask
+    uint32_t *bitsZ = smem_base + gm.zbits_off;                                     // [rows_s][row_words] in-frame & ~mask
+    float4 *lut = reinterpret_cast<float4 *>(smem_base + gm.lut_off);               // {a, a, 1-a, 1-a} x 16, then lut_pos
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *queue = smem_base + gm.queue_off + warp * K3W_QCAP;
+
+    const long long t = blockIdx.y;                  // grid = (strips, frames): no division
+    const int y0 = (int)blockIdx.x * th;
+    const uint8_t *orig_t = orig + t * gm.frame_bytes;
+    uint8_t *out_t = out + t * gm.frame_bytes;
+    const uint32_t strip_bytes = (uint32_t)(min(th, H0 - y0) * W0 * 3);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, strip_bytes);
+        const uint8_t *src = orig_t + (long long)y0 * W0 * 3;
+        for (uint32_t off = 0; off < strip_bytes; off += 32768u)
+            bulk_g2s(strip + off, src + off, min(32768u, strip_bytes - off), bar);
+    }
+
+    // ---------------- phase 1: bit rows [y0 - 2, y0 + th + 2) of both polarities, one zero pad word on each side
+    const uint32_t last_valid = (W0 & 31) ? ((1u << (W0 & 31)) - 1u) : 0xffffffffu;   // valid bits of frame word Wpc - 1
+    if (BITS) {
+        for (int i = warp; i < rows_s; i += NTH / 32) {
+            const int y = y0 - 2 + i;
+            const bool row_ok = y >= 0 && y < H0;
+            const uint32_t *src = mask_bits + t * gm.bits_frame_words + (long long)y * Wpc;
+            for (int k = lane; k < row_words; k += 32) {
+                uint32_t m = 0, z = 0;
+                if (row_ok && k >= 1 && k <= Wpc) {
+                    const uint32_t valid = k == Wpc ? last_valid : 0xffffffffu;
+                    m = __ldg(src + (k - 1)) & valid;
+                    z = ~m & valid;
+                }
+                bitsM[i * row_words + k] = m;
+                bitsZ[i * row_words + k] = z;
+            }
+        }
+    } else {
+        uint16_t *m16 = reinterpret_cast<uint16_t *>(bitsM), *z16 = reinterpret_cast<uint16_t *>(bitsZ);
+        const int halves = 2 * row_words;
+        const uint8_t *mask_t = mask + t * gm.mask_frame_bytes;
+        for (int id = threadIdx.x; id < rows_s * halves; id += NTH) {
+            const int i = id / halves, hw = id - i * halves;
+            const int y = y0 - 2 + i, x0 = (hw - 2) * 16;
+            uint32_t v = 0, z = 0;
+            if (y >= 0 && y < H0 && x0 >= 0 && x0 < W0) {
+                v = nonzero_bits16(ldg128(mask_t + (long long)y * W0 + x0));
+                z = ~v & 0xffffu;
+            }
+            m16[id] = (uint16_t)v;
+            z16[id] = (uint16_t)z;
+        }
+    }
+    if (warp == 0) {
+        // alpha levels: index = class (0 = no hit within the window, 1..5 = cost classes 1, 1.4, 2, 2.1969, 2.8) | inside << 3
+        const int cls = lane & 7, inside = (lane >> 3) & 1;
+        const float cost = cls == 1 ? 1.0f : cls == 2 ? 1.4f : cls == 3 ? 2.0f : cls == 4 ? 2.1969f : __fadd_rn(1.4f, 1.4f);
+        float a = inside ? 1.f : 0.f;
+        if (cls >= 1 && cls <= 5) a = inside ? alpha_from(cost, 0.f, div) : alpha_from(0.f, cost, div);
+        const float na = __fsub_rn(1.f, a);
+        if (lane < 16) lut[lane] = make_float4(a, a, na, na);
+        const uint32_t posmask = __ballot_sync(0xffffffffu, lane < 16 && a > 0.f);     // which LUT levels have alpha > 0
+        if (lane == 0) reinterpret_cast<uint32_t *>(lut + 16)[0] = posmask;
+    }
+    __syncthreads();
+
+    const uint32_t lut_pos = reinterpret_cast<const uint32_t *>(lut + 16)[0];
+    // outside classes 1..5 that still blend (alpha > 0), as masks applied to p1..p5
+    const uint32_t e1 = (lut_pos >> 1) & 1u ? ~0u : 0u, e2 = (lut_pos >> 2) & 1u ? ~0u : 0u, e3 = (lut_pos >> 3) & 1u ? ~0u : 0u,
+                   e4 = (lut_pos >> 4) & 1u ? ~0u : 0u, e5 = (lut_pos >> 5) & 1u ? ~0u : 0u;
+
+    const uint8_t *inp_t = inp + t * gm.inp_frame_bytes;
+    const f32x2 one2 = pack2(one, one), magic2 = pack2(12582912.f, 12582912.f), unbias2 = pack2(-8388608.f, -8388608.f);
+
+    // ---- worker: one 4-pixel quad per lane
+    auto work = [&](const uint32_t item) {
+        const int xq = (int)(item & 0x3ffu) << 2, r = (int)(item >> 10) & 0x3f;
+        const int yy = y0 + r;
+        uint32_t a0, a1, a2, b0, b1, b2, wa = 0, wb = 0;
+        if (VX2) {
+            const int j = yy >> 1;                                           // source row of weight 3/4
+            const int ja = (yy & 1) ? min(j + 1, h - 1) : max(j - 1, 0);     // source row of weight 1/4
+            x2_load_row(inp_t + ja * w * 3, xq, W0, a0, a1, a2);
+            x2_load_row(inp_t + j * w * 3, xq, W0, b0, b1, b2);
+        } else {
+            const Tap ty = yt[yy];
+            wa = (uint32_t)(ty.w & 0xffff) << 20, wb = ((uint32_t)ty.w >> 16) << 20;
+            const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
+            if (HR == 4) {
+                x4_load_row(inp_t + ya * w * 3, xq, W0, a0, a1, a2);
+                x4_load_row(inp_t + yb * w * 3, xq, W0, b0, b1, b2);
+            } else {
+                x2_load_row(inp_t + ya * w * 3, xq, W0, a0, a1, a2);
+                x2_load_row(inp_t + yb * w * 3, xq, W0, b0, b1, b2);
+            }
+        }
+        uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
+        const uint32_t o0 = sp[0], o1 = sp[1], o2 = sp[2];
+        // plane nibbles of the quad in the item: L0 @ bits 16-19, L1 @ 20-23, L2 @ 24-27, inside @ 28-31 (bit i = pixel i).
+        // LUT byte offset of pixel i = 16 * (L0 | L1 << 1 | L2 << 2 | inside << 3): 0x1248 = 2^12 + 2^9 + 2^6 + 2^3 sends
+        // bits 0, 4, 8, 12 to bits 12..15; no two partial products share a bit position, so there are no carries.
+        const uint8_t *lutb = reinterpret_cast<const uint8_t *>(lut);
+        auto lut_at = [&](int i) {
+            const uint32_t tsel = (item >> (16 + i)) & 0x1111u;
+            return *reinterpret_cast<const float4 *>(lutb + (((tsel * 0x1248u) >> 8) & 0xf0u));
+        };
+        const float4 l0 = lut_at(0), l1 = lut_at(1), l2 = lut_at(2), l3 = lut_at(3);
+        uint32_t ma[6], mb[6], up[6];
+        if (HR == 4) {
+            x4_hpass(a0, a1, a2, ma);
+            x4_hpass(b0, b1, b2, mb);
+        } else {
+            x2_hpass(a0, a1, a2, ma);
+            x2_hpass(b0, b1, b2, mb);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (VX2) {
+                up[k] = x2_vpass(ma[k], mb[k]);
+            } else {
+                // (b * (h >> 4)) >> 16 with h >> 4 == 32 m (x2) or 16 m (x4): umulhi(b << 20, m << 1 or m)
+                const uint32_t am = HR == 4 ? ma[k] : ma[k] << 1, bm = HR == 4 ? mb[k] : mb[k] << 1;   // lanes <= 2040 / 4080: no carry
+                const uint32_t lo = (__umulhi(wa, am & 0xffffu) + __umulhi(wb, bm & 0xffffu) + 2u) >> 2;
+                const uint32_t hi = (__umulhi(wa, am >> 16) + __umulhi(wb, bm >> 16) + 2u) >> 2;
+                up[k] = lo | (hi << 16);
+            }
+        }
+        // byte pair p = bytes (2p, 2p+1) of the 12-byte quad; byte k belongs to pixel k / 3
+        const f32x2 al[6] = {pack2(l0.x, l0.y), pack2(l0.x, l1.x), pack2(l1.x, l1.y),
+                             pack2(l2.x, l2.y), pack2(l2.x, l3.x), pack2(l3.x, l3.y)};
+        const f32x2 nl[6] = {pack2(l0.z, l0.w), pack2(l0.z, l1.z), pack2(l1.z, l1.w),
+                             pack2(l2.z, l2.w), pack2(l2.z, l3.z), pack2(l3.z, l3.w)};
+        const uint32_t ow[3] = {o0, o1, o2};
+        uint32_t rb[12];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+            // u8 -> f32 through the mantissa: bits(2^23 + b) - 2^23 (both lanes at once)
+            const f32x2 uf = fadd2(pack2u(__byte_perm(up[p], 0x4b000000u, 0x7540u), __byte_perm(up[p], 0x4b000000u, 0x7542u)),
+                                   unbias2);
+            const uint32_t wsrc = ow[p >> 1];
+            const uint32_t s0 = 0x7540u | (uint32_t)((2 * p) & 3), s1 = 0x7540u | (uint32_t)((2 * p + 1) & 3);
+            const f32x2 of = fadd2(pack2u(__byte_perm(wsrc, 0x4b000000u, s0), __byte_perm(wsrc, 0x4b000000u, s1)), unbias2);
+            // f32(a * up) + f32((1 - a) * orig), then round half to even through the mantissa
+            const f32x2 v = fadd2(ffma2(fmul2(al[p], uf), one2, fmul2(nl[p], of)), magic2);
+            unpack2u(v, rb[2 * p], rb[2 * p + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            sp[j] = __byte_perm(__byte_perm(rb[4 * j], rb[4 * j + 1], 0x0040), __byte_perm(rb[4 * j + 2], rb[4 * j + 3], 0x0040),
+                                0x5410);
+    };
+
+    // ---------------- phase 2: classification, one 32-pixel word of one strip row per lane and step
+    const int n_tasks = gm.n_tasks, n_steps = gm.n_steps;
+    int qcount = 0;
+    bool landed = false;
+#pragma unroll 1
+    for (int step = 0; step <= n_steps; ++step) {
+        const bool drain = step == n_steps;
+        uint32_t need = 0, L0 = 0, L1 = 0, L2 = 0, M2 = 0, base = 0;
+        // Each warp's 32 lanes sample the strip evenly (8 runs of 4 consecutive tasks, NTH / 8 tasks apart), so that
+        // the warps of a CTA get the same amount of blend work whatever the mask looks like.
+        const int id = step * NTH + (lane >> 2) * (NTH / 8) + (warp << 2) + (lane & 3);
+        if (!drain && id < n_tasks) {
+            const int rr = id / Wpc, k = id - rr * Wpc;
+            if (y0 + rr < H0) {
+                // bit row rr + d <-> frame row y0 + rr - 2 + d; word index k + 1 in the padded row, pm points at word k - 1
+                const uint32_t *pm = bitsM + rr * row_words + k;
+                uint32_t Sp[5], Sc[5], Sn[5];
+#pragma unroll
+                for (int d = 0; d < 5; ++d) Sp[d] = pm[d * row_words], Sc[d] = pm[d * row_words + 1], Sn[d] = pm[d * row_words + 2];
+                M2 = Sc[2];
+                uint32_t A1p = Sp[1] | Sp[3], A1c = Sc[1] | Sc[3], A1n = Sn[1] | Sn[3];
+                uint32_t A0p = Sp[0] | Sp[4], A0c = Sc[0] | Sc[4], A0n = Sn[0] | Sn[4];
+                // any mask pixel in the 5 x 36 window of this word?
+                const uint32_t anyM = (M2 | A1c | A0c) | ((Sp[2] | A1p | A0p) >> 30) | ((Sn[2] | A1n | A0n) << 30);
+                if (anyM) {
+                    auto classes = [](uint32_t s2p, uint32_t s2c, uint32_t s2n, uint32_t a1p, uint32_t a1c, uint32_t a1n,
+                                      uint32_t a0p, uint32_t a0c, uint32_t a0n, uint32_t *hc) {
+                        // column shifts with the carry-in of the neighbour word: x-1 / x-2 from the previous word's top
+                        // bits (funnel shift left), x+1 / x+2 from the next word's low bits (funnel shift right)
+                        hc[0] = __funnelshift_l(s2p, s2c, 1) | __funnelshift_r(s2c, s2n, 1) | a1c;              // cost 1
+                        hc[1] = __funnelshift_l(a1p, a1c, 1) | __funnelshift_r(a1c, a1n, 1);                    // 1.4
+                        hc[2] = __funnelshift_l(s2p, s2c, 2) | __funnelshift_r(s2c, s2n, 2) | a0c;              // 2
+                        hc[3] = __funnelshift_l(a0p, a0c, 1) | __funnelshift_r(a0c, a0n, 1) |
+                                __funnelshift_l(a1p, a1c, 2) | __funnelshift_r(a1c, a1n, 2);                    // 2.1969
+                        hc[4] = __funnelshift_l(a0p, a0c, 2) | __funnelshift_r(a0c, a0n, 2);                    // 2.8
+                    };
+                    uint32_t hm[5], hz[5];
+                    classes(Sp[2], Sc[2], Sn[2], A1p, A1c, A1n, A0p, A0c, A0n, hm);
+                    const uint32_t *pz = bitsZ + rr * row_words + k;
+#pragma unroll
+                    for (int d = 0; d < 5; ++d) Sp[d] = pz[d * row_words], Sc[d] = pz[d * row_words + 1], Sn[d] = pz[d * row_words + 2];
+                    A1p = Sp[1] | Sp[3], A1c = Sc[1] | Sc[3], A1n = Sn[1] | Sn[3];
+                    A0p = Sp[0] | Sp[4], A0c = Sc[0] | Sc[4], A0n = Sn[0] | Sn[4];
+                    classes(Sp[2], Sc[2], Sn[2], A1p, A1c, A1n, A0p, A0c, A0n, hz);
+                    uint32_t hsel[5];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) hsel[c] = (hz[c] & M2) | (hm[c] & ~M2);   // inside pixels look for zeros
+                    const uint32_t p1 = hsel[0];
+                    const uint32_t p2 = hsel[1] & ~p1;
+                    const uint32_t s12 = p1 | hsel[1];
+                    const uint32_t p3 = hsel[2] & ~s12;
+                    const uint32_t s123 = s12 | hsel[2];
+                    const uint32_t p4 = hsel[3] & ~s123;
+                    const uint32_t p5 = hsel[4] & ~(s123 | hsel[3]);
+                    L0 = p1 | p3 | p5, L1 = p2 | p3, L2 = p4 | p5;
+                    // alpha > 0: every inside pixel, and outside pixels whose first hit has alpha > 0; only pixels of the frame
+                    const uint32_t pos = M2 | (p1 & e1) | (p2 & e2) | (p3 & e3) | (p4 & e4) | (p5 & e5);
+                    need = pos & (k == Wpc - 1 ? last_valid : 0xffffffffu);
+                    base = (uint32_t)(k << 3) | ((uint32_t)rr << 10);
+                }
+            }
+        }
+        // ---- warp-level compaction: every quad with a pixel to blend becomes one work item
+        if (__ballot_sync(0xffffffffu, need != 0)) {                         // warp-uniform
+            const uint32_t nzq = (need | (need >> 1) | (need >> 2) | (need >> 3)) & 0x11111111u;   // bit 4q = quad q has work
+            const int qn = __popc(nzq);
+            int pre = qn;                                                    // inclusive scan over lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, d);
+                if (lane >= d) pre += v;
+            }
+            int pos = qcount + pre - qn;
+            qcount += __shfl_sync(0xffffffffu, pre, 31);
+            if (need) {
+                // byte j of P01e / P23e = [L1 : L0] / [inside : L2] nibbles of quad 2j, of P01o / P23o those of quad 2j + 1
+                const uint32_t P01e = (L0 & 0x0f0f0f0fu) | ((L1 << 4) & 0xf0f0f0f0u), P01o = ((L0 >> 4) & 0x0f0f0f0fu) | (L1 & 0xf0f0f0f0u);
+                const uint32_t P23e = (L2 & 0x0f0f0f0fu) | ((M2 << 4) & 0xf0f0f0f0u), P23o = ((L2 >> 4) & 0x0f0f0f0fu) | (M2 & 0xf0f0f0f0u);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int j = q >> 1;
+                    const uint32_t sel = (uint32_t)(((4 + j) << 12) | (j << 8) | ((4 + j) << 4) | j);   // bytes 2, 3 = P01.j, P23.j
+                    const uint32_t nib = __byte_perm((q & 1) ? P01o : P01e, (q & 1) ? P23o : P23e, sel);
+                    if ((nzq >> (4 * q)) & 1u) queue[pos++] = (nib & 0xffff0000u) | (base + (uint32_t)q);
+                }
+            }
+            __syncwarp();
+        }
+        if (qcount >= 32 || (drain && qcount > 0)) {                         // warp-uniform
+            if (!landed) {
+                mbar_wait(bar, 0);
+                landed = true;
+            }
+            do {
+                const int take = min(qcount, 32);
+                qcount -= take;
+                if (lane < take) work(queue[qcount + lane]);
+            } while (qcount >= 32);
+            __syncwarp();              // the queue tail is overwritten by the next pushes
+        }
+    }
+    fence_proxy_async();                 // the patched quads must be visible to the bulk store
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!landed) mbar_wait(bar, 0);
+        uint8_t *dst = out_t + (long long)y0 * W0 * 3;
+        for (uint32_t off = 0; off < strip_bytes; off += 32768u)
+            bulk_s2g(dst + off, strip + off, min(32768u, strip_bytes - off));
+        bulk_commit_and_wait_read();     // shared memory must outlive the reads of the store
+    }
+}
+
 // Host: float32 Dijkstra over the 5x5-chamfer step set (same construction as
 // oracle/prepost.py chamfer_cost_table, verified bit-exact against cv2.distanceTransform).
 static void build_feather_table(float feather_px, FeatherTable *ft) {
@@ -1181,18 +1471,22 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
     const int hr = W0 == 2 * w ? 2 : (W0 == 4 * w ? 4 : 0);
     if (vec && small_r && x2opt >= 2 && get_option(OPT_K3_TMA) != 0 && hr != 0 && w >= 4 && (w * 3) % 4 == 0 &&
         ((uintptr_t)inp % 4 == 0)) {
-        // dynamic shared memory (words): [mbarrier 4][strip][bit rows][pad to 4][lut 16 x float4 + lut_pos 4][queues]
+        // dynamic shared memory (words): [mbarrier 4][strip][bit rows (k3_fastw: M rows, Z rows)][pad to 4]
+        //                                [lut 16 x float4 + lut_pos 4][queues]
         int fth = 0;
         size_t fsm = 0;
         FastGeom gm = {};
+        // word tasks (k3_fastw, default) or 16-pixel rolling tasks (k3_fast, option k3_x2 = 2)
+        const bool wordtasks = x2opt >= 3 && W0 <= 4096;
         // 512 threads x 2 CTAs per SM (default) or 256 threads x 4 CTAs per SM with shorter strips
         const int nth = (hr == 2 && get_option(OPT_K3_TMA_THREADS) <= 256) ? 256 : 512;
         const size_t smem_cap = nth == 256 ? 56 * 1024 : 113 * 1024;
         for (fth = min(16, max(2, get_option(OPT_K3_TMA_ROWS))); fth >= 2; --fth) {
             gm.bits_off = fth * W0 * 3 / 4 + 4;
-            gm.lut_off = (gm.bits_off + (fth + 4) * (Wp + 2) + 3) & ~3;
+            gm.zbits_off = gm.bits_off + (fth + 4) * (Wp + 2);
+            gm.lut_off = ((wordtasks ? gm.zbits_off : gm.bits_off) + (fth + 4) * (Wp + 2) + 3) & ~3;
             gm.queue_off = gm.lut_off + 16 * 4 + 4;
-            fsm = ((size_t)gm.queue_off + (nth / 32) * K3F_QCAP * 2) * 4;
+            fsm = ((size_t)gm.queue_off + (nth / 32) * (wordtasks ? K3W_QCAP : K3F_QCAP * 2)) * 4;
             if (fsm <= smem_cap) break;
         }
         if (fth >= 2) {
@@ -1216,9 +1510,13 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
             gm.frame_bytes = (long long)H0 * W0 * 3, gm.mask_frame_bytes = (long long)H0 * W0;
             gm.inp_frame_bytes = (long long)h * w * 3, gm.bits_frame_words = (long long)H0 * Wp;
             gm.div = ft.div, gm.one = 1.0f;
-#define VV_K3_FAST(V, B, N)                                                                                     \
+            if (wordtasks) {      // one 32-pixel word of one strip row per lane and step
+                gm.n_tasks = Wp * fth;
+                gm.n_steps = ceil_div(gm.n_tasks, nth);
+            }
+#define VV_K3_FAST(KERNEL, V, B, N, H)                                                                          \
     do {                                                                                                        \
-        auto kfn = k3_fast<V, B, N>;                                                                            \
+        auto kfn = KERNEL<V, B, N, H>;                                                                          \
         VV_K3_SMEM(kfn);                                                                                        \
         for (int t0 = 0; t0 < T; t0 += 32768) {        /* grid.y <= 65535 frames per launch */                  \
             const int tn = min(32768, T - t0);                                                                  \
@@ -1226,45 +1524,35 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
             kfn<<<dim3((unsigned)fstrips, (unsigned)tn), N, smem, st>>>(                                        \
                 inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo,                                         \
                 mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : nullptr, out + fo * 3, yt, gm);                  \
-            VV_POST_LAUNCH("k3_fast");                                                                          \
+            VV_POST_LAUNCH(#KERNEL);                                                                            \
         }                                                                                                       \
     } while (0)
-#define VV_K3_FAST_N(V, B)        \
-    do {                          \
-        if (nth == 256)           \
-            VV_K3_FAST(V, B, 256); \
-        else                      \
-            VV_K3_FAST(V, B, 512); \
+#define VV_K3_FAST_B(KERNEL, V, N, H)      \
+    do {                                   \
+        if (bits)                          \
+            VV_K3_FAST(KERNEL, V, true, N, H);  \
+        else                               \
+            VV_K3_FAST(KERNEL, V, false, N, H); \
     } while (0)
-            if (hr == 4) {        // x4: always table-driven vertical taps, 512 threads
-                if (bits) {
-                    auto kfn = k3_fast<false, true, 512, 4>;
-                    VV_K3_SMEM(kfn);
-                } else {
-                    auto kfn = k3_fast<false, false, 512, 4>;
-                    VV_K3_SMEM(kfn);
-                }
-                for (int t0 = 0; t0 < T; t0 += 32768) {
-                    const int tn = min(32768, T - t0);
-                    const size_t fo = (size_t)t0 * H0 * W0;
-                    const uint32_t *mb = mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : nullptr;
-                    if (bits)
-                        k3_fast<false, true, 512, 4><<<dim3((unsigned)fstrips, (unsigned)tn), 512, smem, st>>>(
-                            inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo, mb, out + fo * 3, yt, gm);
-                    else
-                        k3_fast<false, false, 512, 4><<<dim3((unsigned)fstrips, (unsigned)tn), 512, smem, st>>>(
-                            inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo, mb, out + fo * 3, yt, gm);
-                    VV_POST_LAUNCH("k3_fast");
-                }
-            } else if (vx2 && bits)
-                VV_K3_FAST_N(true, true);
-            else if (vx2)
-                VV_K3_FAST_N(true, false);
-            else if (bits)
-                VV_K3_FAST_N(false, true);
+#define VV_K3_FAST_ALL(KERNEL)                       \
+    do {                                             \
+        if (hr == 4)  /* x4: table-driven vertical taps, 512 threads */ \
+            VV_K3_FAST_B(KERNEL, false, 512, 4);     \
+        else if (vx2 && nth == 256)                  \
+            VV_K3_FAST_B(KERNEL, true, 256, 2);      \
+        else if (vx2)                                \
+            VV_K3_FAST_B(KERNEL, true, 512, 2);      \
+        else if (nth == 256)                         \
+            VV_K3_FAST_B(KERNEL, false, 256, 2);     \
+        else                                         \
+            VV_K3_FAST_B(KERNEL, false, 512, 2);     \
+    } while (0)
+            if (wordtasks)
+                VV_K3_FAST_ALL(k3_fastw);
             else
-                VV_K3_FAST_N(false, false);
-#undef VV_K3_FAST_N
+                VV_K3_FAST_ALL(k3_fast);
+#undef VV_K3_FAST_ALL
+#undef VV_K3_FAST_B
 #undef VV_K3_FAST
             return VV_OK;
         }
