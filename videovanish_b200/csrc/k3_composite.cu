@@ -144,6 +144,21 @@ __device__ __forceinline__ void x2_load_row(const uint8_t *__restrict__ rowp, in
     if (left) r0 = __byte_perm(r0, r1, 0x3543);      // [x x x S0] [S1 S2 S3 S4] -> [S0 S1 S2 S0]
     if (right) r2 = __byte_perm(r1, r2, 0x4324);     // [T7 T8 T9 T10] [T11 x x x] -> [T11 T9 T10 T11]
 }
+// The same 12 bytes addressed through ONE pointer per row: `inw` = the frame as 32-bit words, `row_word` = word
+// offset of the source row.  The border words are not loaded at all (predicated off; the patched bytes replace
+// them), so there is one 64-bit address computation per row instead of three.
+__device__ __forceinline__ void x2_load_row_w(const uint32_t *__restrict__ inw, int row_word, int xq, int W0, uint32_t &r0,
+                                              uint32_t &r1, uint32_t &r2) {
+    const bool left = xq == 0, right = xq == W0 - 4;
+    const int bo = 3 * (xq >> 1) - 3;                                  // -3 at the left border
+    const uint32_t *p = inw + (row_word + (bo >> 2));                  // arithmetic shift: word -1 at the left border
+    const uint32_t w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    const uint32_t w0 = left ? w1 : __ldg(p), w3 = right ? w2 : __ldg(p + 3);
+    const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(bo & 3);
+    r0 = __byte_perm(w0, w1, sel), r1 = __byte_perm(w1, w2, sel), r2 = __byte_perm(w2, w3, sel);
+    if (left) r0 = __byte_perm(r0, r1, 0x3543);      // [x x x S0] [S1 S2 S3 S4] -> [S0 S1 S2 S0]
+    if (right) r2 = __byte_perm(r1, r2, 0x4324);     // [T7 T8 T9 T10] [T11 x x x] -> [T11 T9 T10 T11]
+}
 // Horizontal pass of a quad: m[j] holds channel values 2j (low lane) and 2j+1 (high lane) of the
 // 12 output values (pixel k/3, channel k%3); near = the source pixel of weight 3/4.
 __device__ __forceinline__ void x2_hpass(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t m[6]) {
@@ -748,6 +763,7 @@ struct FastGeom {
     int Wpc, row_words, rows_s;          // mask words per frame row; per shared-memory bit row (+2 pad words); bit rows
     int bits_off, zbits_off, lut_off, queue_off;    // word offsets inside dynamic shared memory (after the strip); zbits: k3_fastw only
     int G, n_tasks, n_steps;
+    uint32_t inv_wpc;                    // floor(2^32 / Wpc) + 1: id / Wpc == umulhi(id, inv_wpc) for id < 65536, Wpc > 1 (k3_fastw)
     long long frame_bytes, mask_frame_bytes, inp_frame_bytes, bits_frame_words;
     float div, one;
 };
@@ -1130,6 +1146,8 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
                    e4 = (lut_pos >> 4) & 1u ? ~0u : 0u, e5 = (lut_pos >> 5) & 1u ? ~0u : 0u;
 
     const uint8_t *inp_t = inp + t * gm.inp_frame_bytes;
+    const uint32_t *inw = reinterpret_cast<const uint32_t *>(inp_t);               // 4-byte aligned rows (host check)
+    const int wq = (w * 3) >> 2;                                                   // words per source row
     const f32x2 one2 = pack2(one, one), magic2 = pack2(12582912.f, 12582912.f), unbias2 = pack2(-8388608.f, -8388608.f);
 
     // ---- worker: one 4-pixel quad per lane
@@ -1140,8 +1158,8 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
         if (VX2) {
             const int j = yy >> 1;                                           // source row of weight 3/4
             const int ja = (yy & 1) ? min(j + 1, h - 1) : max(j - 1, 0);     // source row of weight 1/4
-            x2_load_row(inp_t + ja * w * 3, xq, W0, a0, a1, a2);
-            x2_load_row(inp_t + j * w * 3, xq, W0, b0, b1, b2);
+            x2_load_row_w(inw, ja * wq, xq, W0, a0, a1, a2);
+            x2_load_row_w(inw, j * wq, xq, W0, b0, b1, b2);
         } else {
             const Tap ty = yt[yy];
             wa = (uint32_t)(ty.w & 0xffff) << 20, wb = ((uint32_t)ty.w >> 16) << 20;
@@ -1150,19 +1168,20 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
                 x4_load_row(inp_t + ya * w * 3, xq, W0, a0, a1, a2);
                 x4_load_row(inp_t + yb * w * 3, xq, W0, b0, b1, b2);
             } else {
-                x2_load_row(inp_t + ya * w * 3, xq, W0, a0, a1, a2);
-                x2_load_row(inp_t + yb * w * 3, xq, W0, b0, b1, b2);
+                x2_load_row_w(inw, ya * wq, xq, W0, a0, a1, a2);
+                x2_load_row_w(inw, yb * wq, xq, W0, b0, b1, b2);
             }
         }
         uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
         const uint32_t o0 = sp[0], o1 = sp[1], o2 = sp[2];
         // plane nibbles of the quad in the item: L0 @ bits 16-19, L1 @ 20-23, L2 @ 24-27, inside @ 28-31 (bit i = pixel i).
-        // LUT byte offset of pixel i = 16 * (L0 | L1 << 1 | L2 << 2 | inside << 3): 0x1248 = 2^12 + 2^9 + 2^6 + 2^3 sends
-        // bits 0, 4, 8, 12 to bits 12..15; no two partial products share a bit position, so there are no carries.
+        // LUT byte offset of pixel i = 16 * (L0 | L1 << 1 | L2 << 2 | inside << 3): the multiplier 0x1248 >> i =
+        // 2^(12-i) + 2^(9-i) + 2^(6-i) + 2^(3-i) sends bits 16+i, 20+i, 24+i, 28+i to bits 28..31; no two partial
+        // products share a bit position, so there are no carries (products above bit 31 drop out).
         const uint8_t *lutb = reinterpret_cast<const uint8_t *>(lut);
         auto lut_at = [&](int i) {
-            const uint32_t tsel = (item >> (16 + i)) & 0x1111u;
-            return *reinterpret_cast<const float4 *>(lutb + (((tsel * 0x1248u) >> 8) & 0xf0u));
+            const uint32_t tsel = item & (0x11110000u << i);
+            return *reinterpret_cast<const float4 *>(lutb + (((tsel * (0x1248u >> i)) >> 24) & 0xf0u));
         };
         const float4 l0 = lut_at(0), l1 = lut_at(1), l2 = lut_at(2), l3 = lut_at(3);
         uint32_t ma[6], mb[6], up[6];
@@ -1222,7 +1241,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
         // the warps of a CTA get the same amount of blend work whatever the mask looks like.
         const int id = step * NTH + (lane >> 2) * (NTH / 8) + (warp << 2) + (lane & 3);
         if (!drain && id < n_tasks) {
-            const int rr = id / Wpc, k = id - rr * Wpc;
+            const int rr = Wpc == 1 ? id : (int)__umulhi((uint32_t)id, gm.inv_wpc), k = id - rr * Wpc;   // id / Wpc (id < 65536)
             if (y0 + rr < H0) {
                 // bit row rr + d <-> frame row y0 + rr - 2 + d; word index k + 1 in the padded row, pm points at word k - 1
                 const uint32_t *pm = bitsM + rr * row_words + k;
@@ -1282,7 +1301,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
                 const int v = __shfl_up_sync(0xffffffffu, pre, d);
                 if (lane >= d) pre += v;
             }
-            int pos = qcount + pre - qn;
+            uint32_t *qp = queue + (qcount + pre - qn);
             qcount += __shfl_sync(0xffffffffu, pre, 31);
             if (need) {
                 // byte j of P01e / P23e = [L1 : L0] / [inside : L2] nibbles of quad 2j, of P01o / P23o those of quad 2j + 1
@@ -1293,7 +1312,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
                     const int j = q >> 1;
                     const uint32_t sel = (uint32_t)(((4 + j) << 12) | (j << 8) | ((4 + j) << 4) | j);   // bytes 2, 3 = P01.j, P23.j
                     const uint32_t nib = __byte_perm((q & 1) ? P01o : P01e, (q & 1) ? P23o : P23e, sel);
-                    if ((nzq >> (4 * q)) & 1u) queue[pos++] = (nib & 0xffff0000u) | (base + (uint32_t)q);
+                    if ((nzq >> (4 * q)) & 1u) *qp++ = (nib & 0xffff0000u) | (base + (uint32_t)q);
                 }
             }
             __syncwarp();
@@ -1513,6 +1532,7 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
             if (wordtasks) {      // one 32-pixel word of one strip row per lane and step
                 gm.n_tasks = Wp * fth;
                 gm.n_steps = ceil_div(gm.n_tasks, nth);
+                gm.inv_wpc = (uint32_t)(0x100000000ULL / (unsigned)Wp) + 1u;
             }
 #define VV_K3_FAST(KERNEL, V, B, N, H)                                                                          \
     do {                                                                                                        \
