@@ -159,6 +159,45 @@ __device__ __forceinline__ void x2_load_row_w(const uint32_t *__restrict__ inw, 
     if (left) r0 = __byte_perm(r0, r1, 0x3543);      // [x x x S0] [S1 S2 S3 S4] -> [S0 S1 S2 S0]
     if (right) r2 = __byte_perm(r1, r2, 0x4324);     // [T7 T8 T9 T10] [T11 x x x] -> [T11 T9 T10 T11]
 }
+// Split form for software pipelining: the raw words of a row are fetched one worker round ahead (no use of the
+// loaded values, so nothing waits), and assembled when the round is blended.
+__device__ __forceinline__ void x2_fetch_row(const uint32_t *__restrict__ inw, int row_word, int xq, int W0, uint32_t wv[4]) {
+    const bool left = xq == 0, right = xq == W0 - 4;
+    const int bo = 3 * (xq >> 1) - 3;
+    const uint32_t *p = inw + (row_word + (bo >> 2));
+    wv[1] = __ldg(p + 1), wv[2] = __ldg(p + 2);
+    wv[0] = left ? 0u : __ldg(p), wv[3] = right ? 0u : __ldg(p + 3);  // the patched bytes below never come from these two
+}
+__device__ __forceinline__ void x2_assemble_row(const uint32_t wv[4], int xq, int W0, uint32_t &r0, uint32_t &r1, uint32_t &r2) {
+    const int bo = 3 * (xq >> 1) - 3;
+    const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(bo & 3);
+    r0 = __byte_perm(wv[0], wv[1], sel), r1 = __byte_perm(wv[1], wv[2], sel), r2 = __byte_perm(wv[2], wv[3], sel);
+    if (xq == 0) r0 = __byte_perm(r0, r1, 0x3543);           // [x x x S0] [S1 S2 S3 S4] -> [S0 S1 S2 S0]
+    if (xq == W0 - 4) r2 = __byte_perm(r1, r2, 0x4324);      // [T7 T8 T9 T10] [T11 x x x] -> [T11 T9 T10 T11]
+}
+__device__ __forceinline__ void x4_fetch_row(const uint32_t *__restrict__ inw, int row_word, int xq, int W0, uint32_t wv[4]) {
+    const int bo = xq == 0 ? 0 : 3 * (xq >> 2) - 3;       // left border: start at pixel 0 and duplicate it on assembly
+    const int last = ((W0 >> 2) * 3 - 1) >> 2;            // last word of the row
+    const int wi = bo >> 2;
+    const uint32_t *p = inw + row_word;
+    wv[0] = __ldg(p + wi), wv[1] = __ldg(p + min(wi + 1, last)), wv[2] = __ldg(p + min(wi + 2, last));
+}
+__device__ __forceinline__ void x4_assemble_row(const uint32_t wv[4], int xq, int W0, uint32_t &r0, uint32_t &r1, uint32_t &r2) {
+    const bool left = xq == 0, right = xq == W0 - 4;
+    const int bo = left ? 0 : 3 * (xq >> 2) - 3;
+    const uint32_t sel = 0x3210u + 0x1111u * (uint32_t)(bo & 3);
+    const uint32_t s0 = __byte_perm(wv[0], wv[1], sel), s1 = __byte_perm(wv[1], wv[2], sel), s2 = __byte_perm(wv[2], 0u, sel);
+    r0 = s0, r1 = s1, r2 = s2;
+    if (left) {            // s = [B0 B1 B2 C0] [C1 C2 . .]  ->  A := B
+        r0 = __byte_perm(s0, 0u, 0x0210);
+        r1 = __byte_perm(s0, s1, 0x4321);
+        r2 = s1 >> 8;
+    }
+    if (right) {           // s = [A0 A1 A2 B0] [B1 B2 . .]  ->  C := B
+        r1 = __byte_perm(s0, s1, 0x4354);
+        r2 = s1 >> 8;
+    }
+}
 // Horizontal pass of a quad: m[j] holds channel values 2j (low lane) and 2j+1 (high lane) of the
 // 12 output values (pixel k/3, channel k%3); near = the source pixel of weight 3/4.
 __device__ __forceinline__ void x2_hpass(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t m[6]) {
@@ -761,8 +800,9 @@ constexpr int K3F_QCAP = 128 + 32;      // one classified row of the warp (32 la
 struct FastGeom {
     int h, w, H0, W0, th, rpt;
     int Wpc, row_words, rows_s;          // mask words per frame row; per shared-memory bit row (+2 pad words); bit rows
-    int bits_off, zbits_off, lut_off, queue_off;    // word offsets inside dynamic shared memory (after the strip); zbits: k3_fastw only
+    int bits_off, zbits_off, lut_off, taps_off, queue_off;    // word offsets inside dynamic shared memory (after the strip); zbits: k3_fastw only
     int G, n_tasks, n_steps;
+    uint32_t inv_rw;                     // floor(2^32 / row_words) + 1 (row_words >= 3)
     uint32_t inv_wpc;                    // floor(2^32 / Wpc) + 1: id / Wpc == umulhi(id, inv_wpc) for id < 65536, Wpc > 1 (k3_fastw)
     long long frame_bytes, mask_frame_bytes, inp_frame_bytes, bits_frame_words;
     float div, one;
@@ -1096,19 +1136,30 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
     // ---------------- phase 1: bit rows [y0 - 2, y0 + th + 2) of both polarities, one zero pad word on each side
     const uint32_t last_valid = (W0 & 31) ? ((1u << (W0 & 31)) - 1u) : 0xffffffffu;   // valid bits of frame word Wpc - 1
     if (BITS) {
-        for (int i = warp; i < rows_s; i += NTH / 32) {
-            const int y = y0 - 2 + i;
-            const bool row_ok = y >= 0 && y < H0;
-            const uint32_t *src = mask_bits + t * gm.bits_frame_words + (long long)y * Wpc;
-            for (int k = lane; k < row_words; k += 32) {
-                uint32_t m = 0, z = 0;
-                if (row_ok && k >= 1 && k <= Wpc) {
-                    const uint32_t valid = k == Wpc ? last_valid : 0xffffffffu;
-                    m = __ldg(src + (k - 1)) & valid;
-                    z = ~m & valid;
+        // flat over all (row, word) slots, four per thread and trip: the loads of a trip are all issued before the first
+        // store waits for one (ncu: the row-by-row loop spent 9 % of the kernel's stall samples on its load round trips)
+        const int total = rows_s * row_words;
+        for (int base0 = 0; base0 < total; base0 += 4 * NTH) {
+            uint32_t mv[4], vv_[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base0 + u * NTH + (int)threadIdx.x;
+                const int i = (int)__umulhi((uint32_t)idx, gm.inv_rw), k = idx - i * row_words;
+                const int y = y0 - 2 + i;
+                mv[u] = 0, vv_[u] = 0;
+                if (idx < total && y >= 0 && y < H0 && k >= 1 && k <= Wpc) {
+                    vv_[u] = k == Wpc ? last_valid : 0xffffffffu;
+                    mv[u] = __ldg(mask_bits + t * gm.bits_frame_words + (long long)y * Wpc + (k - 1));
                 }
-                bitsM[i * row_words + k] = m;
-                bitsZ[i * row_words + k] = z;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base0 + u * NTH + (int)threadIdx.x;
+                if (idx < total) {
+                    const uint32_t m = mv[u] & vv_[u];
+                    bitsM[idx] = m;
+                    bitsZ[idx] = ~m & vv_[u];
+                }
             }
         }
     } else {
@@ -1137,6 +1188,8 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
         if (lane < 16) lut[lane] = make_float4(a, a, na, na);
         const uint32_t posmask = __ballot_sync(0xffffffffu, lane < 16 && a > 0.f);     // which LUT levels have alpha > 0
         if (lane == 0) reinterpret_cast<uint32_t *>(lut + 16)[0] = posmask;
+    } else if (!VX2 && warp == 1 && lane < th) {
+        reinterpret_cast<Tap *>(smem_base + gm.taps_off)[lane] = yt[min(y0 + lane, H0 - 1)];
     }
     __syncthreads();
 
@@ -1150,27 +1203,47 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
     const int wq = (w * 3) >> 2;                                                   // words per source row
     const f32x2 one2 = pack2(one, one), magic2 = pack2(12582912.f, 12582912.f), unbias2 = pack2(-8388608.f, -8388608.f);
 
-    // ---- worker: one 4-pixel quad per lane
-    auto work = [&](const uint32_t item) {
+    // ---- worker, software pipelined: `fetch` issues the loads of a quad's two source rows (raw words, nothing waits
+    // on them), `blend` up-scales and blends the quad fetched one round earlier - ncu put 25 % of all stall samples on
+    // the first use of these loads when a round fetched and blended the same quad.
+    const Tap *taps_s = reinterpret_cast<const Tap *>(smem_base + gm.taps_off);    // the strip's vertical taps (!VX2)
+    struct Fetched {
+        uint32_t item, a[4], b[4];
+    };
+    auto fetch = [&](const uint32_t item, Fetched &f) {
         const int xq = (int)(item & 0x3ffu) << 2, r = (int)(item >> 10) & 0x3f;
         const int yy = y0 + r;
-        uint32_t a0, a1, a2, b0, b1, b2, wa = 0, wb = 0;
+        int ra, rb;
         if (VX2) {
-            const int j = yy >> 1;                                           // source row of weight 3/4
-            const int ja = (yy & 1) ? min(j + 1, h - 1) : max(j - 1, 0);     // source row of weight 1/4
-            x2_load_row_w(inw, ja * wq, xq, W0, a0, a1, a2);
-            x2_load_row_w(inw, j * wq, xq, W0, b0, b1, b2);
+            rb = yy >> 1;                                                    // source row of weight 3/4
+            ra = (yy & 1) ? min(rb + 1, h - 1) : max(rb - 1, 0);             // source row of weight 1/4
         } else {
-            const Tap ty = yt[yy];
-            wa = (uint32_t)(ty.w & 0xffff) << 20, wb = ((uint32_t)ty.w >> 16) << 20;
-            const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
-            if (HR == 4) {
-                x4_load_row(inp_t + ya * w * 3, xq, W0, a0, a1, a2);
-                x4_load_row(inp_t + yb * w * 3, xq, W0, b0, b1, b2);
-            } else {
-                x2_load_row_w(inw, ya * wq, xq, W0, a0, a1, a2);
-                x2_load_row_w(inw, yb * wq, xq, W0, b0, b1, b2);
-            }
+            const int ofs = taps_s[r].ofs;
+            ra = min(max(ofs, 0), h - 1), rb = min(max(ofs + 1, 0), h - 1);
+        }
+        f.item = item;
+        if (HR == 4) {
+            x4_fetch_row(inw, ra * wq, xq, W0, f.a);
+            x4_fetch_row(inw, rb * wq, xq, W0, f.b);
+        } else {
+            x2_fetch_row(inw, ra * wq, xq, W0, f.a);
+            x2_fetch_row(inw, rb * wq, xq, W0, f.b);
+        }
+    };
+    auto blend = [&](const Fetched &f) {
+        const uint32_t item = f.item;
+        const int xq = (int)(item & 0x3ffu) << 2, r = (int)(item >> 10) & 0x3f;
+        uint32_t a0, a1, a2, b0, b1, b2, wa = 0, wb = 0;
+        if (!VX2) {
+            const int tw = taps_s[r].w;
+            wa = (uint32_t)(tw & 0xffff) << 20, wb = ((uint32_t)tw >> 16) << 20;
+        }
+        if (HR == 4) {
+            x4_assemble_row(f.a, xq, W0, a0, a1, a2);
+            x4_assemble_row(f.b, xq, W0, b0, b1, b2);
+        } else {
+            x2_assemble_row(f.a, xq, W0, a0, a1, a2);
+            x2_assemble_row(f.b, xq, W0, b0, b1, b2);
         }
         uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
         const uint32_t o0 = sp[0], o1 = sp[1], o2 = sp[2];
@@ -1232,7 +1305,8 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
     // ---------------- phase 2: classification, one 32-pixel word of one strip row per lane and step
     const int n_tasks = gm.n_tasks, n_steps = gm.n_steps;
     int qcount = 0;
-    bool landed = false;
+    bool landed = false, pending = false;
+    Fetched cur = {};
 #pragma unroll 1
     for (int step = 0; step <= n_steps; ++step) {
         const bool drain = step == n_steps;
@@ -1325,11 +1399,16 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
             do {
                 const int take = min(qcount, 32);
                 qcount -= take;
-                if (lane < take) work(queue[qcount + lane]);
+                const bool has = lane < take;
+                Fetched nxt = cur;
+                if (has) fetch(queue[qcount + lane], nxt);
+                if (pending) blend(cur);          // the round fetched before: its loads had a whole round (or step) to land
+                cur = nxt, pending = has;
             } while (qcount >= 32);
             __syncwarp();              // the queue tail is overwritten by the next pushes
         }
     }
+    if (pending) blend(cur);
     fence_proxy_async();                 // the patched quads must be visible to the bulk store
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1504,7 +1583,8 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
             gm.bits_off = fth * W0 * 3 / 4 + 4;
             gm.zbits_off = gm.bits_off + (fth + 4) * (Wp + 2);
             gm.lut_off = ((wordtasks ? gm.zbits_off : gm.bits_off) + (fth + 4) * (Wp + 2) + 3) & ~3;
-            gm.queue_off = gm.lut_off + 16 * 4 + 4;
+            gm.taps_off = gm.lut_off + 16 * 4 + 4;                       // k3_fastw: 16 x Tap
+            gm.queue_off = gm.taps_off + (wordtasks ? 32 : 0);
             fsm = ((size_t)gm.queue_off + (nth / 32) * (wordtasks ? K3W_QCAP : K3F_QCAP * 2)) * 4;
             if (fsm <= smem_cap) break;
         }
@@ -1533,6 +1613,7 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
                 gm.n_tasks = Wp * fth;
                 gm.n_steps = ceil_div(gm.n_tasks, nth);
                 gm.inv_wpc = (uint32_t)(0x100000000ULL / (unsigned)Wp) + 1u;
+                gm.inv_rw = (uint32_t)(0x100000000ULL / (unsigned)(Wp + 2)) + 1u;
             }
 #define VV_K3_FAST(KERNEL, V, B, N, H)                                                                          \
     do {                                                                                                        \
