@@ -1124,9 +1124,8 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
     const uint8_t *orig_t = orig + t * gm.frame_bytes;
     uint8_t *out_t = out + t * gm.frame_bytes;
     const uint32_t strip_bytes = (uint32_t)(min(th, H0 - y0) * W0 * 3);
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {              // the other threads first look at the mbarrier after the __syncthreads below
+        mbar_init(bar, 1);
         mbar_arrive_expect_tx(bar, strip_bytes);
         const uint8_t *src = orig_t + (long long)y0 * W0 * 3;
         for (uint32_t off = 0; off < strip_bytes; off += 32768u)
@@ -1230,20 +1229,30 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
             x2_fetch_row(inw, rb * wq, xq, W0, f.b);
         }
     };
-    auto blend = [&](const Fetched &f) {
-        const uint32_t item = f.item;
+    // `assemble` is the first use of a round's loads (the only place that waits for them); it runs BEFORE the next
+    // round's fetch re-uses the raw-word registers, `finish` after it - no register copies between rounds.
+    struct Assembled {
+        uint32_t item, a0, a1, a2, b0, b1, b2;
+    };
+    auto assemble = [&](const Fetched &f, Assembled &q) {
+        const int xq = (int)(f.item & 0x3ffu) << 2;
+        q.item = f.item;
+        if (HR == 4) {
+            x4_assemble_row(f.a, xq, W0, q.a0, q.a1, q.a2);
+            x4_assemble_row(f.b, xq, W0, q.b0, q.b1, q.b2);
+        } else {
+            x2_assemble_row(f.a, xq, W0, q.a0, q.a1, q.a2);
+            x2_assemble_row(f.b, xq, W0, q.b0, q.b1, q.b2);
+        }
+    };
+    auto finish = [&](const Assembled &q) {
+        const uint32_t item = q.item;
         const int xq = (int)(item & 0x3ffu) << 2, r = (int)(item >> 10) & 0x3f;
-        uint32_t a0, a1, a2, b0, b1, b2, wa = 0, wb = 0;
+        const uint32_t a0 = q.a0, a1 = q.a1, a2 = q.a2, b0 = q.b0, b1 = q.b1, b2 = q.b2;
+        uint32_t wa = 0, wb = 0;
         if (!VX2) {
             const int tw = taps_s[r].w;
             wa = (uint32_t)(tw & 0xffff) << 20, wb = ((uint32_t)tw >> 16) << 20;
-        }
-        if (HR == 4) {
-            x4_assemble_row(f.a, xq, W0, a0, a1, a2);
-            x4_assemble_row(f.b, xq, W0, b0, b1, b2);
-        } else {
-            x2_assemble_row(f.a, xq, W0, a0, a1, a2);
-            x2_assemble_row(f.b, xq, W0, b0, b1, b2);
         }
         uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
         const uint32_t o0 = sp[0], o1 = sp[1], o2 = sp[2];
@@ -1400,15 +1409,20 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
                 const int take = min(qcount, 32);
                 qcount -= take;
                 const bool has = lane < take;
-                Fetched nxt = cur;
-                if (has) fetch(queue[qcount + lane], nxt);
-                if (pending) blend(cur);          // the round fetched before: its loads had a whole round (or step) to land
-                cur = nxt, pending = has;
+                Assembled q;
+                if (pending) assemble(cur, q);    // the round fetched before: its loads had a whole round (or step) to land
+                if (has) fetch(queue[qcount + lane], cur);
+                if (pending) finish(q);
+                pending = has;
             } while (qcount >= 32);
             __syncwarp();              // the queue tail is overwritten by the next pushes
         }
     }
-    if (pending) blend(cur);
+    if (pending) {
+        Assembled q;
+        assemble(cur, q);
+        finish(q);
+    }
     fence_proxy_async();                 // the patched quads must be visible to the bulk store
     __syncthreads();
     if (threadIdx.x == 0) {
