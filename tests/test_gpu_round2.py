@@ -85,7 +85,7 @@ def test_k3_fast_kernel(ops, h0, w0, h, w, f):
     got_bits = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))
     variants = {}
     try:
-        for thr, rows in ((256, 16), (256, 6), (512, 5)):
+        for thr, rows in ((256, 16), (256, 6), (512, 5), (384, 16), (384, 3)):
             _lib.set_option("k3_tma_threads", thr)
             _lib.set_option("k3_tma_rows", rows)
             variants["w-threads%d-rows%d" % (thr, rows)] = host(ops.upscale_feather_composite(d_inp, d_fr, d_dil, feather_px=f, mask_bits=bits))

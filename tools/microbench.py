@@ -103,11 +103,14 @@ def main():
         report("K3 composite (box mask)", k3b, K3(box_dil, box_bits), k3_x2=x2, bits=1)
         report("K3 composite 960x536 (synthetic mask)", k3b536, K3(dil, bits, inp536), k3_x2=x2, bits=1)
     _lib.set_option("k3_x2", 3)
-    for thr, rows_list in ((512, (8, 12, 14)), (256, (16, 6, 7))):
+    for thr, rows_list in ((384, (16, 8, 6)), (512, (12, 14)), (256, (16, 7))):
         _lib.set_option("k3_tma_threads", thr)
         for rows in rows_list:
             _lib.set_option("k3_tma_rows", rows)
             report("K3 composite (synthetic mask)", k3b, K3(dil, bits), k3_x2=3, bits=1, rows=rows, threads=thr)
+            if thr == 384:
+                report("K3 composite 960x536 (synthetic mask)", k3b536, K3(dil, bits, inp536), k3_x2=3, bits=1, rows=rows, threads=thr)
+                report("K3 composite (box mask)", k3b, K3(box_dil, box_bits), k3_x2=3, bits=1, rows=rows, threads=thr)
     _lib.set_option("k3_tma_rows", 16)
     _lib.set_option("k3_tma_threads", 512)
     for x2 in (1, 0):                                       # round-1 kernels

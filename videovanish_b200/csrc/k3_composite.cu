@@ -218,6 +218,13 @@ __device__ __forceinline__ uint32_t x2_vpass(uint32_t m_a, uint32_t m_b) {
     return ((m_a >> 2) + (((m_b * 3u) >> 2) & 0x3fff3fffu) + 0x00020002u) >> 2;
 }
 
+// The same value with fewer ALU-pipe instructions, left in BYTES 1 AND 3 of the word:  (x >> 2) + (y >> 2) ==
+// ((x & ~3) + (y & ~3)) >> 2, so out == ((m_a & ~3) + (3 m_b & ~3) + 8) >> 4; the lanes stay below 4096, and the
+// final shift is a left shift by 4 instead (multiply pipe), which byte-aligns bits 4..11 of both lanes.
+__device__ __forceinline__ uint32_t x2_vpass_b13(uint32_t m_a, uint32_t m_b) {
+    return ((m_a & 0xfffcfffcu) + ((m_b * 3u) & 0xfffcfffcu) + 0x00080008u) << 4;
+}
+
 // ---- exact x4 horizontal up-scale (W0 == 4w: 4K <- 960 wide, BASELINE config 4) ---------------------------
 // OpenCV's horizontal taps are then (768,1280), (256,1792), (1792,256), (1280,768) of 2048 for the four pixels of
 // a quad = 256 * (3,5), (1,7), (7,1), (5,3): with A, B, C = source pixels i-1, i, i+1 (i = xq / 4, clamped at the
@@ -1103,7 +1110,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
 constexpr int K3W_QCAP = 256 + 32;      // one classified word per lane (32 lanes x 8 quads) + carried-over items
 
 template <bool VX2, bool BITS, int NTH, int HR = 2>
-__global__ void __launch_bounds__(NTH, 1024 / NTH)
+__global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
     k3_fastw(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ mask,
              const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ yt,
              const __grid_constant__ FastGeom gm) {
@@ -1277,7 +1284,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             if (VX2) {
-                up[k] = x2_vpass(ma[k], mb[k]);
+                up[k] = x2_vpass_b13(ma[k], mb[k]);                 // results in bytes 1 and 3
             } else {
                 // (b * (h >> 4)) >> 16 with h >> 4 == 32 m (x2) or 16 m (x4): umulhi(b << 20, m << 1 or m)
                 const uint32_t am = HR == 4 ? ma[k] : ma[k] << 1, bm = HR == 4 ? mb[k] : mb[k] << 1;   // lanes <= 2040 / 4080: no carry
@@ -1296,8 +1303,8 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
             // u8 -> f32 through the mantissa: bits(2^23 + b) - 2^23 (both lanes at once)
-            const f32x2 uf = fadd2(pack2u(__byte_perm(up[p], 0x4b000000u, 0x7540u), __byte_perm(up[p], 0x4b000000u, 0x7542u)),
-                                   unbias2);
+            const f32x2 uf = fadd2(pack2u(__byte_perm(up[p], 0x4b000000u, VX2 ? 0x7541u : 0x7540u),
+                                          __byte_perm(up[p], 0x4b000000u, VX2 ? 0x7543u : 0x7542u)), unbias2);
             const uint32_t wsrc = ow[p >> 1];
             const uint32_t s0 = 0x7540u | (uint32_t)((2 * p) & 3), s1 = 0x7540u | (uint32_t)((2 * p + 1) & 3);
             const f32x2 of = fadd2(pack2u(__byte_perm(wsrc, 0x4b000000u, s0), __byte_perm(wsrc, 0x4b000000u, s1)), unbias2);
@@ -1591,8 +1598,9 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         // word tasks (k3_fastw, default) or 16-pixel rolling tasks (k3_fast, option k3_x2 = 2)
         const bool wordtasks = x2opt >= 3 && W0 <= 4096;
         // 512 threads x 2 CTAs per SM (default) or 256 threads x 4 CTAs per SM with shorter strips
-        const int nth = (hr == 2 && get_option(OPT_K3_TMA_THREADS) <= 256) ? 256 : 512;
-        const size_t smem_cap = nth == 256 ? 56 * 1024 : 113 * 1024;
+        const int thr_opt = get_option(OPT_K3_TMA_THREADS);
+        const int nth = (hr == 2 && thr_opt <= 256) ? 256 : (hr == 2 && wordtasks && thr_opt == 384) ? 384 : 512;
+        const size_t smem_cap = nth == 256 ? 56 * 1024 : nth == 384 ? 75 * 1024 : 113 * 1024;
         for (fth = min(16, max(2, get_option(OPT_K3_TMA_ROWS))); fth >= 2; --fth) {
             gm.bits_off = fth * W0 * 3 / 4 + 4;
             gm.zbits_off = gm.bits_off + (fth + 4) * (Wp + 2);
@@ -1655,6 +1663,10 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
             VV_K3_FAST_B(KERNEL, false, 512, 4);     \
         else if (vx2 && nth == 256)                  \
             VV_K3_FAST_B(KERNEL, true, 256, 2);      \
+        else if (vx2 && nth == 384)                  \
+            VV_K3_FAST_B(k3_fastw, true, 384, 2);    \
+        else if (nth == 384)                         \
+            VV_K3_FAST_B(k3_fastw, false, 384, 2);   \
         else if (vx2)                                \
             VV_K3_FAST_B(KERNEL, true, 512, 2);      \
         else if (nth == 256)                         \
