@@ -1107,7 +1107,10 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH)
 //     bits 0..9 quad index in the row (x / 4), 10..15 row in strip, 16..31 plane nibbles [L0 | L1 | L2 | inside]
 // and the worker's LUT index is again one multiply (0x1248 sends bits 0, 4, 8, 12 to bits 12..15 without carries).
 // Requires W0 <= 4096.  Worker arithmetic is k3_fast's.
-constexpr int K3W_QCAP = 256 + 32;      // one classified word per lane (32 lanes x 8 quads) + carried-over items
+// Two-ended per-warp queue: quads to BLEND grow from the bottom; from the top, one entry per fully INTERIOR word
+// (every pixel of the word and of its 5 x 36 window is masked: alpha == 1, the result is the up-scaled pixel itself,
+// no LUT, no blend).  A lane-step adds at most 256 entries, at most 31 + 3 are carried over between steps.
+constexpr int K3W_QCAP = 256 + 48;
 
 template <bool VX2, bool BITS, int NTH, int HR = 2>
 __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
@@ -1252,7 +1255,7 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
             x2_assemble_row(f.b, xq, W0, q.b0, q.b1, q.b2);
         }
     };
-    auto finish = [&](const Assembled &q) {
+    auto finish = [&](const Assembled &q, const bool interior) {     // `interior` is warp-uniform
         const uint32_t item = q.item;
         const int xq = (int)(item & 0x3ffu) << 2, r = (int)(item >> 10) & 0x3f;
         const uint32_t a0 = q.a0, a1 = q.a1, a2 = q.a2, b0 = q.b0, b1 = q.b1, b2 = q.b2;
@@ -1262,17 +1265,6 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
             wa = (uint32_t)(tw & 0xffff) << 20, wb = ((uint32_t)tw >> 16) << 20;
         }
         uint32_t *sp = reinterpret_cast<uint32_t *>(strip + (r * W0 + xq) * 3);
-        const uint32_t o0 = sp[0], o1 = sp[1], o2 = sp[2];
-        // plane nibbles of the quad in the item: L0 @ bits 16-19, L1 @ 20-23, L2 @ 24-27, inside @ 28-31 (bit i = pixel i).
-        // LUT byte offset of pixel i = 16 * (L0 | L1 << 1 | L2 << 2 | inside << 3): the multiplier 0x1248 >> i =
-        // 2^(12-i) + 2^(9-i) + 2^(6-i) + 2^(3-i) sends bits 16+i, 20+i, 24+i, 28+i to bits 28..31; no two partial
-        // products share a bit position, so there are no carries (products above bit 31 drop out).
-        const uint8_t *lutb = reinterpret_cast<const uint8_t *>(lut);
-        auto lut_at = [&](int i) {
-            const uint32_t tsel = item & (0x11110000u << i);
-            return *reinterpret_cast<const float4 *>(lutb + (((tsel * (0x1248u >> i)) >> 24) & 0xf0u));
-        };
-        const float4 l0 = lut_at(0), l1 = lut_at(1), l2 = lut_at(2), l3 = lut_at(3);
         uint32_t ma[6], mb[6], up[6];
         if (HR == 4) {
             x4_hpass(a0, a1, a2, ma);
@@ -1293,6 +1285,22 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
                 up[k] = lo | (hi << 16);
             }
         }
+        if (interior) {                  // alpha == 1 on all four pixels: the 12 up-scaled bytes as they are
+#pragma unroll
+            for (int j = 0; j < 3; ++j) sp[j] = __byte_perm(up[2 * j], up[2 * j + 1], VX2 ? 0x7531u : 0x6420u);
+            return;
+        }
+        const uint32_t o0 = sp[0], o1 = sp[1], o2 = sp[2];
+        // plane nibbles of the quad in the item: L0 @ bits 16-19, L1 @ 20-23, L2 @ 24-27, inside @ 28-31 (bit i = pixel i).
+        // LUT byte offset of pixel i = 16 * (L0 | L1 << 1 | L2 << 2 | inside << 3): the multiplier 0x1248 >> i =
+        // 2^(12-i) + 2^(9-i) + 2^(6-i) + 2^(3-i) sends bits 16+i, 20+i, 24+i, 28+i to bits 28..31; no two partial
+        // products share a bit position, so there are no carries (products above bit 31 drop out).
+        const uint8_t *lutb = reinterpret_cast<const uint8_t *>(lut);
+        auto lut_at = [&](int i) {
+            const uint32_t tsel = item & (0x11110000u << i);
+            return *reinterpret_cast<const float4 *>(lutb + (((tsel * (0x1248u >> i)) >> 24) & 0xf0u));
+        };
+        const float4 l0 = lut_at(0), l1 = lut_at(1), l2 = lut_at(2), l3 = lut_at(3);
         // byte pair p = bytes (2p, 2p+1) of the 12-byte quad; byte k belongs to pixel k / 3
         const f32x2 al[6] = {pack2(l0.x, l0.y), pack2(l0.x, l1.x), pack2(l1.x, l1.y),
                              pack2(l2.x, l2.y), pack2(l2.x, l3.x), pack2(l3.x, l3.y)};
@@ -1320,13 +1328,14 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
 
     // ---------------- phase 2: classification, one 32-pixel word of one strip row per lane and step
     const int n_tasks = gm.n_tasks, n_steps = gm.n_steps;
-    int qcount = 0;
-    bool landed = false, pending = false;
+    int qcount = 0, qwords = 0;          // quads to blend (bottom of the queue) / interior words (top)
+    bool landed = false, pending = false, pending_interior = false;
     Fetched cur = {};
 #pragma unroll 1
     for (int step = 0; step <= n_steps; ++step) {
         const bool drain = step == n_steps;
         uint32_t need = 0, L0 = 0, L1 = 0, L2 = 0, M2 = 0, base = 0;
+        bool intr = false;               // this lane's word is fully interior
         // Each warp's 32 lanes sample the strip evenly (8 runs of 4 consecutive tasks, NTH / 8 tasks apart), so that
         // the warps of a CTA get the same amount of blend work whatever the mask looks like.
         const int id = step * NTH + (lane >> 2) * (NTH / 8) + (warp << 2) + (lane & 3);
@@ -1362,29 +1371,35 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
                     for (int d = 0; d < 5; ++d) Sp[d] = pz[d * row_words], Sc[d] = pz[d * row_words + 1], Sn[d] = pz[d * row_words + 2];
                     A1p = Sp[1] | Sp[3], A1c = Sc[1] | Sc[3], A1n = Sn[1] | Sn[3];
                     A0p = Sp[0] | Sp[4], A0c = Sc[0] | Sc[4], A0n = Sn[0] | Sn[4];
-                    classes(Sp[2], Sc[2], Sn[2], A1p, A1c, A1n, A0p, A0c, A0n, hz);
-                    uint32_t hsel[5];
+                    // no unmasked frame pixel in the 5 x 36 window: every pixel of the word has alpha == 1
+                    intr = ((Sc[2] | A1c | A0c) | ((Sp[2] | A1p | A0p) >> 30) | ((Sn[2] | A1n | A0n) << 30)) == 0u;
+                    need = M2;           // interior word: all of its (frame) pixels, straight from the up-scaled image
+                    if (!intr) {
+                        classes(Sp[2], Sc[2], Sn[2], A1p, A1c, A1n, A0p, A0c, A0n, hz);
+                        uint32_t hsel[5];
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) hsel[c] = (hz[c] & M2) | (hm[c] & ~M2);   // inside pixels look for zeros
-                    const uint32_t p1 = hsel[0];
-                    const uint32_t p2 = hsel[1] & ~p1;
-                    const uint32_t s12 = p1 | hsel[1];
-                    const uint32_t p3 = hsel[2] & ~s12;
-                    const uint32_t s123 = s12 | hsel[2];
-                    const uint32_t p4 = hsel[3] & ~s123;
-                    const uint32_t p5 = hsel[4] & ~(s123 | hsel[3]);
-                    L0 = p1 | p3 | p5, L1 = p2 | p3, L2 = p4 | p5;
-                    // alpha > 0: every inside pixel, and outside pixels whose first hit has alpha > 0; only pixels of the frame
-                    const uint32_t pos = M2 | (p1 & e1) | (p2 & e2) | (p3 & e3) | (p4 & e4) | (p5 & e5);
-                    need = pos & (k == Wpc - 1 ? last_valid : 0xffffffffu);
+                        for (int c = 0; c < 5; ++c) hsel[c] = (hz[c] & M2) | (hm[c] & ~M2);   // inside pixels look for zeros
+                        const uint32_t p1 = hsel[0];
+                        const uint32_t p2 = hsel[1] & ~p1;
+                        const uint32_t s12 = p1 | hsel[1];
+                        const uint32_t p3 = hsel[2] & ~s12;
+                        const uint32_t s123 = s12 | hsel[2];
+                        const uint32_t p4 = hsel[3] & ~s123;
+                        const uint32_t p5 = hsel[4] & ~(s123 | hsel[3]);
+                        L0 = p1 | p3 | p5, L1 = p2 | p3, L2 = p4 | p5;
+                        // alpha > 0: every inside pixel, and outside pixels whose first hit has alpha > 0; only pixels of the frame
+                        const uint32_t pos = M2 | (p1 & e1) | (p2 & e2) | (p3 & e3) | (p4 & e4) | (p5 & e5);
+                        need = pos & (k == Wpc - 1 ? last_valid : 0xffffffffu);
+                    }
                     base = (uint32_t)(k << 3) | ((uint32_t)rr << 10);
                 }
             }
         }
-        // ---- warp-level compaction: every quad with a pixel to blend becomes one work item
-        if (__ballot_sync(0xffffffffu, need != 0)) {                         // warp-uniform
-            const uint32_t nzq = (need | (need >> 1) | (need >> 2) | (need >> 3)) & 0x11111111u;   // bit 4q = quad q has work
-            const int qn = __popc(nzq);
+        // ---- warp-level compaction: every quad with a pixel to blend becomes one work item, every interior word one entry
+        const uint32_t bal_b = __ballot_sync(0xffffffffu, need != 0 && !intr), bal_i = __ballot_sync(0xffffffffu, need != 0 && intr);
+        const uint32_t nzq = (need | (need >> 1) | (need >> 2) | (need >> 3)) & 0x11111111u;       // bit 4q = quad q has work
+        if (bal_b) {                                                         // warp-uniform
+            const int qn = intr ? 0 : __popc(nzq);
             int pre = qn;                                                    // inclusive scan over lanes
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -1393,7 +1408,7 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
             }
             uint32_t *qp = queue + (qcount + pre - qn);
             qcount += __shfl_sync(0xffffffffu, pre, 31);
-            if (need) {
+            if (qn) {
                 // byte j of P01e / P23e = [L1 : L0] / [inside : L2] nibbles of quad 2j, of P01o / P23o those of quad 2j + 1
                 const uint32_t P01e = (L0 & 0x0f0f0f0fu) | ((L1 << 4) & 0xf0f0f0f0u), P01o = ((L0 >> 4) & 0x0f0f0f0fu) | (L1 & 0xf0f0f0f0u);
                 const uint32_t P23e = (L2 & 0x0f0f0f0fu) | ((M2 << 4) & 0xf0f0f0f0u), P23o = ((L2 >> 4) & 0x0f0f0f0fu) | (M2 & 0xf0f0f0f0u);
@@ -1405,6 +1420,13 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
                     if ((nzq >> (4 * q)) & 1u) *qp++ = (nib & 0xffff0000u) | (base + (uint32_t)q);
                 }
             }
+            __syncwarp();
+        }
+        if (bal_i) {                     // entry = position of the word's first quad | number of its quads << 16 (frame pixels are
+                                         // a prefix of the word), pushed downwards from the top of the queue
+            if (need != 0 && intr)
+                queue[K3W_QCAP - 1 - (qwords + __popc(bal_i & ((1u << lane) - 1u)))] = base | ((uint32_t)__popc(nzq) << 16);
+            qwords += __popc(bal_i);
             __syncwarp();
         }
         if (qcount >= 32 || (drain && qcount > 0)) {                         // warp-uniform
@@ -1419,16 +1441,35 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
                 Assembled q;
                 if (pending) assemble(cur, q);    // the round fetched before: its loads had a whole round (or step) to land
                 if (has) fetch(queue[qcount + lane], cur);
-                if (pending) finish(q);
-                pending = has;
+                if (pending) finish(q, pending_interior);
+                pending = has, pending_interior = false;
             } while (qcount >= 32);
             __syncwarp();              // the queue tail is overwritten by the next pushes
+        }
+        if (qwords >= 4 || (drain && qwords > 0)) {                          // warp-uniform: four words = 32 quads per round
+            if (!landed) {
+                mbar_wait(bar, 0);
+                landed = true;
+            }
+            do {
+                const int take = min(qwords, 4);
+                qwords -= take;
+                uint32_t e = 0;
+                if ((lane >> 3) < take) e = queue[K3W_QCAP - 1 - (qwords + (lane >> 3))];
+                const bool has = (uint32_t)(lane & 7) < (e >> 16);
+                Assembled q;
+                if (pending) assemble(cur, q);
+                if (has) fetch((e & 0xffffu) + (uint32_t)(lane & 7), cur);
+                if (pending) finish(q, pending_interior);
+                pending = has, pending_interior = true;
+            } while (qwords >= 4);
+            __syncwarp();
         }
     }
     if (pending) {
         Assembled q;
         assemble(cur, q);
-        finish(q);
+        finish(q, pending_interior);
     }
     fence_proxy_async();                 // the patched quads must be visible to the bulk store
     __syncthreads();
