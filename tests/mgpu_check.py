@@ -59,6 +59,17 @@ def main():
                 chunking.blend_rank_boundaries(mine, overlap, mode=mode, window=window)
             torch.cuda.synchronize()
             good = good and np.array_equal(mine.cpu().numpy(), expect) and not window.error()
+        # the overlapped form: the block is "produced" (a device copy here) boundary frames first, the exchange runs
+        # on a side stream underneath the production of the rest; same bytes, several epochs back to back
+        src2 = torch.from_numpy(clips[rank]).to(dev)
+        for _ in range(3):
+            mine.fill_(0)
+            chunking.produce_and_blend_boundaries(mine, overlap, lambda lo, hi: mine[lo:hi].copy_(src2[lo:hi]), mode=mode,
+                                                  window=window)
+        torch.cuda.synchronize()
+        good_ov = np.array_equal(mine.cpu().numpy(), expect) and (window is None or not window.error())
+        print("rank %d mode %-4s overlapped production + exchange parity %s" % (rank, mode, good_ov), flush=True)
+        good = good and good_ov
         ok &= good
         # timing at 1080p, 16-frame overlap
         big = torch.randint(0, 256, (32, 1080, 1920, 3), dtype=torch.uint8, device=dev)

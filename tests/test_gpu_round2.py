@@ -60,6 +60,26 @@ def test_k1_returns_its_bit_plane(ops, h, w, n):
     assert np.array_equal(host(low2), np.stack([op.ref_resize_nearest(m, h // 2, w // 2) for m in ref]))
 
 
+# ------------------------------------------------------------------------------- K3 composited in parts
+@pytest.mark.parametrize("h0,w0,h,w", [(120, 176, 60, 88), (120, 176, 56, 88)])
+def test_k3_in_chained_parts_equals_one_call(ops, h0, w0, h, w):
+    """A clip composited in three back-to-back K3 calls (boundary frames first, the later calls chained to the one
+    before: programmatic stream serialisation, no drain bubble) gives the bytes of one call over the clip."""
+    t = 12
+    fr, inp = synth.frames(t, h0, w0, seed=71), synth.noise_frames(t, h, w, seed=72)
+    dil, _, bits = ops.binarize_dilate(dev(synth.masks(t, h0, w0, seed=73, salt=0.004)), 3, return_bits=True)
+    d_inp, d_fr = dev(inp), dev(fr)
+    whole = ops.upscale_feather_composite(d_inp, d_fr, dil, 3, mask_bits=bits)
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], host(dil)[i], True, 3) for i in range(t)])
+    assert np.array_equal(host(whole), ref)
+    for rep in range(3):
+        parts = torch.zeros_like(whole)
+        for n, (lo, hi) in enumerate([(0, 3), (9, 12), (3, 9)]):
+            ops.upscale_feather_composite(d_inp[lo:hi], d_fr[lo:hi], dil[lo:hi], 3, out=parts[lo:hi], mask_bits=bits[lo:hi],
+                                          chain_previous=n > 0)
+        assert torch.equal(parts, whole)
+
+
 # ------------------------------------------------------------------------------- k3_fast
 @pytest.mark.parametrize("h0,w0,h,w", [(120, 176, 60, 88), (120, 176, 56, 88), (16, 16, 8, 8), (66, 80, 33, 40),
                                        (72, 128, 32, 64), (100, 96, 48, 48), (30, 48, 16, 24),

@@ -33,6 +33,11 @@ def _worker(rank, world, port, overlap, t, ret):
     mine = torch.from_numpy(rng.integers(0, 256, (t, 5, 7, 3), dtype=np.uint8))
     orig = mine.clone()
     moved = chunking.blend_rank_boundaries(mine, overlap, mode="nccl", blend_fn=blend)
+    # the produce-then-exchange form (on CPU tensors: production, then the same exchange) gives the same block
+    mine2 = torch.zeros_like(orig)
+    moved2 = chunking.produce_and_blend_boundaries(mine2, overlap, lambda lo, hi: mine2[lo:hi].copy_(orig[lo:hi]), mode="nccl",
+                                                   blend_fn=blend)
+    assert torch.equal(mine2, mine) and moved2 == moved
     ret[rank] = (orig.numpy(), mine.numpy(), moved)
     dist.destroy_process_group()
 

@@ -13,6 +13,7 @@ all: with ``mode="peer"`` the neighbour's frames are mapped through CUDA IPC and
 place over NVLink while it blends.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -206,6 +207,60 @@ def blend_rank_boundaries(out, overlap, group=None, mode="nccl", blend_fn=_defau
     if recv_prev is not None:
         blend_fn(recv_prev, out[half:overlap], half, overlap, out[half:overlap])
         moved += recv_prev.numel()
+    return moved
+
+
+_side_streams = {}
+HALO_CTAS_OVERLAPPED = int(os.environ.get("VV_HALO_CTAS", "128"))
+
+
+def produce_and_blend_boundaries(out, overlap, produce, group=None, mode="nccl", blend_fn=_default_blend, window=None,
+                                 stream=None, events=None):
+    """``blend_rank_boundaries`` for a block that is still being produced, with the exchange hidden behind the
+    production: ``produce(lo, hi)`` writes ``out[lo:hi]`` on the current stream.  The frames the halo exchange touches
+    (this rank's first / last ``overlap`` frames - the only ones a neighbour reads or this rank blends) are produced
+    first; the exchange (NVLink peer reads + blend, or send/recv + blend) then runs on a side stream while ``produce``
+    fills the rest, and the current stream joins it at the end.  ``events`` = optional (start, end) CUDA events recorded
+    around the exchange on the side stream.  Returns the bytes received from / read on peers."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    t = out.shape[0]
+    if world == 1 or overlap == 0 or not out.is_cuda:
+        produce(0, t)
+        return blend_rank_boundaries(out, overlap, group, mode=mode, blend_fn=blend_fn, window=window) if world > 1 else 0
+    if t < 2 * overlap:
+        raise ValueError("produce_and_blend_boundaries: a rank needs at least 2 x overlap frames (%d < %d)" % (t, 2 * overlap))
+    has_prev, has_next = rank > 0, rank < world - 1
+    main = torch.cuda.current_stream(out.device)
+    side = stream
+    if side is None:
+        side = _side_streams.get(out.device.index)
+        if side is None:
+            # high priority: its few CTAs take the next SM slots the producing kernel frees instead of queueing behind its grid
+            side = _side_streams[out.device.index] = torch.cuda.Stream(out.device, priority=-1)
+    if has_prev:
+        produce(0, overlap)
+    if has_next:
+        produce(t - overlap, t)
+    ready = torch.cuda.Event()
+    ready.record(main)
+    side.wait_event(ready)
+    with torch.cuda.stream(side):
+        if events is not None:
+            events[0].record(side)
+        # a small grid: the exchange is NVLink-latency work and must not take the SM slots of the producing kernel
+        full = _lib.get_option("k5_halo_ctas")
+        _lib.set_option("k5_halo_ctas", HALO_CTAS_OVERLAPPED)
+        try:
+            moved = blend_rank_boundaries(out, overlap, group, mode=mode, blend_fn=blend_fn, window=window)
+        finally:
+            _lib.set_option("k5_halo_ctas", full)
+        if events is not None:
+            events[1].record(side)
+        done = torch.cuda.Event()
+        done.record(side)
+    produce(overlap if has_prev else 0, t - overlap if has_next else t)
+    main.wait_event(done)
     return moved
 
 

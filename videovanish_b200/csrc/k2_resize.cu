@@ -212,13 +212,18 @@ extern "C" int vv_inference_size(int H0, int W0, int max_img_size, int *h, int *
 
 namespace vv {
 // Shared with K3: builds x/y LINEAR tap tables for (H,W) -> (h,w) into `workspace`.
-int build_linear_taps(void *workspace, int H, int W, int h, int w, const Tap **xt, const Tap **yt, cudaStream_t st) {
+// which: 1 = the x table, 2 = the y table, 3 = both (a caller that uses one axis in closed form skips that launch)
+int build_linear_taps(void *workspace, int H, int W, int h, int w, const Tap **xt, const Tap **yt, cudaStream_t st, int which) {
     Tap *x = (Tap *)workspace;
     Tap *y = (Tap *)((uint8_t *)workspace + align_up((size_t)w * sizeof(Tap), 256));
-    k2_make_linear_taps<<<ceil_div(w, 256), 256, 0, st>>>(x, w, W, 1);
-    VV_POST_LAUNCH("k2_make_linear_taps(x)");
-    k2_make_linear_taps<<<ceil_div(h, 256), 256, 0, st>>>(y, h, H, 0);
-    VV_POST_LAUNCH("k2_make_linear_taps(y)");
+    if (which & 1) {
+        k2_make_linear_taps<<<ceil_div(w, 256), 256, 0, st>>>(x, w, W, 1);
+        VV_POST_LAUNCH("k2_make_linear_taps(x)");
+    }
+    if (which & 2) {
+        k2_make_linear_taps<<<ceil_div(h, 256), 256, 0, st>>>(y, h, H, 0);
+        VV_POST_LAUNCH("k2_make_linear_taps(y)");
+    }
     *xt = x, *yt = y;
     return VV_OK;
 }
@@ -259,7 +264,7 @@ extern "C" int vv_resize(const uint8_t *src, int T, int H, int W, int C, uint8_t
         return VV_OK;
     }
     const Tap *xt, *yt;
-    int rc = build_linear_taps(workspace, H, W, h, w, &xt, &yt, st);
+    int rc = build_linear_taps(workspace, H, W, h, w, &xt, &yt, st, 3);
     if (rc) return rc;
     if (C == 3 && W == 2 * w && w % 16 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0) {
         const int grid = (int)min((long long)ceil_div((long long)T * h * (w / 16), 256), (long long)max_grid);

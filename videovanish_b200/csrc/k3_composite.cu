@@ -42,7 +42,7 @@ struct Tap {
     int ofs;
     int w;
 };
-int build_linear_taps(void *workspace, int H, int W, int h, int w, const Tap **xt, const Tap **yt, cudaStream_t st);
+int build_linear_taps(void *workspace, int H, int W, int h, int w, const Tap **xt, const Tap **yt, cudaStream_t st, int which);
 
 constexpr int K3_TH = 16;          // maximum output rows per CTA strip
 constexpr int K3_MAX_CLASSES = 31;    // distinct chamfer costs < feather_px (30 at the maximum feather of 8): 5 bit planes
@@ -1118,6 +1118,10 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
              const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ yt,
              const __grid_constant__ FastGeom gm) {
     extern __shared__ __align__(128) uint32_t smem_base[];
+    // Launches of this kernel never depend on each other (different frames).  A following launch that is CHAINED
+    // (option k3_chain: programmatic stream serialisation) may therefore start as soon as every CTA of this one has
+    // started - back-to-back launches over parts of a clip then leave no drain / ramp bubble between them.
+    asm volatile("griddepcontrol.launch_dependents;");
     const int h = gm.h, w = gm.w, H0 = gm.H0, W0 = gm.W0, th = gm.th;
     const int Wpc = gm.Wpc, row_words = gm.row_words, rows_s = gm.rows_s;
     const float div = gm.div, one = gm.one;
@@ -1565,9 +1569,9 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         return VV_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const Tap *xt, *yt;
-    int rc = build_linear_taps(workspace, h, w, H0, W0, &xt, &yt, st);
-    if (rc) return rc;
+    const Tap *xt = nullptr, *yt = nullptr;
+    int rc = VV_OK;
+    bool taps_built = false;             // k3_fast / k3_fastw need no x table, and no y table for an exact x2 either
 
     // the table only depends on feather_px: keep the last one (the GUI never changes it from 3)
     static std::mutex ft_mu;
@@ -1655,6 +1659,8 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
             const int fstrips = ceil_div(H0, fth);
             const bool vx2 = hr == 2 && H0 == 2 * h;
             const bool bits = mask_bits != nullptr && get_option(OPT_K3_BITS) != 0;
+            if ((rc = build_linear_taps(workspace, h, w, H0, W0, &xt, &yt, st, vx2 ? 0 : 2))) return rc;
+            taps_built = true;
             // rows per classification task: 4 when that still gives most threads a task, else 2
             int rpt = 4;
             for (int cand : {4, 3, 2})                      // fewest idle threads in the first pass over the tasks
@@ -1685,9 +1691,20 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         for (int t0 = 0; t0 < T; t0 += 32768) {        /* grid.y <= 65535 frames per launch */                  \
             const int tn = min(32768, T - t0);                                                                  \
             const size_t fo = (size_t)t0 * H0 * W0;                                                             \
-            kfn<<<dim3((unsigned)fstrips, (unsigned)tn), N, smem, st>>>(                                        \
-                inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo,                                         \
-                mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : nullptr, out + fo * 3, yt, gm);                  \
+            cudaLaunchConfig_t cfg = {};                                                                        \
+            cfg.gridDim = dim3((unsigned)fstrips, (unsigned)tn);                                                \
+            cfg.blockDim = dim3(N);                                                                             \
+            cfg.dynamicSmemBytes = smem;                                                                        \
+            cfg.stream = st;                                                                                    \
+            cudaLaunchAttribute attr[1];                                                                        \
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                    \
+            attr[0].val.programmaticStreamSerializationAllowed = 1;                                             \
+            cfg.attrs = attr;                                                                                   \
+            cfg.numAttrs = chain ? 1 : 0;                                                                       \
+            cudaError_t le = cudaLaunchKernelEx(&cfg, kfn, inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo,  \
+                                                mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : (const uint32_t *)nullptr, \
+                                                out + fo * 3, yt, gm);                                          \
+            if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(" #KERNEL ")");                     \
             VV_POST_LAUNCH(#KERNEL);                                                                            \
         }                                                                                                       \
     } while (0)
@@ -1715,6 +1732,8 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         else                                         \
             VV_K3_FAST_B(KERNEL, false, 512, 2);     \
     } while (0)
+            // chained launch: only ever set for a k3_fastw launch that directly follows another one in the stream
+            const bool chain = wordtasks && get_option(OPT_K3_CHAIN) != 0;
             if (wordtasks)
                 VV_K3_FAST_ALL(k3_fastw);
             else
@@ -1726,6 +1745,7 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         }
     }
 
+    if (!taps_built && (rc = build_linear_taps(workspace, h, w, H0, W0, &xt, &yt, st, 3))) return rc;
 #define VV_K3_LAUNCH(V, S, N, M, ...)                                                                                \
     do {                                                                                                        \
         auto kfn = k3_upscale_feather_composite<V, S, N, M, ##__VA_ARGS__>;                                                    \

@@ -112,13 +112,17 @@ __global__ void __launch_bounds__(256)
         uint8_t *o = job.out + k * frame_bytes;
         const long long n16 = frame_bytes / 16, stride = (long long)gridDim.x * blockDim.x;
         long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-        // plain (coherent) loads: one operand is another GPU's memory that was written during this epoch
-        for (; i + stride < n16; i += 2 * stride) {
-            const uint4 va = a[i], vb = b[i], vc = a[i + stride], vd = b[i + stride];
-            stg128_stream(o + 16 * i, make_uint4(blend4(va.x, vb.x, w, nw), blend4(va.y, vb.y, w, nw),
-                                                 blend4(va.z, vb.z, w, nw), blend4(va.w, vb.w, w, nw)));
-            stg128_stream(o + 16 * (i + stride), make_uint4(blend4(vc.x, vd.x, w, nw), blend4(vc.y, vd.y, w, nw),
-                                                            blend4(vc.z, vd.z, w, nw), blend4(vc.w, vd.w, w, nw)));
+        // plain (coherent) loads: one operand is another GPU's memory that was written during this epoch.  Four
+        // independent pairs per trip: NVLink reads take microseconds, and with the small grid of the overlapped mode
+        // (the exchange runs underneath K3 and must not take its SM slots) bytes in flight are what sets the rate.
+        for (; i + 3 * stride < n16; i += 4 * stride) {
+            uint4 va[4], vb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) va[j] = a[i + j * stride], vb[j] = b[i + j * stride];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                stg128_stream(o + 16 * (i + j * stride), make_uint4(blend4(va[j].x, vb[j].x, w, nw), blend4(va[j].y, vb[j].y, w, nw),
+                                                                    blend4(va[j].z, vb[j].z, w, nw), blend4(va[j].w, vb[j].w, w, nw)));
         }
         for (; i < n16; i += stride) {
             const uint4 va = a[i], vb = b[i];
@@ -189,8 +193,11 @@ extern "C" int vv_halo_blend(uint8_t *out, int T, size_t frame_bytes, int overla
     }
     const int frames = nj.n + pj.n;
     VV_CHECK_ARG(frames > 0, "vv_halo_blend: no neighbour given");
+    // CTA budget: the whole machine a few times over when the exchange runs alone, a few dozen CTAs when it runs on a side
+    // stream underneath another kernel (option k5_halo_ctas, set by chunking.produce_and_blend_boundaries)
+    const int budget = max(frames, get_option(OPT_K5_HALO_CTAS));
     const long long gx = max(1LL, min((long long)ceil_div((long long)frame_bytes / 16, 256 * 4),
-                                      (long long)ceil_div(148 * 8, frames)));
+                                      (long long)(budget / frames)));
     dim3 grid((unsigned)gx, (unsigned)frames);
     k5_halo_blend<<<grid, 256, 0, (cudaStream_t)stream>>>(nj, pj, (long long)frame_bytes, overlap, my_flags, next_flags,
                                                          prev_flags, epoch);

@@ -91,10 +91,13 @@ def resize(src, h, w, interpolation=INTER_LINEAR):
     return dst.squeeze(-1) if squeeze else dst
 
 
-def upscale_feather_composite(inpainted, orig, mask, feather_px=3, keep_unmasked_original=True, out=None, mask_bits=None):
+def upscale_feather_composite(inpainted, orig, mask, feather_px=3, keep_unmasked_original=True, out=None, mask_bits=None,
+                              chain_previous=False):
     """K3.  inpainted u8 [T,h,w,3], orig u8 [T,H0,W0,3], mask u8 [T,H0,W0] -> u8 [T,H0,W0,3]
     (diffuerase.py:70-112 applied to every frame).  ``mask_bits``: the same mask as K1's 1-bit plane
-    (``binarize_dilate(return_bits=True)``); kernels that can use it skip the u8 mask."""
+    (``binarize_dilate(return_bits=True)``); kernels that can use it skip the u8 mask.
+    ``chain_previous=True``: this call directly follows another K3 call on the same stream that produced OTHER frames
+    (a clip composited in parts); its launch may then begin while the previous one drains."""
     _require_cuda(inpainted, orig, mask, mask_bits)
     t, h, w, _ = inpainted.shape
     if keep_unmasked_original:
@@ -112,11 +115,17 @@ def upscale_feather_composite(inpainted, orig, mask, feather_px=3, keep_unmasked
             out = torch.empty((t, h0, w0, 3), dtype=torch.uint8, device=inpainted.device)
         nbytes = lib.vv_composite_workspace_bytes(h0, w0)
         ws = _ws(nbytes, inpainted.device)
-        _lib.check(lib.vv_upscale_feather_composite_bits(
-            _ptr(inpainted), t, h, w, _ptr(orig) if keep_unmasked_original else None,
-            _ptr(mask) if keep_unmasked_original else None, _ptr(mask_bits) if keep_unmasked_original else None,
-            h0, w0, float(feather_px), 1 if keep_unmasked_original else 0, _ptr(out), _ptr(ws), nbytes, _stream()),
-            "vv_upscale_feather_composite")
+        if chain_previous:
+            _lib.set_option("k3_chain", 1)
+        try:
+            _lib.check(lib.vv_upscale_feather_composite_bits(
+                _ptr(inpainted), t, h, w, _ptr(orig) if keep_unmasked_original else None,
+                _ptr(mask) if keep_unmasked_original else None, _ptr(mask_bits) if keep_unmasked_original else None,
+                h0, w0, float(feather_px), 1 if keep_unmasked_original else 0, _ptr(out), _ptr(ws), nbytes, _stream()),
+                "vv_upscale_feather_composite")
+        finally:
+            if chain_previous:
+                _lib.set_option("k3_chain", 0)
     return out
 
 
