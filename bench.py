@@ -432,14 +432,20 @@ def extra_blocks(dev, device, t, out_buf, step, stages, args):
 
     # ---- K3 against mask density: HBM bound on sparse masks, issue bound on the dense synthetic one
     box_only = torch.from_numpy(synth.masks(t, H0, W0, seed=11, salt=0.0)).to(device)
-    masks_k3 = {"empty": torch.zeros((t, H0, W0), dtype=torch.uint8, device=device),
-                "box_only_dilated": ops.binarize_dilate(box_only, DILATE),
-                "bench_mask": ops.binarize_dilate(dev["masks"], DILATE)}
+    # (dilated u8 mask, K1's 1-bit plane of it): the pipeline hands K3 both, as in the timed step
+    full = torch.full((t, H0, W0), 255, dtype=torch.uint8, device=device)
+    masks_k3 = {"empty": (torch.zeros((t, H0, W0), dtype=torch.uint8, device=device), None),
+                "box_only_dilated": ops.binarize_dilate(box_only, DILATE, return_bits=True)[::2],
+                "bench_mask": ops.binarize_dilate(dev["masks"], DILATE, return_bits=True)[::2],
+                "full": (full, None)}
+    masks_k3["empty"] = (masks_k3["empty"][0], torch.zeros_like(masks_k3["bench_mask"][1]))
+    masks_k3["full"] = (full, torch.full_like(masks_k3["bench_mask"][1], -1))
     k3_density = {}
-    for name, mk in masks_k3.items():
-        ms = timed_ms(lambda: ops.upscale_feather_composite(dev["inpainted"], dev["frames"], mk, FEATHER, out=out_buf))
+    for name, (mk, mb) in masks_k3.items():
+        ms = timed_ms(lambda: ops.upscale_feather_composite(dev["inpainted"], dev["frames"], mk, FEATHER, out=out_buf, mask_bits=mb))
         k3_density[name] = {"masked_fraction": float((mk > 0).float().mean()), "ms": ms,
                             "frac": alg_k3 / (ms * 1e-3) / 1e9 / peak}
+    del full
     del masks_k3
     res["k3_vs_mask_density"] = k3_density
 

@@ -11,12 +11,13 @@ import sys
 # (bucket, marker that starts it) in file order, per kernel generation
 # Only source lines that own SASS appear in the report, so the markers are code lines (alternatives per bucket).
 FAST = [("prologue", ["extern __shared__", "const int h = gm.h", "const int strip_words"]),
-        ("phase 1 (mask -> bit rows)", ["for (int i = warp; i < rows_s", "if (BITS) {"]),
+        ("phase 1 (mask -> bit rows)", ["for (int i = warp; i < rows_s", "const uint32_t last_valid = (W0 & 31)", "if (BITS) {"]),
         ("alpha LUT / setup", ["if (warp == 0) {", "if (threadIdx.x < 16) {"]),
-        ("worker: quad up-scale + blend", ["const int xq = item.x & 0xffff"]),
+        ("worker: quad up-scale + blend", ["const int xq = item.x & 0xffff", "const Tap *taps_s = reinterpret_cast<const Tap *>",
+                                           "const int xq = (int)(item & 0x3ffu) << 2"]),
         ("phase 2: classification", ["const int G = gm.G", "const int G = W0 >> 4;", "int qcount = 0, it = 0, j = 0;",
                                      "for (int step = 0; step <= n_steps", "const bool drain = step == n_steps;"]),
-        ("compaction (queue push)", ["if (__ballot_sync(0xffffffffu, need != 0))"]),
+        ("compaction (queue push)", ["if (__ballot_sync(0xffffffffu, need != 0))", "const uint32_t bal_b = __ballot_sync"]),
         ("worker loop control", ["if (qcount >= 32 || (drain", "if (qcount >= 32) {"]),
         ("epilogue (bulk store)", ["fence_proxy_async();"])]
 OLD = [("prologue", ["extern __shared__", "const int nthreads = TMA"]),
@@ -61,7 +62,7 @@ def main():
         buckets = collections.Counter()
         for (f, ln), (s, n) in lines.items():
             if f == main_file:
-                name = "helpers above the kernel (bit_window, x2/x4 load + hpass + vpass)" if ln < first else \
+                name = "helpers above the kernel (bit_window, x2/x4 fetch / assemble + hpass + vpass)" if ln < first else \
                     [nm for nm, start in marks if start <= ln][-1]
             elif f == "common.cuh":
                 name = "common.cuh (u8<->f32, nonzero_bits16, TMA wrappers)"

@@ -813,6 +813,8 @@ struct FastGeom {
     uint32_t inv_wpc;                    // floor(2^32 / Wpc) + 1: id / Wpc == umulhi(id, inv_wpc) for id < 65536, Wpc > 1 (k3_fastw)
     long long frame_bytes, mask_frame_bytes, inp_frame_bytes, bits_frame_words;
     float div, one;
+    float alpha[16];                     // k3_fastw: alpha of LUT level class | inside << 3 (host_alpha_levels)
+    uint32_t alpha_pos;                  // bit i: level i has alpha > 0
 };
 
 template <bool VX2, bool BITS, int NTH, int HR = 2>
@@ -1149,32 +1151,40 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
     // ---------------- phase 1: bit rows [y0 - 2, y0 + th + 2) of both polarities, one zero pad word on each side
     const uint32_t last_valid = (W0 & 31) ? ((1u << (W0 & 31)) - 1u) : 0xffffffffu;   // valid bits of frame word Wpc - 1
     if (BITS) {
-        // flat over all (row, word) slots, four per thread and trip: the loads of a trip are all issued before the first
-        // store waits for one (ncu: the row-by-row loop spent 9 % of the kernel's stall samples on its load round trips)
-        const int total = rows_s * row_words;
-        for (int base0 = 0; base0 < total; base0 += 4 * NTH) {
-            uint32_t mv[4], vv_[4];
+        // a warp owns rows warp, warp + NTH/32, ..., a lane the words lane, lane + 32, ...; the (up to) four loads of
+        // two rows x two words are all issued before the first store waits for one (ncu: a row-by-row loop spent 9 % of
+        // the kernel's stall samples on its load round trips), and nothing divides
+        const uint32_t *fbits = mask_bits + t * gm.bits_frame_words;
+        for (int i0 = warp; i0 < rows_s; i0 += 2 * (NTH / 32))
+            for (int k0 = lane; k0 < row_words; k0 += 64) {
+                uint32_t mv[2][2], vv_[2][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = base0 + u * NTH + (int)threadIdx.x;
-                const int i = (int)__umulhi((uint32_t)idx, gm.inv_rw), k = idx - i * row_words;
-                const int y = y0 - 2 + i;
-                mv[u] = 0, vv_[u] = 0;
-                if (idx < total && y >= 0 && y < H0 && k >= 1 && k <= Wpc) {
-                    vv_[u] = k == Wpc ? last_valid : 0xffffffffu;
-                    mv[u] = __ldg(mask_bits + t * gm.bits_frame_words + (long long)y * Wpc + (k - 1));
+                for (int ra = 0; ra < 2; ++ra) {
+                    const int i = i0 + ra * (NTH / 32), y = y0 - 2 + i;
+                    const bool row_ok = i < rows_s && y >= 0 && y < H0;
+                    const int rowbase = y * Wpc - 1;
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const int k = k0 + 32 * kb;
+                        const bool ok = row_ok && k >= 1 && k <= Wpc;
+                        vv_[ra][kb] = !ok ? 0u : (k == Wpc ? last_valid : 0xffffffffu);
+                        mv[ra][kb] = ok ? __ldg(fbits + (rowbase + k)) : 0u;
+                    }
+                }
+#pragma unroll
+                for (int ra = 0; ra < 2; ++ra) {
+                    const int i = i0 + ra * (NTH / 32);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const int k = k0 + 32 * kb;
+                        if (i < rows_s && k < row_words) {
+                            const uint32_t m = mv[ra][kb] & vv_[ra][kb];
+                            bitsM[i * row_words + k] = m;
+                            bitsZ[i * row_words + k] = ~m & vv_[ra][kb];
+                        }
+                    }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = base0 + u * NTH + (int)threadIdx.x;
-                if (idx < total) {
-                    const uint32_t m = mv[u] & vv_[u];
-                    bitsM[idx] = m;
-                    bitsZ[idx] = ~m & vv_[u];
-                }
-            }
-        }
     } else {
         uint16_t *m16 = reinterpret_cast<uint16_t *>(bitsM), *z16 = reinterpret_cast<uint16_t *>(bitsZ);
         const int halves = 2 * row_words;
@@ -1192,15 +1202,13 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
         }
     }
     if (warp == 0) {
-        // alpha levels: index = class (0 = no hit within the window, 1..5 = cost classes 1, 1.4, 2, 2.1969, 2.8) | inside << 3
-        const int cls = lane & 7, inside = (lane >> 3) & 1;
-        const float cost = cls == 1 ? 1.0f : cls == 2 ? 1.4f : cls == 3 ? 2.0f : cls == 4 ? 2.1969f : __fadd_rn(1.4f, 1.4f);
-        float a = inside ? 1.f : 0.f;
-        if (cls >= 1 && cls <= 5) a = inside ? alpha_from(cost, 0.f, div) : alpha_from(0.f, cost, div);
-        const float na = __fsub_rn(1.f, a);
-        if (lane < 16) lut[lane] = make_float4(a, a, na, na);
-        const uint32_t posmask = __ballot_sync(0xffffffffu, lane < 16 && a > 0.f);     // which LUT levels have alpha > 0
-        if (lane == 0) reinterpret_cast<uint32_t *>(lut + 16)[0] = posmask;
+        // alpha levels (index = class | inside << 3) come from the host (FastGeom): computing them here put two IEEE
+        // divisions per level on warp 0 - about a thousand instructions the other 15 warps waited for at the barrier
+        if (lane < 16) {
+            const float a = gm.alpha[lane], na = __fsub_rn(1.f, a);
+            lut[lane] = make_float4(a, a, na, na);
+        }
+        if (lane == 0) reinterpret_cast<uint32_t *>(lut + 16)[0] = gm.alpha_pos;
     } else if (!VX2 && warp == 1 && lane < th) {
         reinterpret_cast<Tap *>(smem_base + gm.taps_off)[lane] = yt[min(y0 + lane, H0 - 1)];
     }
@@ -1486,6 +1494,28 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
     }
 }
 
+// Host: the 16 alpha levels of the small-radius kernels, index = class (0 = no hit within the window, 1..5 = cost
+// classes 1, 1.4, 2, 2.1969, 2.8) | inside << 3; the same IEEE float32 operations as alpha_from() on the device
+// (diffuerase.py:99-100: 0.5 + (d_in - d_out) / (2 F), clipped).
+static void host_alpha_levels(float div, float alpha[16], uint32_t *pos) {
+    volatile float b14 = 1.4f;
+    volatile float c28 = b14 + b14;
+    const float cost[6] = {0.f, 1.0f, 1.4f, 2.0f, 2.1969f, c28};
+    *pos = 0;
+    for (int i = 0; i < 16; ++i) {
+        const int cls = i & 7, inside = i >> 3;
+        float a = inside ? 1.f : 0.f;
+        if (cls >= 1 && cls <= 5) {
+            volatile float diff = inside ? cost[cls] - 0.f : 0.f - cost[cls];
+            volatile float q = diff / div;
+            volatile float v = 0.5f + q;
+            a = fminf(fmaxf(v, 0.f), 1.f);
+        }
+        alpha[i] = a;
+        if (a > 0.f) *pos |= 1u << i;
+    }
+}
+
 // Host: float32 Dijkstra over the 5x5-chamfer step set (same construction as
 // oracle/prepost.py chamfer_cost_table, verified bit-exact against cv2.distanceTransform).
 static void build_feather_table(float feather_px, FeatherTable *ft) {
@@ -1683,6 +1713,7 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
                 gm.n_steps = ceil_div(gm.n_tasks, nth);
                 gm.inv_wpc = (uint32_t)(0x100000000ULL / (unsigned)Wp) + 1u;
                 gm.inv_rw = (uint32_t)(0x100000000ULL / (unsigned)(Wp + 2)) + 1u;
+                host_alpha_levels(ft.div, gm.alpha, &gm.alpha_pos);
             }
 #define VV_K3_FAST(KERNEL, V, B, N, H)                                                                          \
     do {                                                                                                        \
