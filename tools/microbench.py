@@ -123,13 +123,18 @@ def main():
     # ---- K4: step-kernel variants
     pbuf = torch.empty((t, HS, WS), dtype=torch.int32, device=dev)
     k4b = t * 56 * spx
+    for persist, sc in ((1, 5), (1, 4), (0, 5)):
+        _lib.set_option("k4_persist", persist)
+        _lib.set_option("k4_step_ctas", sc)
+        report("K4 propagate 50+10 windows", k4b, lambda: ops.propagate(small, low, ff, fb, out=pbuf), k4_persist=persist, k4_step_ctas=sc)
+    _lib.set_option("k4_persist", 0)
     for pre, lean, npt, sc, spec in ((1, 5, 1, 5, 1), (0, 5, 1, 5, 1), (1, 6, 1, 6, 1), (1, 8, 1, 8, 1), (1, 8, 1, 6, 1), (1, 5, 1, 5, 0),
                                      (1, 4, 2, 4, 1), (1, 3, 2, 3, 1), (1, 6, 1, 8, 1)):
         for k, v in dict(k4_precheck=pre, k4_lean=lean, k4_npt=npt, k4_step_ctas=sc, k4_speculate=spec).items():
             _lib.set_option(k, v)
         report("K4 propagate 50+10 windows", k4b, lambda: ops.propagate(small, low, ff, fb, out=pbuf), k4_precheck=pre, k4_lean=lean,
                k4_npt=npt, k4_step_ctas=sc, k4_speculate=spec)
-    for k, v in dict(k4_precheck=0, k4_lean=5, k4_npt=1, k4_step_ctas=5, k4_speculate=1).items():
+    for k, v in dict(k4_precheck=0, k4_lean=5, k4_npt=1, k4_step_ctas=5, k4_speculate=1, k4_persist=0).items():
         _lib.set_option(k, v)
     report("K4 propagate 50+10 windows (fresh output tensor)", k4b, lambda: ops.propagate(small, low, ff, fb))
     del pbuf

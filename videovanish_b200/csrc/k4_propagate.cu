@@ -104,13 +104,15 @@ __device__ __forceinline__ FlowTaps load_flow_taps(const Taps &t, const float2 *
     if (t.yb && t.xb) c.c11 = __ldg(flow_check + (t.i00 + (uint32_t)w + 1u));
     return c;
 }
+// CG: the state was written by other CTAs of the SAME launch (k4_steps_persistent): read it from L2, never from L1
+template <bool CG = false>
 __device__ __forceinline__ StateTaps load_state_taps(const Taps &t, const uint32_t *prev, int w) {
     StateTaps p;
     p.p00 = p.p01 = p.p10 = p.p11 = 0;                              // out-of-frame taps: zeros padding, not a hole
-    if (t.ya && t.xa) p.p00 = prev[t.i00];
-    if (t.ya && t.xb) p.p01 = prev[t.i00 + 1u];
-    if (t.yb && t.xa) p.p10 = prev[t.i00 + (uint32_t)w];
-    if (t.yb && t.xb) p.p11 = prev[t.i00 + (uint32_t)w + 1u];
+    if (t.ya && t.xa) p.p00 = CG ? __ldcg(prev + t.i00) : prev[t.i00];
+    if (t.ya && t.xb) p.p01 = CG ? __ldcg(prev + (t.i00 + 1u)) : prev[t.i00 + 1u];
+    if (t.yb && t.xa) p.p10 = CG ? __ldcg(prev + (t.i00 + (uint32_t)w)) : prev[t.i00 + (uint32_t)w];
+    if (t.yb && t.xb) p.p11 = CG ? __ldcg(prev + (t.i00 + (uint32_t)w + 1u)) : prev[t.i00 + (uint32_t)w + 1u];
     return p;
 }
 // fbConsistencyCheck for one pixel: bilinear (zeros padding, torch CPU FMA chain) warp of the check flow at the
@@ -141,12 +143,13 @@ __device__ __forceinline__ uint32_t fill_from_prev(const Taps &t, uint32_t cur, 
 }
 
 // One hole pixel, everything in one go (forward pass; backward pass when nothing was precomputed).
+template <bool CG = false>
 __device__ __forceinline__ uint32_t propagate_pixel(int x, int y, int h, int w, uint32_t cur, const float2 f,
                                                     const float2 *__restrict__ flow_check, const uint32_t *prev) {
     const float2 pos = sample_pos(x, y, f, h, w);
     const Taps t = make_taps(pos.x, pos.y, h, w);
     const FlowTaps c = load_flow_taps(t, flow_check, w);           // all eight taps requested together
-    const StateTaps p = load_state_taps(t, prev, w);
+    const StateTaps p = load_state_taps<CG>(t, prev, w);
     return flow_consistent(f, t, c) ? fill_from_prev(t, cur, p) : cur;
 }
 
@@ -521,6 +524,132 @@ __global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS)
     if (relist) lean_flush(q, sw);
 }
 
+
+// ---- k4_steps_persistent: the whole serial scan (both passes, every time step of every window) in ONE launch ----
+// The 2 * (window - 1) steps are dependent, and as separate launches each of them pays the turnaround of a dependent
+// kernel (grid drain, completion, launch, ramp-up: a few microseconds even with programmatic dependent launch) for
+// 5 - 10 us of latency-bound gathers.  Here a resident grid (cooperative launch: every CTA is on an SM) walks the
+// steps itself and meets at a grid-wide barrier in between - one atomic per CTA on a counter in L2 and an acquire
+// spin.  Everything another CTA wrote earlier in the launch (state frames, forward hole lists, their counters) is
+// read from L2 (ld.global.cg), the flows (read-only for the whole launch) through the read-only path.  The step
+// arithmetic is k4_step_lean's.  blockIdx.y = sub-video window, as there.
+// MEASURED (B200, 240 frames 960x540): 1.59 ms against 1.36 ms for the chain of launches - 740 same-address arrivals
+// and an L2 polling round trip per barrier cost more than the turnaround programmatic dependent launch leaves, and
+// the launch chain already loads a step's first list entries before the previous step has retired.  Option
+// k4_persist = 1, off by default; kept for A/B runs and tested for parity.
+struct PersistArgs {
+    SubBatch b;
+    uint32_t *out, *pads;
+    const float2 *ff, *fb;
+    HoleLists l1, l2;
+    long long npx;
+    int h, w, blen, speculate;
+    uint32_t *barrier;           // zeroed before the launch
+};
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// All threads of all CTAs call; `target` = arrivals expected so far (monotonic counter, never reset).
+__device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                     // this CTA's writes are visible before its arrival
+        atomicAdd(bar, 1u);
+        while ((int32_t)(ld_acquire_gpu(bar) - target) < 0) {
+        }
+    }
+    __syncthreads();
+}
+
+template <bool PASS2>
+__device__ __forceinline__ void persistent_step(const StepWin &sw, LeanQueue &q, int h, int w, int speculate) {
+    const bool relist = !PASS2 && sw.next_flow != nullptr;   // holes that stay holes go to the forward list
+    if (!PASS2) {
+        if (threadIdx.x == 0) q.count = 0;
+        __syncthreads();
+    }
+    const uint32_t stride = gridDim.x * K4_BLOCK;
+    const uint32_t first = blockIdx.x * K4_BLOCK + (threadIdx.x & ~31u);      // warp-uniform loop bounds
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = __ldcg(sw.count);
+    uint32_t xy = 0;
+    float2 f = make_float2(0.f, 0.f);
+    {
+        const uint32_t i = first + lane;
+        if (i < n) xy = __ldcg(sw.lxy + i), f = __ldcg(sw.lflow + i);
+    }
+    // backward pass: block-uniform trip count (the queue flush has barriers)
+    const uint32_t n_loop = PASS2 ? n : min(n + (K4_BLOCK - 1), 0xffffff00u) / K4_BLOCK * K4_BLOCK;
+    int trip = 0;
+    for (uint32_t base = first; base < n_loop; base += stride, ++trip) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        const uint32_t xy_cur = xy;
+        const float2 f_cur = f;
+        const uint32_t inext = i + stride;                   // the next trip's entry, requested before this trip's taps
+        if (inext < n) xy = __ldcg(sw.lxy + inext), f = __ldcg(sw.lflow + inext);
+        const int x = (int)(xy_cur & 0xffffu), y = (int)((xy_cur >> 16) & 0x7fffu);
+        const uint32_t pix = (uint32_t)y * (uint32_t)w + (uint32_t)x;
+        uint32_t nv = ST_HOLE | ST_ZERO;
+        float2 nf = make_float2(0.f, 0.f);
+        if (valid) {
+            if (relist && speculate) nf = __ldg(sw.next_flow + pix);
+            nv = propagate_pixel<true>(x, y, h, w, ST_HOLE | ST_ZERO, f_cur, sw.flow_check, sw.prev);
+            if (nv != (ST_HOLE | ST_ZERO)) sw.cur[pix] = nv;
+            else if (relist && !speculate) nf = __ldg(sw.next_flow + pix);
+        }
+        if (relist) {                       // still a hole: the forward pass gets another chance
+            const bool take = valid && nv == (ST_HOLE | ST_ZERO);
+            const uint32_t m = __ballot_sync(0xffffffffu, take);
+            if (m) {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(&q.count, (uint32_t)__popc(m));
+                at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+                if (take) q.xy[at] = xy_cur & ~XY_INVALID, q.flow[at] = nf;
+            }
+            if ((trip % K4_LEAN_ROUNDS) == K4_LEAN_ROUNDS - 1) lean_flush(q, sw);
+        }
+    }
+    if (relist) lean_flush(q, sw);
+}
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(K4_BLOCK, MIN_CTAS) k4_steps_persistent(const __grid_constant__ PersistArgs a) {
+    __shared__ LeanQueue q;
+    __shared__ StepWin s_sw;
+    const SubDesc &sd = a.b.sub[blockIdx.y];
+    const uint32_t n_ctas = gridDim.x * gridDim.y;
+    uint32_t arrivals = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int step = 1; step < a.blen; ++step) {
+            const bool active = step < sd.len;               // block-uniform: shorter windows only keep the barrier
+            if (active) {
+                if (threadIdx.x == 0) {
+                    StepWin sw = StepWin();
+                    const int idx = pass ? step : sd.len - 1 - step;
+                    const long long gframe = sd.start + idx, of = sd.out_frame + idx;
+                    const HoleLists &li = pass ? a.l2 : a.l1;
+                    sw.cur = frame_ptr(sd, idx, a.out, a.pads, a.npx);
+                    sw.prev = frame_ptr(sd, pass ? idx - 1 : idx + 1, a.out, a.pads, a.npx);
+                    sw.flow_check = pass ? a.ff + (gframe - 1) * a.npx : a.fb + gframe * a.npx;
+                    sw.next_flow = (!pass && idx >= 1) ? a.fb + (gframe - 1) * a.npx : nullptr;
+                    sw.lxy = li.xy + of * a.npx, sw.lflow = li.flow + of * a.npx, sw.count = li.count + of;
+                    sw.oxy = a.l2.xy + of * a.npx, sw.oflow = a.l2.flow + of * a.npx, sw.ocount = a.l2.count + of;
+                    s_sw = sw;
+                }
+                __syncthreads();
+                if (pass)
+                    persistent_step<true>(s_sw, q, a.h, a.w, a.speculate);
+                else
+                    persistent_step<false>(s_sw, q, a.h, a.w, a.speculate);
+            }
+            arrivals += n_ctas;
+            grid_barrier(a.barrier, arrivals);
+        }
+}
+
 __global__ void __launch_bounds__(256)
     k4_unpack(const uint32_t *__restrict__ packed, long long n, uint8_t zero_level, uint8_t *__restrict__ rgb,
               uint8_t *__restrict__ hole) {
@@ -587,6 +716,8 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
     l1.count = (uint32_t *)(wsp + 2 * (l4 + l8));
     l2.count = l1.count + total;
     uint32_t *pads = (uint32_t *)(wsp + 2 * (l4 + l8) + align_up((size_t)total * 8, 256));
+    // the grid barrier of k4_steps_persistent lives in the 256 spare bytes behind the pad frames
+    uint32_t *barrier = (uint32_t *)((uint8_t *)pads + align_up((size_t)(total - kept) * npx * 4, 256));
     const float2 *ff = (const float2 *)flows_f, *fb = (const float2 *)flows_b;
     cudaError_t e = cudaMemsetAsync(l1.count, 0, (size_t)total * 8, st);
     if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
@@ -634,6 +765,39 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
         dim3 grid(max(1, min(ceil_div(npx / 4, 256), ceil_div(148 * 16, b.n))), b.n);
         const int per_sm = get_option(OPT_K4_STEP_CTAS);
         if (per_sm > 0) grid.x = max(1, min(ceil_div(npx / 4, 256), (148 * per_sm) / b.n));
+        if (get_option(OPT_K4_PERSIST) != 0 && blen > 1 && !pre) {
+            // one cooperative launch for the whole scan; the grid must be resident (occupancy x SMs)
+            static std::atomic<int> occ_cache[64];
+            int dev_id = 0, sms = 148;
+            cudaGetDevice(&dev_id);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+            dev_id = min(max(dev_id, 0), 63);
+            int occp = occ_cache[dev_id].load();
+            if (occp == 0) {
+                cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k4_steps_persistent<5>, K4_BLOCK, 0);
+                if (oe != cudaSuccess || occp < 1) return fail_cuda(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(k4_steps_persistent)");
+                occ_cache[dev_id].store(occp);
+            }
+            const int want = per_sm > 0 ? min(per_sm, occp) : occp;
+            dim3 pgrid(max(1, min(ceil_div(npx / 4, 256), (sms * want) / b.n)), b.n);
+            PersistArgs pa;
+            pa.b = b, pa.out = out, pa.pads = pads, pa.ff = ff, pa.fb = fb, pa.l1 = l1, pa.l2 = l2, pa.npx = npx;
+            pa.h = h, pa.w = w, pa.blen = blen, pa.speculate = get_option(OPT_K4_SPECULATE), pa.barrier = barrier;
+            if ((e = cudaMemsetAsync(barrier, 0, 16, st)) != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(barrier)");
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = pgrid;
+            cfg.blockDim = dim3(K4_BLOCK);
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, k4_steps_persistent<5>, pa);
+            if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_steps_persistent)");
+            VV_POST_LAUNCH("k4_steps_persistent");
+            continue;
+        }
         const int pdl = get_option(OPT_K4_PDL) != 0;
         const int lean = get_option(OPT_K4_LEAN);
         const int spec = get_option(OPT_K4_SPECULATE);
