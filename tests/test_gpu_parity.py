@@ -98,7 +98,8 @@ def test_k1_fused_lowres_mask(ops):
 # ------------------------------------------------------------------------------- K2
 RESIZE = [(540, 960, 1080, 1920), (176, 320, 360, 640), (1080, 1920, 540, 960), (1080, 1920, 536, 960),
           (97, 131, 200, 333), (200, 333, 97, 131), (7, 5, 31, 47), (1, 1, 8, 8), (360, 640, 176, 320),
-          (64, 64, 64, 200), (300, 400, 150, 100), (50, 70, 50, 70)]
+          (64, 64, 64, 200), (300, 400, 150, 100), (50, 70, 50, 70),
+          (270, 480, 67, 120), (128, 256, 32, 64), (135, 3840, 34, 960)]        # W == 4w: the 4K -> 960-wide path
 
 
 @pytest.mark.parametrize("sh,sw,dh,dw", RESIZE)

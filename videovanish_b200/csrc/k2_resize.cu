@@ -96,14 +96,19 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// ------------------------------------------------------------------ LINEAR, W == 2*w (RGB)
-// Horizontal taps are the pair (2x, 2x+1) with equal weights (1024, 1024); the vertical axis
-// stays table driven, so this covers 1080p -> 960x540 (box) and 1080p -> 960x536 alike.
-// One thread = 16 destination pixels: 2 source rows x 96 B in, 48 B out, all 128-bit.
+// ------------------------------------------------------------------ LINEAR, W == R*w, R = 2 or 4 (RGB)
+// OpenCV's horizontal taps are then the pair (2x, 2x+1) resp. (4x+1, 4x+2) with equal weights (1024, 1024) - the
+// sample position R*(x + 0.5) - 0.5 lies exactly between them; the vertical axis stays table driven, so this covers
+// 1080p -> 960x540 (box), 1080p -> 960x536 and 4K -> 960x536 alike.
+// One thread = 32 source pixels of two source rows (2 x 96 B, all 128-bit loads) -> 32/R destination pixels.  For
+// R = 4 the generic gather kernel touched the same sectors pixel by pixel (77 % of the formula bytes); only two of
+// every ~four source rows are read at all, which is why this path can exceed the formula roofline.
+template <int R>
 __global__ void __launch_bounds__(256)
-    k2_resize_linear_half_rgb(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const Tap *__restrict__ yt,
-                              int H, int W, int h, int w, long long T) {
-    const int groups = w >> 4;
+    k2_resize_linear_ratio_rgb(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, const Tap *__restrict__ yt,
+                               int H, int W, int h, int w, long long T) {
+    constexpr int NPX = 32 / R, NW = 3 * NPX / 4;        // destination pixels / words per thread (12 or 6)
+    const int groups = w / NPX;
     const long long total = T * h * groups;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -123,24 +128,29 @@ __global__ void __launch_bounds__(256)
             a[4 * k] = va.x, a[4 * k + 1] = va.y, a[4 * k + 2] = va.z, a[4 * k + 3] = va.w;
             b[4 * k] = vb.x, b[4 * k + 1] = vb.y, b[4 * k + 2] = vb.z, b[4 * k + 3] = vb.w;
         }
-        uint32_t o[12];
+        uint32_t o[NW];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) o[k] = 0;
+        for (int k = 0; k < NW; ++k) o[k] = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < NPX; ++j) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const int i0 = 6 * j + c, i1 = i0 + 3;      // source byte indices in the 96-byte span
+                const int i0 = 3 * (R * j + R / 2 - 1) + c, i1 = i0 + 3;      // source byte indices in the 96-byte span
                 const int h0 = (int)(byte_of(a[i0 >> 2], i0 & 3) + byte_of(a[i1 >> 2], i1 & 3)) << 10;
                 const int h1 = (int)(byte_of(b[i0 >> 2], i0 & 3) + byte_of(b[i1 >> 2], i1 & 3)) << 10;
                 const int ob = 3 * j + c;
                 o[ob >> 2] |= (uint32_t)vlin(b0, b1, h0, h1) << (8 * (ob & 3));
             }
         }
-        uint8_t *op = dst + ((t * h + y) * (long long)w + g * 16) * 3;
-        stg128_stream(op, make_uint4(o[0], o[1], o[2], o[3]));
-        stg128_stream(op + 16, make_uint4(o[4], o[5], o[6], o[7]));
-        stg128_stream(op + 32, make_uint4(o[8], o[9], o[10], o[11]));
+        uint8_t *op = dst + ((t * h + y) * (long long)w + g * NPX) * 3;
+        if (R == 2) {
+            stg128_stream(op, make_uint4(o[0], o[1], o[2], o[3]));
+            stg128_stream(op + 16, make_uint4(o[4], o[5], o[6], o[7]));
+            stg128_stream(op + 32, make_uint4(o[NW - 4], o[NW - 3], o[NW - 2], o[NW - 1]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < NW; k += 2) *reinterpret_cast<uint2 *>(op + 4 * k) = make_uint2(o[k], o[k + 1]);
+        }
     }
 }
 
@@ -268,8 +278,14 @@ extern "C" int vv_resize(const uint8_t *src, int T, int H, int W, int C, uint8_t
     if (rc) return rc;
     if (C == 3 && W == 2 * w && w % 16 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0) {
         const int grid = (int)min((long long)ceil_div((long long)T * h * (w / 16), 256), (long long)max_grid);
-        k2_resize_linear_half_rgb<<<grid, 256, 0, st>>>(src, dst, yt, H, W, h, w, T);
-        VV_POST_LAUNCH("k2_resize_linear_half_rgb");
+        k2_resize_linear_ratio_rgb<2><<<grid, 256, 0, st>>>(src, dst, yt, H, W, h, w, T);
+        VV_POST_LAUNCH("k2_resize_linear_ratio_rgb<2>");
+        return VV_OK;
+    }
+    if (C == 3 && W == 4 * w && w % 8 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 8 == 0) {
+        const int grid = (int)min((long long)ceil_div((long long)T * h * (w / 8), 256), (long long)max_grid);
+        k2_resize_linear_ratio_rgb<4><<<grid, 256, 0, st>>>(src, dst, yt, H, W, h, w, T);
+        VV_POST_LAUNCH("k2_resize_linear_ratio_rgb<4>");
         return VV_OK;
     }
     const int words_ok = ((w * C) % 4 == 0) && ((uintptr_t)dst % 4 == 0);
