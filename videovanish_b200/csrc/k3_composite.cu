@@ -770,36 +770,6 @@ __global__ void __launch_bounds__(TMA ? K3_THREADS_TMA : K3_THREADS, TMA ? 2 : 4
 //            products, one rounded sum - exactly np.float32 arithmetic.
 //   VX2      vertical axis also exact x2 (closed form); otherwise table-driven vertical taps on the closed-form
 //            horizontal pass (h >> 4 == 32 * (far + 3 * near), so (b * (h >> 4)) >> 16 == (b * m) >> 11).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2u(f32x2 v, uint32_t &lo, uint32_t &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
 constexpr int K3F_THREADS = 512;
 constexpr int K3F_QCAP = 128 + 32;      // one classified row of the warp (32 lanes x 4 quads) + carried-over items
 

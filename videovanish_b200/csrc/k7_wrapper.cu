@@ -125,7 +125,7 @@ __device__ __forceinline__ int k7_reflect101(int i, int n) {
 template <bool BLENDED>
 __global__ void __launch_bounds__(K7_THREADS)
     k7_wrapper_compose(const uint8_t *__restrict__ img, const uint8_t *__restrict__ frames, const uint8_t *__restrict__ mask,
-                       uint8_t *__restrict__ out, int h, int w, int th, int hs_stride, int vec,
+                       uint8_t *__restrict__ out, int h, int w, int th, int hs_stride, int vec, float one,
                        const __grid_constant__ ComposeTables tab) {
     extern __shared__ __align__(16) uint32_t k7_smem[];
     const int Wp = (w + 31) >> 5, roww = Wp + 2, R = th + 2 * K7_R, G8 = (w + 7) >> 3;
@@ -185,76 +185,116 @@ __global__ void __launch_bounds__(K7_THREADS)
     }
     __syncthreads();
 
-    // vertical pass + blend, 4 pixels per thread
+    // vertical pass + blend, 4 pixels per thread: a warp walks the rows, its lanes the 4-pixel groups of a row (no index
+    // division).  The frame words (and the model-output words wherever a mask bit is near) are requested BEFORE the
+    // vertical pass, so that their latency hides behind its ~100 instructions (ncu: 47 % of the stall samples sat on the
+    // first use of these loads); the blend runs in packed fp32 and truncates through the mantissa (add.rm with 2^23)
+    // instead of the conversion pipe.
     const int G4 = (w + 3) >> 2;
     const uint8_t *it_ = img + t * npx * 3, *ft = frames + t * npx * 3;
     uint8_t *ot = out + t * npx * 3;
-    for (int id = threadIdx.x; id < th * G4; id += K7_THREADS) {
-        const int r = id / G4, g = id - r * G4, x0 = g * 4, y = y0 + r;
-        if (y >= h) continue;
-        const int n = min(4, w - x0);
-        const long long po = ((long long)y * w + x0) * 3;
-        uint32_t alpha[4] = {0, 0, 0, 0};
-        uint32_t m4 = 0;
-        if (vec) {
-            m4 = __ldg(reinterpret_cast<const uint32_t *>(mt + (long long)y * w + x0));
-        } else {
-            for (int i = 0; i < n; ++i) m4 |= (uint32_t)mt[(long long)y * w + x0 + i] << (8 * i);
-        }
-        if (!BLENDED) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) alpha[i] = byte_of(m4, i);
-        } else if ((((((unsigned long long)colflag[2 * (x0 >> 3) + 1] << 32) | colflag[2 * (x0 >> 3)]) >> r) & 0x1fffffull) &&
-                   !(byte_of(m4, 0) && byte_of(m4, 1) && byte_of(m4, 2) && byte_of(m4, 3))) {
-            // some buffer row r .. r+20 (the 21 taps of output row r) sees a mask bit, and not every pixel is masked
-            // taps 0 and 20 are zero and the kernel is symmetric: rows d and 20-d are added first, two u16
-            // lanes per word.  sum_{d=1..9} K[d] * 512 = 57 856 < 2^16, so the lanes cannot carry into each
-            // other; the centre tap is added after unpacking.
-            constexpr uint32_t K[11] = {0, 2, 2, 4, 6, 11, 15, 20, 25, 28, 30};
-            uint2 acc = make_uint2(0u, 0u);
-#pragma unroll
-            for (int d = 1; d < 10; ++d) {
-                const uint2 u = *reinterpret_cast<const uint2 *>(hs + (r + d) * hs_stride + x0);
-                const uint2 v = *reinterpret_cast<const uint2 *>(hs + (r + 20 - d) * hs_stride + x0);
-                acc.x += K[d] * (u.x + v.x), acc.y += K[d] * (u.y + v.y);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const f32x2 one2 = pack2(one, one), big2 = pack2(8388608.f, 8388608.f), unbias2 = pack2(-8388608.f, -8388608.f);
+    for (int r = warp; r < th; r += K7_THREADS / 32) {
+        const int y = y0 + r;
+        if (y >= h) break;
+        // the mask word and the frame words of a group are requested one trip ahead (the branch on the mask word is the
+        // first thing a trip does)
+        uint32_t m4n = 0, fwn[3] = {0, 0, 0};
+        auto request = [&](int gg) {
+            if (vec && gg < G4) {
+                const long long pn = ((long long)y * w + gg * 4) * 3;
+                m4n = __ldg(reinterpret_cast<const uint32_t *>(mt + (long long)y * w + gg * 4));
+                const uint32_t *f32p = reinterpret_cast<const uint32_t *>(ft + pn);
+                fwn[0] = __ldg(f32p), fwn[1] = __ldg(f32p + 1), fwn[2] = __ldg(f32p + 2);
             }
-            const uint2 c = *reinterpret_cast<const uint2 *>(hs + (r + 10) * hs_stride + x0);
-            const uint32_t s[4] = {(acc.x & 0xffffu) + K[10] * (c.x & 0xffffu), (acc.x >> 16) + K[10] * (c.x >> 16),
-                                   (acc.y & 0xffffu) + K[10] * (c.y & 0xffffu), (acc.y >> 16) + K[10] * (c.y >> 16)};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t blur = (255u * s[i] + 32768u) >> 16;
-                alpha[i] = byte_of(m4, i) ? 255u : alut[blur];
+        };
+        request(lane);
+        for (int g = lane; g < G4; g += 32) {
+            const int x0 = g * 4;
+            const int n = min(4, w - x0);
+            const long long po = ((long long)y * w + x0) * 3;
+            uint32_t alpha[4] = {0, 0, 0, 0};
+            uint32_t m4 = m4n;
+            uint32_t fw[3] = {fwn[0], fwn[1], fwn[2]}, iw[3] = {0, 0, 0};
+            request(g + 32);
+            if (!vec) {
+                for (int i = 0; i < n; ++i) m4 |= (uint32_t)mt[(long long)y * w + x0 + i] << (8 * i);
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) alpha[i] = byte_of(m4, i) ? 255u : 0u;
-        }
-        const uint32_t amin = min(min(alpha[0], alpha[1]), min(alpha[2], alpha[3]));
-        const uint32_t amax = max(max(alpha[0], alpha[1]), max(alpha[2], alpha[3]));
-        if (vec) {
-            uint32_t *o32 = reinterpret_cast<uint32_t *>(ot + po);
-            if (amax == 0u || amin == 255u) {        // a == 0 -> the frame, a == 1 -> the model output, exactly
-                const uint32_t *s32 = reinterpret_cast<const uint32_t *>((amax == 0u ? ft : it_) + po);
-                o32[0] = __ldg(s32), o32[1] = __ldg(s32 + 1), o32[2] = __ldg(s32 + 2);
-                continue;
+            // some buffer row r .. r+20 (the 21 taps of output row r) sees a mask bit
+            const unsigned long long rowflags = ((unsigned long long)colflag[2 * (x0 >> 3) + 1] << 32) | colflag[2 * (x0 >> 3)];
+            const bool near_mask = BLENDED && ((rowflags >> r) & 0x1fffffull) != 0;
+            if (vec && (near_mask || m4)) {
+                const uint32_t *i32 = reinterpret_cast<const uint32_t *>(it_ + po);
+                iw[0] = __ldg(i32), iw[1] = __ldg(i32 + 1), iw[2] = __ldg(i32 + 2);
             }
-            const uint32_t *i32 = reinterpret_cast<const uint32_t *>(it_ + po), *f32p = reinterpret_cast<const uint32_t *>(ft + po);
-            const uint32_t iw[3] = {__ldg(i32), __ldg(i32 + 1), __ldg(i32 + 2)};
-            const uint32_t fw[3] = {__ldg(f32p), __ldg(f32p + 1), __ldg(f32p + 2)};
-            uint32_t ow[3] = {0, 0, 0};
+            if (!BLENDED) {
 #pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                const float a = fa[alpha[k / 3]], na = __fsub_rn(1.f, a);
-                const float v = __fadd_rn(__fmul_rn(u8_to_float(iw[k >> 2], k & 3), a), __fmul_rn(u8_to_float(fw[k >> 2], k & 3), na));
-                ow[k >> 2] |= (__float2uint_rz(v) & 0xffu) << (8 * (k & 3));
+                for (int i = 0; i < 4; ++i) alpha[i] = byte_of(m4, i);
+            } else if (near_mask && !(byte_of(m4, 0) && byte_of(m4, 1) && byte_of(m4, 2) && byte_of(m4, 3))) {
+                // not every pixel is masked: taps 0 and 20 are zero and the kernel is symmetric: rows d and 20-d are added
+                // first, two u16 lanes per word.  sum_{d=1..9} K[d] * 512 = 57 856 < 2^16, so the lanes cannot carry into
+                // each other; the centre tap is added after unpacking.
+                constexpr uint32_t K[11] = {0, 2, 2, 4, 6, 11, 15, 20, 25, 28, 30};
+                uint2 acc = make_uint2(0u, 0u);
+#pragma unroll
+                for (int d = 1; d < 10; ++d) {
+                    const uint2 u = *reinterpret_cast<const uint2 *>(hs + (r + d) * hs_stride + x0);
+                    const uint2 v = *reinterpret_cast<const uint2 *>(hs + (r + 20 - d) * hs_stride + x0);
+                    acc.x += K[d] * (u.x + v.x), acc.y += K[d] * (u.y + v.y);
+                }
+                const uint2 c = *reinterpret_cast<const uint2 *>(hs + (r + 10) * hs_stride + x0);
+                const uint32_t s[4] = {(acc.x & 0xffffu) + K[10] * (c.x & 0xffffu), (acc.x >> 16) + K[10] * (c.x >> 16),
+                                       (acc.y & 0xffffu) + K[10] * (c.y & 0xffffu), (acc.y >> 16) + K[10] * (c.y >> 16)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t blur = (255u * s[i] + 32768u) >> 16;
+                    alpha[i] = byte_of(m4, i) ? 255u : alut[blur];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) alpha[i] = byte_of(m4, i) ? 255u : 0u;
             }
-            o32[0] = ow[0], o32[1] = ow[1], o32[2] = ow[2];
-        } else {
-            for (int k = 0; k < 3 * n; ++k) {
-                const float a = fa[alpha[k / 3]], na = __fsub_rn(1.f, a);
-                const float v = __fadd_rn(__fmul_rn((float)it_[po + k], a), __fmul_rn((float)ft[po + k], na));
-                ot[po + k] = (uint8_t)__float2uint_rz(v);
+            const uint32_t amin = min(min(alpha[0], alpha[1]), min(alpha[2], alpha[3]));
+            const uint32_t amax = max(max(alpha[0], alpha[1]), max(alpha[2], alpha[3]));
+            if (vec) {
+                uint32_t *o32 = reinterpret_cast<uint32_t *>(ot + po);
+                if (amax == 0u) {                      // a == 0 -> the frame, exactly
+                    o32[0] = fw[0], o32[1] = fw[1], o32[2] = fw[2];
+                    continue;
+                }
+                if (amin == 255u) {                    // a == 1 -> the model output, exactly (every pixel masked: loaded above)
+                    o32[0] = iw[0], o32[1] = iw[1], o32[2] = iw[2];
+                    continue;
+                }
+                // 0 < a somewhere: blurred alphas only occur near a mask bit, so the model-output words were requested
+                float fa4[4], na4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) fa4[i] = fa[alpha[i]], na4[i] = __fsub_rn(1.f, fa4[i]);
+                uint32_t rb[12];
+#pragma unroll
+                for (int p = 0; p < 6; ++p) {          // byte pair p = bytes (2p, 2p+1) of the 12-byte group; byte k belongs to pixel k / 3
+                    const int k0 = 2 * p, k1 = 2 * p + 1;
+                    const f32x2 a2 = pack2(fa4[k0 / 3], fa4[k1 / 3]), n2 = pack2(na4[k0 / 3], na4[k1 / 3]);
+                    const uint32_t wi = iw[p >> 1], wf = fw[p >> 1];
+                    const uint32_t s0 = 0x7540u | (uint32_t)(k0 & 3), s1 = 0x7540u | (uint32_t)(k1 & 3);
+                    const f32x2 xi = fadd2(pack2u(__byte_perm(wi, 0x4b000000u, s0), __byte_perm(wi, 0x4b000000u, s1)), unbias2);
+                    const f32x2 xf = fadd2(pack2u(__byte_perm(wf, 0x4b000000u, s0), __byte_perm(wf, 0x4b000000u, s1)), unbias2);
+                    // f32(img * a) + f32(frame * (1 - a)) (two rounded products, one rounded sum), then astype(uint8) =
+                    // truncation: 2^23 + v rounded DOWN leaves floor(v) in the mantissa
+                    const f32x2 v = fadd2_rm(ffma2(fmul2(xi, a2), one2, fmul2(xf, n2)), big2);
+                    unpack2u(v, rb[k0], rb[k1]);
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    o32[j] = __byte_perm(__byte_perm(rb[4 * j], rb[4 * j + 1], 0x0040), __byte_perm(rb[4 * j + 2], rb[4 * j + 3], 0x0040),
+                                         0x5410);
+            } else {
+                for (int k = 0; k < 3 * n; ++k) {
+                    const float a = fa[alpha[k / 3]], na = __fsub_rn(1.f, a);
+                    const float v = __fadd_rn(__fmul_rn((float)it_[po + k], a), __fmul_rn((float)ft[po + k], na));
+                    ot[po + k] = (uint8_t)__float2uint_rz(v);
+                }
             }
         }
     }
@@ -349,9 +389,9 @@ extern "C" int vv_wrapper_compose(const uint8_t *img, const uint8_t *frames, con
         smem_set[blended ? 1 : 0].store(smem);
     }
     if (blended)
-        k7_wrapper_compose<true><<<grid, K7_THREADS, smem, (cudaStream_t)stream>>>(img, frames, mask255, out, h, w, th, hs_stride, vec, tab);
+        k7_wrapper_compose<true><<<grid, K7_THREADS, smem, (cudaStream_t)stream>>>(img, frames, mask255, out, h, w, th, hs_stride, vec, 1.0f, tab);
     else
-        k7_wrapper_compose<false><<<grid, K7_THREADS, smem, (cudaStream_t)stream>>>(img, frames, mask255, out, h, w, th, hs_stride, vec, tab);
+        k7_wrapper_compose<false><<<grid, K7_THREADS, smem, (cudaStream_t)stream>>>(img, frames, mask255, out, h, w, th, hs_stride, vec, 1.0f, tab);
     VV_POST_LAUNCH("k7_wrapper_compose");
     return VV_OK;
 }
