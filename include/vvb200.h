@@ -62,9 +62,13 @@ VV_API void vv_reset_launch_count(void);
  *                flight per thread, fewer resident CTAs).
  *   "k3_bits"    1 (default) = K3 reads the dilated 1-bit mask plane K1 left in its workspace when the caller
  *                passes it (vv_upscale_feather_composite_bits); 0 = always rebuild the bit rows from the u8 mask.
- *   "k3_x2"      2 (default) = the k3_fast kernel whenever W0 == 2w (closed-form horizontal pass, closed-form or
- *                table-driven vertical pass, rolling classification, packed-fp32 blend); 1 = the older closed-form
- *                worker (needs H0 == 2h as well); 0 = the generic tap-table worker for every ratio.
+ *   "k3_x2"      3 (default) = the k3_fastw kernel whenever W0 == 2w or 4w (W0 <= 4096): closed-form horizontal pass,
+ *                closed-form or table-driven vertical pass, 32-pixel word classification tasks, interior words without
+ *                blend, software-pipelined worker, packed-fp32 blend; 2 = k3_fast, its predecessor (16-pixel rolling
+ *                tasks); 1 = the round-1 closed-form worker (needs H0 == 2h as well); 0 = the generic tap-table worker.
+ *   "k3_chain"   1 = the next k3_fastw launch is chained to the K3 launch before it in the stream (programmatic stream
+ *                serialisation; it may start while that one drains).  Only for back-to-back K3 calls over DIFFERENT
+ *                frames of a clip; the Python front end sets it per call (chain_previous=True).  Default 0.
  *   "k4_pack_ctas" k4_pack launches about 148 x this many CTAs per call (more, shorter CTAs shrink the tail
  *                of the last wave; default 128);  "k4_pack_occ" 4 (default), 5 or 6 = CTAs per SM the kernel is
  *                compiled for.
@@ -77,7 +81,11 @@ VV_API void vv_reset_launch_count(void);
  *                flow taps ride along with the state taps in one latency-bound round trip, in the bandwidth-bound pack
  *                they cost their full, badly coalesced bytes) = the steps do it all.
  *   "k4_speculate" 1 (default, measured faster) = the backward pass fetches the forward-pass flow of a hole
- *                together with its taps; 0 = only after the hole turned out to stay a hole. */
+ *                together with its taps; 0 = only after the hole turned out to stay a hole.
+ *   "k4_persist" 1 = the whole propagation scan as ONE persistent cooperative launch with grid-wide barriers instead of
+ *                one launch per time step (measured slower on B200: default 0).
+ *   "k5_halo_ctas" CTA budget of vv_halo_blend (default 148 x 8; chunking.produce_and_blend_boundaries lowers it to
+ *                128 while the exchange runs on a side stream underneath K3). */
 VV_API int vv_set_option(const char *name, int value);
 VV_API int vv_get_option(const char *name, int *value);
 
