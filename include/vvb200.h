@@ -284,6 +284,20 @@ VV_API int vv_pipeline_upload(vv_pipeline *p, const uint8_t *const *src, int T, 
 VV_API int vv_pipeline_download(vv_pipeline *p, const uint8_t *dev_src, int T, size_t frame_bytes,
                                 uint8_t *const *dst, void *stream);
 
+/* Row-bounded results.  The composite (diffuerase.py:70-112) only changes pixels within the feather radius of a mask
+ * pixel, so outside the row range [lo, hi) of a frame the finished frame equals the input frame (`orig`, :108).
+ * vv_mask_row_bounds: bounds[2t] = lo, bounds[2t+1] = hi (exclusive) of frame t from K1's dilated 1-bit plane
+ *   (i32 device array of 2T; `margin` rows added either side: the feather radius; (0, 0) for an empty mask).
+ * vv_pipeline_host_rows_begin: starts copying the rows OUTSIDE [lo, hi) from the caller's input frames `src` to the
+ *   result frames `dst` on a background memcpy pool (host pointers; arrays of T); returns at once.
+ * vv_pipeline_download_rows: the rows INSIDE [lo, hi) of the device frames -> `dst` (page-locked), waits for the
+ *   background copy; like vv_pipeline_download it first waits for the work enqueued on `stream`. */
+VV_API int vv_mask_row_bounds(const uint32_t *mask_bits, int T, int H, int Wp, int margin, int *bounds, void *stream);
+VV_API int vv_pipeline_host_rows_begin(vv_pipeline *p, int T, int H, size_t row_bytes, uint8_t *const *dst,
+                                       const uint8_t *const *src, const int *lo, const int *hi);
+VV_API int vv_pipeline_download_rows(vv_pipeline *p, const uint8_t *dev_src, int T, int H, size_t row_bytes,
+                                     uint8_t *const *dst, const int *lo, const int *hi, void *stream);
+
 /* Peer-memory helpers for the multi-GPU halo blend (one process per GPU). */
 /* handle of the allocation that contains dev_ptr + the offset of dev_ptr inside it */
 VV_API int vv_ipc_get_handle(const void *dev_ptr, void *handle_out_64B, size_t *offset_out);

@@ -280,6 +280,53 @@ def test_device_resident_dropin_matches_full_path_oracle(ops, t, h0, w0, size, d
     assert np.array_equal(np.stack(frames), fr) and np.array_equal(np.stack(masks), mk), "inputs must not be mutated"
 
 
+def test_mask_row_bounds_kernel(ops):
+    t, h, w = 6, 75, 200
+    dil = np.zeros((t, h, w), np.uint8)
+    dil[0, 10:20, 5:9] = 255
+    dil[1, 0, 199] = 255                      # first row, last column
+    dil[2, 74, 0] = 255                       # last row
+    dil[3] = 255
+    dil[5, 30, 64] = dil[5, 50, 3] = 255      # frame 4 stays empty
+    wp = (w + 31) // 32
+    padded = np.zeros((t, h, wp * 32), np.uint8)
+    padded[:, :, :w] = dil > 0
+    bits = dev(np.packbits(padded.reshape(t, h, wp, 32), axis=-1, bitorder="little").view(np.int32).reshape(t, h, wp))
+    for margin in (0, 3):
+        got = host(ops.mask_row_bounds(bits, margin))
+        for i in range(t):
+            ys = np.nonzero(dil[i].any(axis=1))[0]
+            want = (0, 0) if len(ys) == 0 else (max(0, ys[0] - margin), min(h, ys[-1] + 1 + margin))
+            assert tuple(got[i]) == want, (i, margin)
+
+
+@pytest.mark.parametrize("t,h0,w0,size,dilate,feather", [(12, 180, 320, 160, 5, 3), (9, 90, 160, 80, 2, 6.5), (5, 72, 128, 64, 3, 0)])
+def test_device_resident_row_bounded_results(ops, t, h0, w0, size, dilate, feather):
+    """One-object masks: only the rows the dilated mask (+ feather radius) reaches are downloaded, the rest of every
+    finished frame is copied from the caller's input frame on the host - same bytes as the full download and as the
+    composition of the stage oracles."""
+    vvd_max[0] = size
+    vvd = _install_adapters(seed=t)
+    fr, mk = synth.frames(t, h0, w0, seed=t + 1), synth.masks(t, h0, w0, seed=t + 2, salt=0.0)
+    mk[t // 2] = 0                                               # a frame without any mask: copied entirely on the host
+    want = ofp.run(list(fr), list(mk), _flow_fn_np(t), mask_dilation_iter=dilate, max_img_size=size, feather_px=feather)
+    try:
+        assert vvd.ROW_BOUNDED_RESULTS
+        out = vvd.run_infill_on_frames(list(fr), list(mk), mask_dilation_iter=dilate, max_img_size=size, feather_px=feather)
+        info = dict(vvd.last_call_info)
+        vvd.ROW_BOUNDED_RESULTS = False
+        full = vvd.run_infill_on_frames(list(fr), list(mk), mask_dilation_iter=dilate, max_img_size=size, feather_px=feather)
+        info_full = dict(vvd.last_call_info)
+    finally:
+        vvd.ROW_BOUNDED_RESULTS = True
+        vvd.propainter = None
+    assert info["row_bounded"] and 0 < info["rows_downloaded"] < 0.75 * t * h0
+    assert not info_full["row_bounded"] and info_full["rows_downloaded"] == t * h0
+    assert all(o.dtype == np.uint8 and o.flags.c_contiguous and o.shape == (h0, w0, 3) for o in out)
+    assert np.array_equal(np.stack(out), np.stack(want))
+    assert np.array_equal(np.stack(full), np.stack(want))
+
+
 def test_wrapper_adapters_keep_the_upstream_host_signatures(ops):
     """The adapters also work as plain host-list models behind the reference's calls (diffuerase.py:52-57, :62-67)."""
     from videovanish_b200 import wrappers

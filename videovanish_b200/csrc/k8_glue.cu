@@ -137,6 +137,34 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Rows of each frame that the composite can change: [first row with a mask bit - margin, last such row + margin],
+// clipped to the frame, as (lo, hi) with hi exclusive; (0, 0) for an empty mask.  One CTA per frame over K1's 1-bit plane.
+// The host-list front end then moves only these rows of the finished frames across PCIe (hostpipe / diffuerase).
+__global__ void __launch_bounds__(256) k8_mask_row_bounds(const uint32_t *__restrict__ bits, int H, int Wp, int margin,
+                                                          int *__restrict__ bounds) {
+    __shared__ int s_lo, s_hi;
+    if (threadIdx.x == 0) s_lo = H, s_hi = -1;
+    __syncthreads();
+    const uint32_t *fb = bits + (long long)blockIdx.x * H * Wp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int lo = H, hi = -1;
+    for (int y = warp; y < H; y += 8) {
+        uint32_t any = 0;
+        for (int k = lane; k < Wp; k += 32) any |= __ldg(fb + (long long)y * Wp + k);
+        if (__ballot_sync(0xffffffffu, any != 0)) lo = min(lo, y), hi = max(hi, y);
+    }
+    if (lane == 0) {
+        atomicMin(&s_lo, lo);
+        atomicMax(&s_hi, hi);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bool empty = s_hi < 0;
+        bounds[2 * blockIdx.x] = empty ? 0 : max(0, s_lo - margin);
+        bounds[2 * blockIdx.x + 1] = empty ? 0 : min(H, s_hi + 1 + margin);
+    }
+}
+
 }  // namespace vv
 
 using namespace vv;
@@ -168,6 +196,13 @@ extern "C" int vv_apply_mask(const uint8_t *frames, const uint8_t *mask, int T, 
     else
         k8_apply_mask<false><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, mask, out, n_px);
     VV_POST_LAUNCH("k8_apply_mask");
+    return VV_OK;
+}
+
+extern "C" int vv_mask_row_bounds(const uint32_t *mask_bits, int T, int H, int Wp, int margin, int *bounds, void *stream) {
+    VV_CHECK_ARG(mask_bits && bounds && T > 0 && H > 0 && Wp > 0 && margin >= 0, "vv_mask_row_bounds: bad argument");
+    k8_mask_row_bounds<<<T, 256, 0, (cudaStream_t)stream>>>(mask_bits, H, Wp, margin, bounds);
+    VV_POST_LAUNCH("k8_mask_row_bounds");
     return VV_OK;
 }
 

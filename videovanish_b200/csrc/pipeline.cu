@@ -124,6 +124,8 @@ struct vv_pipeline {
     size_t big_in, big_out, small, maskb, ws_bytes, pin_in_bytes, pin_out_bytes;
     std::vector<Slot> slots;
     CopyPool *pool;
+    CopyPool *row_pool;       // second pool for vv_pipeline_host_rows_begin (runs while uploads may use `pool`)
+    std::thread *row_thread;  // the background copy of the rows outside the mask bounds, joined by the download
     uint8_t *res_masks;       // resident dilated masks of the last vv_pipeline_pre
     int res_frames, res_cap;
     std::mutex mu;            // one job at a time, like the reference's _job_running guard
@@ -230,6 +232,7 @@ extern "C" int vv_pipeline_create(vv_pipeline **out, int device, int H0, int W0,
     p->pin_in_bytes = p->big_in + p->small + p->maskb;
     p->pin_out_bytes = p->big_out + p->small;
     p->res_masks = nullptr, p->res_frames = 0, p->res_cap = 0;
+    p->row_pool = nullptr, p->row_thread = nullptr;
     unsigned hc = std::thread::hardware_concurrency();
     p->pool = new CopyPool((int)std::min(7u, hc > 1 ? hc - 1 : 1u));
     p->slots.resize(n_slots);
@@ -263,6 +266,11 @@ extern "C" void vv_pipeline_destroy(vv_pipeline *p) {
         if (s.st) cudaStreamDestroy(s.st);
     }
     if (p->res_masks) cudaFree(p->res_masks);
+    if (p->row_thread) {
+        p->row_thread->join();
+        delete p->row_thread;
+    }
+    delete p->row_pool;
     delete p->pool;
     delete p;
 }
@@ -437,5 +445,73 @@ extern "C" int vv_pipeline_download(vv_pipeline *p, const uint8_t *dev_src, int 
     }
     rc = finish(p, rc);
     cudaEventDestroy(ready);
+    return rc;
+}
+
+// ---- row-bounded results ---------------------------------------------------------------------------------------
+// The composite (diffuerase.py:70-112) only changes pixels within the feather radius of a mask pixel: outside the row
+// range [lo, hi) of a frame (vv_mask_row_bounds over K1's bit plane) the finished frame IS the input frame.  The
+// host-list front end therefore copies those rows host -> host from the caller's input frames, on a memcpy pool in the
+// background while the clip is uploaded and processed, and only the rows inside the range cross PCIe on the way back.
+extern "C" int vv_pipeline_host_rows_begin(vv_pipeline *p, int T, int H, size_t row_bytes, uint8_t *const *dst,
+                                           const uint8_t *const *src, const int *lo, const int *hi) {
+    VV_CHECK_ARG(p && dst && src && lo && hi && T > 0 && H > 0 && row_bytes > 0, "vv_pipeline_host_rows_begin: bad argument");
+    std::lock_guard<std::mutex> g(p->mu);
+    if (p->row_thread) {                 // a previous call whose download never came: finish it first
+        p->row_thread->join();
+        delete p->row_thread;
+        p->row_thread = nullptr;
+    }
+    if (!p->row_pool) {
+        unsigned hc = std::thread::hardware_concurrency();
+        p->row_pool = new CopyPool((int)std::min(7u, hc > 1 ? hc - 1 : 1u));
+    }
+    std::vector<CopyJob> jobs;
+    for (int i = 0; i < T; ++i) {
+        VV_CHECK_ARG(dst[i] && src[i] && lo[i] >= 0 && lo[i] <= hi[i] && hi[i] <= H,
+                     "vv_pipeline_host_rows_begin: bad row range [%d,%d) of frame %d", lo[i], hi[i], i);
+        if (lo[i] > 0) jobs.push_back({dst[i], src[i], (size_t)lo[i] * row_bytes});
+        if (hi[i] < H) jobs.push_back({dst[i] + (size_t)hi[i] * row_bytes, src[i] + (size_t)hi[i] * row_bytes,
+                                       (size_t)(H - hi[i]) * row_bytes});
+    }
+    CopyPool *pool = p->row_pool;
+    p->row_thread = new std::thread([pool, jobs] { pool->run(jobs); });
+    return VV_OK;
+}
+
+extern "C" int vv_pipeline_download_rows(vv_pipeline *p, const uint8_t *dev_src, int T, int H, size_t row_bytes,
+                                         uint8_t *const *dst, const int *lo, const int *hi, void *stream) {
+    VV_CHECK_ARG(p && dev_src && dst && lo && hi && T > 0 && H > 0 && row_bytes > 0, "vv_pipeline_download_rows: bad argument");
+    VV_CHECK_ARG((size_t)H * row_bytes <= (size_t)p->H0 * p->W0 * 3, "vv_pipeline_download_rows: frame larger than the context geometry");
+    std::lock_guard<std::mutex> g(p->mu);
+    VV_CUDA(cudaSetDevice(p->device));
+    for (int i = 0; i < T; ++i)
+        VV_CHECK_ARG(dst[i] && lo[i] >= 0 && lo[i] <= hi[i] && hi[i] <= H && is_pinned(dst[i]),
+                     "vv_pipeline_download_rows: frame %d needs a page-locked destination and a row range inside the frame", i);
+    cudaEvent_t ready;
+    VV_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ready, (cudaStream_t)stream);
+    int rc = e == cudaSuccess ? VV_OK : fail_cuda(e, "cudaEventRecord");
+    const size_t frame_bytes = (size_t)H * row_bytes;
+    for (int s = 0; s < p->n_slots && !rc; ++s)
+        if ((e = cudaStreamWaitEvent(p->slots[s].st, ready, 0)) != cudaSuccess) rc = fail_cuda(e, "cudaStreamWaitEvent");
+    for (int i = 0; i < T && !rc; ++i) {
+        if (hi[i] <= lo[i]) continue;
+        Slot &s = p->slots[(i / p->fpb) % p->n_slots];
+        const size_t off = (size_t)lo[i] * row_bytes;
+        e = cudaMemcpyAsync(dst[i] + off, dev_src + (size_t)i * frame_bytes + off, (size_t)(hi[i] - lo[i]) * row_bytes,
+                            cudaMemcpyDeviceToHost, s.st);
+        if (e != cudaSuccess) rc = fail_cuda(e, "cudaMemcpyAsync(rows)");
+    }
+    for (int s = 0; s < p->n_slots; ++s) {                       // also on the error path: no DMA into freed buffers
+        e = cudaStreamSynchronize(p->slots[s].st);
+        if (e != cudaSuccess && !rc) rc = fail_cuda(e, "cudaStreamSynchronize");
+    }
+    cudaEventDestroy(ready);
+    if (p->row_thread) {                                         // the rows copied from the input frames
+        p->row_thread->join();
+        delete p->row_thread;
+        p->row_thread = nullptr;
+    }
     return rc;
 }

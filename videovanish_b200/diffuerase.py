@@ -17,11 +17,19 @@ When every model in play offers ``forward_device`` (the adapters of ``wrappers.p
 the call is device-resident: frames and masks are uploaded once, K1 -> [prior stages] -> [DiffuEraser
 wrapper stages] -> K3 run back to back in HBM, and only the finished frames come back.
 """
+import math
+
 import numpy as np
 
 from . import hostpipe
 
 BUG_COMPAT = False           # True: reproduce the early return of diffuerase.py:114
+# Device-resident route: when the dilated masks leave most rows untouched, only the rows they reach are downloaded
+# and the rest of each finished frame is copied from the caller's input frame on the host (same bytes, see
+# _run_on_device).  Used when the rows to download are at most this fraction of the clip.
+ROW_BOUNDED_RESULTS = True
+ROW_BOUNDED_MAX_FRACTION = 0.75
+last_call_info = {}          # what the last device-resident call did: {"row_bounded": bool, "rows_downloaded": int}
 
 device = None
 last_ckpt = None
@@ -140,6 +148,23 @@ def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_
         h, w = ops.inference_size(H0, W0, max_img_size)
         dil, low, bits = ops.binarize_dilate(masks, mask_dilation_iter, lowres_size=(h, w), return_bits=True)   # K1
         del masks
+        # Row-bounded result: outside the rows a frame's dilated mask (+ feather radius) reaches, the finished frame IS
+        # the input frame (alpha = 0 -> rint(orig) = orig, diffuerase.py:112), so those rows are copied host -> host from
+        # the caller's frames in the background and only the rows in between come back over PCIe.
+        rows = None
+        if (ROW_BOUNDED_RESULTS and keep_unmasked_original and not BUG_COMPAT and not resident and not keep_on_device
+                and bits is not None and all(isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.flags.c_contiguous
+                                             and f.shape == (H0, W0, 3) for f in frames_rgb)):
+            margin = max(0, int(math.ceil(float(feather_px))) - 1) + 1 if feather_px > 0 else 1
+            bounds = ops.mask_row_bounds(bits, margin).cpu().numpy()          # tiny; waits for the mask upload + K1 only
+            lo, hi = bounds[:, 0], bounds[:, 1]
+            if int((hi - lo).sum()) <= ROW_BOUNDED_MAX_FRACTION * t * H0:
+                from .hostpipe import pinned_frames
+                result = pinned_frames(t, (H0, W0, 3))
+                pipe.host_rows_begin(result, list(frames_rgb), lo, hi)
+                rows = (result, lo, hi)
+        last_call_info["row_bounded"] = rows is not None
+        last_call_info["rows_downloaded"] = int((rows[2] - rows[1]).sum()) if rows is not None else t * H0
         frames = up.upload(frames_rgb, (H0, W0, 3))
         clip = wrappers.DeviceClip(frames, dil, lowres=low)
         clip.mask_bits = bits
@@ -167,6 +192,8 @@ def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_
         if resident and n == t:
             from .tools import DeviceFrames
             return DeviceFrames(out)
+        if rows is not None and tuple(out.shape) == (t, H0, W0, 3):
+            return pipe.download_rows(out, *rows)
         result = pipe.download(out)
         if n < t and out is not inpainted:
             result += pipe.download(inpainted[n:])

@@ -141,6 +141,34 @@ class HostPipeline:
         self._inflight = keep        # keep converted copies alive until the next call
         return out
 
+    def host_rows_begin(self, dst, src, lo, hi):
+        """Starts copying, in the background, the rows OUTSIDE [lo[i], hi[i]) of every input frame ``src[i]`` into the
+        result frame ``dst[i]`` (lists of C-contiguous uint8 host arrays of one shape).  ``download_rows`` joins it."""
+        t = len(dst)
+        shape = tuple(dst[0].shape)
+        row_bytes = int(np.prod(shape[1:]))
+        lo_a = (ctypes.c_int * t)(*[int(v) for v in lo])
+        hi_a = (ctypes.c_int * t)(*[int(v) for v in hi])
+        src_arr, keep = _ptr_array(src, shape)
+        self._rows_keep = (keep, src)                      # the sources stay alive until the copy has been joined
+        _lib.check(lib.vv_pipeline_host_rows_begin(self._h, t, shape[0], row_bytes, _ptr_array(dst)[0], src_arr, lo_a, hi_a),
+                   "vv_pipeline_host_rows_begin")
+
+    def download_rows(self, tensor, dst, lo, hi):
+        """Rows [lo[i], hi[i]) of every frame of the u8 device tensor [T,H,...] -> the page-locked host arrays ``dst``;
+        waits for the work enqueued on the current torch stream and for ``host_rows_begin``'s copy."""
+        t = tensor.shape[0]
+        shape = tuple(tensor.shape[1:])
+        lo_a = (ctypes.c_int * t)(*[int(v) for v in lo])
+        hi_a = (ctypes.c_int * t)(*[int(v) for v in hi])
+        with torch.cuda.device(self.device):
+            _lib.check(lib.vv_pipeline_download_rows(self._h, ctypes.c_void_p(tensor.data_ptr()), t, shape[0],
+                                                     int(np.prod(shape[1:])), _ptr_array(dst)[0], lo_a, hi_a,
+                                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                       "vv_pipeline_download_rows")
+        self._rows_keep = None
+        return dst
+
     def download(self, tensor):
         """u8 device tensor [T, ...] -> list of T host arrays (page-locked when the budget allows); waits for
         the work enqueued on the current torch stream."""

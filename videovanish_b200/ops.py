@@ -129,6 +129,19 @@ def upscale_feather_composite(inpainted, orig, mask, feather_px=3, keep_unmasked
     return out
 
 
+def mask_row_bounds(mask_bits, margin=0):
+    """Per frame, the rows a composite with this (dilated) mask can change: i32 [T,2] = (lo, hi), hi exclusive, from K1's
+    1-bit plane i32 [T,H,ceil(W/32)]; ``margin`` rows (the feather radius) are added either side; (0, 0) = empty mask."""
+    _require_cuda(mask_bits)
+    if mask_bits.dtype != torch.int32 or mask_bits.dim() != 3:
+        raise ValueError("mask_row_bounds: mask_bits must be int32 [T,H,ceil(W/32)]")
+    t, h, wp = mask_bits.shape
+    with torch.cuda.device(mask_bits.device):
+        out = torch.empty((t, 2), dtype=torch.int32, device=mask_bits.device)
+        _lib.check(lib.vv_mask_row_bounds(_ptr(mask_bits), t, h, wp, int(margin), _ptr(out), _stream()), "vv_mask_row_bounds")
+    return out
+
+
 def subvideo_plan(video_length, subvideo_length=50, pad_len=10):
     """Windows of propainter/inference.py's image-propagation loop: (s_f, e_f, pad_s, pad_e)."""
     sub = min(100, subvideo_length)
