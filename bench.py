@@ -801,6 +801,35 @@ def run_ours(args, rank, world, local_rank):
     e2e_prepost = {"value": world * t / float(pp_dt.item()), "unit": "frames/s",
                    "h2d_bytes_per_step": t * (3 * px + 3 * spx + 3 * px), "d2h_bytes_per_step": t * (px + 3 * px),
                    "stages": "K1+K3 via the host pipeline, stub models that take and return host lists"}
+    # the same with the one-object mask: `post` moves only the rows the resident dilated masks reach (row bounded)
+    if rank == 0 and world == 1 and not args.no_extras:
+        from videovanish_b200 import synth
+        box_np = synth.masks(t, H0, W0, seed=11, salt=0.0)
+        box_host = hostpipe.pinned_frames(t, (H0, W0, 3))
+        for i in range(t):
+            box_host[i][...] = box_np[i]
+        del box_np
+        pp_box = {}
+        for label, flag in (("row_bounded", 1), ("whole_frames", 0)):
+            _lib.set_option("pipe_rows", flag)
+            for _ in range(2):
+                res = vvd.run_infill_on_frames(frames_host, box_host, DILATE, propainer_frames=frames_host, max_img_size=960)
+                del res
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                res = None
+                res = vvd.run_infill_on_frames(frames_host, box_host, DILATE, propainer_frames=frames_host, max_img_size=960)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / e2e_steps
+            del res
+            moved, total = vvd._pipeline.last_rows()
+            pp_box[label] = {"value": t / dt, "unit": "frames/s", "rows_moved_fraction": moved / max(total, 1),
+                             "h2d_bytes_per_step": t * (3 * px + 3 * spx) + moved * W0 * 3,
+                             "d2h_bytes_per_step": t * px + moved * W0 * 3}
+        _lib.set_option("pipe_rows", 1)
+        e2e_prepost["box_mask"] = pp_box
+        del box_host
 
     # (3) BASELINE config 5 idea: a long clip (pageable host arrays, results beyond the pinned budget) through the ring
     c5 = None

@@ -273,6 +273,12 @@ VV_API int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted, int
                             const uint8_t *const *orig, const uint8_t *const *dilated, int T,
                             float feather_px, int keep_unmasked, uint8_t *const *out);
 
+/* Frame rows per direction that the last vv_pipeline_post moved over PCIe, and frames x H0 (equal unless the call was
+ * row bounded: page-locked orig / out buffers, resident masks, at most 75 % of the rows inside the masks' row ranges
+ * + feather radius; the other rows of `out` are then host copies of `orig`, diffuerase.py:108-112 with alpha = 0).
+ * Option "pipe_rows" = 0 switches the row-bounded mode off. */
+VV_API int vv_pipeline_last_rows(vv_pipeline *p, long long *rows_moved, long long *rows_total);
+
 /* Device-resident clips (the adapter around the two networks, videovanish_b200/wrappers.py): T per-frame host
  * buffers of `frame_bytes` each -> one contiguous device array, and back.  `stream` is the stream that consumes
  * (upload) / produced (download) the device data: the upload makes it wait on the copies, the download waits

@@ -603,6 +603,38 @@ def test_dropin_option_combinations(ops, keep, feather):
     assert np.array_equal(np.stack(out), np.stack(ref))
 
 
+@pytest.mark.parametrize("feather", [3, 0, 6.5])
+def test_dropin_host_lists_row_bounded_post(ops, feather):
+    """Host-list route with page-locked frames and one-object masks: `post` uploads and downloads only the rows the
+    resident dilated masks (+ feather radius) reach and copies the rest of each frame from the original on the host -
+    same bytes as the reference and as the whole-frame transfers (option pipe_rows = 0)."""
+    from videovanish_b200 import _lib, diffuerase as vvd, hostpipe
+    t, h0, w0 = 9, 180, 320
+    h, w = ops.inference_size(h0, w0, 160)
+    fr, mk, inp = synth.frames(t, h0, w0, seed=121), synth.masks(t, h0, w0, seed=122, salt=0.0), synth.noise_frames(t, h, w, seed=123)
+    mk[4] = 0                                                     # a frame without a mask: copied entirely on the host
+    frames = hostpipe.pinned_frames(t, (h0, w0, 3))
+    for i in range(t):
+        frames[i][...] = fr[i]
+    ref = op.ref_run_infill_on_frames(list(fr), list(mk), lambda *a, **k: [x.copy() for x in inp], mask_dilation_iter=4,
+                                      propainer_frames=list(fr), max_img_size=160, feather_px=feather)
+    vvd.set_models(diffueraser=_StubDiffuEraser(list(inp)))
+    assert _lib.get_option("pipe_rows") == 1
+    out = vvd.run_infill_on_frames(frames, list(mk), mask_dilation_iter=4, propainer_frames=frames, max_img_size=160, feather_px=feather)
+    moved, total = vvd._pipeline.last_rows()
+    assert total == t * h0 and 0 < moved < 0.75 * total
+    try:
+        _lib.set_option("pipe_rows", 0)
+        whole = vvd.run_infill_on_frames(frames, list(mk), mask_dilation_iter=4, propainer_frames=frames, max_img_size=160,
+                                         feather_px=feather)
+        assert vvd._pipeline.last_rows() == (total, total)
+    finally:
+        _lib.set_option("pipe_rows", 1)
+    assert np.array_equal(np.stack(out), np.stack(ref))
+    assert np.array_equal(np.stack(whole), np.stack(ref))
+    assert np.array_equal(np.stack(frames), fr), "inputs must not be mutated"
+
+
 def test_dropin_same_size_model_output(ops):
     """Model output already at the original size: the reference skips cv2.resize (:72) but still composites."""
     from videovanish_b200 import diffuerase as vvd

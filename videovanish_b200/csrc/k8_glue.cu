@@ -165,6 +165,43 @@ __global__ void __launch_bounds__(256) k8_mask_row_bounds(const uint32_t *__rest
     }
 }
 
+// The same from a dilated u8 mask [n,H,W] (the host-list pipeline keeps these resident between pre and post).
+__global__ void __launch_bounds__(256) k8_mask_row_bounds_u8(const uint8_t *__restrict__ mask, int H, int W, int *__restrict__ bounds) {
+    __shared__ int s_lo, s_hi;
+    if (threadIdx.x == 0) s_lo = H, s_hi = -1;
+    __syncthreads();
+    const uint8_t *fm = mask + (long long)blockIdx.x * H * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool words = (W % 4 == 0) && ((uintptr_t)mask % 4 == 0);
+    int lo = H, hi = -1;
+    for (int y = warp; y < H; y += 8) {
+        uint32_t any = 0;
+        const uint8_t *row = fm + (long long)y * W;
+        if (words) {
+            for (int k = lane; k < W / 4; k += 32) any |= __ldg(reinterpret_cast<const uint32_t *>(row) + k);
+        } else {
+            for (int k = lane; k < W; k += 32) any |= row[k];
+        }
+        if (__ballot_sync(0xffffffffu, any != 0)) lo = min(lo, y), hi = max(hi, y);
+    }
+    if (lane == 0) {
+        atomicMin(&s_lo, lo);
+        atomicMax(&s_hi, hi);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bool empty = s_hi < 0;
+        bounds[2 * blockIdx.x] = empty ? 0 : s_lo;
+        bounds[2 * blockIdx.x + 1] = empty ? 0 : s_hi + 1;
+    }
+}
+
+int mask_row_bounds_u8(const uint8_t *mask, int n, int H, int W, int *bounds, cudaStream_t st) {
+    k8_mask_row_bounds_u8<<<n, 256, 0, st>>>(mask, H, W, bounds);
+    VV_POST_LAUNCH("k8_mask_row_bounds_u8");
+    return VV_OK;
+}
+
 }  // namespace vv
 
 using namespace vv;

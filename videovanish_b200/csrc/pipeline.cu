@@ -12,11 +12,16 @@
 #include <thread>
 #include <vector>
 
+#include <math.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
 namespace vv {
+
+int mask_row_bounds_u8(const uint8_t *mask, int n, int H, int W, int *bounds, cudaStream_t st);   // k8_glue.cu
 
 // ------------------------------------------------------------------ parallel memcpy pool
 struct CopyJob {
@@ -128,6 +133,9 @@ struct vv_pipeline {
     std::thread *row_thread;  // the background copy of the rows outside the mask bounds, joined by the download
     uint8_t *res_masks;       // resident dilated masks of the last vv_pipeline_pre
     int res_frames, res_cap;
+    long long last_rows, last_rows_total;   // rows per direction the last vv_pipeline_post moved / frames x H0
+    int *res_bounds_dev;      // their per-frame row ranges (first row with a mask pixel, last + 1), device and host copy
+    std::vector<int> res_bounds;
     std::mutex mu;            // one job at a time, like the reference's _job_running guard
 };
 
@@ -232,7 +240,8 @@ extern "C" int vv_pipeline_create(vv_pipeline **out, int device, int H0, int W0,
     p->pin_in_bytes = p->big_in + p->small + p->maskb;
     p->pin_out_bytes = p->big_out + p->small;
     p->res_masks = nullptr, p->res_frames = 0, p->res_cap = 0;
-    p->row_pool = nullptr, p->row_thread = nullptr;
+    p->row_pool = nullptr, p->row_thread = nullptr, p->res_bounds_dev = nullptr;
+    p->last_rows = p->last_rows_total = 0;
     unsigned hc = std::thread::hardware_concurrency();
     p->pool = new CopyPool((int)std::min(7u, hc > 1 ? hc - 1 : 1u));
     p->slots.resize(n_slots);
@@ -266,6 +275,7 @@ extern "C" void vv_pipeline_destroy(vv_pipeline *p) {
         if (s.st) cudaStreamDestroy(s.st);
     }
     if (p->res_masks) cudaFree(p->res_masks);
+    if (p->res_bounds_dev) cudaFree(p->res_bounds_dev);
     if (p->row_thread) {
         p->row_thread->join();
         delete p->row_thread;
@@ -290,9 +300,13 @@ extern "C" int vv_pipeline_pre(vv_pipeline *p, const uint8_t *const *masks, int 
         if (p->res_masks) VV_CUDA(cudaFree(p->res_masks));
         p->res_masks = nullptr, p->res_cap = 0;
         VV_CUDA(cudaMalloc((void **)&p->res_masks, (size_t)T * px));
+        if (p->res_bounds_dev) VV_CUDA(cudaFree(p->res_bounds_dev));
+        p->res_bounds_dev = nullptr;
+        VV_CUDA(cudaMalloc((void **)&p->res_bounds_dev, (size_t)T * 2 * sizeof(int)));
         p->res_cap = T;
     }
     p->res_frames = resident ? T : 0;
+    p->res_bounds.clear();
     int rc = VV_OK;
     for (int b = 0, t0 = 0; t0 < T && !rc; ++b, t0 += p->fpb) {
         Slot &s = p->slots[b % p->n_slots];
@@ -303,12 +317,18 @@ extern "C" int vv_pipeline_pre(vv_pipeline *p, const uint8_t *const *masks, int 
         rc = vv_binarize_dilate(s.dev_big_in, n, p->H0, p->W0, C, iterations, dil, lowres_out ? s.dev_small : nullptr,
                                 lh, lw, s.ws, p->ws_bytes, s.st);
         if (rc) break;
+        if (resident && (rc = mask_row_bounds_u8(dil, n, p->H0, p->W0, p->res_bounds_dev + 2 * t0, s.st))) break;
         if (dilated_out && (rc = download(p, s, dil, dilated_out + t0, n, px, 0))) break;
         if (lowres_out && (rc = download(p, s, s.dev_small, lowres_out + t0, n, spx, p->big_out))) break;
         VV_CUDA(cudaEventRecord(s.done, s.st));
         s.pending = true;
     }
-    return finish(p, rc);
+    rc = finish(p, rc);
+    if (!rc && resident) {               // every slot stream has been waited for: the row ranges are complete
+        p->res_bounds.resize((size_t)T * 2);
+        VV_CUDA(cudaMemcpy(p->res_bounds.data(), p->res_bounds_dev, (size_t)T * 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return rc;
 }
 
 extern "C" int vv_pipeline_downsize(vv_pipeline *p, const uint8_t *const *frames, int T, int h, int w,
@@ -349,6 +369,51 @@ extern "C" int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted,
                  "vv_pipeline_post: no dilated masks supplied and none resident from vv_pipeline_pre");
     VV_CUDA(cudaSetDevice(p->device));
     const size_t px = (size_t)p->H0 * p->W0, spx = (size_t)h * w;
+    // Row-bounded mode: outside the rows a frame's (resident) dilated mask + feather radius reaches, the composite
+    // returns the original frame (alpha = 0 -> rint(orig) = orig, diffuerase.py:112).  Those rows are copied host ->
+    // host from `orig` to `out` by a background memcpy pool; only the rows in between are uploaded, and downloaded.
+    // K3 still runs over whole frames (its time is noise next to PCIe): the device rows that were not uploaded hold
+    // stale bytes, which only reach output rows that are not downloaded.
+    std::vector<int> lo, hi;
+    const size_t row_bytes = (size_t)p->W0 * 3;
+    if (keep_unmasked && !dilated && p->res_bounds.size() >= (size_t)T * 2 && get_option(OPT_PIPE_ROWS) != 0) {
+        const int margin = (feather_px > 0.f ? std::max(0, (int)ceilf(feather_px) - 1) : 0) + 1;
+        long long rows = 0;
+        bool ok = true;
+        lo.resize(T), hi.resize(T);
+        for (int i = 0; i < T && ok; ++i) {
+            const int a = p->res_bounds[2 * i], z = p->res_bounds[2 * i + 1];
+            lo[i] = z > a ? std::max(0, (a - margin) & ~15) : 0;                       // 16-row aligned (K3 strips), (0,0) = empty
+            hi[i] = z > a ? std::min(p->H0, (z + margin + 15) & ~15) : 0;
+            rows += hi[i] - lo[i];
+            ok = orig[i] && out[i] && orig[i] != out[i] && is_pinned(orig[i]) && is_pinned(out[i]);
+        }
+        if (!ok || rows * 4 > (long long)T * p->H0 * 3) lo.clear(), hi.clear();      // worth it below 75 % of the rows
+    }
+    const bool by_rows = !lo.empty();
+    p->last_rows_total = (long long)T * p->H0;
+    p->last_rows = p->last_rows_total;
+    if (by_rows) {
+        p->last_rows = 0;
+        for (int i = 0; i < T; ++i) p->last_rows += hi[i] - lo[i];
+        if (p->row_thread) {
+            p->row_thread->join();
+            delete p->row_thread;
+            p->row_thread = nullptr;
+        }
+        if (!p->row_pool) {
+            unsigned hc = std::thread::hardware_concurrency();
+            p->row_pool = new CopyPool((int)std::min(7u, hc > 1 ? hc - 1 : 1u));
+        }
+        std::vector<CopyJob> jobs;
+        for (int i = 0; i < T; ++i) {
+            if (lo[i] > 0) jobs.push_back({out[i], orig[i], (size_t)lo[i] * row_bytes});
+            if (hi[i] < p->H0)
+                jobs.push_back({out[i] + (size_t)hi[i] * row_bytes, orig[i] + (size_t)hi[i] * row_bytes, (size_t)(p->H0 - hi[i]) * row_bytes});
+        }
+        CopyPool *pool = p->row_pool;
+        p->row_thread = new std::thread([pool, jobs] { pool->run(jobs); });
+    }
     int rc = VV_OK;
     for (int b = 0, t0 = 0; t0 < T && !rc; ++b, t0 += p->fpb) {
         Slot &s = p->slots[b % p->n_slots];
@@ -356,6 +421,36 @@ extern "C" int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted,
         if ((rc = slot_wait(p, s))) break;
         if ((rc = upload(p, s, inpainted + t0, n, spx * 3, s.dev_small, p->big_in))) break;
         const uint8_t *mk = nullptr;
+        if (by_rows) {
+            cudaError_t ce = cudaSuccess;
+            for (int i = 0; i < n && ce == cudaSuccess; ++i) {
+                const int f = t0 + i;
+                if (hi[f] > lo[f])
+                    ce = cudaMemcpyAsync(s.dev_big_in + i * px * 3 + (size_t)lo[f] * row_bytes, orig[f] + (size_t)lo[f] * row_bytes,
+                                         (size_t)(hi[f] - lo[f]) * row_bytes, cudaMemcpyHostToDevice, s.st);
+            }
+            if (ce != cudaSuccess) {
+                rc = fail_cuda(ce, "cudaMemcpyAsync(orig rows)");
+                break;
+            }
+            mk = p->res_masks + (size_t)t0 * px;
+            rc = vv_upscale_feather_composite(s.dev_small, n, h, w, s.dev_big_in, mk, p->H0, p->W0, feather_px, keep_unmasked,
+                                              s.dev_big_out, s.ws, p->ws_bytes, s.st);
+            if (rc) break;
+            for (int i = 0; i < n && ce == cudaSuccess; ++i) {
+                const int f = t0 + i;
+                if (hi[f] > lo[f])
+                    ce = cudaMemcpyAsync(out[f] + (size_t)lo[f] * row_bytes, s.dev_big_out + i * px * 3 + (size_t)lo[f] * row_bytes,
+                                         (size_t)(hi[f] - lo[f]) * row_bytes, cudaMemcpyDeviceToHost, s.st);
+            }
+            if (ce != cudaSuccess) {
+                rc = fail_cuda(ce, "cudaMemcpyAsync(out rows)");
+                break;
+            }
+            VV_CUDA(cudaEventRecord(s.done, s.st));
+            s.pending = true;
+            continue;
+        }
         if (keep_unmasked) {
             if ((rc = upload(p, s, orig + t0, n, px * 3, s.dev_big_in, 0))) break;
             if (dilated) {
@@ -372,7 +467,13 @@ extern "C" int vv_pipeline_post(vv_pipeline *p, const uint8_t *const *inpainted,
         VV_CUDA(cudaEventRecord(s.done, s.st));
         s.pending = true;
     }
-    return finish(p, rc);
+    rc = finish(p, rc);
+    if (p->row_thread) {                 // the rows copied from the original frames (also on the error path)
+        p->row_thread->join();
+        delete p->row_thread;
+        p->row_thread = nullptr;
+    }
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -514,4 +615,11 @@ extern "C" int vv_pipeline_download_rows(vv_pipeline *p, const uint8_t *dev_src,
         p->row_thread = nullptr;
     }
     return rc;
+}
+
+extern "C" int vv_pipeline_last_rows(vv_pipeline *p, long long *rows_moved, long long *rows_total) {
+    VV_CHECK_ARG(p && rows_moved && rows_total, "vv_pipeline_last_rows: NULL argument");
+    std::lock_guard<std::mutex> g(p->mu);
+    *rows_moved = p->last_rows, *rows_total = p->last_rows_total;
+    return VV_OK;
 }

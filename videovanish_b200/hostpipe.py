@@ -141,6 +141,12 @@ class HostPipeline:
         self._inflight = keep        # keep converted copies alive until the next call
         return out
 
+    def last_rows(self):
+        """(rows per direction the last ``post`` moved over PCIe, frames x H0): equal unless it was row bounded."""
+        a, b = ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.check(lib.vv_pipeline_last_rows(self._h, ctypes.byref(a), ctypes.byref(b)), "vv_pipeline_last_rows")
+        return int(a.value), int(b.value)
+
     def host_rows_begin(self, dst, src, lo, hi):
         """Starts copying, in the background, the rows OUTSIDE [lo[i], hi[i]) of every input frame ``src[i]`` into the
         result frame ``dst[i]`` (lists of C-contiguous uint8 host arrays of one shape).  ``download_rows`` joins it."""
