@@ -156,7 +156,7 @@ class HostPipeline:
         lo_a = (ctypes.c_int * t)(*[int(v) for v in lo])
         hi_a = (ctypes.c_int * t)(*[int(v) for v in hi])
         src_arr, keep = _ptr_array(src, shape)
-        self._rows_keep = (keep, src)                      # the sources stay alive until the copy has been joined
+        self._rows_keep = (keep, src, dst)                 # sources AND destinations stay alive until the copy has been joined
         _lib.check(lib.vv_pipeline_host_rows_begin(self._h, t, shape[0], row_bytes, _ptr_array(dst)[0], src_arr, lo_a, hi_a),
                    "vv_pipeline_host_rows_begin")
 
