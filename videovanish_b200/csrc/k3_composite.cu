@@ -177,10 +177,11 @@ __device__ __forceinline__ void x2_assemble_row(const uint32_t wv[4], int xq, in
 }
 __device__ __forceinline__ void x4_fetch_row(const uint32_t *__restrict__ inw, int row_word, int xq, int W0, uint32_t wv[4]) {
     const int bo = xq == 0 ? 0 : 3 * (xq >> 2) - 3;       // left border: start at pixel 0 and duplicate it on assembly
-    const int last = ((W0 >> 2) * 3 - 1) >> 2;            // last word of the row
-    const int wi = bo >> 2;
-    const uint32_t *p = inw + row_word;
-    wv[0] = __ldg(p + wi), wv[1] = __ldg(p + min(wi + 1, last)), wv[2] = __ldg(p + min(wi + 2, last));
+    // one address per row: the second word always lies inside the row (bo <= 3w - 6), the third one only leaves it at
+    // the right border quad, where the assembly replaces the bytes that would come from it (C := B)
+    const uint32_t *p = inw + (row_word + (bo >> 2));
+    wv[0] = __ldg(p), wv[1] = __ldg(p + 1);
+    wv[2] = xq == W0 - 4 ? 0u : __ldg(p + 2);
 }
 __device__ __forceinline__ void x4_assemble_row(const uint32_t wv[4], int xq, int W0, uint32_t &r0, uint32_t &r1, uint32_t &r2) {
     const bool left = xq == 0, right = xq == W0 - 4;
