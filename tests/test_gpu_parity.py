@@ -119,6 +119,15 @@ def test_k2_nearest_bit_exact_vs_cv2(ops, sh, sw, dh, dw):
     assert np.array_equal(host(ops.resize(dev(src), dh, dw, ops.INTER_NEAREST)), ref)
 
 
+@pytest.mark.parametrize("sh,sw,dh,dw", RESIZE + [(64, 512, 16, 128), (33, 64, 17, 32)])
+def test_k2_nearest_masks_bit_exact_vs_cv2(ops, sh, sw, dh, dw):
+    """Single-channel NEAREST (the dilated masks): the exact x2 / x4 column paths and the gather kernel."""
+    rng = np.random.default_rng(sh + 7 * dw)
+    src = ((rng.random((3, sh, sw)) < 0.3) * rng.integers(1, 256, (3, sh, sw))).astype(np.uint8)
+    ref = np.stack([op.ref_resize_nearest(s, dh, dw) for s in src])
+    assert np.array_equal(host(ops.resize(dev(src), dh, dw, ops.INTER_NEAREST)), ref)
+
+
 # ------------------------------------------------------------------------------- K3
 @pytest.mark.parametrize("f", [3, 1, 2, 2.5, 0, -1, 0.5, 3.5, 4, 5, 6.5, 8])
 def test_k3_feather_values(ops, f):
