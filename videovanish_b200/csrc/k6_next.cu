@@ -103,16 +103,19 @@ __device__ __forceinline__ uint32_t k6_hits16(const MaskT *__restrict__ p) {   /
 template <typename MaskT, bool X2>
 __global__ void __launch_bounds__(256)
     k6_paint_masks_rows(const MaskT *__restrict__ masks, int K, int mh, int mw, uint8_t *__restrict__ out, int H0, int W0,
-                        long long T, const int *__restrict__ yo, const __grid_constant__ PaintColors colors) {
+                        long long T, const int *__restrict__ yo, int pair_rows, const __grid_constant__ PaintColors colors) {
+    // pair_rows (H0 == 2 * mh: output rows 2j and 2j+1 both come from source row j): one work item paints both, so the
+    // mask planes are read and tested once per source row instead of twice
     const int groups = W0 >> 4;
-    const long long total = T * H0 * (long long)groups;
+    const int rows = pair_rows ? H0 >> 1 : H0;
+    const long long total = T * rows * (long long)groups;
     const long long plane = (long long)mh * mw;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int g = (int)(idx % groups);
         const long long q = idx / groups;
-        const int y = (int)(q % H0);
-        const long long t = q / H0;
+        const int y = pair_rows ? 2 * (int)(q % rows) : (int)(q % rows);
+        const long long t = q / rows;
         const MaskT *src = masks + t * K * plane + (long long)yo[y] * mw + (X2 ? g * 8 : g * 16);
         // ascending object order, later objects overwrite (sam2_masker.py:159-173); up to 8 planes in flight
         uint32_t px[16];
@@ -143,6 +146,12 @@ __global__ void __launch_bounds__(256)
         stg128_stream(o, make_uint4(ow[0], ow[1], ow[2], ow[3]));
         stg128_stream(o + 1, make_uint4(ow[4], ow[5], ow[6], ow[7]));
         stg128_stream(o + 2, make_uint4(ow[8], ow[9], ow[10], ow[11]));
+        if (pair_rows) {
+            uint4 *o2 = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(o) + (long long)W0 * 3);
+            stg128_stream(o2, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+            stg128_stream(o2 + 1, make_uint4(ow[4], ow[5], ow[6], ow[7]));
+            stg128_stream(o2 + 2, make_uint4(ow[8], ow[9], ow[10], ow[11]));
+        }
     }
 }
 
@@ -238,10 +247,11 @@ extern "C" int vv_paint_masks(const void *masks, int mask_is_f32, int T, int K, 
                          ((uintptr_t)masks % (mask_is_f32 ? 16 : src_per_16) == 0) &&
                          (((size_t)mw * esz) % (mask_is_f32 ? 16 : src_per_16) == 0);
     if (rows_ok) {
-        const long long tot16 = (long long)T * H0 * (W0 / 16);
+        const int pair_rows = (H0 == 2 * mh) ? 1 : 0;        // NEAREST row of y is floor(y / 2) exactly
+        const long long tot16 = (long long)T * (pair_rows ? H0 / 2 : H0) * (W0 / 16);
         const int g16 = (int)min((long long)ceil_div(tot16, 256), (long long)148 * 32);
 #define VV_K6_ROWS(MT, X2) \
-    k6_paint_masks_rows<MT, X2><<<g16, 256, 0, st>>>((const MT *)masks, K, mh, mw, out, H0, W0, T, yo, pc)
+    k6_paint_masks_rows<MT, X2><<<g16, 256, 0, st>>>((const MT *)masks, K, mh, mw, out, H0, W0, T, yo, pair_rows, pc)
         if (mask_is_f32 && twice_w)
             VV_K6_ROWS(float, true);
         else if (mask_is_f32)
