@@ -84,6 +84,12 @@ VV_API void vv_reset_launch_count(void);
  *                together with its taps; 0 = only after the hole turned out to stay a hole.
  *   "k4_persist" 1 = the whole propagation scan as ONE persistent cooperative launch with grid-wide barriers instead of
  *                one launch per time step (measured slower on B200: default 0).
+ *   "k4_streams" G (default 2, 1..4): the propagation windows of a call are dealt to G groups (window s -> group s % G)
+ *                and every group runs its chain of dependent step launches on its own stream (group 0 on the caller's,
+ *                the others on internal side streams forked behind k4_pack): independent chains fill each other's
+ *                launch / round-trip bubbles.  The caller's stream waits for all of them before vv_propagate's work
+ *                counts as done.  1 = one chain on the caller's stream.
+ *   "k4_chain_ctas" CTAs per SM of all G > 1 chains together (default 8; "k4_step_ctas" applies to G == 1).
  *   "k5_halo_ctas" CTA budget of vv_halo_blend (default 148 x 8; chunking.produce_and_blend_boundaries lowers it to
  *                128 while the exchange runs on a side stream underneath K3). */
 VV_API int vv_set_option(const char *name, int value);

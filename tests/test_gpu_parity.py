@@ -263,9 +263,11 @@ def test_k4_zero_padding_fill(ops):
 @pytest.mark.parametrize("variant", [dict(k4_pdl=1), dict(k4_pdl=0), dict(k4_lean=8, k4_step_ctas=0),
                                      dict(k4_lean=6, k4_precheck=1, k4_step_ctas=1), dict(k4_precheck=1), dict(k4_precheck=1, k4_npt=2, k4_lean=4), dict(k4_npt=2, k4_lean=3, k4_step_ctas=3),
                                      dict(k4_npt=2, k4_lean=4, k4_step_ctas=4, k4_speculate=0),
-                                     dict(k4_pack_ctas=1, k4_pack_occ=4), dict(k4_pack_ctas=1024, k4_pack_occ=6)],
+                                     dict(k4_pack_ctas=1, k4_pack_occ=4), dict(k4_pack_ctas=1024, k4_pack_occ=6),
+                                     dict(k4_streams=1), dict(k4_streams=3, k4_chain_ctas=6), dict(k4_streams=4, k4_pdl=0),
+                                     dict(k4_streams=2, k4_precheck=1, k4_chain_ctas=1)],
                          ids=["lean-pdl", "lean", "lean8-wide-grid", "lean6-precheck", "precheck", "precheck-npt2", "two-per-trip-3", "two-per-trip-4",
-                              "pack-few-ctas", "pack-many-ctas"])
+                              "pack-few-ctas", "pack-many-ctas", "one-chain", "three-chains", "four-chains-no-pdl", "two-chains-precheck"])
 def test_k4_kernel_variants(ops, variant, persist):
     """Every step-kernel / pack-kernel variant gives the same state (and the pad frames kept in scratch
     never leak into the [N,h,w] result), with the scan as one launch per step (the default) or as one persistent
@@ -275,6 +277,7 @@ def test_k4_kernel_variants(ops, variant, persist):
     fr, m, ff, fb = prop_clip(26, 96, 160, seed=91)
     want = opp.model_propagate_clip(fr, m, ff, fb, subvideo_length=8, pad_len=3)
     assert _lib.get_option("k4_persist") == 0
+    streams_default = _lib.get_option("k4_streams")
     try:
         _lib.set_option("k4_persist", persist)
         for k, v in variant.items():
@@ -282,7 +285,7 @@ def test_k4_kernel_variants(ops, variant, persist):
         got = host(ops.propagate(dev(fr), dev(m), dev(ff), dev(fb), subvideo_length=8, pad_len=3)).view(np.uint32)
     finally:
         for k, v in dict(k4_pdl=1, k4_npt=1, k4_lean=5, k4_precheck=0, k4_step_ctas=5, k4_pack_ctas=128, k4_pack_occ=4,
-                         k4_speculate=1, k4_persist=0).items():
+                         k4_speculate=1, k4_persist=0, k4_streams=streams_default, k4_chain_ctas=8).items():
             _lib.set_option(k, v)
     assert np.array_equal(got, want)
 

@@ -28,13 +28,13 @@ if [[ $what == *refarm* ]]; then
 fi
 if [[ $what == *ncu* ]]; then
   B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras"
-  # launch list + DRAM traffic of exactly one step (145 launches per step; skip the 3 warm-up steps): cold-cache,
+  # launch list + DRAM traffic of exactly one step (283 launches per step with two K4 step chains; skip the 3 warm-up steps): cold-cache,
   # serialised under the profiler -> compare SHARES with the bench's stage times, not absolutes
   timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-      -k 'regex:^k[1-5]' --launch-skip 435 --launch-count 145 --csv --log-file gpurun_out/step_metrics.csv \
+      -k 'regex:^k[1-5]' --launch-skip 849 --launch-count 283 --csv --log-file gpurun_out/step_metrics.csv \
       $B > gpurun_out/bench_under_ncu.log 2>&1
   # full captures of the hot kernels inside the same command (4th step = after warm-up)
-  for spec in "k3_fastw:3" "k1a_binarize:3" "k1b_dilate:3" "k2_resize_linear_ratio:3" "k4_pack:3" "k4_step_lean:450" "k4_step_lean:520"; do
+  for spec in "k3_fastw:3" "k1a_binarize:3" "k1b_dilate:3" "k2_resize_linear_ratio:3" "k4_pack:3" "k4_step_lean:880" "k4_step_lean:1060"; do
     k=${spec%%:*}; skip=${spec##*:}
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f \
         -o gpurun_out/prof_${k}_s$skip $B > gpurun_out/ncu_${k}_s$skip.log 2>&1

@@ -26,6 +26,7 @@
 // frames (which upstream computes and discards) in workspace scratch, so the result needs no
 // compaction copy afterwards (`frame_ptr`).
 #include "common.cuh"
+#include <mutex>
 
 namespace vv {
 
@@ -665,6 +666,34 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Side streams of "k4_streams" (one set per device, created on first use; the mutex keeps the event record -> wait
+// pairs of concurrent vv_propagate calls apart - sharing the streams between calls only serialises their side chains).
+constexpr int K4_MAX_STREAMS = 4;
+struct SideStreams {
+    std::mutex mu;
+    cudaStream_t s[K4_MAX_STREAMS - 1];
+    cudaEvent_t fork, join[K4_MAX_STREAMS - 1];
+    bool ready = false;
+};
+static SideStreams *side_streams() {
+    static SideStreams pool[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStreams &p = pool[dev];
+    std::lock_guard<std::mutex> lk(p.mu);
+    if (!p.ready) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (int i = 0; i < K4_MAX_STREAMS - 1; ++i) {
+            if (cudaStreamCreateWithPriority(&p.s[i], cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        p.ready = true;
+    }
+    return &p;
+}
+
 }  // namespace vv
 
 using namespace vv;
@@ -759,13 +788,33 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
 #undef VV_K4_PACK
             VV_POST_LAUNCH("k4_pack");
         }
+        // "k4_streams" = G > 1: the windows of the batch are dealt to G groups (window s -> group s % G) and every
+        // group runs its own chain of dependent step launches on its own stream (group 0 on the caller's, the others
+        // on internal side streams of the same priority, forked behind k4_pack and joined at the end).  A step is
+        // partly latency bound (launch turnaround, then count -> list entry -> taps, three dependent round trips, for a
+        // few trips per thread), so chains of independent windows fill each other's bubbles.  Measured and dropped:
+        // side streams of higher priority (their pre-launched, waiting CTAs keep the other chain off the SMs: 1.40 ->
+        // 1.9 ms) and starting chain g underneath the pack of group g + 1 (two pack launches: 1.40 -> 1.48 ms).
+        const bool persist = get_option(OPT_K4_PERSIST) != 0 && blen > 1 && !pre;
+        const int groups = (persist || blen <= 1) ? 1 : max(1, min(min(get_option(OPT_K4_STREAMS), K4_MAX_STREAMS), b.n));
+        SideStreams *side = nullptr;
+        std::unique_lock<std::mutex> side_lock;
+        if (groups > 1) {
+            side = side_streams();
+            if (side == nullptr) return fail_cuda(cudaGetLastError(), "vv_propagate: side streams");
+            side_lock = std::unique_lock<std::mutex>(side->mu);       // record -> wait pairs of one call stay together
+            if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return fail_cuda(e, "cudaEventRecord(fork)");
+            for (int g = 1; g < groups; ++g)
+                if ((e = cudaStreamWaitEvent(side->s[g - 1], side->fork, 0)) != cudaSuccess)
+                    return fail_cuda(e, "cudaStreamWaitEvent(fork)");
+        }
         // The serial scans touch hole pixels only.  The hole counts live on the device: "k4_step_ctas" > 0 =
         // that many CTAs per SM in total (a resident grid that strides over the lists), 0 = about one thread
         // per hole at a 25 % hole fraction.
         dim3 grid(max(1, min(ceil_div(npx / 4, 256), ceil_div(148 * 16, b.n))), b.n);
         const int per_sm = get_option(OPT_K4_STEP_CTAS);
         if (per_sm > 0) grid.x = max(1, min(ceil_div(npx / 4, 256), (148 * per_sm) / b.n));
-        if (get_option(OPT_K4_PERSIST) != 0 && blen > 1 && !pre) {
+        if (persist) {
             // one cooperative launch for the whole scan; the grid must be resident (occupancy x SMs)
             static std::atomic<int> occ_cache[64];
             int dev_id = 0, sms = 148;
@@ -803,52 +852,65 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
         const int spec = get_option(OPT_K4_SPECULATE);
         const int npt = get_option(OPT_K4_NPT) >= 2 ? 2 : 1;
         for (int pass = 0; pass < 2; ++pass)
-            for (int step = 1; step < blen; ++step) {
-                StepArgs sa;
-                for (int s = 0; s < K4_MAX_SUB; ++s) {
-                    StepWin &sw = sa.win[s];
-                    sw = StepWin();
-                    if (s >= b.n || step >= b.sub[s].len) continue;
-                    const SubDesc &sd = b.sub[s];
-                    const int idx = pass ? step : sd.len - 1 - step;
-                    const long long gframe = sd.start + idx, of = sd.out_frame + idx;
-                    const HoleLists &li = pass ? l2 : l1;
-                    sw.cur = frame_ptr(sd, idx, out, pads, npx);
-                    sw.prev = frame_ptr(sd, pass ? idx - 1 : idx + 1, out, pads, npx);
-                    // check flow: backward pass flows_b[idx] (prop = flows_f[idx]), forward pass flows_f[idx-1]
-                    sw.flow_check = pass ? ff + (gframe - 1) * npx : fb + gframe * npx;
-                    sw.next_flow = (!pass && idx >= 1) ? fb + (gframe - 1) * npx : nullptr;
-                    sw.lxy = li.xy + of * npx, sw.lflow = li.flow + of * npx, sw.count = li.count + of;
-                    sw.oxy = l2.xy + of * npx, sw.oflow = l2.flow + of * npx, sw.ocount = l2.count + of;
-                }
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = grid;
-                cfg.blockDim = dim3(K4_BLOCK);
-                cfg.stream = st;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = attr;
-                // the first step after k4_pack is an ordinary launch: backward steps read the lists k4_pack
-                // wrote BEFORE their griddepcontrol.wait, and only a full stream dependency makes those visible
-                cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
-                cudaError_t le;
-                // backward pass with precheck: PRE kernel; forward pass always carries flows
+            for (int step = 1; step < blen; ++step)
+                for (int g = 0; g < groups; ++g) {
+                    StepArgs sa;
+                    int ng = 0;                                        // windows of this group that take this step
+                    for (int s = g; s < b.n; s += groups) {
+                        if (step >= b.sub[s].len) continue;
+                        StepWin &sw = sa.win[ng++];
+                        const SubDesc &sd = b.sub[s];
+                        const int idx = pass ? step : sd.len - 1 - step;
+                        const long long gframe = sd.start + idx, of = sd.out_frame + idx;
+                        const HoleLists &li = pass ? l2 : l1;
+                        sw.cur = frame_ptr(sd, idx, out, pads, npx);
+                        sw.prev = frame_ptr(sd, pass ? idx - 1 : idx + 1, out, pads, npx);
+                        // check flow: backward pass flows_b[idx] (prop = flows_f[idx]), forward pass flows_f[idx-1]
+                        sw.flow_check = pass ? ff + (gframe - 1) * npx : fb + gframe * npx;
+                        sw.next_flow = (!pass && idx >= 1) ? fb + (gframe - 1) * npx : nullptr;
+                        sw.lxy = li.xy + of * npx, sw.lflow = li.flow + of * npx, sw.count = li.count + of;
+                        sw.oxy = l2.xy + of * npx, sw.oflow = l2.flow + of * npx, sw.ocount = l2.count + of;
+                    }
+                    if (ng == 0) continue;
+                    for (int s = ng; s < K4_MAX_SUB; ++s) sa.win[s] = StepWin();
+                    dim3 ggrid(grid.x, ng);
+                    // several chains share the SMs: "k4_chain_ctas" CTAs per SM for all of them together
+                    const int budget = groups > 1 ? max(1, get_option(OPT_K4_CHAIN_CTAS)) : per_sm;
+                    if (budget > 0) ggrid.x = max(1, min(ceil_div(npx / 4, 256), (148 * budget) / (groups * ng)));
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = ggrid;
+                    cfg.blockDim = dim3(K4_BLOCK);
+                    cfg.stream = g == 0 ? st : side->s[g - 1];
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    attr[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = attr;
+                    // the first step after k4_pack (or after the fork) is an ordinary launch: backward steps read the
+                    // lists k4_pack wrote BEFORE their griddepcontrol.wait, and only a full stream dependency makes
+                    // those visible
+                    cfg.numAttrs = (pdl && !(pass == 0 && step == 1)) ? 1 : 0;
+                    cudaError_t le;
+                    // backward pass with precheck: PRE kernel; forward pass always carries flows
 #define VV_K4_LEAN(O, N)                                                                              \
     (pass == 0 ? (pre ? cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, true, N>, sa, h, w, spec)      \
                       : cudaLaunchKernelEx(&cfg, k4_step_lean<false, O, false, N>, sa, h, w, spec))    \
                : cudaLaunchKernelEx(&cfg, k4_step_lean<true, O, false, N>, sa, h, w, spec))
-                if (npt == 2)
-                    le = lean == 4 ? VV_K4_LEAN(4, 2) : VV_K4_LEAN(3, 2);
-                else if (lean >= 8)
-                    le = VV_K4_LEAN(8, 1);
-                else if (lean >= 6)
-                    le = VV_K4_LEAN(6, 1);
-                else
-                    le = VV_K4_LEAN(5, 1);
+                    if (npt == 2)
+                        le = lean == 4 ? VV_K4_LEAN(4, 2) : VV_K4_LEAN(3, 2);
+                    else if (lean >= 8)
+                        le = VV_K4_LEAN(8, 1);
+                    else if (lean >= 6)
+                        le = VV_K4_LEAN(6, 1);
+                    else
+                        le = VV_K4_LEAN(5, 1);
 #undef VV_K4_LEAN
-                if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step_lean)");
-                VV_POST_LAUNCH("k4_step_lean");
+                    if (le != cudaSuccess) return fail_cuda(le, "cudaLaunchKernelEx(k4_step_lean)");
+                    VV_POST_LAUNCH("k4_step_lean");
+                }
+        if (side != nullptr)                                           // join: the caller's stream waits for every chain
+            for (int g = 1; g < groups; ++g) {
+                if ((e = cudaEventRecord(side->join[g - 1], side->s[g - 1])) != cudaSuccess) return fail_cuda(e, "cudaEventRecord(join)");
+                if ((e = cudaStreamWaitEvent(st, side->join[g - 1], 0)) != cudaSuccess) return fail_cuda(e, "cudaStreamWaitEvent(join)");
             }
     }
     return VV_OK;
