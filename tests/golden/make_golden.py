@@ -60,6 +60,19 @@ def main():
         print(name, "dilated px", int(np.stack(dil).astype(bool).sum()), "out", np.stack(outs).shape)
 
 
+def main_mask_size():
+    """tests/golden/other_mask_size.npz: masks of ANOTHER size than the frames - the reference dilates them at their own
+    size and fits them with INTER_NEAREST in the post loop (diffuerase.py:85-86).  Same reference calls as `main`."""
+    t, h0, w0, h, w, hm, wm, n, f, seed = 3, 90, 160, 40, 80, 67, 101, 3, 3, 300
+    fr, _, inp = inputs(t, h0, w0, h, w, seed)
+    mk = synth.masks(t, hm, wm, seed=seed + 1, salt=0.002)
+    outs, dil = rh.ref_post_all_frames(list(fr), list(mk), list(inp), mask_dilation_iter=n, keep_unmasked_original=True,
+                                       feather_px=f)
+    np.savez_compressed(os.path.join(OUT, "other_mask_size.npz"), args=np.array([t, h0, w0, h, w, n, seed], np.int64),
+                        mask_hw=np.array([hm, wm], np.int64), feather=np.float64(f), dilated=np.stack(dil), out=np.stack(outs))
+    print("other_mask_size", np.stack(dil).shape, np.stack(outs).shape)
+
+
 def main_paint():
     """tests/golden/paint.npz: the UNMODIFIED sam2_masker.run_sam2_on_frames (stub SAM2 predictor that
     replays seeded logits) -> colour-painted mask frames (SURVEY next row N3)."""
@@ -85,3 +98,4 @@ def main_paint():
 if __name__ == "__main__":
     main()
     main_paint()
+    main_mask_size()

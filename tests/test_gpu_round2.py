@@ -280,6 +280,38 @@ def test_device_resident_dropin_matches_full_path_oracle(ops, t, h0, w0, size, d
     assert np.array_equal(np.stack(frames), fr) and np.array_equal(np.stack(masks), mk), "inputs must not be mutated"
 
 
+def test_dropin_masks_of_another_size(ops):
+    """Masks that do not have the frames' size (diffuerase.py:85-86): K1 runs at the masks' own size - that is what the
+    models are handed, like in the reference - and the post stage fits them with INTER_NEAREST (K2).  Host-list route
+    against the golden vector of the unmodified reference, device-resident route against the full-path oracle."""
+    from tests.test_oracle import other_mask_size_case
+    from videovanish_b200 import diffuerase as vvd
+
+    class Stub:
+        def forward(self, frames, masks, priors, **kw):
+            self.masks = [m.copy() for m in masks]
+            return [x.copy() for x in self.inpainted]
+
+    z, fr, mk, inp, n, f = other_mask_size_case()
+    stub = Stub()
+    stub.inpainted = list(inp)
+    vvd.set_models(diffueraser=stub)
+    out = vvd.run_infill_on_frames(list(fr), list(mk), mask_dilation_iter=n, propainer_frames=list(fr), feather_px=f)
+    assert np.array_equal(np.stack(stub.masks), z["dilated"]), "the models get the masks dilated at their own size"
+    assert np.array_equal(np.stack(out), z["out"])
+    # device-resident route: same geometry, longer clip
+    t, (h0, w0), (hm, wm) = 9, fr.shape[1:3], mk.shape[1:3]
+    fr2, mk2 = synth.frames(t, h0, w0, seed=5), synth.masks(t, hm, wm, seed=6, salt=0.001)
+    vvd_max[0] = 80
+    vvd = _install_adapters(seed=t)
+    try:
+        got = vvd.run_infill_on_frames(list(fr2), list(mk2), mask_dilation_iter=n, max_img_size=80, feather_px=f)
+    finally:
+        vvd.propainter = None
+    want = ofp.run(list(fr2), list(mk2), _flow_fn_np(t), mask_dilation_iter=n, max_img_size=80, feather_px=f)
+    assert np.array_equal(np.stack(got), np.stack(want))
+
+
 def test_mask_row_bounds_kernel(ops):
     t, h, w = 6, 75, 200
     dil = np.zeros((t, h, w), np.uint8)

@@ -16,7 +16,7 @@ cv2 = pytest.importorskip("cv2")
 scipy_ndimage = pytest.importorskip("scipy.ndimage")
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if os.path.basename(p) != "paint.npz")
+                if os.path.basename(p) not in ("paint.npz", "other_mask_size.npz"))
 
 
 def load_case(path):
@@ -52,6 +52,28 @@ def test_oracle_matches_golden(path):
             assert d.max() <= 1
     assert bool(z["literal_rest_raw"])          # reference bug :114 - frames 1.. returned raw
     assert np.array_equal(z["literal_frame0"], z["out"][0])
+
+
+def other_mask_size_case():
+    """Masks of ANOTHER size than the frames (diffuerase.py:85-86), golden from the unmodified reference."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "other_mask_size.npz"))
+    t, h0, w0, h, w, n, seed = [int(v) for v in z["args"]]
+    hm, wm = [int(v) for v in z["mask_hw"]]
+    fr, _, inp = golden_inputs(t, h0, w0, h, w, seed)
+    mk = synth.masks(t, hm, wm, seed=seed + 1, salt=0.002)
+    return z, fr, mk, inp, n, float(z["feather"])
+
+
+def test_oracle_matches_golden_with_masks_of_another_size():
+    """The reference dilates such masks at their own size and fits them with INTER_NEAREST in the post loop; both
+    oracle flavours reproduce its outputs bit for bit."""
+    z, fr, mk, inp, n, f = other_mask_size_case()
+    assert mk.shape[1:3] != fr.shape[1:3]
+    dil_ref, dil_model = op.ref_binarize_dilate(list(mk), n), op.model_binarize_dilate(list(mk), n)
+    assert np.array_equal(np.stack(dil_ref), z["dilated"]) and np.array_equal(np.stack(dil_model), z["dilated"])
+    for i in range(len(fr)):
+        assert np.array_equal(op.ref_post_frame(inp[i], fr[i], dil_ref[i], True, f), z["out"][i])
+        assert np.array_equal(op.model_post_frame(inp[i], fr[i], dil_model[i], True, f), z["out"][i])
 
 
 @pytest.mark.reference

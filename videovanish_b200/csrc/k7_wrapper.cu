@@ -337,11 +337,15 @@ extern "C" int vv_wrapper_mask(const uint8_t *mask, int T, int h, int w, int dil
         return VV_ERR_UNSUPPORTED;
     }
     const size_t smem = (size_t)2 * (th + 2 * H) * Wp * 4;
-    static std::atomic<size_t> smem_set{48 * 1024};
-    if (smem > smem_set.load()) {
+    // cudaFuncSetAttribute is per device: remember the opt-in shared-memory size per device
+    static std::atomic<size_t> smem_set[64];
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    dev_id = min(max(dev_id, 0), 63);
+    if (smem > 48 * 1024 && smem > smem_set[dev_id].load()) {
         cudaError_t e = cudaFuncSetAttribute(k7_wrapper_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(k7_wrapper_mask)");
-        smem_set.store(smem);
+        smem_set[dev_id].store(smem);
     }
     const int vec = (w % 16 == 0) && ((uintptr_t)mask % 16 == 0) && ((uintptr_t)out % 16 == 0);
     k7_wrapper_mask<<<dim3(ceil_div(h, th), T), K7_THREADS, smem, (cudaStream_t)stream>>>(mask, out, h, w, dilation_iter, (int)th,
@@ -381,12 +385,16 @@ extern "C" int vv_wrapper_compose(const uint8_t *img, const uint8_t *frames, con
     const int vec = (w % 4 == 0) && ((uintptr_t)img % 4 == 0) && ((uintptr_t)frames % 4 == 0) && ((uintptr_t)out % 4 == 0) &&
                     ((uintptr_t)mask255 % 16 == 0) && (w % 16 == 0);
     dim3 grid(ceil_div(h, th), T);
-    static std::atomic<size_t> smem_set[2] = {{48 * 1024}, {48 * 1024}};
-    if (smem > smem_set[blended ? 1 : 0].load()) {
+    static std::atomic<size_t> smem_set_c[2][64];      // per (variant, device): cudaFuncSetAttribute is per device
+    int dev_c = 0;
+    cudaGetDevice(&dev_c);
+    std::atomic<size_t> *smem_set = &smem_set_c[0][min(max(dev_c, 0), 63)];
+    constexpr int SMEM_VARIANT_STRIDE = 64;
+    if (smem > 48 * 1024 && smem > smem_set[blended ? SMEM_VARIANT_STRIDE : 0].load()) {
         cudaError_t e = blended ? cudaFuncSetAttribute(k7_wrapper_compose<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                 : cudaFuncSetAttribute(k7_wrapper_compose<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(k7_wrapper_compose)");
-        smem_set[blended ? 1 : 0].store(smem);
+        smem_set[blended ? SMEM_VARIANT_STRIDE : 0].store(smem);
     }
     if (blended)
         k7_wrapper_compose<true><<<grid, K7_THREADS, smem, (cudaStream_t)stream>>>(img, frames, mask255, out, h, w, th, hs_stride, vec, 1.0f, tab);

@@ -71,7 +71,17 @@ def run_infill_on_frames(frames_rgb, mask_frames, mask_dilation_iter=8, ckpt="2-
                               keep_unmasked_original, feather_px, prog)
 
     if prog is not None: prog(5, "dilating frames")
-    dilated_mask_frames = pipe.pre(mask_frames, mask_dilation_iter)                      # :27-31 (K1)
+    mask_size = _frame_size(mask_frames)
+    if mask_size == (H0, W0):
+        dilated_mask_frames = pipe.pre(mask_frames, mask_dilation_iter)                  # :27-31 (K1)
+    else:
+        # masks of another size than the frames: K1 at the masks' own size (what the models get, like in the reference);
+        # the post stage fits them to the frames with INTER_NEAREST (:85-86)
+        mask_pipe = hostpipe.HostPipeline(*mask_size)
+        try:
+            dilated_mask_frames = mask_pipe.pre(mask_frames, mask_dilation_iter)
+        finally:
+            mask_pipe.close()
 
     if prog is not None: prog(10, "loading weights")
     if last_ckpt != ckpt:                                                                # :35-45
@@ -106,11 +116,23 @@ def run_infill_on_frames(frames_rgb, mask_frames, mask_dilation_iter=8, ckpt="2-
         return inpainted_frames                                                          # nothing to do (:72, :75)
     if fh * fw > H0 * W0:             # never produced by the model wrapper (row A9 only shrinks)
         raise ValueError("inpainted frames (%dx%d) larger than the originals (%dx%d)" % (fh, fw, H0, W0))
-    # the dilated masks are still on the device from `pre`
-    out = pipe.post(inpainted_frames[:n], frames_rgb[:n], None, feather_px, keep_unmasked_original)   # :70-112 (K3)
+    # the dilated masks are still on the device from `pre` (unless they had to be fitted to the frames' size)
+    fitted = None
+    if mask_size != (H0, W0) and keep_unmasked_original:
+        fitted = _fit_masks(dilated_mask_frames[:n], H0, W0)                                          # :85-86 (K2 NEAREST)
+    out = pipe.post(inpainted_frames[:n], frames_rgb[:n], fitted, feather_px, keep_unmasked_original)   # :70-112 (K3)
     for i in range(n):
         inpainted_frames[i] = out[i]
     return inpainted_frames
+
+
+def _fit_masks(dilated, h0, w0):
+    """diffuerase.py:85-86: dilated masks of another size -> the frames' size with cv2.INTER_NEAREST semantics (K2)."""
+    import torch
+
+    from . import ops
+    d = torch.from_numpy(np.ascontiguousarray(np.stack(dilated))).cuda()
+    return list(ops.resize(d, h0, w0, ops.INTER_NEAREST).cpu().numpy())
 
 
 def _frame_size(frames):
@@ -146,7 +168,14 @@ def _run_on_device(pipe, frames_rgb, mask_frames, mask_dilation_iter, propainer_
         if prog is not None: prog(5, "dilating frames")
         masks = up.upload(mask_frames, _frame_shape(mask_frames), is_mask=True)
         h, w = ops.inference_size(H0, W0, max_img_size)
-        dil, low, bits = ops.binarize_dilate(masks, mask_dilation_iter, lowres_size=(h, w), return_bits=True)   # K1
+        if tuple(masks.shape[1:3]) == (H0, W0):
+            dil, low, bits = ops.binarize_dilate(masks, mask_dilation_iter, lowres_size=(h, w), return_bits=True)   # K1
+        else:
+            # masks of another size than the frames: K1 at their own size; the model-side mask is their INTER_NEAREST
+            # down-size (straight from that size), the post stage gets them fitted to the frames' size (:85-86)
+            dil, low = ops.binarize_dilate(masks, mask_dilation_iter, lowres_size=(h, w))
+            dil = ops.resize(dil, H0, W0, ops.INTER_NEAREST)
+            bits = None
         del masks
         # Row-bounded result: outside the rows a frame's dilated mask (+ feather radius) reaches, the finished frame IS
         # the input frame (alpha = 0 -> rint(orig) = orig, diffuerase.py:112), so those rows are copied host -> host from
