@@ -56,7 +56,7 @@ def test_golden_pre_and_post(ops, path):
 
 
 # ------------------------------------------------------------------------------- K1
-@pytest.mark.parametrize("n", [1, 2, 4, 5, 8, 9, 16, 17, 25, 32, 33, 40, 70])
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 24, 25, 26, 31, 32, 33, 40, 70])
 def test_k1_dilation_radii(ops, n):
     mk = synth.masks(2, 150, 208, seed=n, salt=0.001)
     ref = np.stack(op.model_binarize_dilate(list(mk), n))
@@ -69,6 +69,30 @@ def test_k1_shapes_and_channels(ops, h, w, c):
     mk = (rng.integers(0, 256, (3, h, w, c)) * (rng.random((3, h, w, c)) < 0.004)).astype(np.uint8)
     ref = np.stack([op.model_dilate_l1(op.model_binarize(m), 6) for m in mk])
     assert np.array_equal(host(ops.binarize_dilate(dev(mk), 6)), ref)
+
+
+@pytest.mark.parametrize("diag", [1, 0], ids=["diagonal-blocks", "cross-rounds"])
+@pytest.mark.parametrize("h,w", [(97, 131), (40, 2048 + 16), (33, 1000), (64, 64), (9, 31)])
+def test_k1_large_radii_at_frame_edges(ops, h, w, diag):
+    """Radii 9..16 per pass run as a diamond of radius 2K built from two diagonal segments by doubling, plus cross
+    rounds (k1b_diag): set pixels in the corners, along the edges and at word / tile boundaries, every radius that
+    picks another block, with and without the blocks."""
+    from videovanish_b200 import _lib
+    rng = np.random.default_rng(h + w)
+    mk = np.zeros((3, h, w, 1), np.uint8)
+    for y, x in ((0, 0), (0, w - 1), (h - 1, 0), (h - 1, w - 1), (h // 2, 0), (h // 2, w - 1), (0, w // 2), (h - 1, w // 2)):
+        mk[0, y, x] = 255
+    for x in (31, 32, 63, 64, 959, 960, 961, 991, 992):          # word and 30-word tile boundaries
+        if x < w:
+            mk[1, rng.integers(0, h), x] = 7
+    mk[2] = (rng.random((h, w, 1)) < 0.002) * 255
+    try:
+        _lib.set_option("k1b_diag", diag)
+        for n in (9, 10, 11, 12, 13, 14, 15, 16, 25, 29):
+            ref = np.stack([op.model_dilate_l1(op.model_binarize(m), n) for m in mk])
+            assert np.array_equal(host(ops.binarize_dilate(dev(mk), n)), ref), n
+    finally:
+        _lib.set_option("k1b_diag", 1)
 
 
 def test_k1_iterations_zero_fills(ops):

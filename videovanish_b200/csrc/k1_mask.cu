@@ -103,11 +103,45 @@ __device__ __forceinline__ void cross_round(uint32_t (&r)[ROWS]) {
     }
 }
 
+// Diamond of radius 2K + 1 in 10 shift-OR steps instead of 2K + 1 cross rounds.  In the rotated lattice the L1 ball is a
+// square: {|x| + |y| <= 2K, x + y even} = S1 (+) S2 with the diagonal segments S1 = {i (1,1)}, S2 = {j (1,-1)}, |i|, |j| <= K,
+// and one cross round on top fills the odd parity and reaches radius 2K + 1.  A segment of L = 2K + 1 points grows by
+// doubling (1, 2, 4, 8, then L - 8 more: K = 4..7), one-sided towards +x; dilation commutes with translation, so both
+// segments are grown one-sided and the plane is shifted back by 2K pixels once at the end.  A diagonal step costs one
+// shuffle, one funnel shift and one OR per row (a cross round: two shuffles, two funnel shifts, three ORs).
+// Everything an output word of lanes 1..30 depends on lies within 2K <= 14 pixels and rows of it at every stage, i.e.
+// inside the halo lanes / rows; what the halo lanes pick up from their missing neighbour travels at most 4K <= 28 pixels
+// and never reaches a word that is read for an output.
+template <int D, int ROWS>
+__device__ __forceinline__ void diag_step_down(uint32_t (&r)[ROWS]) {   // a set pixel (x, y) sets (x + D, y + D)
+#pragma unroll
+    for (int i = ROWS - 1; i >= D; --i) {          // rows descending: in place
+        const uint32_t c = r[i - D];
+        r[i] |= __funnelshift_l(__shfl_up_sync(0xffffffffu, c, 1), c, D);
+    }
+}
+template <int D, int ROWS>
+__device__ __forceinline__ void diag_step_up(uint32_t (&r)[ROWS]) {     // (x, y) sets (x + D, y - D)
+#pragma unroll
+    for (int i = 0; i + D < ROWS; ++i) {           // rows ascending: in place
+        const uint32_t c = r[i + D];
+        r[i] |= __funnelshift_l(__shfl_up_sync(0xffffffffu, c, 1), c, D);
+    }
+}
+template <int K, int ROWS>
+__device__ __forceinline__ void diamond_block(uint32_t (&r)[ROWS]) {
+    diag_step_down<1, ROWS>(r), diag_step_down<2, ROWS>(r), diag_step_down<4, ROWS>(r), diag_step_down<2 * K + 1 - 8, ROWS>(r);
+    diag_step_up<1, ROWS>(r), diag_step_up<2, ROWS>(r), diag_step_up<4, ROWS>(r), diag_step_up<2 * K + 1 - 8, ROWS>(r);
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i)                 // back by 2K pixels
+        r[i] = __funnelshift_r(r[i], __shfl_down_sync(0xffffffffu, r[i], 1), 2 * K);
+}
+
 template <int NMAX, int RB, bool EXACT>
 __global__ void __launch_bounds__(128)
     k1b_dilate_expand(const uint32_t *__restrict__ bits_in, uint32_t *__restrict__ bits_out, uint8_t *__restrict__ out,
                       uint8_t *__restrict__ half_out, int H, int W, int Wp, int n_iter, int tiles_x, int tiles_y,
-                      long long n_tiles, int vec_ok) {
+                      long long n_tiles, int vec_ok, int diag) {
     constexpr int ROWS = RB + 2 * NMAX;
     const int lane = threadIdx.x & 31;
     const long long tile = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -134,8 +168,16 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int it = 0; it < NMAX; ++it) cross_round<NMAX, ROWS>(r);
     } else {
+        int rounds = n_iter;
+        if (NMAX >= 16 && diag) {                 // kernel-uniform: a radius >= 9 starts with the largest diagonal block,
+                                                  // which stands for 2K rounds once at least one cross round follows it
+            if (rounds >= 15) diamond_block<7, ROWS>(r), rounds -= 14;
+            else if (rounds >= 13) diamond_block<6, ROWS>(r), rounds -= 12;
+            else if (rounds >= 11) diamond_block<5, ROWS>(r), rounds -= 10;
+            else if (rounds >= 9) diamond_block<4, ROWS>(r), rounds -= 8;
+        }
 #pragma unroll 1
-        for (int it = 0; it < n_iter; ++it) cross_round<NMAX, ROWS>(r);
+        for (int it = 0; it < rounds; ++it) cross_round<NMAX, ROWS>(r);
     }
 
     // ---- output stage.  The dilated words go through shared memory so that this part is a short
@@ -312,7 +354,7 @@ static int launch_k1b(const uint32_t *in, uint32_t *bits_out, uint8_t *out, uint
     const long long n_tiles = (long long)T * tiles_x * tiles_y;
     const int grid = ceil_div(n_tiles, 4);
     k1b_dilate_expand<NMAX, RB, EXACT><<<grid, 128, 0, st>>>(in, bits_out, out, half_out, H, W, Wp, n_iter, tiles_x,
-                                                             tiles_y, n_tiles, vec ? 1 : 0);
+                                                             tiles_y, n_tiles, vec ? 1 : 0, get_option(OPT_K1B_DIAG));
     VV_POST_LAUNCH("k1b_dilate_expand");
     return VV_OK;
 }
