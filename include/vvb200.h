@@ -53,8 +53,9 @@ VV_API unsigned long long vv_launch_count(void);
 VV_API void vv_reset_launch_count(void);
 /* Kernel-variant switches used for A/B measurements (defaults are the tuned choices):
  *   "k1b_exact"  1 = fully unrolled 8-round dilation for the default radius, 0 = generic loop.
- *   "k1b_diag"   1 (default) = a dilation pass of radius 9..16 starts with the diamond of radius 2K (K = 4..7) built from two
- *                diagonal segments by doubling (10 shift-OR steps for up to 14 cross rounds); 0 = cross rounds only.
+ *   "k1b_diag"   1 = a dilation pass of radius 9..16 starts with the diamond of radius 2K (K = 4..7) built from two
+ *                diagonal segments by doubling (9 shift-OR steps for up to 14 cross rounds); 2 (default) = also the
+ *                unrolled radius-8 pass (radius-6 diamond in 7 steps + two cross rounds); 0 = cross rounds only.
  *   "k3_nt"      16-pixel groups per thread and iteration in K3 (1 or 2).
  *   "k3_tma"     1 = K3 stages the original strip through shared memory with bulk async copies
  *                (TMA) when the frame is 16-byte aligned, 0 = register pass-through kernel.

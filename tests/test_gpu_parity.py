@@ -71,7 +71,7 @@ def test_k1_shapes_and_channels(ops, h, w, c):
     assert np.array_equal(host(ops.binarize_dilate(dev(mk), 6)), ref)
 
 
-@pytest.mark.parametrize("diag", [1, 0], ids=["diagonal-blocks", "cross-rounds"])
+@pytest.mark.parametrize("diag", [1, 0, 2], ids=["diagonal-blocks", "cross-rounds", "diagonal-blocks-8"])
 @pytest.mark.parametrize("h,w", [(97, 131), (40, 2048 + 16), (33, 1000), (64, 64), (9, 31)])
 def test_k1_large_radii_at_frame_edges(ops, h, w, diag):
     """Radii 9..16 per pass run as a diamond of radius 2K built from two diagonal segments by doubling, plus cross
@@ -88,11 +88,11 @@ def test_k1_large_radii_at_frame_edges(ops, h, w, diag):
     mk[2] = (rng.random((h, w, 1)) < 0.002) * 255
     try:
         _lib.set_option("k1b_diag", diag)
-        for n in (9, 10, 11, 12, 13, 14, 15, 16, 25, 29):
+        for n in (8, 9, 10, 11, 12, 13, 14, 15, 16, 25, 29):
             ref = np.stack([op.model_dilate_l1(op.model_binarize(m), n) for m in mk])
             assert np.array_equal(host(ops.binarize_dilate(dev(mk), n)), ref), n
     finally:
-        _lib.set_option("k1b_diag", 1)
+        _lib.set_option("k1b_diag", 2)
 
 
 def test_k1_iterations_zero_fills(ops):

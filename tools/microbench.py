@@ -80,11 +80,14 @@ def main():
     _lib.set_option("k1b_exact", 1)
     report("K1 dilate8 + generic low-res (536)", t * (4 * px + 536 * 960),
            lambda: ops.binarize_dilate(mk, 8, lowres_size=(536, 960)))
+    for diag in (2, 1):
+        _lib.set_option("k1b_diag", diag)
+        report("K1 dilate8 + half-res mask", t * (4 * px + spx), lambda: ops.binarize_dilate(mk, 8, lowres_size=(HS, WS)), k1b_diag=diag)
     for diag in (1, 0):
         _lib.set_option("k1b_diag", diag)
         for n in (12, 16, 25):
             report("K1 dilate%d" % n, t * 4 * px, lambda: ops.binarize_dilate(mk, n), k1b_diag=diag)
-    _lib.set_option("k1b_diag", 1)
+    _lib.set_option("k1b_diag", 2)
     report("K2 resize 1080p->540p", t * (3 * px + 3 * spx), lambda: ops.resize(fr, HS, WS))
     report("K2 resize 1080p->536p", t * (3 * px + 3 * 536 * 960), lambda: ops.resize(fr, 536, 960))
     report("K2 nearest mask 1080p->540p", t * (px + spx), lambda: ops.resize(dil, HS, WS, ops.INTER_NEAREST))

@@ -137,6 +137,15 @@ __device__ __forceinline__ void diamond_block(uint32_t (&r)[ROWS]) {
         r[i] = __funnelshift_r(r[i], __shfl_down_sync(0xffffffffu, r[i], 1), 2 * K);
 }
 
+// radius 6 (K = 3): segments of 7 points = 1, 2, 4, then 3 more
+template <int ROWS>
+__device__ __forceinline__ void diamond_block6(uint32_t (&r)[ROWS]) {
+    diag_step_down<1, ROWS>(r), diag_step_down<2, ROWS>(r), diag_step_down<3, ROWS>(r);
+    diag_step_up<1, ROWS>(r), diag_step_up<2, ROWS>(r), diag_step_up<3, ROWS>(r);
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) r[i] = __funnelshift_r(r[i], __shfl_down_sync(0xffffffffu, r[i], 1), 6);
+}
+
 template <int NMAX, int RB, bool EXACT>
 __global__ void __launch_bounds__(128)
     k1b_dilate_expand(const uint32_t *__restrict__ bits_in, uint32_t *__restrict__ bits_out, uint8_t *__restrict__ out,
@@ -165,8 +174,13 @@ __global__ void __launch_bounds__(128)
     }
 
     if (EXACT) {
+        if (NMAX == 8 && diag == 2) {             // radius 8 = diagonal block of radius 6 + two cross rounds
+            diamond_block6<ROWS>(r);
+            cross_round<NMAX, ROWS>(r), cross_round<NMAX, ROWS>(r);
+        } else {
 #pragma unroll
-        for (int it = 0; it < NMAX; ++it) cross_round<NMAX, ROWS>(r);
+            for (int it = 0; it < NMAX; ++it) cross_round<NMAX, ROWS>(r);
+        }
     } else {
         int rounds = n_iter;
         if (NMAX >= 16 && diag) {                 // kernel-uniform: a radius >= 9 starts with the largest diagonal block,
