@@ -799,10 +799,18 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
         const int groups = (persist || blen <= 1) ? 1 : max(1, min(min(get_option(OPT_K4_STREAMS), K4_MAX_STREAMS), b.n));
         SideStreams *side = nullptr;
         std::unique_lock<std::mutex> side_lock;
+        struct SideGuard {           // an error exit must not leave side-stream work running on buffers the caller frees
+            SideStreams *side = nullptr;
+            int n = 0;
+            ~SideGuard() {
+                for (int i = 0; side != nullptr && i < n; ++i) cudaStreamSynchronize(side->s[i]);
+            }
+        } guard;
         if (groups > 1) {
             side = side_streams();
             if (side == nullptr) return fail_cuda(cudaGetLastError(), "vv_propagate: side streams");
             side_lock = std::unique_lock<std::mutex>(side->mu);       // record -> wait pairs of one call stay together
+            guard.side = side, guard.n = groups - 1;                  // error exits wait for what the side chains got
             if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return fail_cuda(e, "cudaEventRecord(fork)");
             for (int g = 1; g < groups; ++g)
                 if ((e = cudaStreamWaitEvent(side->s[g - 1], side->fork, 0)) != cudaSuccess)
@@ -912,6 +920,7 @@ extern "C" int vv_propagate(const uint8_t *frames, const uint8_t *masks, const f
                 if ((e = cudaEventRecord(side->join[g - 1], side->s[g - 1])) != cudaSuccess) return fail_cuda(e, "cudaEventRecord(join)");
                 if ((e = cudaStreamWaitEvent(st, side->join[g - 1], 0)) != cudaSuccess) return fail_cuda(e, "cudaStreamWaitEvent(join)");
             }
+        guard.side = nullptr;                                          // joined on the caller's stream: nothing to wait for
     }
     return VV_OK;
 }
