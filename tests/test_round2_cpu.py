@@ -95,3 +95,25 @@ def test_synth_config_table_matches_the_inference_size_rule():
             assert hw == (540, 960) and rule == (536, 960)
         else:
             assert hw == rule, name
+
+
+def test_every_tuning_option_is_documented_and_readable():
+    """vv_set_option / vv_get_option work without a GPU; every option the library knows (capi.cu) is described in
+    include/vvb200.h, and the documented defaults are the ones the library starts with."""
+    import ctypes
+    import os
+    import re
+    from videovanish_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    capi = open(os.path.join(root, "videovanish_b200", "csrc", "capi.cu")).read()
+    names = re.search(r"g_option_names\[OPT_COUNT\] = \{([^}]*)\}", capi).group(1)
+    names = re.findall(r'"([a-z0-9_]+)"', names)
+    assert len(names) >= 20 and len(set(names)) == len(names)
+    header = open(os.path.join(root, "include", "vvb200.h")).read()
+    for n in names:
+        assert '"%s"' % n in header, "option %s is not documented in include/vvb200.h" % n
+        v = ctypes.c_int(-12345)
+        assert _lib.lib.vv_get_option(n.encode(), ctypes.byref(v)) == 0 and v.value != -12345
+    assert _lib.get_option("k4_streams") == 2 and _lib.get_option("k4_chain_ctas") == 8 and _lib.get_option("k1b_diag") == 2
+    v = ctypes.c_int(0)
+    assert _lib.lib.vv_get_option(b"no_such_option", ctypes.byref(v)) != 0
