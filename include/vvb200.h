@@ -144,7 +144,7 @@ VV_API int vv_inference_size(int H0, int W0, int max_img_size, int *h, int *w);
  *   hard composite; out = u8(rint(f32(alpha*up) + f32((1-alpha)*orig))), round-half-even.
  *   feather_px up to VV_MAX_FEATHER is supported.
  * --------------------------------------------------------------------------------- */
-#define VV_MAX_FEATHER 8.0f
+#define VV_MAX_FEATHER 32.0f
 VV_API size_t vv_composite_workspace_bytes(int H0, int W0);
 VV_API int vv_upscale_feather_composite(const uint8_t *inp, int T, int h, int w,
                                  const uint8_t *orig, const uint8_t *mask, int H0, int W0,

@@ -11,7 +11,6 @@ Two layers, both pure CPU:
   blend).  They are the arithmetic spec of the CUDA kernels, and
   ``tests/test_oracle.py`` proves ``model_* == ref_*`` bit for bit.
 """
-import heapq
 import math
 
 import numpy as np
@@ -196,36 +195,46 @@ _cost_cache = {}
 
 
 def chamfer_cost_table(radius):
-    """float32 [2R+1, 2R+1] free-space 5x5-chamfer path cost of every offset.
+    """float32 [2R+1, 2R+1]: ``tab[dy + R, dx + R]`` = what ``cv2.distanceTransform(m, DIST_L2, 5)`` yields at a pixel p
+    whose only zero pixel sits at p + (dy, dx).
 
-    ``cv2.distanceTransform(m, DIST_L2, 5)`` is the two-pass chamfer transform with
-    float32 steps a=1, b=1.4 (diagonal), c=2.1969 (knight); its value at p is
-    ``min_q cost(p-q)`` over zero pixels q, out-of-image pixels being non-zero
-    ("far") (KAT T6).  The table is the float32 Dijkstra shortest path over those
-    13x... step vectors; verified bit-exact against cv2 4.13.0 for d < 8.
+    The transform is the two-pass raster chamfer transform with float32 steps a = 1, b = 1.4 (diagonal), c = 2.1969
+    (knight): a forward pass (rows top -> bottom, pixels left -> right; neighbours (-1, -2..2), (-2, +-1) and (0, -1)) and
+    its mirror image backwards, every step one float32 addition.  Its value at p is therefore the minimum, over the zero
+    pixels q and over the step sequences the two passes can realise from q to p, of the LEFT-TO-RIGHT float32 sum of the
+    steps - and since float32 addition is monotone, that equals ``min_q tab[q - p]`` with the table of ONE zero pixel
+    (out-of-image pixels are non-zero, "far": KAT T6).  Floating-point addition is not associative, so the table is NOT
+    symmetric from d ~ 12 on (the raster order decides in which order long paths add up their steps); a
+    direction-blind shortest-path table (round 1 used Dijkstra) is exact only for d < 9.  Verified bit-exact against cv2
+    4.13.0 (IPP 2022.2) for every feather_px <= 32 (tests/test_oracle.py); from d >= 32 on IPP leaves a family of offsets
+    next to the knight diagonals of one quadrant one ulp above this two-pass value, hence VV_MAX_FEATHER = 32.
     """
     if radius in _cost_cache:
         return _cost_cache[radius]
-    lim = 3 * radius + 6
-    steps = [(1, 0, _CHAMFER_A), (-1, 0, _CHAMFER_A), (0, 1, _CHAMFER_A), (0, -1, _CHAMFER_A)]
-    steps += [(sx, sy, _CHAMFER_B) for sx in (1, -1) for sy in (1, -1)]
-    steps += [(2 * sx, sy, _CHAMFER_C) for sx in (1, -1) for sy in (1, -1)]
-    steps += [(sx, 2 * sy, _CHAMFER_C) for sx in (1, -1) for sy in (1, -1)]
-    dist = {}
-    pq = [(np.float32(0), 0, 0)]
-    while pq:
-        d, x, y = heapq.heappop(pq)
-        if (x, y) in dist:
-            continue
-        dist[(x, y)] = d
-        for dx, dy, c in steps:
-            nx, ny = x + dx, y + dy
-            if abs(nx) <= lim and abs(ny) <= lim and (nx, ny) not in dist:
-                heapq.heappush(pq, (np.float32(d + c), nx, ny))
-    tab = np.empty((2 * radius + 1, 2 * radius + 1), np.float32)
-    for dy in range(-radius, radius + 1):
-        for dx in range(-radius, radius + 1):
-            tab[dy + radius, dx + radius] = dist[(dx, dy)]
+    n = 2 * radius + 1 + 8                    # margin: the optimal path to an offset never leaves its bounding box by more
+    c = n // 2
+    d = np.full((n + 4, n + 4), np.inf, np.float32)
+    d[c + 2, c + 2] = 0
+    up = [(-1, -2, _CHAMFER_C), (-1, -1, _CHAMFER_B), (-1, 0, _CHAMFER_A), (-1, 1, _CHAMFER_B), (-1, 2, _CHAMFER_C),
+          (-2, -1, _CHAMFER_C), (-2, 1, _CHAMFER_C)]
+
+    def row_pass(i, sgn):
+        row = d[i]
+        for di, dj, cost in up:               # the row(s) before, in pass direction
+            cand = (np.roll(d[i + sgn * di], -sgn * dj) + cost).astype(np.float32)
+            np.minimum(row[2:n + 2], cand[2:n + 2], out=row[2:n + 2])
+        js = range(2, n + 2) if sgn > 0 else range(n + 1, 1, -1)
+        for j in js:                          # then the pixel before, in pass direction (sequential)
+            t = np.float32(row[j - sgn] + _CHAMFER_A)
+            if t < row[j]:
+                row[j] = t
+
+    for i in range(2, n + 2):
+        row_pass(i, 1)
+    for i in range(n + 1, 1, -1):
+        row_pass(i, -1)
+    src = d[2:-2, 2:-2][c - radius:c + radius + 1, c - radius:c + radius + 1]     # value at offset (oy, ox) FROM the zero pixel
+    tab = src[::-1, ::-1].copy()              # pixel p looks at a zero pixel at p + (dy, dx): offset of p from it is -(dy, dx)
     _cost_cache[radius] = tab
     return tab
 

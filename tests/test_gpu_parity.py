@@ -237,6 +237,30 @@ def test_k3_empty_full_masks_and_no_keep(ops):
     assert np.array_equal(host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(z), keep_unmasked_original=False)), up)
 
 
+@pytest.mark.parametrize("f", [8.5, 9, 12.5, 16, 24, 31.5, 32])
+@pytest.mark.parametrize("h0,w0,h,w,bits", [(97, 131, 40, 56, False), (120, 176, 60, 88, True), (72, 128, 72, 128, False),
+                                             (64, 4096 + 52, 32, 2048 + 26, False)])
+def test_k3_big_feather(ops, h0, w0, h, w, bits, f):
+    """feather_px in (8, 32]: k3_bigfeather walks the cost-sorted table of the two raster passes (not symmetric from
+    d ~ 12 on) - bit-exact against the reference's own cv2.distanceTransform calls, on ragged sizes, with masks touching
+    all borders, from the u8 mask and from K1's bit plane."""
+    t = 4
+    fr = synth.frames(t, h0, w0, seed=int(f * 2))
+    inp = synth.noise_frames(t, h, w, seed=int(f * 2) + 1)
+    mk = synth.masks(t, h0, w0, seed=int(f * 2) + 2, salt=0.0004)
+    mk[1] = 0
+    mk[1, h0 // 3:h0 // 3 + 9, w0 // 2:w0 // 2 + 40] = 255            # one object, far from everything else
+    mk[2] = 255
+    mk[2, h0 // 2, w0 // 3] = 0                                       # one hole in a full mask
+    mk[3, :2] = mk[3, -1:] = 255
+    mk[3, :, :3] = mk[3, :, -2:] = 255
+    d_dil, _, d_bits = ops.binarize_dilate(dev(mk), 2, return_bits=True)
+    dil = host(d_dil)
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, f) for i in range(t)])
+    got = host(ops.upscale_feather_composite(dev(inp), dev(fr), d_dil, feather_px=f, mask_bits=d_bits if bits else None))
+    assert np.array_equal(got, ref)
+
+
 def test_k3_unsupported_feather_raises(ops):
     fr = synth.frames(1, 32, 32, seed=1)
     with pytest.raises(RuntimeError, match="feather_px"):

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libvvb200.so")
 
 VV_INTER_NEAREST = 0
 VV_INTER_LINEAR = 1
-VV_MAX_FEATHER = 8.0
+VV_MAX_FEATHER = 32.0
 
 if not os.path.isfile(LIB_PATH):
     raise ImportError(

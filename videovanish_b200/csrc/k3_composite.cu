@@ -30,7 +30,6 @@
 
 #include <algorithm>
 #include <mutex>
-#include <queue>
 #include <tuple>
 #include <vector>
 
@@ -45,7 +44,7 @@ struct Tap {
 int build_linear_taps(void *workspace, int H, int W, int h, int w, const Tap **xt, const Tap **yt, cudaStream_t st, int which);
 
 constexpr int K3_TH = 16;          // maximum output rows per CTA strip
-constexpr int K3_MAX_CLASSES = 31;    // distinct chamfer costs < feather_px (30 at the maximum feather of 8): 5 bit planes
+constexpr int K3_MAX_CLASSES = 31;    // distinct chamfer costs < feather_px (30 at feather 8, the limit of this table): 5 bit planes
 constexpr int K3_MAX_ENTRIES = 224;   // window offsets with cost < feather_px, radius <= 7
 
 struct FeatherTable {      // passed by value as a kernel parameter (constant bank, uniform reads)
@@ -1465,6 +1464,176 @@ __global__ void __launch_bounds__(NTH, NTH == 384 ? 3 : 1024 / NTH)
     }
 }
 
+// =====================================================================================================
+// k3_bigfeather: feather_px in (8, 32] (window radius 8..31; the GUI always passes 3, the reference accepts any float).
+// Correctness first, one simple pass per strip of 8 rows:
+//   phase 1  mask strip + R halo rows -> bit rows in shared memory (K1's 1-bit plane when the caller has it)
+//   phase 2  per 16-pixel group, bit-parallel: walk the cost-sorted offset table (device memory; up to ~3 100 offsets with
+//            two-pass chamfer cost < feather_px) until every undecided pixel of the group has met its first opposite
+//            pixel = its distance; groups without any opposite pixel in reach are pruned first.  The entry index of a
+//            pixel's first hit goes to a u16 plane in shared memory
+//   phase 3  per 4-pixel quad: alpha from the entry's cost, generic tap-table up-scale, non-FMA fp32 blend
+// The table is the single-zero-pixel result of the two raster passes (build_chamfer_table): NOT symmetric, the entry of
+// offset (dx, dy) is what cv2.distanceTransform yields at a pixel whose only zero pixel sits at (x + dx, y + dy).
+struct BigEntry {
+    float cost;
+    short dx, dy;
+};
+constexpr int K3_BIG_MAX_ENTRIES = 4096;
+constexpr int K3_BIG_TH = 8;
+constexpr int K3_BIG_THREADS = 256;
+
+__global__ void __launch_bounds__(K3_BIG_THREADS)
+    k3_bigfeather(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ mask,
+                  const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ xt,
+                  const Tap *__restrict__ yt, const BigEntry *__restrict__ tab, int n_entries, int R, float div, int h, int w,
+                  int H0, int W0, int words_ok) {
+    extern __shared__ __align__(16) uint32_t big_smem[];
+    const int Wp = (W0 + 31) >> 5, row_words = Wp + 3;            // one zero pad word on the left, two on the right
+    const int rows_s = K3_BIG_TH + 2 * R;
+    uint32_t *bits = big_smem;                                    // [rows_s][row_words], bit p of a row = column p - 32
+    uint16_t *cls = reinterpret_cast<uint16_t *>(big_smem + rows_s * row_words);   // [K3_BIG_TH][W0]: first-hit entry + 1
+    const long long t = blockIdx.y;
+    const int y0 = (int)blockIdx.x * K3_BIG_TH;
+    const uint8_t *mask_t = mask + t * H0 * (long long)W0;
+    const uint8_t *orig_t = orig + t * H0 * (long long)W0 * 3;
+    const uint8_t *inp_t = inp + t * h * (long long)w * 3;
+    uint8_t *out_t = out + t * H0 * (long long)W0 * 3;
+
+    // ---------------- phase 1
+    for (int id = threadIdx.x; id < rows_s * row_words; id += K3_BIG_THREADS) {
+        const int i = id / row_words, k = id - i * row_words - 1, y = y0 - R + i;
+        uint32_t v = 0;
+        if (y >= 0 && y < H0 && k >= 0 && k < Wp) {
+            if (mask_bits != nullptr) {
+                v = __ldg(mask_bits + (t * H0 + y) * Wp + k);
+            } else {
+                const uint8_t *p = mask_t + (long long)y * W0 + k * 32;
+                const int n = min(32, W0 - k * 32);
+                for (int q = 0; q < n; ++q) v |= (uint32_t)(p[q] != 0) << q;
+            }
+            if (k == Wp - 1 && (W0 & 31)) v &= (1u << (W0 & 31)) - 1u;
+        }
+        bits[id] = v;
+    }
+    for (int id = threadIdx.x; id < (K3_BIG_TH * W0 + 1) / 2; id += K3_BIG_THREADS) reinterpret_cast<uint32_t *>(cls)[id] = 0;
+    __syncthreads();
+
+    // 16 mask bits of bit row `row` starting at frame column `col` (-32 <= col <= W0 + 31)
+    auto window16 = [&](const uint32_t *row, int col) -> uint32_t {
+        const int p = col + 32;
+        return __funnelshift_r(row[p >> 5], row[(p >> 5) + 1], p & 31) & 0xffffu;
+    };
+    // bits i of a 16-pixel window at column `col` that lie inside the frame
+    auto valid16 = [&](int col) -> uint32_t {
+        const int lo = max(0, -col), hi = min(16, W0 - col);
+        return hi <= lo ? 0u : (((1u << hi) - 1u) & ~((1u << lo) - 1u));
+    };
+
+    // ---------------- phase 2
+    const int G = (W0 + 15) >> 4;
+    for (int task = threadIdx.x; task < K3_BIG_TH * G; task += K3_BIG_THREADS) {
+        const int r = task / G, x0 = (task - r * G) * 16, y = y0 + r;
+        if (y >= H0) continue;
+        const uint32_t *brow = bits + (r + R) * row_words;
+        const uint32_t px = valid16(x0);
+        const uint32_t inside = window16(brow, x0) & px;
+        // any masked / any unmasked frame pixel within reach of the group (columns x0 - R .. x0 + 15 + R, rows y - R .. y + R)?
+        const int c_lo = max(0, x0 - R), c_hi = min(W0 - 1, x0 + 15 + R);
+        const int w_lo = (c_lo + 32) >> 5, w_hi = (c_hi + 32) >> 5;
+        uint32_t anyM = 0, anyZ = 0;
+        for (int d = -R; d <= R && !(anyM && anyZ); ++d) {
+            const int yy = y + d;
+            if (yy < 0 || yy >= H0) continue;
+            const uint32_t *row = brow + d * row_words;
+            for (int wi = w_lo; wi <= w_hi; ++wi) {
+                uint32_t rng = 0xffffffffu;
+                if (wi == w_lo) rng &= 0xffffffffu << ((c_lo + 32) & 31);
+                if (wi == w_hi) rng &= 0xffffffffu >> (31 - ((c_hi + 32) & 31));
+                const uint32_t m = row[wi];
+                anyM |= m & rng, anyZ |= ~m & rng;
+            }
+        }
+        uint32_t und = ((anyZ ? inside : 0u) | (anyM ? ~inside : 0u)) & px;
+        for (int e = 0; e < n_entries && und; ++e) {
+            const BigEntry en = tab[e];
+            const int yy = y + en.dy;
+            if (yy < 0 || yy >= H0) continue;                     // out-of-image pixels are "far" for both transforms
+            const int col = x0 + en.dx;
+            const uint32_t v = valid16(col);
+            const uint32_t m = window16(brow + en.dy * row_words, col) & v;
+            const uint32_t hit = (((~m & v) & inside) | (m & ~inside)) & und;      // inside pixels look for unmasked ones
+            if (hit) {
+                uint32_t hh = hit;
+                while (hh) {
+                    const int i = __ffs(hh) - 1;
+                    hh &= hh - 1;
+                    cls[r * W0 + x0 + i] = (uint16_t)(e + 1);
+                }
+                und &= ~hit;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 3
+    const int Q = (W0 + 3) >> 2;
+    const bool inp_aligned4 = ((w * 3) % 4 == 0) && ((uintptr_t)inp_t % 4 == 0);
+    for (int task = threadIdx.x; task < K3_BIG_TH * Q; task += K3_BIG_THREADS) {
+        const int r = task / Q, xq = (task - r * Q) * 4, y = y0 + r;
+        if (y >= H0) continue;
+        const int n = min(4, W0 - xq);
+        const long long po = ((long long)y * W0 + xq) * 3;
+        uint32_t o[3] = {0, 0, 0};
+        const bool whole = words_ok && n == 4;                    // 12 bytes, 4-byte aligned
+        if (whole) {
+            const uint32_t *op = reinterpret_cast<const uint32_t *>(orig_t + po);
+            o[0] = __ldg(op), o[1] = __ldg(op + 1), o[2] = __ldg(op + 2);
+        } else {
+            for (int k = 0; k < 3 * n; ++k) o[k >> 2] |= (uint32_t)orig_t[po + k] << (8 * (k & 3));
+        }
+        const uint32_t in4 = window16(bits + (r + R) * row_words, xq) & 15u;
+        const Tap ty = yt[y];
+        const uint32_t b0s = (uint32_t)(ty.w & 0xffff) << 16, b1s = (uint32_t)ty.w & 0xffff0000u;
+        const int ya = min(max(ty.ofs, 0), h - 1), yb = min(max(ty.ofs + 1, 0), h - 1);
+        const uint8_t *r0 = inp_t + (long long)ya * w * 3, *r1 = inp_t + (long long)yb * w * 3;
+        for (int i = 0; i < n; ++i) {
+            const bool inside = (in4 >> i) & 1u;
+            const uint32_t c = cls[r * W0 + xq + i];
+            float a = inside ? 1.f : 0.f;
+            if (c != 0) {
+                const float cost = tab[c - 1].cost;
+                a = inside ? alpha_from(cost, 0.f, div) : alpha_from(0.f, cost, div);
+            }
+            if (a > 0.f) {
+                const Tap tx = xt[xq + i];
+                const PixelPair p0 = load_pixel_pair(r0, tx.ofs, w, inp_aligned4), p1 = load_pixel_pair(r1, tx.ofs, w, inp_aligned4);
+                const uint32_t wts = (uint32_t)tx.w;
+                uint32_t cr = vpass(b0s, b1s, hpass<0>(p0, wts), hpass<0>(p1, wts));
+                uint32_t cg = vpass(b0s, b1s, hpass<1>(p0, wts), hpass<1>(p1, wts));
+                uint32_t cb = vpass(b0s, b1s, hpass<2>(p0, wts), hpass<2>(p1, wts));
+                if (a < 1.f) {
+                    const float na = __fsub_rn(1.f, a);
+                    cr = blend_u8(a, na, cr, byte_of(o[(3 * i) >> 2], (3 * i) & 3));
+                    cg = blend_u8(a, na, cg, byte_of(o[(3 * i + 1) >> 2], (3 * i + 1) & 3));
+                    cb = blend_u8(a, na, cb, byte_of(o[(3 * i + 2) >> 2], (3 * i + 2) & 3));
+                }
+                const uint32_t rgb[3] = {cr, cg, cb};
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int k = 3 * i + ch;
+                    o[k >> 2] = (o[k >> 2] & ~(0xffu << (8 * (k & 3)))) | ((rgb[ch] & 0xffu) << (8 * (k & 3)));
+                }
+            }
+        }
+        if (whole) {
+            uint32_t *dp = reinterpret_cast<uint32_t *>(out_t + po);
+            dp[0] = o[0], dp[1] = o[1], dp[2] = o[2];
+        } else {
+            for (int k = 0; k < 3 * n; ++k) out_t[po + k] = (uint8_t)byte_of(o[k >> 2], k & 3);
+        }
+    }
+}
+
 // Host: the 16 alpha levels of the small-radius kernels, index = class (0 = no hit within the window, 1..5 = cost
 // classes 1, 1.4, 2, 2.1969, 2.8) | inside << 3; the same IEEE float32 operations as alpha_from() on the device
 // (diffuerase.py:99-100: 0.5 + (d_in - d_out) / (2 F), clipped).
@@ -1487,8 +1656,58 @@ static void host_alpha_levels(float div, float alpha[16], uint32_t *pos) {
     }
 }
 
-// Host: float32 Dijkstra over the 5x5-chamfer step set (same construction as
-// oracle/prepost.py chamfer_cost_table, verified bit-exact against cv2.distanceTransform).
+// Host: the chamfer table of ONE zero pixel = what cv2.distanceTransform(DIST_L2, 5) yields around it: the two raster
+// passes (forward: neighbours (-1, -2..2), (-2, +-1), (0, -1); backward: their mirror images), every step one float32
+// addition.  With several zero pixels the transform is the minimum of the shifted tables (float32 addition is monotone).
+// Float addition is not associative, so the table is not symmetric from d ~ 12 on; same construction as
+// oracle/prepost.py chamfer_cost_table, verified bit-exact against cv2 4.13 / IPP for feather_px <= 32.
+// at(oy, ox) of the result = value at offset (oy, ox) FROM the zero pixel, |oy|, |ox| <= R.
+static std::vector<float> build_chamfer_table(int R) {
+    const float A = 1.0f, B = 1.4f, Cc = 2.1969f;
+    const int n = 2 * R + 1 + 8, c = n / 2, S = n + 4;
+    std::vector<float> d((size_t)S * S, INFINITY);
+    auto at = [&](int i, int j) -> float & { return d[(size_t)i * S + j]; };
+    at(c + 2, c + 2) = 0.f;
+    const int udi[7] = {-1, -1, -1, -1, -1, -2, -2}, udj[7] = {-2, -1, 0, 1, 2, -1, 1};
+    const float uc[7] = {Cc, B, A, B, Cc, Cc, Cc};
+    for (int pass = 0; pass < 2; ++pass) {
+        const int sgn = pass ? -1 : 1;
+        for (int ii = 0; ii < n; ++ii) {
+            const int i = pass ? n + 1 - ii : 2 + ii;
+            for (int jj = 0; jj < n; ++jj) {
+                const int j = pass ? n + 1 - jj : 2 + jj;
+                float v = at(i, j);
+                for (int k = 0; k < 7; ++k) {
+                    volatile float t = at(i + sgn * udi[k], j + sgn * udj[k]) + uc[k];   // force a rounded fp32 sum
+                    if (t < v) v = t;
+                }
+                volatile float t = at(i, j - sgn) + A;
+                if (t < v) v = t;
+                at(i, j) = v;
+            }
+        }
+    }
+    std::vector<float> tab((size_t)(2 * R + 1) * (2 * R + 1));
+    for (int oy = -R; oy <= R; ++oy)
+        for (int ox = -R; ox <= R; ++ox) tab[(size_t)(oy + R) * (2 * R + 1) + (ox + R)] = at(c + 2 + oy, c + 2 + ox);
+    return tab;
+}
+
+// Offsets (dy, dx) at which a pixel p may find its nearest opposite pixel (at p + (dx, dy)), cost < feather_px, sorted by
+// cost: the offset of p FROM that pixel is -(dx, dy).
+static std::vector<std::tuple<float, int, int>> chamfer_entries(float feather_px, int R) {
+    const std::vector<float> tab = build_chamfer_table(R);
+    std::vector<std::tuple<float, int, int>> ent;
+    for (int dy = -R; dy <= R; ++dy)
+        for (int dx = -R; dx <= R; ++dx) {
+            if (!dx && !dy) continue;
+            const float c = tab[(size_t)(-dy + R) * (2 * R + 1) + (-dx + R)];
+            if (c < feather_px) ent.push_back(std::make_tuple(c, dy, dx));
+        }
+    std::sort(ent.begin(), ent.end());
+    return ent;
+}
+
 static void build_feather_table(float feather_px, FeatherTable *ft) {
     ft->div = (float)(2.0 * (double)feather_px);
     ft->n = 0;
@@ -1498,46 +1717,15 @@ static void build_feather_table(float feather_px, FeatherTable *ft) {
     const int R = (int)ceilf(feather_px) - 1;
     ft->radius = R < 0 ? 0 : R;
     if (R <= 0) return;       // every neighbour is >= 1 >= F away: alpha is the hard mask
-    const int lim = 3 * R + 6, S = 2 * lim + 1;
-    std::vector<float> dist(S * S, -1.f);
-    typedef std::tuple<float, int, int> Node;
-    std::priority_queue<Node, std::vector<Node>, std::greater<Node>> pq;
-    const float A = 1.0f, B = 1.4f, Cc = 2.1969f;
-    const int sx[16] = {1, -1, 0, 0, 1, 1, -1, -1, 2, 2, -2, -2, 1, 1, -1, -1};
-    const int sy[16] = {0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 2, -2, 2, -2};
-    const float sc[16] = {A, A, A, A, B, B, B, B, Cc, Cc, Cc, Cc, Cc, Cc, Cc, Cc};
-    pq.push(Node(0.f, 0, 0));
-    while (!pq.empty()) {
-        Node nd = pq.top();
-        pq.pop();
-        const float d = std::get<0>(nd);
-        const int x = std::get<1>(nd), y = std::get<2>(nd);
-        float &slot = dist[(y + lim) * S + (x + lim)];
-        if (slot >= 0.f) continue;
-        slot = d;
-        for (int k = 0; k < 16; ++k) {
-            const int nx = x + sx[k], ny = y + sy[k];
-            if (abs(nx) > lim || abs(ny) > lim) continue;
-            if (dist[(ny + lim) * S + (nx + lim)] >= 0.f) continue;
-            volatile float nd2 = d + sc[k];   // force a rounded fp32 sum
-            pq.push(Node(nd2, nx, ny));
-        }
-    }
-    std::vector<std::tuple<float, int, int>> ent;
-    for (int dy = -R; dy <= R; ++dy)
-        for (int dx = -R; dx <= R; ++dx) {
-            if (!dx && !dy) continue;
-            const float c = dist[(dy + lim) * S + (dx + lim)];
-            if (c < feather_px) ent.push_back(std::make_tuple(c, dy, dx));
-        }
-    std::sort(ent.begin(), ent.end());
+    if (R > 7) return;        // k3_bigfeather walks its own table in device memory
+    const std::vector<std::tuple<float, int, int>> ent = chamfer_entries(feather_px, R);
     ft->n_cls = 0;
     for (size_t i = 0; i < ent.size() && i < (size_t)K3_MAX_ENTRIES; ++i) {
         ft->cost[i] = std::get<0>(ent[i]);
         ft->dy[i] = (int8_t)std::get<1>(ent[i]);
         ft->dx[i] = (int8_t)std::get<2>(ent[i]);
         if (i == 0 || ft->cost[i] != ft->cost[i - 1]) {
-            if (ft->n_cls == K3_MAX_CLASSES) break;          // cannot happen for feather_px <= VV_MAX_FEATHER
+            if (ft->n_cls == K3_MAX_CLASSES) break;          // cannot happen for feather_px <= 8 (radius <= 7)
             ft->ccost[++ft->n_cls] = ft->cost[i];
         }
         ft->cls[i] = (uint8_t)ft->n_cls;
@@ -1549,7 +1737,11 @@ static void build_feather_table(float feather_px, FeatherTable *ft) {
 
 using namespace vv;
 
-extern "C" size_t vv_composite_workspace_bytes(int H0, int W0) { return vv_resize_workspace_bytes(H0, W0); }
+// tap tables of the resize-back + room for the offset table of k3_bigfeather (feather_px > 8)
+extern "C" size_t vv_composite_workspace_bytes(int H0, int W0) {
+    const size_t taps = vv_resize_workspace_bytes(H0, W0);
+    return taps ? align_up(taps, 256) + K3_BIG_MAX_ENTRIES * sizeof(BigEntry) : 0;
+}
 
 static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t *orig, const uint8_t *mask,
                           const uint32_t *mask_bits, int H0, int W0, float feather_px, int keep_unmasked, uint8_t *out,
@@ -1587,9 +1779,59 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         }
         ft = ft_cache;
     }
+    const int Wp = ceil_div(W0, 32);
+    if (ft.radius > 7) {
+        // ---- feather_px in (8, 32]: k3_bigfeather with its cost-sorted offset table in device memory (behind the taps)
+        static std::vector<BigEntry> big_cache;
+        static float big_key = -12345.f;
+        BigEntry *dtab = (BigEntry *)((uint8_t *)workspace + align_up(vv_resize_workspace_bytes(H0, W0), 256));
+        int n_entries = 0;
+        {
+            std::lock_guard<std::mutex> g(ft_mu);
+            if (big_key != feather_px) {
+                const std::vector<std::tuple<float, int, int>> ent = chamfer_entries(feather_px, ft.radius);
+                big_cache.clear();
+                for (const auto &e : ent) big_cache.push_back(BigEntry{std::get<0>(e), (short)std::get<2>(e), (short)std::get<1>(e)});
+                big_key = feather_px;
+            }
+            n_entries = (int)big_cache.size();
+            if (n_entries > K3_BIG_MAX_ENTRIES) {
+                set_error("vv_upscale_feather_composite: offset table of feather_px %.3f too large", feather_px);
+                return VV_ERR_UNSUPPORTED;
+            }
+            // pageable source: the runtime stages it before the call returns, so the cache may change afterwards
+            cudaError_t ce = cudaMemcpyAsync(dtab, big_cache.data(), (size_t)n_entries * sizeof(BigEntry), cudaMemcpyHostToDevice, st);
+            if (ce != cudaSuccess) return fail_cuda(ce, "cudaMemcpyAsync(feather table)");
+        }
+        if ((rc = build_linear_taps(workspace, h, w, H0, W0, &xt, &yt, st, 3))) return rc;
+        const size_t smem = ((size_t)(K3_BIG_TH + 2 * ft.radius) * (Wp + 3)) * 4 + align_up((size_t)K3_BIG_TH * W0 * 2, 4);
+        if (smem > 200 * 1024) {
+            set_error("vv_upscale_feather_composite: feather_px > 8 supports frames up to about 10000 pixels wide");
+            return VV_ERR_UNSUPPORTED;
+        }
+        int dev_big = 0;
+        cudaGetDevice(&dev_big);
+        dev_big = min(max(dev_big, 0), 63);
+        static std::atomic<size_t> big_smem_set[64];
+        if (smem > 48 * 1024 && smem > big_smem_set[dev_big].load()) {
+            cudaError_t e = cudaFuncSetAttribute(k3_bigfeather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(k3_bigfeather)");
+            big_smem_set[dev_big].store(smem);
+        }
+        const int words_ok = (W0 % 4 == 0) && ((uintptr_t)orig % 4 == 0) && ((uintptr_t)out % 4 == 0);
+        const int bstrips = ceil_div(H0, K3_BIG_TH);
+        for (int t0 = 0; t0 < T; t0 += 32768) {          // grid.y <= 65535 frames per launch
+            const int tn = min(32768, T - t0);
+            const size_t fo = (size_t)t0 * H0 * W0;
+            k3_bigfeather<<<dim3((unsigned)bstrips, (unsigned)tn), K3_BIG_THREADS, smem, st>>>(
+                inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo, mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : nullptr,
+                out + fo * 3, xt, yt, dtab, n_entries, ft.radius, ft.div, h, w, H0, W0, words_ok);
+            VV_POST_LAUNCH("k3_bigfeather");
+        }
+        return VV_OK;
+    }
     const bool small_r = feather_px > 0.f && ft.radius <= 2;
     const int R = small_r ? 2 : ft.radius;
-    const int Wp = ceil_div(W0, 32);
     const bool vec = (W0 % 16 == 0) && ((uintptr_t)orig % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                      ((uintptr_t)mask % 16 == 0);
     // TMA-staged variant: strip rows chosen so that strip + bit rows + queues fit twice per SM
