@@ -69,6 +69,8 @@ VV_API void vv_reset_launch_count(void);
  *                closed-form or table-driven vertical pass, 32-pixel word classification tasks, interior words without
  *                blend, software-pipelined worker, packed-fp32 blend; 2 = k3_fast, its predecessor (16-pixel rolling
  *                tasks); 1 = the round-1 closed-form worker (needs H0 == 2h as well); 0 = the generic tap-table worker.
+ *   "k3_big_from" smallest feather window radius (ceil(feather_px) - 1) that runs k3_bigfeather, the table-walking kernel of
+ *                feather_px in (8, 32]; default 8, 3..7 send those radii there as well instead of to the round-1 generic kernel.
  *   "k3_chain"   1 = the next k3_fastw launch is chained to the K3 launch before it in the stream (programmatic stream
  *                serialisation; it may start while that one drains).  Only for back-to-back K3 calls over DIFFERENT
  *                frames of a clip; the Python front end sets it per call (chain_previous=True).  Default 0.

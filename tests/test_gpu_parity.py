@@ -261,6 +261,23 @@ def test_k3_big_feather(ops, h0, w0, h, w, bits, f):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("f", [3.5, 5, 6.5, 8])
+def test_k3_table_walking_kernel_on_small_radii(ops, f):
+    """k3_big_from = 3 sends the radii 3..7 to k3_bigfeather as well: same bytes as the generic kernel and the oracle."""
+    from videovanish_b200 import _lib
+    t, h0, w0, h, w = 3, 97, 131, 40, 56
+    fr, inp = synth.frames(t, h0, w0, seed=3), synth.noise_frames(t, h, w, seed=4)
+    dil = np.stack(op.model_binarize_dilate(list(synth.masks(t, h0, w0, seed=5, salt=0.002)), 2))
+    ref = np.stack([op.ref_post_frame(inp[i], fr[i], dil[i], True, f) for i in range(t)])
+    generic = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=f))
+    try:
+        _lib.set_option("k3_big_from", 3)
+        walked = host(ops.upscale_feather_composite(dev(inp), dev(fr), dev(dil), feather_px=f))
+    finally:
+        _lib.set_option("k3_big_from", 8)
+    assert np.array_equal(generic, ref) and np.array_equal(walked, ref)
+
+
 def test_k3_unsupported_feather_raises(ops):
     fr = synth.frames(1, 32, 32, seed=1)
     with pytest.raises(RuntimeError, match="feather_px"):

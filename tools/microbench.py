@@ -126,6 +126,14 @@ def main():
     report("K3 composite 960x536 (synthetic mask)", k3b536, K3(dil, None, inp536), k3_x2=0, bits=0)
     _lib.set_option("k3_x2", 3)
     report("K3 composite feather 5 (generic path)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
+    report("K3 composite feather 8 (generic path)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 8, out=out))
+    _lib.set_option("k3_big_from", 3)
+    report("K3 composite feather 5 (k3_bigfeather)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 5, out=out))
+    report("K3 composite feather 8 (k3_bigfeather)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 8, out=out))
+    _lib.set_option("k3_big_from", 8)
+    report("K3 composite feather 16 (k3_bigfeather)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 16, out=out))
+    report("K3 composite feather 32 (k3_bigfeather)", k3b, lambda: ops.upscale_feather_composite(inp, fr, dil, 32, out=out))
+    report("K3 composite feather 16, box mask (k3_bigfeather)", k3b, lambda: ops.upscale_feather_composite(inp, fr, box_dil, 16, out=out))
     del dil_b, full_bits, box_dil, box_bits, inp536, empty_bits
     # ---- K4: step-kernel variants
     pbuf = torch.empty((t, HS, WS), dtype=torch.int32, device=dev)

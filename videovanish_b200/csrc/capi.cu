@@ -9,8 +9,8 @@ namespace vv {
 
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-static std::atomic<int> g_options[OPT_COUNT] = {{1}, {2}, {1}, {16}, {512}, {1}, {1}, {1}, {3}, {128}, {4}, {5}, {0}, {5}, {1}, {148 * 8}, {0}, {0}, {1}, {2}, {8}, {2}};
-static const char *const g_option_names[OPT_COUNT] = {"k1b_exact", "k3_nt", "k3_tma", "k3_tma_rows", "k3_tma_threads", "k4_pdl", "k4_npt", "k3_bits", "k3_x2", "k4_pack_ctas", "k4_pack_occ", "k4_lean", "k4_precheck", "k4_step_ctas", "k4_speculate", "k5_halo_ctas", "k3_chain", "k4_persist", "pipe_rows", "k4_streams", "k4_chain_ctas", "k1b_diag"};
+static std::atomic<int> g_options[OPT_COUNT] = {{1}, {2}, {1}, {16}, {512}, {1}, {1}, {1}, {3}, {128}, {4}, {5}, {0}, {5}, {1}, {148 * 8}, {0}, {0}, {1}, {2}, {8}, {2}, {8}};
+static const char *const g_option_names[OPT_COUNT] = {"k1b_exact", "k3_nt", "k3_tma", "k3_tma_rows", "k3_tma_threads", "k4_pdl", "k4_npt", "k3_bits", "k3_x2", "k4_pack_ctas", "k4_pack_occ", "k4_lean", "k4_precheck", "k4_step_ctas", "k4_speculate", "k5_halo_ctas", "k3_chain", "k4_persist", "pipe_rows", "k4_streams", "k4_chain_ctas", "k1b_diag", "k3_big_from"};
 
 int get_option(int opt) { return g_options[opt].load(std::memory_order_relaxed); }
 

@@ -13,7 +13,7 @@ namespace vv {
 void set_error(const char *fmt, ...);
 
 // Tuning switches (vv_set_option): variants kept side by side so that one GPU run can A/B them.
-enum Option { OPT_K1B_EXACT = 0, OPT_K3_NT, OPT_K3_TMA, OPT_K3_TMA_ROWS, OPT_K3_TMA_THREADS, OPT_K4_PDL, OPT_K4_NPT, OPT_K3_BITS, OPT_K3_X2, OPT_K4_PACK_CTAS, OPT_K4_PACK_OCC, OPT_K4_LEAN, OPT_K4_TAPS, OPT_K4_STEP_CTAS, OPT_K4_SPECULATE, OPT_K5_HALO_CTAS, OPT_K3_CHAIN, OPT_K4_PERSIST, OPT_PIPE_ROWS, OPT_K4_STREAMS, OPT_K4_CHAIN_CTAS, OPT_K1B_DIAG, OPT_COUNT };
+enum Option { OPT_K1B_EXACT = 0, OPT_K3_NT, OPT_K3_TMA, OPT_K3_TMA_ROWS, OPT_K3_TMA_THREADS, OPT_K4_PDL, OPT_K4_NPT, OPT_K3_BITS, OPT_K3_X2, OPT_K4_PACK_CTAS, OPT_K4_PACK_OCC, OPT_K4_LEAN, OPT_K4_TAPS, OPT_K4_STEP_CTAS, OPT_K4_SPECULATE, OPT_K5_HALO_CTAS, OPT_K3_CHAIN, OPT_K4_PERSIST, OPT_PIPE_ROWS, OPT_K4_STREAMS, OPT_K4_CHAIN_CTAS, OPT_K1B_DIAG, OPT_K3_BIG_FROM, OPT_COUNT };
 int get_option(int opt);
 extern std::atomic<unsigned long long> g_launches;
 

@@ -1487,7 +1487,7 @@ __global__ void __launch_bounds__(K3_BIG_THREADS)
     k3_bigfeather(const uint8_t *__restrict__ inp, const uint8_t *__restrict__ orig, const uint8_t *__restrict__ mask,
                   const uint32_t *__restrict__ mask_bits, uint8_t *__restrict__ out, const Tap *__restrict__ xt,
                   const Tap *__restrict__ yt, const BigEntry *__restrict__ tab, int n_entries, int R, float div, int h, int w,
-                  int H0, int W0, int words_ok) {
+                  int H0, int W0, int words_ok, int mask_vec) {
     extern __shared__ __align__(16) uint32_t big_smem[];
     const int Wp = (W0 + 31) >> 5, row_words = Wp + 3;            // one zero pad word on the left, two on the right
     const int rows_s = K3_BIG_TH + 2 * R;
@@ -1510,7 +1510,11 @@ __global__ void __launch_bounds__(K3_BIG_THREADS)
             } else {
                 const uint8_t *p = mask_t + (long long)y * W0 + k * 32;
                 const int n = min(32, W0 - k * 32);
-                for (int q = 0; q < n; ++q) v |= (uint32_t)(p[q] != 0) << q;
+                if (mask_vec && n == 32) {
+                    v = nonzero_bits16(ldg128(p)) | (nonzero_bits16(ldg128(p + 16)) << 16);
+                } else {
+                    for (int q = 0; q < n; ++q) v |= (uint32_t)(p[q] != 0) << q;
+                }
             }
             if (k == Wp - 1 && (W0 & 31)) v &= (1u << (W0 & 31)) - 1u;
         }
@@ -1780,8 +1784,8 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
         ft = ft_cache;
     }
     const int Wp = ceil_div(W0, 32);
-    if (ft.radius > 7) {
-        // ---- feather_px in (8, 32]: k3_bigfeather with its cost-sorted offset table in device memory (behind the taps)
+    if (ft.radius > 7 || (ft.radius > 2 && ft.radius >= max(3, get_option(OPT_K3_BIG_FROM)))) {
+        // ---- feather_px in (8, 32] (and smaller radii >= "k3_big_from"): k3_bigfeather with its cost-sorted offset table in device memory (behind the taps)
         static std::vector<BigEntry> big_cache;
         static float big_key = -12345.f;
         BigEntry *dtab = (BigEntry *)((uint8_t *)workspace + align_up(vv_resize_workspace_bytes(H0, W0), 256));
@@ -1819,13 +1823,14 @@ static int composite_impl(const uint8_t *inp, int T, int h, int w, const uint8_t
             big_smem_set[dev_big].store(smem);
         }
         const int words_ok = (W0 % 4 == 0) && ((uintptr_t)orig % 4 == 0) && ((uintptr_t)out % 4 == 0);
+        const int mask_vec = (W0 % 16 == 0) && ((uintptr_t)mask % 16 == 0);
         const int bstrips = ceil_div(H0, K3_BIG_TH);
         for (int t0 = 0; t0 < T; t0 += 32768) {          // grid.y <= 65535 frames per launch
             const int tn = min(32768, T - t0);
             const size_t fo = (size_t)t0 * H0 * W0;
             k3_bigfeather<<<dim3((unsigned)bstrips, (unsigned)tn), K3_BIG_THREADS, smem, st>>>(
                 inp + (size_t)t0 * h * w * 3, orig + fo * 3, mask + fo, mask_bits ? mask_bits + (size_t)t0 * H0 * Wp : nullptr,
-                out + fo * 3, xt, yt, dtab, n_entries, ft.radius, ft.div, h, w, H0, W0, words_ok);
+                out + fo * 3, xt, yt, dtab, n_entries, ft.radius, ft.div, h, w, H0, W0, words_ok, mask_vec);
             VV_POST_LAUNCH("k3_bigfeather");
         }
         return VV_OK;
