@@ -30,6 +30,8 @@ CASES = [
     ("same_size", 2, 72, 128, 72, 128, 2, 3, True),             # no resize-back branch
     ("frac_feather", 2, 80, 112, 40, 56, 2, 2.5, True),         # float feather_px
     ("hd_crop", 1, 270, 480, 136, 240, 8, 3, True),
+    ("feather12_5", 2, 120, 176, 56, 88, 3, 12.5, True),        # beyond 8: the two-pass chamfer table is not symmetric any more
+    ("feather32", 2, 150, 200, 72, 96, 5, 32, True),            # VV_MAX_FEATHER
 ]
 
 
