@@ -160,6 +160,11 @@ VV_API int vv_upscale_feather_composite_bits(const uint8_t *inp, int T, int h, i
                                  int H0, int W0, float feather_px, int keep_unmasked, uint8_t *out,
                                  void *workspace, size_t workspace_bytes, void *stream);
 
+/* The chamfer table the feather stage works from (host code, needs no GPU): table[(oy + R) * (2R + 1) + (ox + R)] =
+ * what cv2.distanceTransform(DIST_L2, 5) (diffuerase.py:95-96) yields at offset (oy, ox) FROM a single zero pixel - the
+ * float32 result of its two raster passes, not symmetric from d ~ 12 on.  0 <= R <= 31; table: (2R + 1)^2 floats. */
+VV_API int vv_chamfer_table(int R, float *table);
+
 /* ---------------------------------------------------------------------------------
  * K4  ProPainter-style flow-guided propagation prior (image propagation, 'nearest').
  *   Replaces the un-vendored propainter.forward call at diffuerase.py:49-57

@@ -117,3 +117,22 @@ def test_every_tuning_option_is_documented_and_readable():
     assert _lib.get_option("k4_streams") == 2 and _lib.get_option("k4_chain_ctas") == 8 and _lib.get_option("k1b_diag") == 2
     v = ctypes.c_int(0)
     assert _lib.lib.vv_get_option(b"no_such_option", ctypes.byref(v)) != 0
+
+
+def test_host_chamfer_table_equals_cv2_and_the_oracle():
+    """The table the feather kernels work from is built on the HOST (k3_composite.cu build_chamfer_table): without a GPU
+    it can be compared with the oracle's construction and with cv2.distanceTransform around one zero pixel."""
+    import ctypes
+    import cv2
+    from oracle import prepost as op
+    from videovanish_b200 import _lib
+    for r in (2, 7, 15, 31):
+        n = 2 * r + 1
+        buf = (ctypes.c_float * (n * n))()
+        assert _lib.lib.vv_chamfer_table(r, buf) == 0
+        tab = np.frombuffer(buf, np.float32).reshape(n, n)
+        m = np.full((n, n), 255, np.uint8)
+        m[r, r] = 0
+        assert np.array_equal(tab, cv2.distanceTransform(m, cv2.DIST_L2, 5))
+        assert np.array_equal(tab[::-1, ::-1], op.chamfer_cost_table(r))
+    assert _lib.lib.vv_chamfer_table(32, buf) != 0

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "vv_pipeline_upload": (c_int, [c_void_p, _pp, c_int, c_size_t, _u8p, c_void_p]),
     "vv_pipeline_download": (c_int, [c_void_p, _u8p, c_int, c_size_t, _pp, c_void_p]),
     "vv_pipeline_last_rows": (c_int, [c_void_p, POINTER(ctypes.c_longlong), POINTER(ctypes.c_longlong)]),
+    "vv_chamfer_table": (c_int, [c_int, POINTER(c_float)]),
     "vv_mask_row_bounds": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vv_pipeline_host_rows_begin": (c_int, [c_void_p, c_int, c_int, c_size_t, _pp, _pp, POINTER(c_int), POINTER(c_int)]),
     "vv_pipeline_download_rows": (c_int, [c_void_p, _u8p, c_int, c_int, c_size_t, _pp, POINTER(c_int), POINTER(c_int), c_void_p]),

@@ -1741,6 +1741,13 @@ static void build_feather_table(float feather_px, FeatherTable *ft) {
 
 using namespace vv;
 
+extern "C" int vv_chamfer_table(int R, float *table) {
+    VV_CHECK_ARG(table && R >= 0 && R <= 31, "vv_chamfer_table: 0 <= R <= 31 and a table of (2R + 1)^2 floats required");
+    const std::vector<float> t = build_chamfer_table(R);
+    std::copy(t.begin(), t.end(), table);
+    return VV_OK;
+}
+
 // tap tables of the resize-back + room for the offset table of k3_bigfeather (feather_px > 8)
 extern "C" size_t vv_composite_workspace_bytes(int H0, int W0) {
     const size_t taps = vv_resize_workspace_bytes(H0, W0);
