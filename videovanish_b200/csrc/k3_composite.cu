@@ -1559,22 +1559,33 @@ __global__ void __launch_bounds__(K3_BIG_THREADS)
             }
         }
         uint32_t und = ((anyZ ? inside : 0u) | (anyM ? ~inside : 0u)) & px;
-        for (int e = 0; e < n_entries && und; ++e) {
-            const BigEntry en = tab[e];
-            const int yy = y + en.dy;
-            if (yy < 0 || yy >= H0) continue;                     // out-of-image pixels are "far" for both transforms
-            const int col = x0 + en.dx;
-            const uint32_t v = valid16(col);
-            const uint32_t m = window16(brow + en.dy * row_words, col) & v;
-            const uint32_t hit = (((~m & v) & inside) | (m & ~inside)) & und;      // inside pixels look for unmasked ones
-            if (hit) {
-                uint32_t hh = hit;
-                while (hh) {
-                    const int i = __ffs(hh) - 1;
-                    hh &= hh - 1;
-                    cls[r * W0 + x0 + i] = (uint16_t)(e + 1);
+        // four entries per trip: their table words and bit-row words are requested together (the walk is bound by the
+        // latency of these dependent loads, not by instructions); hits are still taken in table order
+        for (int e0 = 0; e0 < n_entries && und; e0 += 4) {
+            BigEntry en[4];
+            uint32_t m[4], v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) en[u] = tab[min(e0 + u, n_entries - 1)];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int yy = y + en[u].dy, col = x0 + en[u].dx;
+                // out-of-image pixels are "far" for both transforms; the bit rows of such rows exist in shared memory (zeros)
+                const bool ok = e0 + u < n_entries && yy >= 0 && yy < H0;
+                v[u] = ok ? valid16(col) : 0u;
+                m[u] = window16(brow + en[u].dy * row_words, col) & v[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t hit = (((~m[u] & v[u]) & inside) | (m[u] & ~inside)) & und;   // inside pixels look for unmasked ones
+                if (hit) {
+                    uint32_t hh = hit;
+                    while (hh) {
+                        const int i = __ffs(hh) - 1;
+                        hh &= hh - 1;
+                        cls[r * W0 + x0 + i] = (uint16_t)(e0 + u + 1);
+                    }
+                    und &= ~hit;
                 }
-                und &= ~hit;
             }
         }
     }
