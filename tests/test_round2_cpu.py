@@ -136,3 +136,33 @@ def test_host_chamfer_table_equals_cv2_and_the_oracle():
         assert np.array_equal(tab, cv2.distanceTransform(m, cv2.DIST_L2, 5))
         assert np.array_equal(tab[::-1, ::-1], op.chamfer_cost_table(r))
     assert _lib.lib.vv_chamfer_table(32, buf) != 0
+
+
+@pytest.mark.parametrize("k,extra", [(3, 2), (4, 1), (5, 1), (5, 2), (6, 1), (7, 1), (7, 2)])
+def test_diagonal_segments_plus_cross_rounds_make_the_l1_ball(k, extra):
+    """The identity K1's diagonal blocks rest on (k1_mask.cu diamond_block): dilating by the two diagonal segments
+    {i (1,1)}, {j (1,-1)}, |i|, |j| <= K, and then by `extra` >= 1 cross rounds equals 2K + extra cross rounds, i.e. the L1
+    ball of that radius - on random masks with set pixels on the frame edges (the frame is NOT padded for the reference
+    side; intermediate pixels outside the frame must not matter)."""
+    from oracle import prepost as op
+    rng = np.random.default_rng(10 * k + extra)
+    h, w = 41, 57
+    m = rng.random((h, w)) < 0.004
+    m[0, 0] = m[h - 1, w - 1] = m[0, w - 1] = m[h // 2, 0] = True
+    want = op.model_dilate_l1(m.astype(np.uint8), 2 * k + extra) > 0
+    pad = 2 * k + extra + 1                                   # the kernel's halo lanes / rows play this role
+    big = np.zeros((h + 2 * pad, w + 2 * pad), bool)
+    big[pad:pad + h, pad:pad + w] = m
+
+    def shift(a, dy, dx):
+        return np.roll(np.roll(a, dy, axis=0), dx, axis=1)    # the padding keeps the wrap-around out of the frame
+
+    acc = big.copy()
+    for dy_sign in (1, -1):                                   # S1 = (1, 1) direction, S2 = (1, -1)
+        seg = acc.copy()
+        for i in range(1, k + 1):
+            seg |= shift(acc, i * dy_sign, i) | shift(acc, -i * dy_sign, -i)
+        acc = seg
+    for _ in range(extra):
+        acc = acc | shift(acc, 1, 0) | shift(acc, -1, 0) | shift(acc, 0, 1) | shift(acc, 0, -1)
+    assert np.array_equal(acc[pad:pad + h, pad:pad + w], want)
